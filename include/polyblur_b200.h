@@ -1,0 +1,153 @@
+/* polyblur_b200 -- C ABI of the B200-native Polyblur engine (libpolyblur_sm100.so).
+ *
+ * This is the drop-in boundary for the hot path of teboli/polyblur: every entry point
+ * below replaces a Python function of the reference (file:line cited per function,
+ * paths relative to the reference checkout).  The reference has no FFI of its own -- it
+ * is a pure-Python package over ATen -- so the "binding a maintainer would add" is a
+ * ctypes stub; INTEGRATION.md shows it.
+ *
+ * Conventions
+ *   - all image pointers are DEVICE pointers to float32, NCHW, contiguous;
+ *   - the library allocates nothing: scratch lives in a caller-owned device workspace
+ *     of pb_workspace_bytes() bytes (256-byte aligned);
+ *   - work is enqueued on the cudaStream_t passed as `stream` (void* here so that the
+ *     header needs no CUDA include); no entry point synchronises the host;
+ *   - return value 0 = success, negative = error (pb_last_error() gives the text).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point
+ *     returns PB_ERR_CUDA.
+ */
+#ifndef POLYBLUR_B200_H
+#define POLYBLUR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define PB_API __attribute__((visibility("default")))
+#else
+#define PB_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB_VERSION 100            /* 0.1.0 */
+#define PB_KSIZE_MAX 25           /* kernel support of the reference (deblurring.py:24) */
+#define PB_EST_STRIDE 12          /* floats per (iteration, image) in est_out, see below */
+
+/* error codes */
+#define PB_OK 0
+#define PB_ERR_ARG (-1)           /* bad argument (shape, null pointer, unsupported option) */
+#define PB_ERR_WORKSPACE (-2)     /* workspace too small / misaligned */
+#define PB_ERR_CUDA (-3)          /* CUDA runtime error (no device, launch failure) */
+#define PB_ERR_UNSUPPORTED (-4)   /* valid in the reference but not built yet */
+
+/* option flags (keyword arguments of polyblur_deblurring, deblurring.py:23-25) */
+#define PB_FLAG_REMOVE_HALO        0x01u
+#define PB_FLAG_EDGETAPER          0x02u
+#define PB_FLAG_PREFILTER          0x04u  /* bilateral, what prefiltering=True runs (deblurring.py:108) */
+#define PB_FLAG_PREFILTER_RF       0x08u  /* domain-transform RF instead (the commented call, :107) */
+#define PB_FLAG_DISCARD_SATURATION 0x10u
+#define PB_FLAG_EDGETAPER_BATCHMAX 0x20u  /* bug-compatible batch-global max (edgetaper.py:15,21) */
+
+/* deconvolution engine selection (pb_params.engine); AUTO decides per image on device */
+#define PB_ENGINE_AUTO    0
+#define PB_ENGINE_SPATIAL 1       /* sparse-tap fused Horner stencil in shared memory      */
+#define PB_ENGINE_FFT     2       /* on-chip FFT of the padded torus (blur independent)    */
+
+/* Scalars are doubles because the reference receives them as Python floats and rounds
+ * derived quantities (c*c, the polynomial coefficients) to float32 only when they meet a
+ * tensor (blur_estimation.py:176-177, deblurring.py:160-166). */
+typedef struct pb_params {
+    double   c;           /* affine blur model slope      (blur_estimation.py:171-185)  */
+    double   b;           /* affine blur model intercept                                */
+    double   alpha;       /* polynomial parameters        (deblurring.py:160-162)       */
+    double   beta;
+    double   sigma_s;     /* prefilter parameters (RF only; the bilateral ignores them) */
+    double   sigma_r;
+    double   q;           /* quantile of the normalisation (0 = min/max)                */
+    int32_t  n_iter;      /* deblurring.py:23 n_iter                                    */
+    int32_t  ker_size;    /* odd, <= PB_KSIZE_MAX                                       */
+    uint32_t flags;       /* PB_FLAG_*                                                  */
+    int32_t  engine;      /* PB_ENGINE_*                                                */
+    float    tap_rel_threshold; /* spatial engine: drop taps < thr * max tap (0 = default 1e-8) */
+    int32_t  chunk_images;      /* images per launch group (0 = auto); tuning knob only  */
+} pb_params;
+
+/* ---- library / host-only entry points (usable without a GPU) ------------------------- */
+
+PB_API int pb_version(void);
+PB_API const char* pb_last_error(void);
+
+/* Fills p with the defaults of polyblur_deblurring (deblurring.py:23-25). */
+PB_API void pb_default_params(pb_params* p);
+
+/* Polynomial coefficients a3,a2,a1,b of deblurring.py:160-162 -> out[4]. */
+PB_API void pb_polynomial_coefficients(double alpha, double beta, float* out4);
+
+/* (30,7) normalised Keys cubic weights of blur_estimation.py:138-148,157-158 -> out[210]. */
+PB_API void pb_keys_weights(float* out210);
+
+/* Radix sequence the on-chip FFT uses for a length-n transform; returns the number of
+ * stages written to radices (<= 32), or a negative error. */
+PB_API int pb_fft_plan(int n, int* radices);
+
+/* Bytes of device workspace needed by any entry point below for this shape. */
+PB_API size_t pb_workspace_bytes(int B, int C, int H, int W, const pb_params* p);
+
+/* ---- the hot path ---------------------------------------------------------------------- */
+
+/* polyblur_deblurring (deblurring.py:23-96), method='fft' semantics, tensor path.
+ *   in, out : (B,C,H,W) float32 device; out may not alias in.
+ *   est_out : NULL or device float[n_iter][B][PB_EST_STRIDE] =
+ *             {m_0..m_6, theta_deg, sigma, rho, m_normal, m_ortho} per image-iteration
+ *             (the taps gaussian_blur_estimation computes, blur_estimation.py:18-79). */
+PB_API int pb_polyblur_f32(const float* in, float* out, int B, int C, int H, int W,
+                    const pb_params* p, void* workspace, size_t workspace_bytes,
+                    float* est_out, void* stream);
+
+/* ---- stage-level entry points (tests, stage-level drop-ins) --------------------------- */
+
+/* filters.fourier_gradients (filters.py:159-186): spectral derivative of every channel. */
+PB_API int pb_fourier_gradients_f32(const float* img, float* gx, float* gy, int B, int C, int H, int W,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
+/* blur_estimation.gaussian_blur_estimation up to the parameters (blur_estimation.py:18-73):
+ * est = device float[B][PB_EST_STRIDE] as above. */
+PB_API int pb_estimate_f32(const float* img, int B, int C, int H, int W, double c, double b, double q,
+                    uint32_t flags, float* est, void* workspace, size_t workspace_bytes,
+                    void* stream);
+
+/* blur_estimation.create_gaussian_filter (blur_estimation.py:211-232):
+ * theta (radians), sigma, rho: device float[B] -> kernel device float[B][ksize][ksize].
+ * Needs B * 4096 bytes of workspace. */
+PB_API int pb_make_kernel_f32(const float* theta, const float* sigma, const float* rho, int B,
+                       int ksize, float* kernel, void* workspace, size_t workspace_bytes,
+                       void* stream);
+
+/* deblurring.inverse_filtering_rank3 with default flags (deblurring.py:211-239):
+ * replicate pad, polynomial on the torus, crop, clamp to [0,1];
+ * kernel = device float[B][ksize][ksize] (one per image, broadcast over channels). */
+PB_API int pb_deconv_f32(const float* img, float* out, int B, int C, int H, int W,
+                  const float* kernel, int ksize, double alpha, double beta, int engine,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* edgetaper.edgetaper (edgetaper.py:26-33) on an already padded image. */
+PB_API int pb_edgetaper_f32(const float* img, float* out, int B, int C, int H, int W,
+                     const float* kernel, int ksize, int n_tapers, uint32_t flags,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* filters.bilateral_filter (filters.py:107-148), 5x5, sigma_spatial=5, sigma_color=0.1. */
+PB_API int pb_bilateral_f32(const float* img, float* out, int B, int C, int H, int W,
+                     float sigma_spatial, float sigma_color, void* stream);
+
+/* domain_transform.recursive_filter (domain_transform.py:6-85); joint may be NULL. */
+PB_API int pb_recursive_filter_f32(const float* img, const float* joint, float* out, int B, int C, int H,
+                            int W, float sigma_s, float sigma_r, int num_iterations,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POLYBLUR_B200_H */

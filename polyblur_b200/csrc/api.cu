@@ -1,0 +1,354 @@
+// extern "C" entry points of libpolyblur_sm100.so (see include/polyblur_b200.h).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "kernels.cuh"
+
+namespace pb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return PB_OK;
+    set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+    return PB_ERR_CUDA;
+}
+
+int make_fft_plan(int n, FftPlan* plan) {
+    if (n < 1) return PB_ERR_ARG;
+    plan->n = n;
+    plan->ns = 0;
+    int m = n;
+    static const int pref[] = {8, 7, 5, 4, 3, 2};
+    for (int r : pref) {
+        while (m % r == 0) {
+            if (plan->ns >= PB_MAX_STAGES) return PB_ERR_ARG;
+            plan->radix[plan->ns++] = r;
+            m /= r;
+        }
+    }
+    for (int p = 11; m > 1; p += 2) {
+        while (m % p == 0) {
+            if (plan->ns >= PB_MAX_STAGES) return PB_ERR_ARG;
+            plan->radix[plan->ns++] = p;
+            m /= p;
+        }
+        if ((long long)p * p > m && m > 1) {   // m is prime
+            if (plan->ns >= PB_MAX_STAGES) return PB_ERR_ARG;
+            plan->radix[plan->ns++] = m;
+            m = 1;
+        }
+    }
+    return PB_OK;
+}
+
+// ---- workspace layout -------------------------------------------------------------------------
+struct Workspace {
+    size_t off_stats, off_kern, off_twH, off_twW, off_gray, off_gy, off_tmp, total;
+};
+
+static Workspace layout(int B, int C, int H, int W, int n_iter) {
+    Workspace w;
+    size_t o = 0;
+    auto take = [&](size_t bytes) {
+        size_t at = o;
+        o = align_up(o + bytes, 256);
+        return at;
+    };
+    const size_t plane = (size_t)H * W;
+    const size_t nimg = (size_t)B * (C > 0 ? C : 1);   // stage entry points treat channels as images
+    w.off_stats = take(nimg * PB_STATS_STRIDE * sizeof(unsigned));
+    w.off_kern = take(nimg * sizeof(ImgKernel));
+    w.off_twH = take((size_t)H * sizeof(float2));
+    w.off_twW = take((size_t)W * sizeof(float2));
+    w.off_gray = take((size_t)B * plane * sizeof(float));
+    w.off_gy = take((size_t)B * plane * sizeof(float));
+    w.off_tmp = take(n_iter >= 2 ? (size_t)B * C * plane * sizeof(float) : 0);
+    w.total = o;
+    return w;
+}
+
+static int check_shape(int B, int C, int H, int W) {
+    if (B < 1 || C < 1 || H < 1 || W < 1) {
+        set_error("bad shape B=%d C=%d H=%d W=%d", B, C, H, W);
+        return PB_ERR_ARG;
+    }
+    if ((size_t)H * W > (size_t)1 << 31) {
+        set_error("plane of %d x %d exceeds 2^31 pixels", H, W);
+        return PB_ERR_ARG;
+    }
+    return PB_OK;
+}
+
+static int check_ws(const void* ws, size_t have, size_t need) {
+    if (!ws || have < need) {
+        set_error("workspace too small: have %zu bytes, need %zu", have, need);
+        return PB_ERR_WORKSPACE;
+    }
+    if (((uintptr_t)ws & 255u) != 0) {
+        set_error("workspace must be 256-byte aligned");
+        return PB_ERR_WORKSPACE;
+    }
+    return PB_OK;
+}
+
+struct Tables {
+    FftPlan planH, planW;
+    float2 *twH, *twW;
+};
+
+static int prepare_tables(char* ws, const Workspace& L, int H, int W, Tables* t, cudaStream_t stream) {
+    if (make_fft_plan(H, &t->planH) || make_fft_plan(W, &t->planW)) {
+        set_error("cannot plan FFT for %d x %d", H, W);
+        return PB_ERR_ARG;
+    }
+    t->twH = reinterpret_cast<float2*>(ws + L.off_twH);
+    t->twW = reinterpret_cast<float2*>(ws + L.off_twW);
+    int rc = launch_twiddles(t->twH, H, stream);
+    if (rc) return rc;
+    return launch_twiddles(t->twW, W, stream);
+}
+
+static void poly_coeffs(double alpha, double beta, float* o) {
+    // deblurring.py:160-162 (Python doubles, rounded to float32 when they meet the tensor)
+    o[0] = (float)(alpha / 2 - beta + 2);
+    o[1] = (float)(3 * beta - alpha - 6);
+    o[2] = (float)(5 - 3 * beta + alpha / 2);
+    o[3] = (float)beta;
+}
+
+static int estimate_into(const float* img, int B, int C, int H, int W, double c, double b, uint32_t flags,
+                         float* est, char* ws, const Workspace& L, const Tables& T, int ksize,
+                         float tap_thr, int engine, cudaStream_t stream) {
+    unsigned* stats = reinterpret_cast<unsigned*>(ws + L.off_stats);
+    ImgKernel* kern = reinterpret_cast<ImgKernel*>(ws + L.off_kern);
+    float* gray = reinterpret_cast<float*>(ws + L.off_gray);
+    float* gy = reinterpret_cast<float*>(ws + L.off_gy);
+    int rc;
+    if ((rc = launch_init_stats(stats, B, stream))) return rc;
+    if ((rc = launch_cols(true, img, gray, gy, stats, B, C, H, W, T.planH, T.twH, stream))) return rc;
+    if ((rc = launch_rows(true, gray, gy, nullptr, stats, B, H, W, T.planW, T.twW,
+                          (flags & PB_FLAG_DISCARD_SATURATION) ? 1 : 0, stream)))
+        return rc;
+    return launch_params(stats, kern, est, nullptr, nullptr, nullptr, nullptr, nullptr, 0, B, ksize,
+                         (float)(c * c), (float)(b * b), tap_thr, engine, 1 << 30, stream);
+}
+
+}  // namespace pb
+
+using namespace pb;
+
+extern "C" {
+
+int pb_version(void) { return PB_VERSION; }
+
+const char* pb_last_error(void) { return g_err; }
+
+void pb_default_params(pb_params* p) {
+    if (!p) return;
+    memset(p, 0, sizeof(*p));
+    p->n_iter = 1;
+    p->c = 0.352;
+    p->b = 0.768;
+    p->alpha = 2;
+    p->beta = 3;
+    p->sigma_s = 2.0;
+    p->sigma_r = 0.8;
+    p->ker_size = 25;
+    p->q = 0.0;
+    p->flags = 0;
+    p->engine = PB_ENGINE_AUTO;
+    p->tap_rel_threshold = 0.0f;
+    p->chunk_images = 0;
+}
+
+void pb_polynomial_coefficients(double alpha, double beta, float* out4) { poly_coeffs(alpha, beta, out4); }
+
+void pb_keys_weights(float* out210) { keys_weights_host(out210); }
+
+int pb_fft_plan(int n, int* radices) {
+    FftPlan p;
+    if (make_fft_plan(n, &p) != PB_OK) {
+        set_error("cannot plan FFT of length %d", n);
+        return PB_ERR_ARG;
+    }
+    for (int i = 0; i < p.ns; ++i) radices[i] = p.radix[i];
+    return p.ns;
+}
+
+size_t pb_workspace_bytes(int B, int C, int H, int W, const pb_params* p) {
+    if (B < 1 || C < 1 || H < 1 || W < 1) return 0;
+    return layout(B, C, H, W, p ? p->n_iter : 1).total;
+}
+
+static int validate_params(const pb_params* p) {
+    if (!p) {
+        set_error("params is NULL");
+        return PB_ERR_ARG;
+    }
+    if (p->n_iter < 0) {
+        set_error("n_iter must be >= 0");
+        return PB_ERR_ARG;
+    }
+    if (p->ker_size < 1 || p->ker_size > PB_KSIZE_MAX || (p->ker_size & 1) == 0) {
+        set_error("ker_size must be odd and <= %d (got %d)", PB_KSIZE_MAX, p->ker_size);
+        return PB_ERR_ARG;
+    }
+    if (p->q != 0.0) {
+        set_error("q > 0 (quantile normalisation) is not built yet");
+        return PB_ERR_UNSUPPORTED;
+    }
+    const uint32_t unsupported = PB_FLAG_REMOVE_HALO | PB_FLAG_EDGETAPER | PB_FLAG_PREFILTER | PB_FLAG_PREFILTER_RF;
+    if (p->flags & unsupported) {
+        set_error("flags 0x%x: remove_halo / edgetaper / prefilter are not built yet", p->flags & unsupported);
+        return PB_ERR_UNSUPPORTED;
+    }
+    return PB_OK;
+}
+
+int pb_polyblur_f32(const float* in, float* out, int B, int C, int H, int W, const pb_params* p,
+                    void* workspace, size_t workspace_bytes, float* est_out, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc;
+    if ((rc = check_shape(B, C, H, W))) return rc;
+    if ((rc = validate_params(p))) return rc;
+    if (!in || !out || in == out) {
+        set_error("in/out must be distinct non-null device pointers");
+        return PB_ERR_ARG;
+    }
+    const size_t bytes = (size_t)B * C * H * W * sizeof(float);
+    if (p->n_iter == 0) {
+        PB_CUDA_TRY(cudaMemcpyAsync(out, in, bytes, cudaMemcpyDeviceToDevice, stream));
+        return PB_OK;
+    }
+    const Workspace L = layout(B, C, H, W, p->n_iter);
+    if ((rc = check_ws(workspace, workspace_bytes, L.total))) return rc;
+    char* ws = static_cast<char*>(workspace);
+    Tables T;
+    if ((rc = upload_constants(stream))) return rc;
+    if ((rc = prepare_tables(ws, L, H, W, &T, stream))) return rc;
+    float coef[4];
+    poly_coeffs(p->alpha, p->beta, coef);
+    const float thr = p->tap_rel_threshold > 0 ? p->tap_rel_threshold : 1e-8f;
+    float* tmp = reinterpret_cast<float*>(ws + L.off_tmp);
+    ImgKernel* kern = reinterpret_cast<ImgKernel*>(ws + L.off_kern);
+    const float* cur = in;
+    for (int it = 0; it < p->n_iter; ++it) {
+        float* dst = ((p->n_iter - 1 - it) & 1) ? tmp : out;
+        float* est = est_out ? est_out + (size_t)it * B * PB_EST_STRIDE : nullptr;
+        if ((rc = estimate_into(cur, B, C, H, W, p->c, p->b, p->flags, est, ws, L, T, p->ker_size, thr,
+                                PB_ENGINE_SPATIAL, stream)))
+            return rc;
+        if ((rc = launch_deconv_spatial(cur, dst, kern, B, C, H, W, coef[0], coef[1], coef[2], coef[3], 0, stream)))
+            return rc;
+        cur = dst;
+    }
+    return PB_OK;
+}
+
+int pb_fourier_gradients_f32(const float* img, float* gx, float* gy, int B, int C, int H, int W,
+                             void* workspace, size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc;
+    if ((rc = check_shape(B, C, H, W))) return rc;
+    if (!img || !gx || !gy) {
+        set_error("null pointer");
+        return PB_ERR_ARG;
+    }
+    const Workspace L = layout(B, C, H, W, 1);
+    if ((rc = check_ws(workspace, workspace_bytes, L.total))) return rc;
+    char* ws = static_cast<char*>(workspace);
+    Tables T;
+    if ((rc = prepare_tables(ws, L, H, W, &T, stream))) return rc;
+    if ((rc = launch_cols(false, img, nullptr, gy, nullptr, B * C, 1, H, W, T.planH, T.twH, stream))) return rc;
+    return launch_rows(false, img, nullptr, gx, nullptr, B * C, H, W, T.planW, T.twW, 0, stream);
+}
+
+int pb_estimate_f32(const float* img, int B, int C, int H, int W, double c, double b, double q,
+                    uint32_t flags, float* est, void* workspace, size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc;
+    if ((rc = check_shape(B, C, H, W))) return rc;
+    if (!img || !est) {
+        set_error("null pointer");
+        return PB_ERR_ARG;
+    }
+    if (q != 0.0) {
+        set_error("q > 0 (quantile normalisation) is not built yet");
+        return PB_ERR_UNSUPPORTED;
+    }
+    const Workspace L = layout(B, C, H, W, 1);
+    if ((rc = check_ws(workspace, workspace_bytes, L.total))) return rc;
+    char* ws = static_cast<char*>(workspace);
+    Tables T;
+    if ((rc = upload_constants(stream))) return rc;
+    if ((rc = prepare_tables(ws, L, H, W, &T, stream))) return rc;
+    return estimate_into(img, B, C, H, W, c, b, flags, est, ws, L, T, PB_KS, 1e-8f, PB_ENGINE_SPATIAL, stream);
+}
+
+int pb_make_kernel_f32(const float* theta, const float* sigma, const float* rho, int B, int ksize,
+                       float* kernel, void* workspace, size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (B < 1 || !theta || !sigma || !rho || !kernel || ksize < 1 || ksize > PB_KS || !(ksize & 1)) {
+        set_error("bad arguments to pb_make_kernel_f32");
+        return PB_ERR_ARG;
+    }
+    const size_t need = (size_t)B * sizeof(ImgKernel);
+    int rc;
+    if ((rc = check_ws(workspace, workspace_bytes, need))) return rc;
+    return launch_params(nullptr, static_cast<ImgKernel*>(workspace), nullptr, theta, sigma, rho, nullptr,
+                         kernel, 1, B, ksize, 0.f, 0.f, 1e-8f, PB_ENGINE_SPATIAL, 1 << 30, stream);
+}
+
+int pb_deconv_f32(const float* img, float* out, int B, int C, int H, int W, const float* kernel, int ksize,
+                  double alpha, double beta, int engine, void* workspace, size_t workspace_bytes,
+                  void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc;
+    if ((rc = check_shape(B, C, H, W))) return rc;
+    if (!img || !out || !kernel || img == out || ksize < 1 || ksize > PB_KS || !(ksize & 1)) {
+        set_error("bad arguments to pb_deconv_f32 (ksize must be odd and <= 25)");
+        return PB_ERR_ARG;
+    }
+    if (engine == PB_ENGINE_FFT) {
+        set_error("the FFT deconvolution engine is not built yet");
+        return PB_ERR_UNSUPPORTED;
+    }
+    const Workspace L = layout(B, C, H, W, 1);
+    if ((rc = check_ws(workspace, workspace_bytes, L.total))) return rc;
+    char* ws = static_cast<char*>(workspace);
+    ImgKernel* kern = reinterpret_cast<ImgKernel*>(ws + L.off_kern);
+    if ((rc = launch_params(nullptr, kern, nullptr, nullptr, nullptr, nullptr, kernel, nullptr, 2, B, ksize,
+                            0.f, 0.f, 1e-8f, PB_ENGINE_SPATIAL, 1 << 30, stream)))
+        return rc;
+    float coef[4];
+    poly_coeffs(alpha, beta, coef);
+    return launch_deconv_spatial(img, out, kern, B, C, H, W, coef[0], coef[1], coef[2], coef[3], 0, stream);
+}
+
+int pb_edgetaper_f32(const float*, float*, int, int, int, int, const float*, int, int, uint32_t, void*, size_t,
+                     void*) {
+    set_error("pb_edgetaper_f32 is not built yet");
+    return PB_ERR_UNSUPPORTED;
+}
+
+int pb_bilateral_f32(const float*, float*, int, int, int, int, float, float, void*) {
+    set_error("pb_bilateral_f32 is not built yet");
+    return PB_ERR_UNSUPPORTED;
+}
+
+int pb_recursive_filter_f32(const float*, const float*, float*, int, int, int, int, float, float, int, void*,
+                            size_t, void*) {
+    set_error("pb_recursive_filter_f32 is not built yet");
+    return PB_ERR_UNSUPPORTED;
+}
+
+}  // extern "C"

@@ -1,0 +1,174 @@
+// Spatial deconvolution engine: the degree-3 polynomial of the blur applied as three stacked
+// sparse stencils (Horner), fused in shared memory.
+//
+// Reference being replaced: deblurring.inverse_filtering_rank3 with default flags
+// (polyblur/deblurring.py:211-239) = utils.pad_with_kernel (utils.py:48-53) ->
+// compute_polynomial_fft (deblurring.py:141-169) -> utils.crop_with_kernel (utils.py:56-61) ->
+// clamp.  The FFT product there is a circular correlation on the replicate-padded torus of
+// size (H+2P) x (W+2P); SURVEY.md A.6 shows it equals
+//     o = a3 p;  o = K (*) o + a2 p;  o = K (*) o + a1 p;  o = K (*) o + b p
+// with one gather map  src = clamp((coord mod (n + 2P)) - P, 0, n - 1).
+//
+// One CTA produces a 64 x 64 output tile of one channel: it gathers the tile plus a halo of
+// 3 r (r = radius of the taps kept for this image, <= 12) through the torus map, then runs the
+// three stencils shrinking the halo by r each time.  Only taps above the relative threshold
+// are applied (per-row ranges from k_params), so a near-delta kernel costs ~9 FMA per stencil.
+// HBM traffic: 4 B read (+ halo re-reads that hit L2) and 4 B written per pixel-channel.
+#include "kernels.cuh"
+
+namespace pb {
+
+#define DT_W 64
+#define DT_H 64
+#define DC_THREADS 512
+#define DC_MAXEXT (DT_W + 6 * PB_PAD)   // 136
+
+struct DeconvSmem {
+    float k[640];
+    int lo[32];
+    int hi[32];
+    int srcx[DC_MAXEXT + 8];
+    int srcy[DC_MAXEXT + 8];
+};
+
+template <int HX, bool FINAL>
+__device__ __forceinline__ void conv_stage(const float* __restrict__ in, int in_stride,
+                                           float* __restrict__ outb, int out_stride, int RH, int RW,
+                                           int hy, const DeconvSmem& S, const float* __restrict__ P,
+                                           int p_stride, int poff_y, int poff_x, float cK, float cP,
+                                           float* __restrict__ gout, int gy0, int gx0, int H, int W) {
+    const int nsx = RW >> 2;
+    const int nstrips = RH * nsx;
+    for (int s = threadIdx.x; s < nstrips; s += blockDim.x) {
+        const int yo = s / nsx;
+        const int xo = (s - yo * nsx) << 2;
+        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+        for (int dyi = PB_PAD - hy; dyi <= PB_PAD + hy; ++dyi) {
+            const int lo = S.lo[dyi], hi = S.hi[dyi];
+            if (lo > hi) continue;
+            const float* row = in + (yo + hy + dyi - PB_PAD) * in_stride + xo;
+            float seg[2 * HX + 4];
+#pragma unroll
+            for (int q = 0; q < (2 * HX + 4) / 4; ++q) {
+                float4 t = *reinterpret_cast<const float4*>(row + 4 * q);
+                seg[4 * q + 0] = t.x;
+                seg[4 * q + 1] = t.y;
+                seg[4 * q + 2] = t.z;
+                seg[4 * q + 3] = t.w;
+            }
+            const float* wrow = S.k + dyi * PB_KS + PB_PAD - HX;
+#pragma unroll
+            for (int t = 0; t <= 2 * HX; ++t) {
+                const int ti = PB_PAD - HX + t;
+                if (ti >= lo && ti <= hi) {
+                    const float w = wrow[t];
+                    acc0 = fmaf(w, seg[t + 0], acc0);
+                    acc1 = fmaf(w, seg[t + 1], acc1);
+                    acc2 = fmaf(w, seg[t + 2], acc2);
+                    acc3 = fmaf(w, seg[t + 3], acc3);
+                }
+            }
+        }
+        const float4 pv = *reinterpret_cast<const float4*>(P + (yo + poff_y) * p_stride + xo + poff_x);
+        float4 r;
+        r.x = fmaf(cK, acc0, cP * pv.x);
+        r.y = fmaf(cK, acc1, cP * pv.y);
+        r.z = fmaf(cK, acc2, cP * pv.z);
+        r.w = fmaf(cK, acc3, cP * pv.w);
+        if (FINAL) {
+            const int y = gy0 + yo;
+            if (y < H) {
+                float* g = gout + (size_t)y * W + gx0 + xo;
+                const float v[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (gx0 + xo + j < W) g[j] = fminf(fmaxf(v[j], 0.0f), 1.0f);
+            }
+        } else {
+            *reinterpret_cast<float4*>(outb + yo * out_stride + xo) = r;
+        }
+    }
+}
+
+template <int HX>
+__device__ __forceinline__ void horner_tile(float* P, float* O1, float* O2, int hy, const DeconvSmem& S,
+                                            float a3, float a2, float a1, float b0, float* gout,
+                                            int gy0, int gx0, int H, int W) {
+    const int PW = DT_W + 6 * HX, W1 = DT_W + 4 * HX, W2 = DT_W + 2 * HX;
+    conv_stage<HX, false>(P, PW, O1, W1, DT_H + 4 * hy, W1, hy, S, P, PW, hy, HX, a3, a2,
+                          nullptr, 0, 0, 0, 0);
+    __syncthreads();
+    conv_stage<HX, false>(O1, W1, O2, W2, DT_H + 2 * hy, W2, hy, S, P, PW, 2 * hy, 2 * HX, 1.0f, a1,
+                          nullptr, 0, 0, 0, 0);
+    __syncthreads();
+    conv_stage<HX, true>(O2, W2, nullptr, 0, DT_H, DT_W, hy, S, P, PW, 3 * hy, 3 * HX, 1.0f, b0,
+                         gout, gy0, gx0, H, W);
+}
+
+__global__ void __launch_bounds__(DC_THREADS, 1)
+k_deconv_spatial(const float* __restrict__ img, float* __restrict__ out,
+                 const ImgKernel* __restrict__ kern, int C, int H, int W,
+                 float a3, float a2, float a1, float b0, int only_engine) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DeconvSmem& S = *reinterpret_cast<DeconvSmem*>(smem_raw);
+    float* bufs = reinterpret_cast<float*>(smem_raw + sizeof(DeconvSmem));
+
+    const int im = blockIdx.z / C;
+    const ImgKernel* K = kern + im;
+    if (only_engine != 0 && K->engine != only_engine) return;
+    const int r = K->radius;
+    const int pad = K->ksize / 2;
+    const int hy = r;
+    int HX = (r + 3) & ~3;
+    if (HX == 0) HX = 4;
+
+    for (int i = threadIdx.x; i < 640; i += blockDim.x) S.k[i] = (i < PB_KS2) ? K->k[i] : 0.0f;
+    if (threadIdx.x < 32) {
+        S.lo[threadIdx.x] = (threadIdx.x < PB_KS) ? K->lo[threadIdx.x] : PB_KS;
+        S.hi[threadIdx.x] = (threadIdx.x < PB_KS) ? K->hi[threadIdx.x] : -1;
+    }
+    const int gx0 = blockIdx.x * DT_W, gy0 = blockIdx.y * DT_H;
+    const int PW = DT_W + 6 * HX, PH = DT_H + 6 * hy;
+    for (int i = threadIdx.x; i < PW; i += blockDim.x) S.srcx[i] = torus_src(gx0 + pad + i - 3 * HX, W, pad);
+    for (int i = threadIdx.x; i < PH; i += blockDim.x) S.srcy[i] = torus_src(gy0 + pad + i - 3 * hy, H, pad);
+    __syncthreads();
+
+    float* P = bufs;
+    float* O1 = P + PH * PW;
+    float* O2 = O1 + (DT_H + 4 * hy) * (DT_W + 4 * HX);
+    const float* plane = img + (size_t)blockIdx.z * H * W;
+    for (int i = threadIdx.x; i < PH * PW; i += blockDim.x) {
+        const int ly = i / PW, lx = i - ly * PW;
+        P[i] = __ldg(plane + (size_t)S.srcy[ly] * W + S.srcx[lx]);
+    }
+    __syncthreads();
+    float* gout = out + (size_t)blockIdx.z * H * W;
+    switch (HX) {
+        case 4: horner_tile<4>(P, O1, O2, hy, S, a3, a2, a1, b0, gout, gy0, gx0, H, W); break;
+        case 8: horner_tile<8>(P, O1, O2, hy, S, a3, a2, a1, b0, gout, gy0, gx0, H, W); break;
+        default: horner_tile<12>(P, O1, O2, hy, S, a3, a2, a1, b0, gout, gy0, gx0, H, W); break;
+    }
+}
+
+int launch_deconv_spatial(const float* img, float* out, const ImgKernel* kern, int B, int C, int H, int W,
+                          float a3, float a2, float a1, float b0, int only_engine, cudaStream_t stream) {
+    const int ext = DT_W + 6 * PB_PAD;
+    const size_t smem = sizeof(DeconvSmem) +
+                        sizeof(float) * ((size_t)ext * ext + (size_t)(DT_W + 4 * PB_PAD) * (DT_H + 4 * PB_PAD) +
+                                         (size_t)(DT_W + 2 * PB_PAD) * (DT_H + 2 * PB_PAD));
+    static bool attr_set = false;
+    if (!attr_set) {
+        PB_CUDA_TRY(cudaFuncSetAttribute(k_deconv_spatial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    if ((long long)B * C > 65535) {
+        set_error("B*C = %lld exceeds the grid z limit", (long long)B * C);
+        return PB_ERR_ARG;
+    }
+    dim3 grid((W + DT_W - 1) / DT_W, (H + DT_H - 1) / DT_H, B * C);
+    k_deconv_spatial<<<grid, DC_THREADS, smem, stream>>>(img, out, kern, C, H, W, a3, a2, a1, b0, only_engine);
+    PB_LAUNCH_CHECK("k_deconv_spatial");
+    return PB_OK;
+}
+
+}  // namespace pb

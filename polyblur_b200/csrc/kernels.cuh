@@ -1,0 +1,29 @@
+// Host-callable launchers shared between the translation units of libpolyblur_sm100.so.
+#pragma once
+#include "common.cuh"
+
+#define PB_FFT_THREADS 256
+#define PB_STATS_STRIDE 16   // per image: [0] min (ordered), [1] max (ordered), [2..8] 7 maxima
+
+namespace pb {
+
+// estimate.cu
+void keys_weights_host(float* out210);
+int upload_constants(cudaStream_t stream);
+int launch_twiddles(float2* tw, int n, cudaStream_t stream);
+int launch_init_stats(unsigned* stats, int B, cudaStream_t stream);
+int fft_batch_for(int n, int max_nb);
+int launch_cols(bool est, const float* img, float* gray, float* gy, unsigned* stats, int nimg, int C,
+                int H, int W, const FftPlan& planH, const float2* twH, cudaStream_t stream);
+int launch_rows(bool est, const float* plane_in, const float* gy, float* gx, unsigned* stats, int nimg,
+                int H, int W, const FftPlan& planW, const float2* twW, int discard_saturation,
+                cudaStream_t stream);
+int launch_params(const unsigned* stats, ImgKernel* kern, float* est, const float* th, const float* sg,
+                  const float* rh, const float* kin, float* kout, int mode, int B, int ksize, float cc,
+                  float bb, float tap_thr, int engine_req, int fft_radius_min, cudaStream_t stream);
+
+// deconv.cu
+int launch_deconv_spatial(const float* img, float* out, const ImgKernel* kern, int B, int C, int H, int W,
+                          float a3, float a2, float a1, float b0, int only_engine, cudaStream_t stream);
+
+}  // namespace pb

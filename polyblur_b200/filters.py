@@ -1,0 +1,59 @@
+"""Stage-level drop-ins for polyblur/filters.py (reference), backed by the CUDA library."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _prep(images: torch.Tensor, what: str):
+    if not isinstance(images, torch.Tensor) or images.ndim != 4:
+        raise ValueError(f"{what}: expected a (B,C,H,W) tensor")
+    if images.dtype != torch.float32:
+        raise TypeError(f"{what}: float32 only (got {images.dtype}), like the reference")
+    dev = _lib.require_cuda(images)
+    src_device = images.device
+    x = images.detach().to(dev, non_blocking=True).contiguous()
+    return x, dev, src_device
+
+
+def fourier_gradients(images: torch.Tensor):
+    """Spectral derivative along W and H of every channel -> (gx, gy).
+
+    Replaces filters.fourier_gradients (polyblur/filters.py:159-186): full complex fft2,
+    multiply by 2*pi*f*i, ifft2.  Here: independent 1-D spectral derivatives of the rows and
+    the columns, computed by the on-chip FFT kernels (csrc/estimate.cu k_rows / k_cols).
+    """
+    x, dev, src = _prep(images, "fourier_gradients")
+    B, C, H, W = x.shape
+    with torch.cuda.device(dev):
+        p = _lib.default_params()
+        ws = _lib.workspace(B, C, H, W, p, dev)
+        gx = torch.empty_like(x)
+        gy = torch.empty_like(x)
+        rc = _lib.lib().pb_fourier_gradients_f32(x.data_ptr(), gx.data_ptr(), gy.data_ptr(), B, C, H, W,
+                                                 ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
+        _lib.check(rc, "pb_fourier_gradients_f32")
+    return gx.to(src), gy.to(src)
+
+
+def gaussian_filter(sigma, theta, shift=np.array([0.0, 0.0]), k_size=np.array([15, 15])):
+    """NumPy generator of a generalised 2-D Gaussian kernel (polyblur/filters.py:198-234);
+    used by the CLI's synthetic degradation, not on the GPU path."""
+    l1, l2 = sigma
+    th = -theta
+    Q = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+    cov = Q @ np.diag([l1 ** 2, l2 ** 2]) @ Q.T
+    inv = np.linalg.inv(cov)
+    kx, ky = int(k_size[0]), int(k_size[1])
+    mu = np.array([kx // 2, ky // 2], dtype=np.float64) - np.asarray(shift, dtype=np.float64)
+    X, Y = np.meshgrid(np.arange(kx), np.arange(ky))
+    zx, zy = X - mu[0], Y - mu[1]
+    quad = inv[0, 0] * zx * zx + 2 * inv[0, 1] * zx * zy + inv[1, 1] * zy * zy
+    raw = np.exp(-0.5 * quad).astype(np.float32)
+    if raw.sum() < 1e-2:
+        k = np.zeros_like(raw)
+        k[kx // 2, ky // 2] = 1
+        return k
+    return raw / raw.sum()
