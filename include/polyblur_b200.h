@@ -96,6 +96,14 @@ PB_API int pb_fft_plan(int n, int* radices);
 /* Bytes of device workspace needed by any entry point below for this shape. */
 PB_API size_t pb_workspace_bytes(int B, int C, int H, int W, const pb_params* p);
 
+/* Per-kernel timing with CUDA events recorded around every launch the library makes
+ * (bench.py's roofline leg).  begin() resets and enables; end() disables, waits for the
+ * recorded events and returns the number of kernel classes, filling total milliseconds and
+ * launch counts per class (arrays of at least max_classes entries). */
+PB_API int pb_profile_begin(void);
+PB_API int pb_profile_end(float* ms_per_class, int* launches_per_class, int max_classes);
+PB_API const char* pb_profile_class_name(int cls);
+
 /* ---- the hot path ---------------------------------------------------------------------- */
 
 /* polyblur_deblurring (deblurring.py:23-96), method='fft' semantics, tensor path.

@@ -50,6 +50,9 @@ _SIGS = {
     "pb_keys_weights": (None, [C.POINTER(C.c_float)]),
     "pb_fft_plan": (C.c_int, [C.c_int, C.POINTER(C.c_int)]),
     "pb_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(PbParams)]),
+    "pb_profile_begin": (C.c_int, []),
+    "pb_profile_end": (C.c_int, [C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_int]),
+    "pb_profile_class_name": (C.c_char_p, [C.c_int]),
     "pb_polyblur_f32": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(PbParams), _P,
                                   C.c_size_t, _P, _P]),
     "pb_fourier_gradients_f32": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_size_t, _P]),
@@ -128,3 +131,18 @@ def stream_ptr(device: torch.device) -> int:
 
 def ptr(t: torch.Tensor | None) -> int | None:
     return None if t is None else t.data_ptr()
+
+
+def profile_begin() -> None:
+    check(lib().pb_profile_begin(), "pb_profile_begin")
+
+
+def profile_end() -> dict:
+    """-> {kernel class: (total ms, launches)} for every launch since profile_begin()."""
+    n = 16
+    ms = (C.c_float * n)()
+    cnt = (C.c_int * n)()
+    k = lib().pb_profile_end(ms, cnt, n)
+    if k < 0:
+        check(k, "pb_profile_end")
+    return {lib().pb_profile_class_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(k) if cnt[i]}

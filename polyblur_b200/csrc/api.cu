@@ -2,6 +2,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 #include "kernels.cuh"
 
@@ -20,6 +21,36 @@ int check_cuda(cudaError_t e, const char* what) {
     if (e == cudaSuccess) return PB_OK;
     set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
     return PB_ERR_CUDA;
+}
+
+// ---- profiler ------------------------------------------------------------------------------
+struct ProfRec { int cls; cudaEvent_t a, b; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_event_pool;
+static const char* kProfNames[PROF_NCLASSES] = {"setup", "k_cols", "k_rows", "k_params", "k_deconv_spatial",
+                                                "k_fft_rows_fwd", "k_fft_cols", "k_fft_rows_inv", "other"};
+
+static cudaEvent_t get_event() {
+    if (!g_event_pool.empty()) {
+        cudaEvent_t e = g_event_pool.back();
+        g_event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+ProfScope::ProfScope(int cls, cudaStream_t s) : idx(-1), stream(s) {
+    if (!g_prof_on) return;
+    ProfRec r{cls, get_event(), get_event()};
+    cudaEventRecord(r.a, s);
+    idx = (int)g_prof.size();
+    g_prof.push_back(r);
+}
+ProfScope::~ProfScope() {
+    if (idx >= 0) cudaEventRecord(g_prof[idx].b, stream);
 }
 
 int make_fft_plan(int n, FftPlan* plan) {
@@ -333,6 +364,36 @@ int pb_deconv_f32(const float* img, float* out, int B, int C, int H, int W, cons
     poly_coeffs(alpha, beta, coef);
     return launch_deconv_spatial(img, out, kern, B, C, H, W, coef[0], coef[1], coef[2], coef[3], 0, stream);
 }
+
+int pb_profile_begin(void) {
+    for (auto& r : g_prof) {
+        g_event_pool.push_back(r.a);
+        g_event_pool.push_back(r.b);
+    }
+    g_prof.clear();
+    g_prof_on = true;
+    return PB_OK;
+}
+
+int pb_profile_end(float* ms_per_class, int* launches_per_class, int max_classes) {
+    g_prof_on = false;
+    for (int i = 0; i < max_classes; ++i) {
+        if (ms_per_class) ms_per_class[i] = 0.f;
+        if (launches_per_class) launches_per_class[i] = 0;
+    }
+    for (auto& r : g_prof) {
+        PB_CUDA_TRY(cudaEventSynchronize(r.b));
+        float ms = 0.f;
+        PB_CUDA_TRY(cudaEventElapsedTime(&ms, r.a, r.b));
+        if (r.cls < max_classes) {
+            if (ms_per_class) ms_per_class[r.cls] += ms;
+            if (launches_per_class) launches_per_class[r.cls] += 1;
+        }
+    }
+    return PROF_NCLASSES;
+}
+
+const char* pb_profile_class_name(int i) { return (i >= 0 && i < PROF_NCLASSES) ? kProfNames[i] : ""; }
 
 int pb_edgetaper_f32(const float*, float*, int, int, int, int, const float*, int, int, uint32_t, void*, size_t,
                      void*) {

@@ -388,6 +388,7 @@ int upload_constants(cudaStream_t stream) {
 }
 
 int launch_twiddles(float2* tw, int n, cudaStream_t stream) {
+    ProfScope prof(PROF_SETUP, stream);
     k_twiddles<<<(n + 255) / 256, 256, 0, stream>>>(tw, n);
     PB_LAUNCH_CHECK("k_twiddles");
     return PB_OK;
@@ -395,6 +396,7 @@ int launch_twiddles(float2* tw, int n, cudaStream_t stream) {
 
 int launch_init_stats(unsigned* stats, int B, cudaStream_t stream) {
     int n = B * PB_STATS_STRIDE;
+    ProfScope prof(PROF_SETUP, stream);
     k_init_stats<<<(n + 255) / 256, 256, 0, stream>>>(stats, B);
     PB_LAUNCH_CHECK("k_init_stats");
     return PB_OK;
@@ -426,6 +428,7 @@ int launch_cols(bool est, const float* img, float* gray, float* gy, unsigned* st
     const int nb = fft_batch_for(H, 8);
     const size_t smem = (size_t)nb * H * sizeof(float2) * 2;
     dim3 grid((W + 2 * nb - 1) / (2 * nb), nimg);
+    ProfScope prof(PROF_COLS, stream);
     if (est) {
         int rc = set_smem(k_cols<true>, smem);
         if (rc) return rc;
@@ -445,6 +448,7 @@ int launch_rows(bool est, const float* plane_in, const float* gy, float* gx, uns
     const int nb = fft_batch_for(W, 4);
     const size_t smem = (size_t)nb * W * sizeof(float2) * 2;
     dim3 grid((H + 2 * nb - 1) / (2 * nb), nimg);
+    ProfScope prof(PROF_ROWS, stream);
     if (est) {
         int rc = set_smem(k_rows<true>, smem);
         if (rc) return rc;
@@ -463,6 +467,7 @@ int launch_rows(bool est, const float* plane_in, const float* gy, float* gx, uns
 int launch_params(const unsigned* stats, ImgKernel* kern, float* est, const float* th, const float* sg,
                   const float* rh, const float* kin, float* kout, int mode, int B, int ksize, float cc,
                   float bb, float tap_thr, int engine_req, int fft_radius_min, cudaStream_t stream) {
+    ProfScope prof(PROF_PARAMS, stream);
     k_params<<<B, 128, 0, stream>>>(stats, kern, est, th, sg, rh, kin, kout, mode, ksize, cc, bb, tap_thr,
                                     engine_req, fft_radius_min);
     PB_LAUNCH_CHECK("k_params");

@@ -7,6 +7,16 @@
 
 namespace pb {
 
+// ---- optional per-kernel timing with CUDA events (api.cu); used by bench.py ---------------
+enum ProfClass { PROF_SETUP = 0, PROF_COLS, PROF_ROWS, PROF_PARAMS, PROF_DECONV_SPATIAL,
+                 PROF_FFT_ROWS_FWD, PROF_FFT_COLS, PROF_FFT_ROWS_INV, PROF_OTHER, PROF_NCLASSES };
+struct ProfScope {
+    int idx;
+    cudaStream_t stream;
+    ProfScope(int cls, cudaStream_t s);
+    ~ProfScope();
+};
+
 // estimate.cu
 void keys_weights_host(float* out210);
 int upload_constants(cudaStream_t stream);

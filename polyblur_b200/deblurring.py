@@ -113,7 +113,11 @@ def polyblur_deblurring(img, n_iter=1, c=0.352, b=0.768, alpha=2, beta=3, sigma_
     if flag_numpy:
         out = utils.to_array(out)
     elif src_device != dev:
-        out = out.to(src_device)
+        # device -> pinned host memory on the same stream, one synchronisation at the end
+        host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
+        host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        out = host
     if return_estimates:
         return out, est.to(src_device)
     return out

@@ -1,0 +1,34 @@
+"""Batch sharding across the GPUs of one box: images are independent, so
+rank r of N owns a contiguous slice of the batch and no collective sits on the data path.
+The only (optional) collective is a final all-gather of the outputs."""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items: int, rank: int, world: int):
+    """Contiguous [start, stop) of rank `rank`; the first n_items % world ranks get one more."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError(f"bad rank/world {rank}/{world}")
+    base, extra = divmod(n_items, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def gather_outputs(local: torch.Tensor, n_items: int, group=None) -> torch.Tensor:
+    """All-gather the per-rank output slices back into the full batch (NCCL on GPUs, gloo on
+    CPU tensors).  Off the timed path; ragged shards are padded to the largest one."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return local
+    sizes = [shard_range(n_items, r, world) for r in range(world)]
+    biggest = max(b - a for a, b in sizes)
+    padded = local
+    if local.shape[0] < biggest:
+        pad = torch.zeros((biggest - local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype,
+                          device=local.device)
+        padded = torch.cat([local, pad], 0)
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded.contiguous(), group=group)
+    return torch.cat([p[: b - a] for p, (a, b) in zip(parts, sizes)], 0)

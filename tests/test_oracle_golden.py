@@ -148,3 +148,18 @@ def test_fp64_truth_is_close_to_fp32():
     x = sc["mosaic_rgb_96x120/in"]
     a = po.polyblur_deblurring(x, n_iter=3, alpha=6, beta=1, dtype=np.float64)
     assert maxabs(a, sc["mosaic_rgb_96x120/a6b1n3/out"]) < 1e-5
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_torch_port_matches_reference(name):
+    """The ATen-CPU port timed as the CPU baseline is pinned to the same golden vectors."""
+    import torch
+    from oracle import polyblur_oracle_torch as pt
+    sc = load("small_cases.npz")
+    x = torch.from_numpy(sc[name + "/in"])
+    tr = []
+    y = pt.polyblur_deblurring(x, n_iter=3, alpha=6, beta=1, trace=tr).numpy()
+    assert maxabs(y, sc[f"{name}/a6b1n3/out"]) < 1e-6
+    np.testing.assert_allclose(np.stack([t["sigma"].numpy() for t in tr]), sc[f"{name}/a6b1n3/sigma"], rtol=1e-6)
+    y = pt.polyblur_deblurring(x, n_iter=1, alpha=2, beta=3).numpy()
+    assert maxabs(y, sc[f"{name}/a2b3n1/out"]) < 1e-6
