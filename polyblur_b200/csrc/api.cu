@@ -83,7 +83,7 @@ int make_fft_plan(int n, FftPlan* plan) {
 
 // ---- workspace layout -------------------------------------------------------------------------
 struct Workspace {
-    size_t off_stats, off_kern, off_twH, off_twW, off_gray, off_gy, off_tmp, total;
+    size_t off_stats, off_kern, off_twH, off_twW, off_omH, off_omW, off_gray, off_gy, off_tmp, total;
 };
 
 static Workspace layout(int B, int C, int H, int W, int n_iter) {
@@ -100,6 +100,8 @@ static Workspace layout(int B, int C, int H, int W, int n_iter) {
     w.off_kern = take(nimg * sizeof(ImgKernel));
     w.off_twH = take((size_t)H * sizeof(float2));
     w.off_twW = take((size_t)W * sizeof(float2));
+    w.off_omH = take((size_t)H * sizeof(float));
+    w.off_omW = take((size_t)W * sizeof(float));
     w.off_gray = take((size_t)B * plane * sizeof(float));
     w.off_gy = take((size_t)B * plane * sizeof(float));
     w.off_tmp = take(n_iter >= 2 ? (size_t)B * C * plane * sizeof(float) : 0);
@@ -134,6 +136,9 @@ static int check_ws(const void* ws, size_t have, size_t need) {
 struct Tables {
     FftPlan planH, planW;
     float2 *twH, *twW;
+    bool fast;                 // both lengths run on the fft2 core (estimate2.cu)
+    Fft2Plan planH2, planW2;
+    float *omH, *omW;
 };
 
 static int prepare_tables(char* ws, const Workspace& L, int H, int W, Tables* t, cudaStream_t stream) {
@@ -145,7 +150,17 @@ static int prepare_tables(char* ws, const Workspace& L, int H, int W, Tables* t,
     t->twW = reinterpret_cast<float2*>(ws + L.off_twW);
     int rc = launch_twiddles(t->twH, H, stream);
     if (rc) return rc;
-    return launch_twiddles(t->twW, W, stream);
+    if ((rc = launch_twiddles(t->twW, W, stream))) return rc;
+    t->fast = fft2_supported(H, W);
+    t->omH = reinterpret_cast<float*>(ws + L.off_omH);
+    t->omW = reinterpret_cast<float*>(ws + L.off_omW);
+    if (t->fast) {
+        make_fft2_plan(H, &t->planH2);
+        make_fft2_plan(W, &t->planW2);
+        if ((rc = launch_fft2_omega(t->omH, t->planH2, stream))) return rc;
+        if ((rc = launch_fft2_omega(t->omW, t->planW2, stream))) return rc;
+    }
+    return PB_OK;
 }
 
 static void poly_coeffs(double alpha, double beta, float* o) {
@@ -165,6 +180,15 @@ static int estimate_into(const float* img, int B, int C, int H, int W, double c,
     float* gy = reinterpret_cast<float*>(ws + L.off_gy);
     int rc;
     if ((rc = launch_init_stats(stats, B, stream))) return rc;
+    if (T.fast) {
+        // rows first (fully coalesced read of the iterate), `gy` holds d g / d x here
+        if ((rc = launch_rows2(true, img, gray, gy, stats, B, C, H, W, T.planW2, T.twW, T.omW, stream))) return rc;
+        if ((rc = launch_cols2(true, gray, gy, nullptr, stats, B, H, W, T.planH2, T.twH, T.omH,
+                               (flags & PB_FLAG_DISCARD_SATURATION) ? 1 : 0, stream)))
+            return rc;
+        return launch_params(stats, kern, est, nullptr, nullptr, nullptr, nullptr, nullptr, 0, B, ksize,
+                             (float)(c * c), (float)(b * b), tap_thr, engine, 1 << 30, stream);
+    }
     if ((rc = launch_cols(true, img, gray, gy, stats, B, C, H, W, T.planH, T.twH, stream))) return rc;
     if ((rc = launch_rows(true, gray, gy, nullptr, stats, B, H, W, T.planW, T.twW,
                           (flags & PB_FLAG_DISCARD_SATURATION) ? 1 : 0, stream)))
@@ -299,6 +323,11 @@ int pb_fourier_gradients_f32(const float* img, float* gx, float* gy, int B, int 
     char* ws = static_cast<char*>(workspace);
     Tables T;
     if ((rc = prepare_tables(ws, L, H, W, &T, stream))) return rc;
+    if (T.fast) {
+        if ((rc = launch_rows2(false, img, nullptr, gx, nullptr, B * C, 1, H, W, T.planW2, T.twW, T.omW, stream)))
+            return rc;
+        return launch_cols2(false, img, nullptr, gy, nullptr, B * C, H, W, T.planH2, T.twH, T.omH, 0, stream);
+    }
     if ((rc = launch_cols(false, img, nullptr, gy, nullptr, B * C, 1, H, W, T.planH, T.twH, stream))) return rc;
     return launch_rows(false, img, nullptr, gx, nullptr, B * C, H, W, T.planW, T.twW, 0, stream);
 }

@@ -1,0 +1,360 @@
+// Blur estimation, second-generation kernels (fast path for lengths whose prime factors are
+// <= 13; estimate.cu keeps the any-length path).
+//
+// Reference being replaced: blur_estimation.gaussian_blur_estimation up to the directional
+// maxima (polyblur/blur_estimation.py:18-65, 96-134) and filters.fourier_gradients
+// (polyblur/filters.py:159-186), which is a per-row / per-column 1-D spectral derivative
+// (SURVEY.md A.2).
+//
+//   k_rows2<EST>  : one CTA owns 2*nb adjacent rows.  Reads the C channels of those rows with
+//                   128-bit loads, forms the channel mean g (blur_estimation.py:36-37), tracks
+//                   min / max (blur_estimation.py:106-108), writes g, and writes d g / d x.
+//   k_cols2<EST>  : one CTA owns 2*nb adjacent columns of g.  Computes d g / d y on chip, reads
+//                   d g / d x back and reduces max |cos(phi_j) gx - sin(phi_j) gy| over its
+//                   pixels for the 7 angles (blur_estimation.py:122-134); nothing is written
+//                   but 7 atomics per CTA.
+//   GRAD variants : the plain filters.fourier_gradients drop-in (planes in, gx / gy out).
+//
+// Two real sequences share one complex transform (real / imaginary part): the derivative
+// multiplier i*omega is Hermitian, so the two results separate by themselves.
+//
+// HBM bytes per pixel of one estimate (C = 3): rows 12 read + 8 written, columns 8 read = 28
+// (algorithmic: 12).  g and gx are scratch that mostly lives in the 126 MB L2
+// when the batch is processed a few images at a time.
+#include "fft.cuh"
+#include "fft2.cuh"
+#include "kernels.cuh"
+
+namespace pb {
+
+// cos / sin of torch.linspace(0, pi, 7) exactly as torch (float32) evaluates them
+// (blur_estimation.py:127-129); same bit patterns as estimate.cu (no relocatable device code,
+// so every translation unit carries its own copy).
+static __constant__ float c_cos7[7] = {0x1.000000p+0f, 0x1.bb67aep-1f, 0x1.fffffep-2f, -0x1.777a5cp-25f,
+                                       -0x1.000002p-1f, -0x1.bb67aep-1f, -0x1.000000p+0f};
+static __constant__ float c_sin7[7] = {0x0.0p+0f, 0x1.000000p-1f, 0x1.bb67aep-1f, 0x1.000000p+0f,
+                                       0x1.bb67aep-1f, 0x1.000002p-1f, -0x1.777a5cp-24f};
+
+// omega[p] = angular frequency (filters.py:175-181 rounding) of the bin held by slot p after
+// the DIF transform of length plan.n.
+__global__ void k_fft2_omega(float* __restrict__ omega, Fft2Plan plan) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < plan.n) omega[p] = bin_omega(fft2_freq_of_slot(p, plan), plan.n);
+}
+
+#define R2_THREADS 256
+
+template <bool EST>
+__global__ void __launch_bounds__(R2_THREADS)
+k_rows2(const float* __restrict__ img, float* __restrict__ gray, float* __restrict__ gx,
+        unsigned* __restrict__ stats, int C, int H, int W, int nb, Fft2Plan plan,
+        const float2* __restrict__ tw, const float* __restrict__ omega) {
+    extern __shared__ __align__(16) float2 sm2[];
+    const int tid = threadIdx.x;
+    const int y0 = blockIdx.x * 2 * nb;
+    const int im = blockIdx.y;
+    const size_t plane = (size_t)H * W;
+    const float* src = img + (size_t)im * (EST ? C : 1) * plane;
+    const float fC = (float)C;
+    float lmin = INFINITY, lmax = -INFINITY;
+
+    if ((W & 3) == 0) {
+        const int w4 = W >> 2;
+        const float inv_w4 = 1.0f / (float)w4;
+        for (int idx = tid; idx < nb * w4; idx += R2_THREADS) {
+            const int p = fast_div(idx, w4, inv_w4);
+            const int x = (idx - p * w4) << 2;
+            float4 g[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int y = y0 + 2 * p + h;
+                g[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (y < H) {
+                    const float* q = src + (size_t)y * W + x;
+                    g[h] = __ldg(reinterpret_cast<const float4*>(q));
+                    if (EST) {
+                        for (int c = 1; c < C; ++c) {
+                            const float4 t = __ldg(reinterpret_cast<const float4*>(q + (size_t)c * plane));
+                            g[h].x = __fadd_rn(g[h].x, t.x);
+                            g[h].y = __fadd_rn(g[h].y, t.y);
+                            g[h].z = __fadd_rn(g[h].z, t.z);
+                            g[h].w = __fadd_rn(g[h].w, t.w);
+                        }
+                        if (C > 1) {
+                            g[h].x = __fdiv_rn(g[h].x, fC);
+                            g[h].y = __fdiv_rn(g[h].y, fC);
+                            g[h].z = __fdiv_rn(g[h].z, fC);
+                            g[h].w = __fdiv_rn(g[h].w, fC);
+                        }
+                        *reinterpret_cast<float4*>(gray + (size_t)im * plane + (size_t)y * W + x) = g[h];
+                        lmin = fminf(lmin, fminf(fminf(g[h].x, g[h].y), fminf(g[h].z, g[h].w)));
+                        lmax = fmaxf(lmax, fmaxf(fmaxf(g[h].x, g[h].y), fmaxf(g[h].z, g[h].w)));
+                    }
+                }
+            }
+            float4* d = reinterpret_cast<float4*>(sm2 + (size_t)p * W + x);
+            d[0] = make_float4(g[0].x, g[1].x, g[0].y, g[1].y);
+            d[1] = make_float4(g[0].z, g[1].z, g[0].w, g[1].w);
+        }
+    } else {
+        const float inv_w = 1.0f / (float)W;
+        for (int idx = tid; idx < nb * W; idx += R2_THREADS) {
+            const int p = fast_div(idx, W, inv_w);
+            const int x = idx - p * W;
+            float g[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int y = y0 + 2 * p + h;
+                g[h] = 0.f;
+                if (y < H) {
+                    const float* q = src + (size_t)y * W + x;
+                    g[h] = __ldg(q);
+                    if (EST) {
+                        for (int c = 1; c < C; ++c) g[h] = __fadd_rn(g[h], __ldg(q + (size_t)c * plane));
+                        if (C > 1) g[h] = __fdiv_rn(g[h], fC);
+                        gray[(size_t)im * plane + (size_t)y * W + x] = g[h];
+                        lmin = fminf(lmin, g[h]);
+                        lmax = fmaxf(lmax, g[h]);
+                    }
+                }
+            }
+            sm2[(size_t)p * W + x] = make_float2(g[0], g[1]);
+        }
+    }
+    __syncthreads();
+    fft2_forward_dif(sm2, W, nb, plan, tw, tid, R2_THREADS);
+    fft2_forward_dit(sm2, W, nb, plan, tw, tid, R2_THREADS, omega);
+    // inverse by forward transform of the swapped data: d(real part) = r.y / n, d(imag part) = r.x / n
+    const float inv = 1.0f / (float)W;
+    float* dst = gx + (size_t)im * plane;
+    if ((W & 3) == 0) {
+        const int w4 = W >> 2;
+        const float inv_w4 = 1.0f / (float)w4;
+        for (int idx = tid; idx < nb * w4; idx += R2_THREADS) {
+            const int p = fast_div(idx, w4, inv_w4);
+            const int x = (idx - p * w4) << 2;
+            const float4* s = reinterpret_cast<const float4*>(sm2 + (size_t)p * W + x);
+            const float4 a = s[0], b = s[1];
+            const int y = y0 + 2 * p;
+            if (y < H)
+                *reinterpret_cast<float4*>(dst + (size_t)y * W + x) =
+                    make_float4(a.y * inv, a.w * inv, b.y * inv, b.w * inv);
+            if (y + 1 < H)
+                *reinterpret_cast<float4*>(dst + (size_t)(y + 1) * W + x) =
+                    make_float4(a.x * inv, a.z * inv, b.x * inv, b.z * inv);
+        }
+    } else {
+        const float inv_w = 1.0f / (float)W;
+        for (int idx = tid; idx < nb * W; idx += R2_THREADS) {
+            const int p = fast_div(idx, W, inv_w);
+            const int x = idx - p * W;
+            const float2 z = sm2[(size_t)p * W + x];
+            const int y = y0 + 2 * p;
+            if (y < H) dst[(size_t)y * W + x] = z.y * inv;
+            if (y + 1 < H) dst[(size_t)(y + 1) * W + x] = z.x * inv;
+        }
+    }
+    if (EST) {
+        lmin = warp_min(lmin);
+        lmax = warp_max(lmax);
+        if ((tid & 31) == 0) {
+            atomicMin(&stats[im * PB_STATS_STRIDE + 0], f2ord(lmin));
+            atomicMax(&stats[im * PB_STATS_STRIDE + 1], f2ord(lmax));
+        }
+    }
+}
+
+template <bool EST, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_cols2(const float* __restrict__ plane_in, const float* __restrict__ gx, float* __restrict__ gy,
+        unsigned* __restrict__ stats, int H, int W, int nb, int stride, Fft2Plan plan,
+        const float2* __restrict__ tw, const float* __restrict__ omega, int discard_saturation) {
+    extern __shared__ __align__(16) float2 sm2[];
+    __shared__ float red[THREADS / 32][8];
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * 2 * nb;
+    const int im = blockIdx.y;
+    const size_t plane = (size_t)H * W;
+    const float* src = plane_in + (size_t)im * plane;
+    const float inv_nb = 1.0f / (float)nb;
+    const bool vec2 = (W & 1) == 0;
+
+    for (int idx = tid; idx < H * nb; idx += THREADS) {
+        const int y = fast_div(idx, nb, inv_nb);
+        const int p = idx - y * nb;
+        const int x = x0 + 2 * p;
+        float2 g = make_float2(0.f, 0.f);
+        if (vec2) {
+            if (x < W) g = __ldg(reinterpret_cast<const float2*>(src + (size_t)y * W + x));
+        } else {
+            if (x < W) g.x = __ldg(src + (size_t)y * W + x);
+            if (x + 1 < W) g.y = __ldg(src + (size_t)y * W + x + 1);
+        }
+        sm2[(size_t)p * stride + y] = g;
+    }
+    __syncthreads();
+    fft2_forward_dif(sm2, stride, nb, plan, tw, tid, THREADS);
+    fft2_forward_dit(sm2, stride, nb, plan, tw, tid, THREADS, omega);
+    const float inv = 1.0f / (float)H;
+
+    if (!EST) {
+        float* dst = gy + (size_t)im * plane;
+        for (int idx = tid; idx < H * nb; idx += THREADS) {
+            const int y = fast_div(idx, nb, inv_nb);
+            const int p = idx - y * nb;
+            const int x = x0 + 2 * p;
+            const float2 z = sm2[(size_t)p * stride + y];
+            const float2 o = make_float2(z.y * inv, z.x * inv);
+            if (vec2) {
+                if (x < W) *reinterpret_cast<float2*>(dst + (size_t)y * W + x) = o;
+            } else {
+                if (x < W) dst[(size_t)y * W + x] = o.x;
+                if (x + 1 < W) dst[(size_t)y * W + x + 1] = o.y;
+            }
+        }
+        return;
+    }
+
+    float m[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) m[j] = 0.0f;
+    const float* gxp = gx + (size_t)im * plane;
+    for (int idx = tid; idx < H * nb; idx += THREADS) {
+        const int y = fast_div(idx, nb, inv_nb);
+        const int p = idx - y * nb;
+        const int x = x0 + 2 * p;
+        if (x >= W) continue;
+        const float2 z = sm2[(size_t)p * stride + y];
+        const float gyv[2] = {z.y * inv, z.x * inv};
+        float gxv[2] = {0.f, 0.f};
+        float gr[2] = {0.f, 0.f};
+        if (vec2) {
+            const float2 t = __ldg(reinterpret_cast<const float2*>(gxp + (size_t)y * W + x));
+            gxv[0] = t.x;
+            gxv[1] = t.y;
+            if (discard_saturation) {
+                const float2 s = __ldg(reinterpret_cast<const float2*>(src + (size_t)y * W + x));
+                gr[0] = s.x;
+                gr[1] = s.y;
+            }
+        } else {
+            gxv[0] = __ldg(gxp + (size_t)y * W + x);
+            if (x + 1 < W) gxv[1] = __ldg(gxp + (size_t)y * W + x + 1);
+            if (discard_saturation) {
+                gr[0] = __ldg(src + (size_t)y * W + x);
+                if (x + 1 < W) gr[1] = __ldg(src + (size_t)y * W + x + 1);
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (x + h >= W) continue;
+            // get_saturation_mask (blur_estimation.py:83-88): un-normalised gray > 0.99
+            if (discard_saturation && gr[h] > 0.99f) continue;
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {
+                const float v = __fsub_rn(__fmul_rn(c_cos7[j], gxv[h]), __fmul_rn(c_sin7[j], gyv[h]));
+                m[j] = fmaxf(m[j], fabsf(v));
+            }
+        }
+    }
+    const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+        const float v = warp_max(m[j]);
+        if (lane == 0) red[warp][j] = v;
+    }
+    __syncthreads();
+    if (tid < 7) {
+        float v = 0.0f;
+        for (int w = 0; w < THREADS / 32; ++w) v = fmaxf(v, red[w][tid]);
+        atomicMax(&stats[im * PB_STATS_STRIDE + 2 + tid], __float_as_uint(v));
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------
+
+int launch_fft2_omega(float* omega, const Fft2Plan& plan, cudaStream_t stream) {
+    ProfScope prof(PROF_SETUP, stream);
+    k_fft2_omega<<<(plan.n + 255) / 256, 256, 0, stream>>>(omega, plan);
+    PB_LAUNCH_CHECK("k_fft2_omega");
+    return PB_OK;
+}
+
+template <typename KernelT>
+static int set_smem2(KernelT kern, size_t bytes) {
+    if (bytes > PB_SMEM_MAX - 2048) {
+        set_error("FFT length needs %zu bytes of shared memory (> %d)", bytes, PB_SMEM_MAX - 2048);
+        return PB_ERR_UNSUPPORTED;
+    }
+    PB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return PB_OK;
+}
+
+// sequences (pairs) per CTA: as many as fit `budget` bytes, at most max_nb, at least 1
+static int pairs_for(int n, int max_nb, size_t budget) {
+    int nb = (int)(budget / ((size_t)(n + 1) * sizeof(float2)));
+    if (nb < 1) nb = 1;
+    if (nb > max_nb) nb = max_nb;
+    return nb;
+}
+
+bool fft2_supported(int H, int W) {
+    Fft2Plan p;
+    if (H < 2 || W < 2) return false;      // a length-1 transform has no stage to fold omega into
+    if (make_fft2_plan(H, &p) || make_fft2_plan(W, &p)) return false;
+    // one pair of rows / columns must fit the shared memory of a CTA
+    const size_t lim = PB_SMEM_MAX - 2048;
+    return (size_t)(W + 1) * sizeof(float2) <= lim && (size_t)(H + 1) * sizeof(float2) <= lim;
+}
+
+int launch_rows2(bool est, const float* img, float* gray, float* gx, unsigned* stats, int nimg, int C,
+                 int H, int W, const Fft2Plan& planW, const float2* twW, const float* omegaW,
+                 cudaStream_t stream) {
+    int nb = pairs_for(W, 8, 64 * 1024);
+    const int pairs_total = (H + 1) / 2;
+    if (nb > pairs_total) nb = pairs_total;
+    const size_t smem = (size_t)nb * W * sizeof(float2);
+    dim3 grid((pairs_total + nb - 1) / nb, nimg);
+    ProfScope prof(PROF_ROWS, stream);
+    int rc;
+    if (est) {
+        if ((rc = set_smem2(k_rows2<true>, smem))) return rc;
+        k_rows2<true><<<grid, R2_THREADS, smem, stream>>>(img, gray, gx, stats, C, H, W, nb, planW, twW, omegaW);
+    } else {
+        if ((rc = set_smem2(k_rows2<false>, smem))) return rc;
+        k_rows2<false><<<grid, R2_THREADS, smem, stream>>>(img, gray, gx, stats, 1, H, W, nb, planW, twW, omegaW);
+    }
+    PB_LAUNCH_CHECK("k_rows2");
+    return PB_OK;
+}
+
+int launch_cols2(bool est, const float* plane_in, const float* gx, float* gy, unsigned* stats, int nimg,
+                 int H, int W, const Fft2Plan& planH, const float2* twH, const float* omegaH,
+                 int discard_saturation, cudaStream_t stream) {
+    // 8 pairs = 16 columns = 64-byte row segments; fall back to fewer when H is very long
+    int nb = pairs_for(H, 8, 200 * 1024);
+    const int pairs_total = (W + 1) / 2;
+    if (nb > pairs_total) nb = pairs_total;
+    const int stride = H | 1;
+    const size_t smem = (size_t)nb * stride * sizeof(float2);
+    dim3 grid((pairs_total + nb - 1) / nb, nimg);
+    ProfScope prof(PROF_COLS, stream);
+    int rc;
+    const bool big = smem > 72 * 1024;
+#define PB_LAUNCH_COLS2(E, T)                                                                          \
+    do {                                                                                               \
+        if ((rc = set_smem2(k_cols2<E, T>, smem))) return rc;                                          \
+        k_cols2<E, T><<<grid, T, smem, stream>>>(plane_in, gx, gy, stats, H, W, nb, stride, planH, twH, \
+                                                 omegaH, discard_saturation);                          \
+    } while (0)
+    if (est) {
+        if (big) PB_LAUNCH_COLS2(true, 512); else PB_LAUNCH_COLS2(true, 256);
+    } else {
+        if (big) PB_LAUNCH_COLS2(false, 512); else PB_LAUNCH_COLS2(false, 256);
+    }
+#undef PB_LAUNCH_COLS2
+    PB_LAUNCH_CHECK("k_cols2");
+    return PB_OK;
+}
+
+}  // namespace pb

@@ -1,0 +1,425 @@
+// In-place large-radix FFT in shared memory (sm_100a), second-generation core.
+//
+// A CTA transforms `nb` complex sequences of length n stored as x[f * stride + i] (stride >= n;
+// an odd stride keeps the transposing loads / stores of the column kernels off one bank).  The forward
+// transform is decimation-in-frequency (natural order in, digit-scrambled order out), the
+// inverse-direction transform is its transpose, decimation-in-time (scrambled in, natural out).
+// A convolution / spectral derivative never needs the spectrum in natural order, so no
+// reordering pass exists: a butterfly reads and writes the same R slots (truly in place, one
+// buffer, one barrier per stage).  Radices up to 16 are done in registers -- 6, 9, 10, 12, 14,
+// 15 and 16 as two nested small DFTs with compile-time inner twiddles -- so the sizes Polyblur
+// meets need three or four stages (1920 = 16*12*10, 1080 = 12*10*9, 1152 = 16*9*8,
+// 3840 = 16*16*15, 2160 = 16*15*9).
+//
+// Everything here is __host__ __device__ with the thread index passed explicitly, so that the
+// arithmetic can be unit-tested on the CPU by running the "threads" one after the other
+// (tests/test_fft2_host.py builds csrc/fft2_host_test.cu).
+//
+// Used by (a) the spectral derivative of filters.fourier_gradients (polyblur/filters.py:159-186)
+// inside the blur estimator and (b) the blur-independent FFT deconvolution engine that replaces
+// compute_polynomial_fft (polyblur/deblurring.py:141-169).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define PB_HD __host__ __device__ __forceinline__
+#else
+#define PB_HD inline
+#endif
+#if defined(__CUDA_ARCH__)
+#define PB_LDG(p) __ldg(p)
+#else
+#define PB_LDG(p) (*(p))
+#endif
+
+#include "fft_twc.cuh"
+
+#define PB_FFT2_MAX_STAGES 8
+
+namespace pb {
+
+struct Fft2Plan {
+    int n;
+    int ns;
+    int radix[PB_FFT2_MAX_STAGES];   // DIF order: radix[0] is applied at sub-length n
+};
+
+// ---- small complex helpers ---------------------------------------------------------------
+PB_HD float2 c_add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+PB_HD float2 c_sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+PB_HD float2 c_mul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+PB_HD float2 c_mul_mi(float2 a) { return make_float2(a.y, -a.x); }     // * (-i)
+PB_HD float2 c_mul_pi(float2 a) { return make_float2(-a.y, a.x); }     // * (+i)
+
+// ---- register butterflies: v <- DFT_R(v), forward sign -------------------------------------
+template <int R>
+struct Dft;
+
+template <>
+struct Dft<2> {
+    static PB_HD void run(float2 (&v)[2]) {
+        const float2 a = v[0], b = v[1];
+        v[0] = c_add(a, b);
+        v[1] = c_sub(a, b);
+    }
+};
+
+template <>
+struct Dft<3> {
+    static PB_HD void run(float2 (&v)[3]) {
+        const float S = 0.86602540378443864676f;
+        const float2 t = c_add(v[1], v[2]);
+        const float2 d = c_sub(v[1], v[2]);
+        const float2 m = make_float2(v[0].x - 0.5f * t.x, v[0].y - 0.5f * t.y);
+        const float2 r = make_float2(S * d.y, -S * d.x);
+        v[0] = c_add(v[0], t);
+        v[1] = c_add(m, r);
+        v[2] = c_sub(m, r);
+    }
+};
+
+template <>
+struct Dft<4> {
+    static PB_HD void run(float2 (&v)[4]) {
+        const float2 t0 = c_add(v[0], v[2]);
+        const float2 t1 = c_sub(v[0], v[2]);
+        const float2 t2 = c_add(v[1], v[3]);
+        const float2 t3 = c_mul_mi(c_sub(v[1], v[3]));
+        v[0] = c_add(t0, t2);
+        v[1] = c_add(t1, t3);
+        v[2] = c_sub(t0, t2);
+        v[3] = c_sub(t1, t3);
+    }
+};
+
+template <>
+struct Dft<5> {
+    static PB_HD void run(float2 (&v)[5]) {
+        const float C1 = 0.30901699437494742410f, C2 = -0.80901699437494742410f;
+        const float S1 = 0.95105651629515357212f, S2 = 0.58778525229247312917f;
+        const float2 a1 = c_add(v[1], v[4]), b1 = c_sub(v[1], v[4]);
+        const float2 a2 = c_add(v[2], v[3]), b2 = c_sub(v[2], v[3]);
+        const float2 e1 = make_float2(v[0].x + C1 * a1.x + C2 * a2.x, v[0].y + C1 * a1.y + C2 * a2.y);
+        const float2 e2 = make_float2(v[0].x + C2 * a1.x + C1 * a2.x, v[0].y + C2 * a1.y + C1 * a2.y);
+        const float2 r1 = c_mul_mi(make_float2(S1 * b1.x + S2 * b2.x, S1 * b1.y + S2 * b2.y));
+        const float2 r2 = c_mul_mi(make_float2(S2 * b1.x - S1 * b2.x, S2 * b1.y - S1 * b2.y));
+        v[0] = make_float2(v[0].x + a1.x + a2.x, v[0].y + a1.y + a2.y);
+        v[1] = c_add(e1, r1);
+        v[4] = c_sub(e1, r1);
+        v[2] = c_add(e2, r2);
+        v[3] = c_sub(e2, r2);
+    }
+};
+
+template <>
+struct Dft<7> {
+    static PB_HD void run(float2 (&v)[7]) {
+        const float C1 = 0.62348980185873353053f, C2 = -0.22252093395631440429f, C3 = -0.90096886790241912624f;
+        const float S1 = 0.78183148246802980871f, S2 = 0.97492791218182360702f, S3 = 0.43388373911755812048f;
+        const float2 a1 = c_add(v[1], v[6]), b1 = c_sub(v[1], v[6]);
+        const float2 a2 = c_add(v[2], v[5]), b2 = c_sub(v[2], v[5]);
+        const float2 a3 = c_add(v[3], v[4]), b3 = c_sub(v[3], v[4]);
+        const float2 e1 = make_float2(v[0].x + C1 * a1.x + C2 * a2.x + C3 * a3.x, v[0].y + C1 * a1.y + C2 * a2.y + C3 * a3.y);
+        const float2 e2 = make_float2(v[0].x + C2 * a1.x + C3 * a2.x + C1 * a3.x, v[0].y + C2 * a1.y + C3 * a2.y + C1 * a3.y);
+        const float2 e3 = make_float2(v[0].x + C3 * a1.x + C1 * a2.x + C2 * a3.x, v[0].y + C3 * a1.y + C1 * a2.y + C2 * a3.y);
+        const float2 r1 = c_mul_mi(make_float2(S1 * b1.x + S2 * b2.x + S3 * b3.x, S1 * b1.y + S2 * b2.y + S3 * b3.y));
+        const float2 r2 = c_mul_mi(make_float2(S2 * b1.x - S3 * b2.x - S1 * b3.x, S2 * b1.y - S3 * b2.y - S1 * b3.y));
+        const float2 r3 = c_mul_mi(make_float2(S3 * b1.x - S1 * b2.x + S2 * b3.x, S3 * b1.y - S1 * b2.y + S2 * b3.y));
+        v[0] = make_float2(v[0].x + a1.x + a2.x + a3.x, v[0].y + a1.y + a2.y + a3.y);
+        v[1] = c_add(e1, r1);
+        v[6] = c_sub(e1, r1);
+        v[2] = c_add(e2, r2);
+        v[5] = c_sub(e2, r2);
+        v[3] = c_add(e3, r3);
+        v[4] = c_sub(e3, r3);
+    }
+};
+
+template <>
+struct Dft<8> {
+    static PB_HD void run(float2 (&v)[8]) {
+        const float H = 0.70710678118654752440f;
+        float2 e[4] = {v[0], v[2], v[4], v[6]};
+        float2 o[4] = {v[1], v[3], v[5], v[7]};
+        Dft<4>::run(e);
+        Dft<4>::run(o);
+        const float2 o1 = make_float2(H * (o[1].x + o[1].y), H * (o[1].y - o[1].x));
+        const float2 o2 = c_mul_mi(o[2]);
+        const float2 o3 = make_float2(H * (o[3].y - o[3].x), -H * (o[3].x + o[3].y));
+        v[0] = c_add(e[0], o[0]);
+        v[4] = c_sub(e[0], o[0]);
+        v[1] = c_add(e[1], o1);
+        v[5] = c_sub(e[1], o1);
+        v[2] = c_add(e[2], o2);
+        v[6] = c_sub(e[2], o2);
+        v[3] = c_add(e[3], o3);
+        v[7] = c_sub(e[3], o3);
+    }
+};
+
+// multiply by the compile-time constant W_R^k (k is a literal once the loops are unrolled)
+template <int R>
+PB_HD float2 mul_twc(float2 a, int k) {
+    k %= R;
+    if (k == 0) return a;
+    if (4 * k == R) return c_mul_mi(a);
+    if (2 * k == R) return make_float2(-a.x, -a.y);
+    if (4 * k == 3 * R) return c_mul_pi(a);
+    return c_mul(a, twc<R>(k));
+}
+
+// DFT of size A*B as A transforms of size B, constant twiddles, B transforms of size A:
+// input index m = n1 + A n2, output index k = B k1 + k2.
+template <int A, int B>
+struct DftAB {
+    static PB_HD void run(float2 (&v)[A * B]) {
+        constexpr int R = A * B;
+        float2 y[A][B];
+#pragma unroll
+        for (int n1 = 0; n1 < A; ++n1) {
+            float2 t[B];
+#pragma unroll
+            for (int n2 = 0; n2 < B; ++n2) t[n2] = v[n1 + A * n2];
+            Dft<B>::run(t);
+#pragma unroll
+            for (int k2 = 0; k2 < B; ++k2) y[n1][k2] = mul_twc<R>(t[k2], n1 * k2);
+        }
+#pragma unroll
+        for (int k2 = 0; k2 < B; ++k2) {
+            float2 t[A];
+#pragma unroll
+            for (int n1 = 0; n1 < A; ++n1) t[n1] = y[n1][k2];
+            Dft<A>::run(t);
+#pragma unroll
+            for (int k1 = 0; k1 < A; ++k1) v[B * k1 + k2] = t[k1];
+        }
+    }
+};
+
+template <> struct Dft<6> { static PB_HD void run(float2 (&v)[6]) { DftAB<2, 3>::run(v); } };
+template <> struct Dft<9> { static PB_HD void run(float2 (&v)[9]) { DftAB<3, 3>::run(v); } };
+template <> struct Dft<10> { static PB_HD void run(float2 (&v)[10]) { DftAB<2, 5>::run(v); } };
+template <> struct Dft<12> { static PB_HD void run(float2 (&v)[12]) { DftAB<3, 4>::run(v); } };
+template <> struct Dft<14> { static PB_HD void run(float2 (&v)[14]) { DftAB<2, 7>::run(v); } };
+template <> struct Dft<15> { static PB_HD void run(float2 (&v)[15]) { DftAB<3, 5>::run(v); } };
+template <> struct Dft<16> { static PB_HD void run(float2 (&v)[16]) { DftAB<4, 4>::run(v); } };
+
+// Odd primes 11 and 13: direct O(R^2) sum with constant twiddles (rare sizes only).
+template <int R>
+struct DftDirect {
+    static PB_HD void run(float2 (&v)[R]) {
+        float2 o[R];
+#pragma unroll
+        for (int k = 0; k < R; ++k) {
+            float2 acc = v[0];
+#pragma unroll
+            for (int m = 1; m < R; ++m) acc = c_add(acc, mul_twc<R>(v[m], m * k));
+            o[k] = acc;
+        }
+#pragma unroll
+        for (int k = 0; k < R; ++k) v[k] = o[k];
+    }
+};
+template <> struct Dft<11> { static PB_HD void run(float2 (&v)[11]) { DftDirect<11>::run(v); } };
+template <> struct Dft<13> { static PB_HD void run(float2 (&v)[13]) { DftDirect<13>::run(v); } };
+
+// exact floor(a / d) for 0 <= a < 2^21, d >= 1, given inv = 1.0f / d
+PB_HD int fast_div(int a, int d, float inv) {
+    int q = (int)(((float)a + 0.5f) * inv);
+    (void)d;
+    return q;
+}
+
+// ---- one DIF stage: sub-length L, radix R, in place -----------------------------------------
+//   v[m] = x[b + j + m M];  V = DFT_R(v);  x[b + j + q M] = V[q] W_L^{j q},   M = L / R
+template <int R>
+PB_HD void fft2_dif_stage(float2* x, int n, int stride, int nb, int L, const float2* __restrict__ tw, int tid,
+                           int nthr) {
+    const int M = L / R;
+    const int bps = n / R;                 // butterflies per sequence
+    const int tws = n / L;
+    const float inv_bps = 1.0f / (float)bps, inv_M = 1.0f / (float)M;
+    const int total = nb * bps;
+    for (int idx = tid; idx < total; idx += nthr) {
+        const int f = fast_div(idx, bps, inv_bps);
+        const int rem = idx - f * bps;
+        const int blk = fast_div(rem, M, inv_M);
+        const int j = rem - blk * M;
+        float2* p = x + f * stride + blk * L + j;
+        float2 v[R];
+#pragma unroll
+        for (int m = 0; m < R; ++m) v[m] = p[m * M];
+        Dft<R>::run(v);
+        p[0] = v[0];
+        if (M == 1) {
+#pragma unroll
+            for (int q = 1; q < R; ++q) p[q] = v[q];
+        } else {
+            const int t1 = j * tws;
+#pragma unroll
+            for (int q = 1; q < R; ++q) p[q * M] = c_mul(v[q], PB_LDG(tw + q * t1));
+        }
+    }
+}
+
+// ---- one DIT stage (the transpose of the DIF stage) -------------------------------------------
+//   v[q] = x[b + j + q M] W_L^{j q};  V = DFT_R(v);  x[b + j + m M] = V[m]
+template <int R>
+PB_HD void fft2_dit_stage(float2* x, int n, int stride, int nb, int L, const float2* __restrict__ tw, int tid,
+                           int nthr, const float* __restrict__ premul = nullptr) {
+    const int M = L / R;
+    const int bps = n / R;
+    const int tws = n / L;
+    const float inv_bps = 1.0f / (float)bps, inv_M = 1.0f / (float)M;
+    const int total = nb * bps;
+    for (int idx = tid; idx < total; idx += nthr) {
+        const int f = fast_div(idx, bps, inv_bps);
+        const int rem = idx - f * bps;
+        const int blk = fast_div(rem, M, inv_M);
+        const int j = rem - blk * M;
+        float2* p = x + f * stride + blk * L + j;
+        float2 v[R];
+        v[0] = p[0];
+        if (M == 1) {
+#pragma unroll
+            for (int q = 1; q < R; ++q) v[q] = p[q];
+            if (premul) {
+                // spectral-derivative multiplier folded into the first inverse stage:
+                // y = i w z, then the re/im swap of the inverse-by-forward trick -> (w z.x, -w z.y)
+                const float* pm = premul + blk * L;
+#pragma unroll
+                for (int q = 0; q < R; ++q) {
+                    const float w = PB_LDG(pm + q);
+                    v[q] = make_float2(w * v[q].x, -w * v[q].y);
+                }
+            }
+        } else {
+            const int t1 = j * tws;
+#pragma unroll
+            for (int q = 1; q < R; ++q) v[q] = c_mul(p[q * M], PB_LDG(tw + q * t1));
+        }
+        Dft<R>::run(v);
+#pragma unroll
+        for (int m = 0; m < R; ++m) p[m * M] = v[m];
+    }
+}
+
+#if defined(__CUDA_ARCH__)
+#define PB_FFT2_SYNC() __syncthreads()
+#else
+#define PB_FFT2_SYNC() ((void)0)
+#endif
+
+#define PB_FFT2_DISPATCH(FN, R_, ...)                         \
+    switch (R_) {                                             \
+        case 2: FN<2>(__VA_ARGS__); break;                    \
+        case 3: FN<3>(__VA_ARGS__); break;                    \
+        case 4: FN<4>(__VA_ARGS__); break;                    \
+        case 5: FN<5>(__VA_ARGS__); break;                    \
+        case 6: FN<6>(__VA_ARGS__); break;                    \
+        case 7: FN<7>(__VA_ARGS__); break;                    \
+        case 8: FN<8>(__VA_ARGS__); break;                    \
+        case 9: FN<9>(__VA_ARGS__); break;                    \
+        case 10: FN<10>(__VA_ARGS__); break;                  \
+        case 11: FN<11>(__VA_ARGS__); break;                  \
+        case 12: FN<12>(__VA_ARGS__); break;                  \
+        case 13: FN<13>(__VA_ARGS__); break;                  \
+        case 14: FN<14>(__VA_ARGS__); break;                  \
+        case 15: FN<15>(__VA_ARGS__); break;                  \
+        default: FN<16>(__VA_ARGS__); break;                  \
+    }
+
+// Forward DFT, natural order in -> scrambled order out.  The caller has made its writes to x
+// visible (barrier) before the call; a barrier has been executed after the last stage.
+// On the host (unit tests) the caller loops tid over [0, nthr) per stage via fft2_*_stage.
+PB_HD void fft2_forward_dif(float2* x, int stride, int nb, const Fft2Plan& plan, const float2* __restrict__ tw,
+                            int tid, int nthr) {
+    int L = plan.n;
+    for (int s = 0; s < plan.ns; ++s) {
+        const int R = plan.radix[s];
+        PB_FFT2_DISPATCH(fft2_dif_stage, R, x, plan.n, stride, nb, L, tw, tid, nthr);
+        PB_FFT2_SYNC();
+        L /= R;
+    }
+}
+
+// Forward-sign DFT, scrambled order in -> natural order out (inverse transform through the
+// swap trick: IDFT(y) = swap(DFT(swap(y))) / n, the swaps are folded into the caller's code).
+PB_HD void fft2_forward_dit(float2* x, int stride, int nb, const Fft2Plan& plan, const float2* __restrict__ tw,
+                            int tid, int nthr, const float* __restrict__ premul = nullptr) {
+    int L = 1;
+    for (int s = plan.ns - 1; s >= 0; --s) {
+        const int R = plan.radix[s];
+        L *= R;
+        PB_FFT2_DISPATCH(fft2_dit_stage, R, x, plan.n, stride, nb, L, tw, tid, nthr,
+                         (s == plan.ns - 1) ? premul : nullptr);
+        PB_FFT2_SYNC();
+    }
+}
+
+// Frequency index k held by slot p after the DIF transform:
+//   p = q_1 M_1 + q_2 M_2 + ... + q_s,  M_i = n / (R_1 ... R_i);   k = q_1 + R_1 (q_2 + R_2 (q_3 + ...))
+PB_HD int fft2_freq_of_slot(int p, const Fft2Plan& plan) {
+    int M = plan.n, k = 0, w = 1;
+    for (int s = 0; s < plan.ns; ++s) {
+        M /= plan.radix[s];
+        const int q = p / M;
+        p -= q * M;
+        k += q * w;
+        w *= plan.radix[s];
+    }
+    return k;
+}
+
+// Slot that holds frequency k after the DIF transform (inverse of fft2_freq_of_slot).
+PB_HD int fft2_slot_of_freq(int k, const Fft2Plan& plan) {
+    int M = plan.n, p = 0;
+    for (int s = 0; s < plan.ns; ++s) {
+        M /= plan.radix[s];
+        const int q = k % plan.radix[s];
+        k /= plan.radix[s];
+        p += q * M;
+    }
+    return p;
+}
+
+// Host: factor n into radices <= 16 with the fewest stages (ties: smaller largest radix), DIF
+// order = descending.  Returns 0 on success, -1 if n has a prime factor > 13 or needs more
+// than PB_FFT2_MAX_STAGES stages.
+inline int make_fft2_plan(int n, Fft2Plan* plan) {
+    if (n < 1) return -1;
+    plan->n = n;
+    plan->ns = 0;
+    if (n == 1) return 0;
+    static const int cand[] = {16, 15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2};
+    // depth-first search for the minimum number of stages (n <= 2^24 keeps this tiny)
+    int best[PB_FFT2_MAX_STAGES], bestn = PB_FFT2_MAX_STAGES + 1, bestmax = 99;
+    int cur[PB_FFT2_MAX_STAGES];
+    struct Rec {
+        static void go(int m, int depth, int start, int curmax, int* cur, int* best, int& bestn, int& bestmax) {
+            if (m == 1) {
+                if (depth < bestn || (depth == bestn && curmax < bestmax)) {
+                    bestn = depth;
+                    bestmax = curmax;
+                    for (int i = 0; i < depth; ++i) best[i] = cur[i];
+                }
+                return;
+            }
+            if (depth >= PB_FFT2_MAX_STAGES || depth + 1 > bestn) return;
+            for (int ci = start; ci < 15; ++ci) {       // non-increasing radices: canonical order
+                const int r = cand[ci];
+                if (m % r) continue;
+                cur[depth] = r;
+                go(m / r, depth + 1, ci, curmax > r ? curmax : r, cur, best, bestn, bestmax);
+            }
+        }
+    };
+    Rec::go(n, 0, 0, 0, cur, best, bestn, bestmax);
+    if (bestn > PB_FFT2_MAX_STAGES) return -1;
+    plan->ns = bestn;
+    for (int i = 0; i < bestn; ++i) plan->radix[i] = best[i];
+    return 0;
+}
+
+}  // namespace pb

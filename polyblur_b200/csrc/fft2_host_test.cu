@@ -1,0 +1,67 @@
+// CPU unit test of the fft2.cuh core: the __host__ __device__ stage functions run with a single
+// simulated thread.  Prints one line per length:  n  stages  err_dif  err_roundtrip  perm_ok
+// (errors relative to the spectrum's max magnitude, against a float64 naive DFT).
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "fft2.cuh"
+
+using namespace pb;
+
+int main(int argc, char** argv) {
+    int worst = 0;
+    for (int a = 1; a < argc; ++a) {
+        const int n = atoi(argv[a]);
+        Fft2Plan plan;
+        if (make_fft2_plan(n, &plan) != 0) {
+            printf("%d noplan\n", n);
+            continue;
+        }
+        long long prod = 1;
+        for (int s = 0; s < plan.ns; ++s) prod *= plan.radix[s];
+        std::vector<float2> tw(n);
+        for (int k = 0; k < n; ++k) {
+            double ang = -2.0 * M_PI * (double)k / (double)n;
+            tw[k] = make_float2((float)cos(ang), (float)sin(ang));
+        }
+        const int nb = 2;
+        const int stride = n + 3;
+        std::vector<float2> x(nb * stride), x0;
+        srand(n);
+        for (auto& v : x) v = make_float2(rand() / (float)RAND_MAX - 0.5f, rand() / (float)RAND_MAX - 0.5f);
+        x0 = x;
+        fft2_forward_dif(x.data(), stride, nb, plan, tw.data(), 0, 1);
+        // naive DFT in double for sequence 1 (subsampled for long n)
+        double err = 0, mag = 0;
+        const int step = n > 4096 ? 37 : 1;
+        bool perm_ok = (prod == n);
+        for (int p = 0; p < n; p += step) {
+            const int k = fft2_freq_of_slot(p, plan);
+            if (fft2_slot_of_freq(k, plan) != p) perm_ok = false;
+            double re = 0, im = 0;
+            for (int m = 0; m < n; ++m) {
+                double ang = -2.0 * M_PI * (double)(((long long)m * k) % n) / (double)n;
+                re += x0[stride + m].x * cos(ang) - x0[stride + m].y * sin(ang);
+                im += x0[stride + m].x * sin(ang) + x0[stride + m].y * cos(ang);
+            }
+            err = fmax(err, fmax(fabs(re - x[stride + p].x), fabs(im - x[stride + p].y)));
+            mag = fmax(mag, hypot(re, im));
+        }
+        // inverse through the swap trick
+        for (auto& v : x) v = make_float2(v.y, v.x);
+        fft2_forward_dit(x.data(), stride, nb, plan, tw.data(), 0, 1);
+        double rt = 0;
+        for (int i = 0; i < nb * stride; ++i) {
+            if (i % stride >= n) continue;
+            rt = fmax(rt, fabs(x[i].y / n - x0[i].x));
+            rt = fmax(rt, fabs(x[i].x / n - x0[i].y));
+        }
+        printf("%d %d %.3e %.3e %d", n, plan.ns, err / (mag > 0 ? mag : 1), rt, perm_ok ? 1 : 0);
+        for (int s = 0; s < plan.ns; ++s) printf(" r%d", plan.radix[s]);
+        printf("\n");
+        if (!perm_ok || err / (mag > 0 ? mag : 1) > 2e-6 || rt > 2e-6) worst = 1;
+    }
+    return worst;
+}

@@ -1,6 +1,7 @@
 // Host-callable launchers shared between the translation units of libpolyblur_sm100.so.
 #pragma once
 #include "common.cuh"
+#include "fft2.cuh"
 
 #define PB_FFT_THREADS 256
 #define PB_STATS_STRIDE 16   // per image: [0] min (ordered), [1] max (ordered), [2..8] 7 maxima
@@ -31,6 +32,16 @@ int launch_rows(bool est, const float* plane_in, const float* gy, float* gx, uns
 int launch_params(const unsigned* stats, ImgKernel* kern, float* est, const float* th, const float* sg,
                   const float* rh, const float* kin, float* kout, int mode, int B, int ksize, float cc,
                   float bb, float tap_thr, int engine_req, int fft_radius_min, cudaStream_t stream);
+
+// estimate2.cu (fast path: lengths with prime factors <= 13)
+bool fft2_supported(int H, int W);
+int launch_fft2_omega(float* omega, const Fft2Plan& plan, cudaStream_t stream);
+int launch_rows2(bool est, const float* img, float* gray, float* gx, unsigned* stats, int nimg, int C,
+                 int H, int W, const Fft2Plan& planW, const float2* twW, const float* omegaW,
+                 cudaStream_t stream);
+int launch_cols2(bool est, const float* plane_in, const float* gx, float* gy, unsigned* stats, int nimg,
+                 int H, int W, const Fft2Plan& planH, const float2* twH, const float* omegaH,
+                 int discard_saturation, cudaStream_t stream);
 
 // deconv.cu
 int launch_deconv_spatial(const float* img, float* out, const ImgKernel* kern, int B, int C, int H, int W,
