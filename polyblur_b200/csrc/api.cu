@@ -29,7 +29,8 @@ static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
 static std::vector<cudaEvent_t> g_event_pool;
 static const char* kProfNames[PROF_NCLASSES] = {"setup", "k_cols", "k_rows", "k_params", "k_deconv_spatial",
-                                                "k_fft_rows_fwd", "k_fft_cols", "k_fft_rows_inv", "other"};
+                                                "k_fft_rows_fwd", "k_fft_cols", "k_fft_rows_inv", "other",
+                                                "k_deconv_narrow"};
 
 static cudaEvent_t get_event() {
     if (!g_event_pool.empty()) {
@@ -83,7 +84,7 @@ int make_fft_plan(int n, FftPlan* plan) {
 
 // ---- workspace layout -------------------------------------------------------------------------
 struct Workspace {
-    size_t off_stats, off_kern, off_twH, off_twW, off_omH, off_omW, off_gray, off_gy, off_tmp, total;
+    size_t off_stats, off_kern, off_cls, off_twH, off_twW, off_omH, off_omW, off_gray, off_gy, off_tmp, total;
 };
 
 static Workspace layout(int B, int C, int H, int W, int n_iter) {
@@ -98,6 +99,7 @@ static Workspace layout(int B, int C, int H, int W, int n_iter) {
     const size_t nimg = (size_t)B * (C > 0 ? C : 1);   // stage entry points treat channels as images
     w.off_stats = take(nimg * PB_STATS_STRIDE * sizeof(unsigned));
     w.off_kern = take(nimg * sizeof(ImgKernel));
+    w.off_cls = take((PB_CLS_COUNT_STRIDE + PB_NCLS * nimg) * sizeof(int));
     w.off_twH = take((size_t)H * sizeof(float2));
     w.off_twW = take((size_t)W * sizeof(float2));
     w.off_omH = take((size_t)H * sizeof(float));
@@ -178,6 +180,7 @@ static int estimate_into(const float* img, int B, int C, int H, int W, double c,
     ImgKernel* kern = reinterpret_cast<ImgKernel*>(ws + L.off_kern);
     float* gray = reinterpret_cast<float*>(ws + L.off_gray);
     float* gy = reinterpret_cast<float*>(ws + L.off_gy);
+    int* cls = reinterpret_cast<int*>(ws + L.off_cls);
     int rc;
     if ((rc = launch_init_stats(stats, B, stream))) return rc;
     if (T.fast) {
@@ -187,14 +190,27 @@ static int estimate_into(const float* img, int B, int C, int H, int W, double c,
                                (flags & PB_FLAG_DISCARD_SATURATION) ? 1 : 0, stream)))
             return rc;
         return launch_params(stats, kern, est, nullptr, nullptr, nullptr, nullptr, nullptr, 0, B, ksize,
-                             (float)(c * c), (float)(b * b), tap_thr, engine, 1 << 30, stream);
+                             (float)(c * c), (float)(b * b), tap_thr, engine, 1 << 30, cls, stream);
     }
     if ((rc = launch_cols(true, img, gray, gy, stats, B, C, H, W, T.planH, T.twH, stream))) return rc;
     if ((rc = launch_rows(true, gray, gy, nullptr, stats, B, H, W, T.planW, T.twW,
                           (flags & PB_FLAG_DISCARD_SATURATION) ? 1 : 0, stream)))
         return rc;
     return launch_params(stats, kern, est, nullptr, nullptr, nullptr, nullptr, nullptr, 0, B, ksize,
-                         (float)(c * c), (float)(b * b), tap_thr, engine, 1 << 30, stream);
+                         (float)(c * c), (float)(b * b), tap_thr, engine, 1 << 30, cls, stream);
+}
+
+// Runs every deconvolution engine over its class of images (lists filled by k_params).
+static int deconv_all(const float* img, float* out, int B, int C, int H, int W, const float* coef, char* ws,
+                      const Workspace& L, cudaStream_t stream) {
+    const ImgKernel* kern = reinterpret_cast<const ImgKernel*>(ws + L.off_kern);
+    const int* cls = reinterpret_cast<const int*>(ws + L.off_cls);
+    int rc;
+    for (int k = PB_CLS_N11; k <= PB_CLS_N22; ++k)
+        if ((rc = launch_deconv_narrow(k, img, out, kern, cls + PB_CLS_COUNT_STRIDE + k * B, cls + k, B, C, H, W,
+                                       coef[0], coef[1], coef[2], coef[3], stream)))
+            return rc;
+    return launch_deconv_spatial(img, out, kern, B, C, H, W, coef[0], coef[1], coef[2], coef[3], 0, stream);
 }
 
 }  // namespace pb
@@ -294,7 +310,6 @@ int pb_polyblur_f32(const float* in, float* out, int B, int C, int H, int W, con
     poly_coeffs(p->alpha, p->beta, coef);
     const float thr = p->tap_rel_threshold > 0 ? p->tap_rel_threshold : 1e-8f;
     float* tmp = reinterpret_cast<float*>(ws + L.off_tmp);
-    ImgKernel* kern = reinterpret_cast<ImgKernel*>(ws + L.off_kern);
     const float* cur = in;
     for (int it = 0; it < p->n_iter; ++it) {
         float* dst = ((p->n_iter - 1 - it) & 1) ? tmp : out;
@@ -302,8 +317,7 @@ int pb_polyblur_f32(const float* in, float* out, int B, int C, int H, int W, con
         if ((rc = estimate_into(cur, B, C, H, W, p->c, p->b, p->flags, est, ws, L, T, p->ker_size, thr,
                                 PB_ENGINE_SPATIAL, stream)))
             return rc;
-        if ((rc = launch_deconv_spatial(cur, dst, kern, B, C, H, W, coef[0], coef[1], coef[2], coef[3], 0, stream)))
-            return rc;
+        if ((rc = deconv_all(cur, dst, B, C, H, W, coef, ws, L, stream))) return rc;
         cur = dst;
     }
     return PB_OK;
@@ -365,7 +379,7 @@ int pb_make_kernel_f32(const float* theta, const float* sigma, const float* rho,
     int rc;
     if ((rc = check_ws(workspace, workspace_bytes, need))) return rc;
     return launch_params(nullptr, static_cast<ImgKernel*>(workspace), nullptr, theta, sigma, rho, nullptr,
-                         kernel, 1, B, ksize, 0.f, 0.f, 1e-8f, PB_ENGINE_SPATIAL, 1 << 30, stream);
+                         kernel, 1, B, ksize, 0.f, 0.f, 1e-8f, PB_ENGINE_SPATIAL, 1 << 30, nullptr, stream);
 }
 
 int pb_deconv_f32(const float* img, float* out, int B, int C, int H, int W, const float* kernel, int ksize,
@@ -386,12 +400,14 @@ int pb_deconv_f32(const float* img, float* out, int B, int C, int H, int W, cons
     if ((rc = check_ws(workspace, workspace_bytes, L.total))) return rc;
     char* ws = static_cast<char*>(workspace);
     ImgKernel* kern = reinterpret_cast<ImgKernel*>(ws + L.off_kern);
+    int* cls = reinterpret_cast<int*>(ws + L.off_cls);
     if ((rc = launch_params(nullptr, kern, nullptr, nullptr, nullptr, nullptr, kernel, nullptr, 2, B, ksize,
-                            0.f, 0.f, 1e-8f, PB_ENGINE_SPATIAL, 1 << 30, stream)))
+                            0.f, 0.f, 1e-8f, engine == PB_ENGINE_AUTO ? PB_ENGINE_SPATIAL : engine, 1 << 30, cls,
+                            stream)))
         return rc;
     float coef[4];
     poly_coeffs(alpha, beta, coef);
-    return launch_deconv_spatial(img, out, kern, B, C, H, W, coef[0], coef[1], coef[2], coef[3], 0, stream);
+    return deconv_all(img, out, B, C, H, W, coef, ws, L, stream);
 }
 
 int pb_profile_begin(void) {

@@ -42,7 +42,9 @@ struct ImgKernel {
     int   ksize;              // odd support actually used (<= 25); taps outside are zero
     int   engine;             // PB_ENGINE_SPATIAL / PB_ENGINE_FFT chosen for this image
     float theta, sigma, rho;  // radians
-    int   pad_;
+    int   rx, ry;             // max |dx|, max |dy| over kept taps
+    int   cls;                // deconvolution engine class (PB_CLS_*), chosen on the device
+    int   pad_[2];
 };
 
 // ---- ordered-int encoding so that atomicMin/atomicMax work on any float -----------------

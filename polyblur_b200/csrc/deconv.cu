@@ -122,7 +122,8 @@ k_deconv_spatial(const float* __restrict__ img, float* __restrict__ out,
 
     const int im = blockIdx.z / C;
     const ImgKernel* K = kern + im;
-    if (only_engine != 0 && K->engine != only_engine) return;
+    if (K->cls != PB_CLS_TILED) return;
+    (void)only_engine;
     const int r = K->radius;
     const int pad = K->ksize / 2;
     const int hy = r;

@@ -201,17 +201,19 @@ __global__ void __launch_bounds__(128)
 k_params(const unsigned* __restrict__ stats, ImgKernel* __restrict__ kern, float* __restrict__ est,
          const float* __restrict__ th_in, const float* __restrict__ sg_in, const float* __restrict__ rh_in,
          const float* __restrict__ kin, float* __restrict__ kout, int mode, int ksize, float cc, float bb,
-         float tap_thr, int engine_req, int fft_radius_min) {
+         float tap_thr, int engine_req, int fft_radius_min, int* __restrict__ cls_buf, int list_stride) {
     __shared__ float s_par[3];
     __shared__ float s_red[4];
     __shared__ float s_k[PB_KS2];
-    __shared__ int s_cnt, s_rad;
+    __shared__ int s_cnt, s_rad, s_rx, s_ry;
     const int im = blockIdx.x;
     const int tid = threadIdx.x;
     ImgKernel* K = kern + im;
     if (tid == 0) {
         s_cnt = 0;
         s_rad = 0;
+        s_rx = 0;
+        s_ry = 0;
         float theta = 0.f, sigma = 0.f, rho = 0.f;
         if (mode == 0) {
             const unsigned* st = stats + im * PB_STATS_STRIDE;
@@ -328,6 +330,10 @@ k_params(const unsigned* __restrict__ stats, ImgKernel* __restrict__ kern, float
         K->hi[tid] = hi;
         atomicAdd(&s_cnt, hi >= lo ? hi - lo + 1 : 0);
         atomicMax(&s_rad, rad);
+        if (hi >= lo) {
+            atomicMax(&s_ry, abs(tid - PB_PAD));
+            atomicMax(&s_rx, max(abs(lo - PB_PAD), abs(hi - PB_PAD)));
+        }
         (void)cnt;
     }
     __syncthreads();
@@ -335,13 +341,26 @@ k_params(const unsigned* __restrict__ stats, ImgKernel* __restrict__ kern, float
         K->radius = s_rad;
         K->ntaps = s_cnt;
         K->ksize = ksize;
-        int eng = engine_req;
-        if (eng == PB_ENGINE_AUTO) eng = (s_rad >= fft_radius_min) ? PB_ENGINE_FFT : PB_ENGINE_SPATIAL;
-        K->engine = eng;
+        // engine class: the FFT engine when asked for (or, on AUTO, for wide kernels), else the
+        // narrowest spatial engine that holds every kept tap
+        int cls;
+        if (engine_req == PB_ENGINE_FFT) cls = PB_CLS_FFT;
+        else if (s_rx <= 1 && s_ry <= 1) cls = PB_CLS_N11;
+        else if (s_rx <= 2 && s_ry <= 2) cls = PB_CLS_N22;
+        else if (engine_req == PB_ENGINE_AUTO && s_rad >= fft_radius_min) cls = PB_CLS_FFT;
+        else cls = PB_CLS_TILED;
+        K->engine = (cls == PB_CLS_FFT) ? PB_ENGINE_FFT : PB_ENGINE_SPATIAL;
+        K->rx = s_rx;
+        K->ry = s_ry;
+        K->cls = cls;
+        if (cls_buf) {
+            const int slot = atomicAdd(&cls_buf[cls], 1);
+            cls_buf[PB_CLS_COUNT_STRIDE + cls * list_stride + slot] = im;
+        }
         K->theta = s_par[0];
         K->sigma = s_par[1];
         K->rho = s_par[2];
-        K->pad_ = 0;
+        K->pad_[0] = K->pad_[1] = 0;
     }
 }
 
@@ -466,10 +485,11 @@ int launch_rows(bool est, const float* plane_in, const float* gy, float* gx, uns
 
 int launch_params(const unsigned* stats, ImgKernel* kern, float* est, const float* th, const float* sg,
                   const float* rh, const float* kin, float* kout, int mode, int B, int ksize, float cc,
-                  float bb, float tap_thr, int engine_req, int fft_radius_min, cudaStream_t stream) {
+                  float bb, float tap_thr, int engine_req, int fft_radius_min, int* cls, cudaStream_t stream) {
     ProfScope prof(PROF_PARAMS, stream);
+    if (cls) PB_CUDA_TRY(cudaMemsetAsync(cls, 0, PB_CLS_COUNT_STRIDE * sizeof(int), stream));
     k_params<<<B, 128, 0, stream>>>(stats, kern, est, th, sg, rh, kin, kout, mode, ksize, cc, bb, tap_thr,
-                                    engine_req, fft_radius_min);
+                                    engine_req, fft_radius_min, cls, B);
     PB_LAUNCH_CHECK("k_params");
     return PB_OK;
 }

@@ -10,7 +10,18 @@ namespace pb {
 
 // ---- optional per-kernel timing with CUDA events (api.cu); used by bench.py ---------------
 enum ProfClass { PROF_SETUP = 0, PROF_COLS, PROF_ROWS, PROF_PARAMS, PROF_DECONV_SPATIAL,
-                 PROF_FFT_ROWS_FWD, PROF_FFT_COLS, PROF_FFT_ROWS_INV, PROF_OTHER, PROF_NCLASSES };
+                 PROF_FFT_ROWS_FWD, PROF_FFT_COLS, PROF_FFT_ROWS_INV, PROF_OTHER, PROF_DECONV_NARROW,
+                 PROF_NCLASSES };
+
+// Deconvolution engine classes.  k_params classifies every image on the device from the extent
+// of its significant taps and appends it to the class's list; each engine's kernel then takes
+// its work grid-stride from that list (an empty class costs one tiny launch, no host sync).
+#define PB_CLS_N11 0      // taps within 3 x 3: register-rolling kernel (deconv_narrow.cu)
+#define PB_CLS_N22 1      // taps within 5 x 5: register-rolling kernel
+#define PB_CLS_TILED 2    // shared-memory tiled Horner stencil (deconv.cu)
+#define PB_CLS_FFT 3      // blur-independent on-chip FFT engine (deconv_fft.cu)
+#define PB_NCLS 4
+#define PB_CLS_COUNT_STRIDE 16   // ints reserved for the counters in front of the lists
 struct ProfScope {
     int idx;
     cudaStream_t stream;
@@ -31,7 +42,7 @@ int launch_rows(bool est, const float* plane_in, const float* gy, float* gx, uns
                 cudaStream_t stream);
 int launch_params(const unsigned* stats, ImgKernel* kern, float* est, const float* th, const float* sg,
                   const float* rh, const float* kin, float* kout, int mode, int B, int ksize, float cc,
-                  float bb, float tap_thr, int engine_req, int fft_radius_min, cudaStream_t stream);
+                  float bb, float tap_thr, int engine_req, int fft_radius_min, int* cls, cudaStream_t stream);
 
 // estimate2.cu (fast path: lengths with prime factors <= 13)
 bool fft2_supported(int H, int W);
@@ -42,6 +53,11 @@ int launch_rows2(bool est, const float* img, float* gray, float* gx, unsigned* s
 int launch_cols2(bool est, const float* plane_in, const float* gx, float* gy, unsigned* stats, int nimg,
                  int H, int W, const Fft2Plan& planH, const float2* twH, const float* omegaH,
                  int discard_saturation, cudaStream_t stream);
+
+// deconv_narrow.cu
+int launch_deconv_narrow(int cls, const float* img, float* out, const ImgKernel* kern, const int* list,
+                         const int* count, int B, int C, int H, int W, float a3, float a2, float a1, float b0,
+                         cudaStream_t stream);
 
 // deconv.cu
 int launch_deconv_spatial(const float* img, float* out, const ImgKernel* kern, int B, int C, int H, int W,
