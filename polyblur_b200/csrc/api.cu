@@ -84,10 +84,15 @@ int make_fft_plan(int n, FftPlan* plan) {
 
 // ---- workspace layout -------------------------------------------------------------------------
 struct Workspace {
-    size_t off_stats, off_kern, off_cls, off_twH, off_twW, off_omH, off_omW, off_gray, off_gy, off_tmp, total;
+    size_t off_stats, off_kern, off_cls, off_twH, off_twW, off_omH, off_omW, off_gray, off_gy, off_tmp, off_fft, total;
+    bool has_fft;
+    FftEngineLayout fft;
 };
 
-static Workspace layout(int B, int C, int H, int W, int n_iter) {
+// Radius (max |tap offset|) from which AUTO hands an image to the FFT engine.
+#define PB_FFT_RADIUS_MIN 4
+
+static Workspace layout(int B, int C, int H, int W, int n_iter, int ksize = PB_KS, int engine = PB_ENGINE_AUTO) {
     Workspace w;
     size_t o = 0;
     auto take = [&](size_t bytes) {
@@ -107,6 +112,9 @@ static Workspace layout(int B, int C, int H, int W, int n_iter) {
     w.off_gray = take((size_t)B * plane * sizeof(float));
     w.off_gy = take((size_t)B * plane * sizeof(float));
     w.off_tmp = take(n_iter >= 2 ? (size_t)B * C * plane * sizeof(float) : 0);
+    w.has_fft = engine != PB_ENGINE_SPATIAL && fft_engine_supported(H, W, ksize / 2);
+    w.off_fft = o;
+    if (w.has_fft) take(fft_engine_workspace(B, C, H, W, ksize / 2, &w.fft));
     w.total = o;
     return w;
 }
@@ -175,7 +183,7 @@ static void poly_coeffs(double alpha, double beta, float* o) {
 
 static int estimate_into(const float* img, int B, int C, int H, int W, double c, double b, uint32_t flags,
                          float* est, char* ws, const Workspace& L, const Tables& T, int ksize,
-                         float tap_thr, int engine, cudaStream_t stream) {
+                         float tap_thr, int engine, int fft_radius_min, cudaStream_t stream) {
     unsigned* stats = reinterpret_cast<unsigned*>(ws + L.off_stats);
     ImgKernel* kern = reinterpret_cast<ImgKernel*>(ws + L.off_kern);
     float* gray = reinterpret_cast<float*>(ws + L.off_gray);
@@ -190,19 +198,19 @@ static int estimate_into(const float* img, int B, int C, int H, int W, double c,
                                (flags & PB_FLAG_DISCARD_SATURATION) ? 1 : 0, stream)))
             return rc;
         return launch_params(stats, kern, est, nullptr, nullptr, nullptr, nullptr, nullptr, 0, B, ksize,
-                             (float)(c * c), (float)(b * b), tap_thr, engine, 1 << 30, cls, stream);
+                             (float)(c * c), (float)(b * b), tap_thr, engine, fft_radius_min, cls, stream);
     }
     if ((rc = launch_cols(true, img, gray, gy, stats, B, C, H, W, T.planH, T.twH, stream))) return rc;
     if ((rc = launch_rows(true, gray, gy, nullptr, stats, B, H, W, T.planW, T.twW,
                           (flags & PB_FLAG_DISCARD_SATURATION) ? 1 : 0, stream)))
         return rc;
     return launch_params(stats, kern, est, nullptr, nullptr, nullptr, nullptr, nullptr, 0, B, ksize,
-                         (float)(c * c), (float)(b * b), tap_thr, engine, 1 << 30, cls, stream);
+                         (float)(c * c), (float)(b * b), tap_thr, engine, fft_radius_min, cls, stream);
 }
 
 // Runs every deconvolution engine over its class of images (lists filled by k_params).
 static int deconv_all(const float* img, float* out, int B, int C, int H, int W, const float* coef, char* ws,
-                      const Workspace& L, cudaStream_t stream) {
+                      const Workspace& L, const FftEngineTables* F, cudaStream_t stream) {
     const ImgKernel* kern = reinterpret_cast<const ImgKernel*>(ws + L.off_kern);
     const int* cls = reinterpret_cast<const int*>(ws + L.off_cls);
     int rc;
@@ -210,7 +218,12 @@ static int deconv_all(const float* img, float* out, int B, int C, int H, int W, 
         if ((rc = launch_deconv_narrow(k, img, out, kern, cls + PB_CLS_COUNT_STRIDE + k * B, cls + k, B, C, H, W,
                                        coef[0], coef[1], coef[2], coef[3], stream)))
             return rc;
-    return launch_deconv_spatial(img, out, kern, B, C, H, W, coef[0], coef[1], coef[2], coef[3], 0, stream);
+    if ((rc = launch_deconv_spatial(img, out, kern, B, C, H, W, coef[0], coef[1], coef[2], coef[3], 0, stream)))
+        return rc;
+    if (F)
+        return launch_deconv_fft(img, out, kern, cls + PB_CLS_COUNT_STRIDE + PB_CLS_FFT * B, cls + PB_CLS_FFT, B, C,
+                                 H, W, *F, coef[0], coef[1], coef[2], coef[3], stream);
+    return PB_OK;
 }
 
 }  // namespace pb
@@ -257,7 +270,7 @@ int pb_fft_plan(int n, int* radices) {
 
 size_t pb_workspace_bytes(int B, int C, int H, int W, const pb_params* p) {
     if (B < 1 || C < 1 || H < 1 || W < 1) return 0;
-    return layout(B, C, H, W, p ? p->n_iter : 1).total;
+    return layout(B, C, H, W, p ? p->n_iter : 1, p ? p->ker_size : PB_KS, p ? p->engine : PB_ENGINE_AUTO).total;
 }
 
 static int validate_params(const pb_params* p) {
@@ -300,12 +313,18 @@ int pb_polyblur_f32(const float* in, float* out, int B, int C, int H, int W, con
         PB_CUDA_TRY(cudaMemcpyAsync(out, in, bytes, cudaMemcpyDeviceToDevice, stream));
         return PB_OK;
     }
-    const Workspace L = layout(B, C, H, W, p->n_iter);
+    const Workspace L = layout(B, C, H, W, p->n_iter, p->ker_size, p->engine);
     if ((rc = check_ws(workspace, workspace_bytes, L.total))) return rc;
+    if (p->engine == PB_ENGINE_FFT && !L.has_fft) {
+        set_error("the FFT engine does not support %d x %d (ker_size %d)", H, W, p->ker_size);
+        return PB_ERR_UNSUPPORTED;
+    }
     char* ws = static_cast<char*>(workspace);
     Tables T;
+    FftEngineTables F;
     if ((rc = upload_constants(stream))) return rc;
     if ((rc = prepare_tables(ws, L, H, W, &T, stream))) return rc;
+    if (L.has_fft && (rc = fft_engine_prepare(ws + L.off_fft, L.fft, &F, stream))) return rc;
     float coef[4];
     poly_coeffs(p->alpha, p->beta, coef);
     const float thr = p->tap_rel_threshold > 0 ? p->tap_rel_threshold : 1e-8f;
@@ -314,10 +333,10 @@ int pb_polyblur_f32(const float* in, float* out, int B, int C, int H, int W, con
     for (int it = 0; it < p->n_iter; ++it) {
         float* dst = ((p->n_iter - 1 - it) & 1) ? tmp : out;
         float* est = est_out ? est_out + (size_t)it * B * PB_EST_STRIDE : nullptr;
-        if ((rc = estimate_into(cur, B, C, H, W, p->c, p->b, p->flags, est, ws, L, T, p->ker_size, thr,
-                                PB_ENGINE_SPATIAL, stream)))
+        if ((rc = estimate_into(cur, B, C, H, W, p->c, p->b, p->flags, est, ws, L, T, p->ker_size, thr, p->engine,
+                                L.has_fft ? PB_FFT_RADIUS_MIN : (1 << 30), stream)))
             return rc;
-        if ((rc = deconv_all(cur, dst, B, C, H, W, coef, ws, L, stream))) return rc;
+        if ((rc = deconv_all(cur, dst, B, C, H, W, coef, ws, L, L.has_fft ? &F : nullptr, stream))) return rc;
         cur = dst;
     }
     return PB_OK;
@@ -365,7 +384,7 @@ int pb_estimate_f32(const float* img, int B, int C, int H, int W, double c, doub
     Tables T;
     if ((rc = upload_constants(stream))) return rc;
     if ((rc = prepare_tables(ws, L, H, W, &T, stream))) return rc;
-    return estimate_into(img, B, C, H, W, c, b, flags, est, ws, L, T, PB_KS, 1e-8f, PB_ENGINE_SPATIAL, stream);
+    return estimate_into(img, B, C, H, W, c, b, flags, est, ws, L, T, PB_KS, 1e-8f, PB_ENGINE_SPATIAL, 1 << 30, stream);
 }
 
 int pb_make_kernel_f32(const float* theta, const float* sigma, const float* rho, int B, int ksize,
@@ -392,22 +411,23 @@ int pb_deconv_f32(const float* img, float* out, int B, int C, int H, int W, cons
         set_error("bad arguments to pb_deconv_f32 (ksize must be odd and <= 25)");
         return PB_ERR_ARG;
     }
-    if (engine == PB_ENGINE_FFT) {
-        set_error("the FFT deconvolution engine is not built yet");
+    const Workspace L = layout(B, C, H, W, 1, ksize, engine);
+    if ((rc = check_ws(workspace, workspace_bytes, L.total))) return rc;
+    if (engine == PB_ENGINE_FFT && !L.has_fft) {
+        set_error("the FFT engine does not support %d x %d (ker_size %d)", H, W, ksize);
         return PB_ERR_UNSUPPORTED;
     }
-    const Workspace L = layout(B, C, H, W, 1);
-    if ((rc = check_ws(workspace, workspace_bytes, L.total))) return rc;
     char* ws = static_cast<char*>(workspace);
     ImgKernel* kern = reinterpret_cast<ImgKernel*>(ws + L.off_kern);
     int* cls = reinterpret_cast<int*>(ws + L.off_cls);
+    FftEngineTables F;
+    if (L.has_fft && (rc = fft_engine_prepare(ws + L.off_fft, L.fft, &F, stream))) return rc;
     if ((rc = launch_params(nullptr, kern, nullptr, nullptr, nullptr, nullptr, kernel, nullptr, 2, B, ksize,
-                            0.f, 0.f, 1e-8f, engine == PB_ENGINE_AUTO ? PB_ENGINE_SPATIAL : engine, 1 << 30, cls,
-                            stream)))
+                            0.f, 0.f, 1e-8f, engine, L.has_fft ? PB_FFT_RADIUS_MIN : (1 << 30), cls, stream)))
         return rc;
     float coef[4];
     poly_coeffs(alpha, beta, coef);
-    return deconv_all(img, out, B, C, H, W, coef, ws, L, stream);
+    return deconv_all(img, out, B, C, H, W, coef, ws, L, L.has_fft ? &F : nullptr, stream);
 }
 
 int pb_profile_begin(void) {

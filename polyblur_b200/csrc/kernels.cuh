@@ -59,6 +59,26 @@ int launch_deconv_narrow(int cls, const float* img, float* out, const ImgKernel*
                          const int* count, int B, int C, int H, int W, float a3, float a2, float a1, float b0,
                          cudaStream_t stream);
 
+// deconv_fft.cu (blur-independent on-chip FFT engine)
+struct FftEngineLayout {
+    int NX, NY;
+    size_t off_twX, off_twY, off_slotX, off_slotY, off_freqY, off_Z, total;
+};
+struct FftEngineTables {
+    int NX, NY;
+    Fft2Plan planX, planY;
+    float2 *twX, *twY;
+    int *slotX, *slotY, *freqY;
+    float2* Z;
+};
+int fft_engine_length(int n);
+bool fft_engine_supported(int H, int W, int pad);
+size_t fft_engine_workspace(int B, int C, int H, int W, int pad, FftEngineLayout* L);
+int fft_engine_prepare(char* base, const FftEngineLayout& L, FftEngineTables* T, cudaStream_t stream);
+int launch_deconv_fft(const float* img, float* out, const ImgKernel* kern, const int* list, const int* count,
+                      int B, int C, int H, int W, const FftEngineTables& T, float a3, float a2, float a1,
+                      float b0, cudaStream_t stream);
+
 // deconv.cu
 int launch_deconv_spatial(const float* img, float* out, const ImgKernel* kern, int B, int C, int H, int W,
                           float a3, float a2, float a1, float b0, int only_engine, cudaStream_t stream);

@@ -198,3 +198,60 @@ def test_white_noise_full_hd_properties(pb):
     ref1 = po.inverse_filtering_rank3(x[:1, :, :256, :256].cpu().numpy(), k, alpha=6, b=1)
     got1 = pb.deblurring.inverse_filtering_rank3(x[:1, :, :256, :256].contiguous(), cu(k), alpha=6, b=1)
     assert maxabs(got1.cpu().numpy(), ref1) < 3e-6
+
+
+# ---------------------------------------------------------------------------------------------
+# deconvolution engines: every engine must give the reference's result for the same kernel
+# ---------------------------------------------------------------------------------------------
+ENGINE_SPATIAL, ENGINE_FFT = 1, 2
+
+
+@pytest.mark.parametrize("engine", [ENGINE_SPATIAL, ENGINE_FFT])
+@pytest.mark.parametrize("shape", [(2, 3, 70, 131), (1, 1, 8, 8), (1, 3, 200, 65), (3, 2, 33, 64),
+                                   (1, 3, 300, 500)])
+def test_deconvolution_engines_vs_oracle(pb, shape, engine):
+    rng = np.random.default_rng(11)
+    B = shape[0]
+    x = rng.random(shape, dtype=np.float32)
+    th = rng.random(B).astype(np.float32) * 3.0
+    sg = (0.3 + 3.7 * rng.random(B)).astype(np.float32)
+    rh = (0.3 + 3.7 * rng.random(B)).astype(np.float32)
+    k = po.gaussian_kernel(th, sg, rh)
+    ref = po.inverse_filtering_rank3(x, k, alpha=6, b=1, dtype=np.float64)
+    out = pb.deblurring.inverse_filtering_rank3(cu(x), cu(k), alpha=6, b=1, engine=engine)
+    assert maxabs(out.cpu().numpy(), ref) < 3e-6
+
+
+@pytest.mark.parametrize("sigma,rho,theta", [(0.3, 0.3, 0.0), (0.45, 0.3, 0.4), (0.42, 0.40, 1.2),
+                                             (0.7, 0.3, 0.0), (0.3, 0.75, 0.0), (1.2, 0.6, 2.0)])
+def test_deconvolution_narrow_and_tiled_classes(pb, sigma, rho, theta):
+    """Kernels that land in each spatial class (3x3, 5x5 register-rolling; tiled), on a shape
+    with ragged tiles and odd width, against the float64 torus restatement."""
+    rng = np.random.default_rng(5)
+    x = rng.random((2, 3, 257, 391), dtype=np.float32)
+    k = po.gaussian_kernel(np.full(2, theta, np.float32), np.full(2, sigma, np.float32),
+                           np.full(2, rho, np.float32))
+    ref = po.inverse_filtering_rank3(x, k, alpha=6, b=1, dtype=np.float64)
+    for engine in (0, ENGINE_SPATIAL, ENGINE_FFT):
+        out = pb.deblurring.inverse_filtering_rank3(cu(x), cu(k), alpha=6, b=1, engine=engine)
+        assert maxabs(out.cpu().numpy(), ref) < 3e-6, engine
+
+
+def test_deconvolution_small_ker_size(pb):
+    """ker_size 15 pads by 7 (utils.py:48-53): every engine follows the smaller torus."""
+    rng = np.random.default_rng(9)
+    x = rng.random((1, 3, 90, 120), dtype=np.float32)
+    k = po.gaussian_kernel(np.array([0.7], np.float32), np.array([1.5], np.float32), np.array([0.8], np.float32),
+                           ksize=15)
+    ref = po.inverse_filtering_rank3(x, k, alpha=2, b=3, dtype=np.float64)
+    for engine in (ENGINE_SPATIAL, ENGINE_FFT):
+        out = pb.deblurring.inverse_filtering_rank3(cu(x), cu(k), alpha=2, b=3, engine=engine)
+        assert maxabs(out.cpu().numpy(), ref) < 3e-6, engine
+
+
+@pytest.mark.parametrize("engine", [0, ENGINE_SPATIAL, ENGINE_FFT])
+def test_end_to_end_engines_agree_with_oracle(pb, engine):
+    x = mosaic(2, 3, 270, 480, seed=4, sigma=(2.4, 1.1), theta_deg=50.0)
+    ref = po.polyblur_deblurring(x, n_iter=3, alpha=6, beta=1)
+    out = pb.polyblur_deblurring(cu(x), n_iter=3, alpha=6, beta=1, engine=engine)
+    assert maxabs(out.cpu().numpy(), ref) < TOL_E2E
