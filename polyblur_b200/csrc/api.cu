@@ -218,7 +218,8 @@ static int deconv_all(const float* img, float* out, int B, int C, int H, int W, 
         if ((rc = launch_deconv_narrow(k, img, out, kern, cls + PB_CLS_COUNT_STRIDE + k * B, cls + k, B, C, H, W,
                                        coef[0], coef[1], coef[2], coef[3], stream)))
             return rc;
-    if ((rc = launch_deconv_spatial(img, out, kern, B, C, H, W, coef[0], coef[1], coef[2], coef[3], 0, stream)))
+    if ((rc = launch_deconv_spatial(img, out, kern, cls + PB_CLS_COUNT_STRIDE + PB_CLS_TILED * B, cls + PB_CLS_TILED,
+                                    B, C, H, W, coef[0], coef[1], coef[2], coef[3], stream)))
         return rc;
     if (F)
         return launch_deconv_fft(img, out, kern, cls + PB_CLS_COUNT_STRIDE + PB_CLS_FFT * B, cls + PB_CLS_FFT, B, C,

@@ -114,64 +114,74 @@ __device__ __forceinline__ void horner_tile(float* P, float* O1, float* O2, int 
 
 __global__ void __launch_bounds__(DC_THREADS, 1)
 k_deconv_spatial(const float* __restrict__ img, float* __restrict__ out,
-                 const ImgKernel* __restrict__ kern, int C, int H, int W,
-                 float a3, float a2, float a1, float b0, int only_engine) {
+                 const ImgKernel* __restrict__ kern, const int* __restrict__ list,
+                 const int* __restrict__ count, int C, int H, int W,
+                 float a3, float a2, float a1, float b0) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DeconvSmem& S = *reinterpret_cast<DeconvSmem*>(smem_raw);
     float* bufs = reinterpret_cast<float*>(smem_raw + sizeof(DeconvSmem));
+    const int tilesX = (W + DT_W - 1) / DT_W, tilesY = (H + DT_H - 1) / DT_H;
+    const int per_plane = tilesX * tilesY;
+    const int per_img = C * per_plane;
+    const int total = count[0] * per_img;      // images of the tiled class (list filled by k_params)
 
-    const int im = blockIdx.z / C;
-    const ImgKernel* K = kern + im;
-    if (K->cls != PB_CLS_TILED) return;
-    (void)only_engine;
-    const int r = K->radius;
-    const int pad = K->ksize / 2;
-    const int hy = r;
-    int HX = (r + 3) & ~3;
-    if (HX == 0) HX = 4;
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int slot = w / per_img;
+        int rr = w - slot * per_img;
+        const int c = rr / per_plane;
+        rr -= c * per_plane;
+        const int tyi = rr / tilesX;
+        const int txi = rr - tyi * tilesX;
+        const int im = list[slot];
+        const ImgKernel* K = kern + im;
+        const int r = K->radius;
+        const int pad = K->ksize / 2;
+        const int hy = r;
+        int HX = (r + 3) & ~3;
+        if (HX == 0) HX = 4;
 
-    for (int i = threadIdx.x; i < 640; i += blockDim.x) S.k[i] = (i < PB_KS2) ? K->k[i] : 0.0f;
-    if (threadIdx.x < 32) {
-        S.lo[threadIdx.x] = (threadIdx.x < PB_KS) ? K->lo[threadIdx.x] : PB_KS;
-        S.hi[threadIdx.x] = (threadIdx.x < PB_KS) ? K->hi[threadIdx.x] : -1;
-    }
-    const int gx0 = blockIdx.x * DT_W, gy0 = blockIdx.y * DT_H;
-    const int PW = DT_W + 6 * HX, PH = DT_H + 6 * hy;
-    for (int i = threadIdx.x; i < PW; i += blockDim.x) S.srcx[i] = torus_src(gx0 + pad + i - 3 * HX, W, pad);
-    for (int i = threadIdx.x; i < PH; i += blockDim.x) S.srcy[i] = torus_src(gy0 + pad + i - 3 * hy, H, pad);
-    __syncthreads();
+        for (int i = threadIdx.x; i < 640; i += blockDim.x) S.k[i] = (i < PB_KS2) ? K->k[i] : 0.0f;
+        if (threadIdx.x < 32) {
+            S.lo[threadIdx.x] = (threadIdx.x < PB_KS) ? K->lo[threadIdx.x] : PB_KS;
+            S.hi[threadIdx.x] = (threadIdx.x < PB_KS) ? K->hi[threadIdx.x] : -1;
+        }
+        const int gx0 = txi * DT_W, gy0 = tyi * DT_H;
+        const int PW = DT_W + 6 * HX, PH = DT_H + 6 * hy;
+        for (int i = threadIdx.x; i < PW; i += blockDim.x) S.srcx[i] = torus_src(gx0 + pad + i - 3 * HX, W, pad);
+        for (int i = threadIdx.x; i < PH; i += blockDim.x) S.srcy[i] = torus_src(gy0 + pad + i - 3 * hy, H, pad);
+        __syncthreads();
 
-    float* P = bufs;
-    float* O1 = P + PH * PW;
-    float* O2 = O1 + (DT_H + 4 * hy) * (DT_W + 4 * HX);
-    const float* plane = img + (size_t)blockIdx.z * H * W;
-    for (int i = threadIdx.x; i < PH * PW; i += blockDim.x) {
-        const int ly = i / PW, lx = i - ly * PW;
-        P[i] = __ldg(plane + (size_t)S.srcy[ly] * W + S.srcx[lx]);
-    }
-    __syncthreads();
-    float* gout = out + (size_t)blockIdx.z * H * W;
-    switch (HX) {
-        case 4: horner_tile<4>(P, O1, O2, hy, S, a3, a2, a1, b0, gout, gy0, gx0, H, W); break;
-        case 8: horner_tile<8>(P, O1, O2, hy, S, a3, a2, a1, b0, gout, gy0, gx0, H, W); break;
-        default: horner_tile<12>(P, O1, O2, hy, S, a3, a2, a1, b0, gout, gy0, gx0, H, W); break;
+        float* P = bufs;
+        float* O1 = P + PH * PW;
+        float* O2 = O1 + (DT_H + 4 * hy) * (DT_W + 4 * HX);
+        const size_t pl = ((size_t)im * C + c) * H * W;
+        const float* plane = img + pl;
+        for (int i = threadIdx.x; i < PH * PW; i += blockDim.x) {
+            const int ly = i / PW, lx = i - ly * PW;
+            P[i] = __ldg(plane + (size_t)S.srcy[ly] * W + S.srcx[lx]);
+        }
+        __syncthreads();
+        float* gout = out + pl;
+        switch (HX) {
+            case 4: horner_tile<4>(P, O1, O2, hy, S, a3, a2, a1, b0, gout, gy0, gx0, H, W); break;
+            case 8: horner_tile<8>(P, O1, O2, hy, S, a3, a2, a1, b0, gout, gy0, gx0, H, W); break;
+            default: horner_tile<12>(P, O1, O2, hy, S, a3, a2, a1, b0, gout, gy0, gx0, H, W); break;
+        }
+        __syncthreads();
     }
 }
 
-int launch_deconv_spatial(const float* img, float* out, const ImgKernel* kern, int B, int C, int H, int W,
-                          float a3, float a2, float a1, float b0, int only_engine, cudaStream_t stream) {
+int launch_deconv_spatial(const float* img, float* out, const ImgKernel* kern, const int* list, const int* count,
+                          int B, int C, int H, int W, float a3, float a2, float a1, float b0, cudaStream_t stream) {
     const int ext = DT_W + 6 * PB_PAD;
     const size_t smem = sizeof(DeconvSmem) +
                         sizeof(float) * ((size_t)ext * ext + (size_t)(DT_W + 4 * PB_PAD) * (DT_H + 4 * PB_PAD) +
                                          (size_t)(DT_W + 2 * PB_PAD) * (DT_H + 2 * PB_PAD));
     PB_CUDA_TRY(cudaFuncSetAttribute(k_deconv_spatial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if ((long long)B * C > 65535) {
-        set_error("B*C = %lld exceeds the grid z limit", (long long)B * C);
-        return PB_ERR_ARG;
-    }
-    dim3 grid((W + DT_W - 1) / DT_W, (H + DT_H - 1) / DT_H, B * C);
+    const long long items = (long long)B * C * ((W + DT_W - 1) / DT_W) * ((H + DT_H - 1) / DT_H);
+    const int grid = (int)(items < 4LL * PB_NUM_SMS ? items : 4LL * PB_NUM_SMS);   // persistent, 1 CTA / SM resident
     ProfScope prof(PROF_DECONV_SPATIAL, stream);
-    k_deconv_spatial<<<grid, DC_THREADS, smem, stream>>>(img, out, kern, C, H, W, a3, a2, a1, b0, only_engine);
+    k_deconv_spatial<<<grid, DC_THREADS, smem, stream>>>(img, out, kern, list, count, C, H, W, a3, a2, a1, b0);
     PB_LAUNCH_CHECK("k_deconv_spatial");
     return PB_OK;
 }

@@ -94,13 +94,14 @@ k_fft_rows_fwd(const float* __restrict__ img, float2* __restrict__ Z, const ImgK
                const int* __restrict__ list, const int* __restrict__ count, int C, int H, int W, int NX, int NY,
                int nb, Fft2Plan planX, const float2* __restrict__ twX, const int* __restrict__ slotX) {
     extern __shared__ __align__(16) float2 smf[];
+    __shared__ int rowsrc[32];
     const int tid = threadIdx.x;
     const int blocks_per_plane = (NY / 2 + nb - 1) / nb;
     const int per_img = C * blocks_per_plane;
     const int total = count[0] * per_img;
     const size_t plane = (size_t)H * W;
     const int half = NX >> 1;
-    const float inv_nx = 1.0f / (float)NX, inv_half = 1.0f / (float)half;
+    const float inv_nb = 1.0f / (float)nb;
 
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
         const int slot = w / per_img;
@@ -111,27 +112,80 @@ k_fft_rows_fwd(const float* __restrict__ img, float2* __restrict__ Z, const ImgK
         const int pad = kern[im].ksize >> 1;
         const float* src = img + ((size_t)im * C + c) * plane;
         const int j0 = rb * 2 * nb;
+        if (tid < 2 * nb) rowsrc[tid] = (j0 + tid < NY) ? ext_src(j0 + tid, H, pad) : -1;
+        __syncthreads();
 
-        for (int idx = tid; idx < nb * NX; idx += FFTD_THREADS) {
-            const int p = fast_div(idx, NX, inv_nx);
-            const int i = idx - p * NX;
-            const int sx = ext_src(i, W, pad);
-            float2 v = make_float2(0.f, 0.f);
-            if (sx >= 0) {
-                const int ja = j0 + 2 * p;
-                const int sa = (ja < NY) ? ext_src(ja, H, pad) : -1;
-                const int sb = (ja + 1 < NY) ? ext_src(ja + 1, H, pad) : -1;
-                if (sa >= 0) v.x = __ldg(src + (size_t)sa * W + sx);
-                if (sb >= 0) v.y = __ldg(src + (size_t)sb * W + sx);
+        const int x_off = 3 * pad;
+        if (((W | x_off) & 3) == 0) {
+            // interior columns: image column x lives at extended column x + 3 pad; 128-bit loads of
+            // both rows of a pair, four pairs of loads in flight per thread
+            const int w4 = W >> 2;
+            const float inv_w4 = 1.0f / (float)w4;
+            const int tot = nb * w4;
+            for (int base = tid; base < tot; base += 4 * FFTD_THREADS) {
+                float4 va[4], vb[4];
+                int off[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int idx = base + u * FFTD_THREADS;
+                    va[u] = vb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    off[u] = -1;
+                    if (idx < tot) {
+                        const int p = fast_div(idx, w4, inv_w4);
+                        const int x = (idx - p * w4) << 2;
+                        const int sa = rowsrc[2 * p], sb = rowsrc[2 * p + 1];
+                        if (sa >= 0) va[u] = __ldg(reinterpret_cast<const float4*>(src + (size_t)sa * W + x));
+                        if (sb >= 0) vb[u] = __ldg(reinterpret_cast<const float4*>(src + (size_t)sb * W + x));
+                        off[u] = p * NX + x_off + x;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (off[u] >= 0) {
+                        float4* d = reinterpret_cast<float4*>(smf + off[u]);
+                        d[0] = make_float4(va[u].x, vb[u].x, va[u].y, vb[u].y);
+                        d[1] = make_float4(va[u].z, vb[u].z, va[u].w, vb[u].w);
+                    }
+                }
             }
-            smf[(size_t)p * NX + i] = v;
+            // the 3 pad columns on the left and everything right of the image: torus map / zero fill
+            const int nbord = NX - W;
+            const float inv_nbord = 1.0f / (float)nbord;
+            for (int idx = tid; idx < nb * nbord; idx += FFTD_THREADS) {
+                const int p = fast_div(idx, nbord, inv_nbord);
+                const int e = idx - p * nbord;
+                const int i = e < x_off ? e : W + e;
+                const int sx = ext_src(i, W, pad);
+                float2 v = make_float2(0.f, 0.f);
+                if (sx >= 0) {
+                    const int sa = rowsrc[2 * p], sb = rowsrc[2 * p + 1];
+                    if (sa >= 0) v.x = __ldg(src + (size_t)sa * W + sx);
+                    if (sb >= 0) v.y = __ldg(src + (size_t)sb * W + sx);
+                }
+                smf[(size_t)p * NX + i] = v;
+            }
+        } else {
+            const float inv_nx = 1.0f / (float)NX;
+            for (int idx = tid; idx < nb * NX; idx += FFTD_THREADS) {
+                const int p = fast_div(idx, NX, inv_nx);
+                const int i = idx - p * NX;
+                const int sx = ext_src(i, W, pad);
+                float2 v = make_float2(0.f, 0.f);
+                if (sx >= 0) {
+                    const int sa = rowsrc[2 * p], sb = rowsrc[2 * p + 1];
+                    if (sa >= 0) v.x = __ldg(src + (size_t)sa * W + sx);
+                    if (sb >= 0) v.y = __ldg(src + (size_t)sb * W + sx);
+                }
+                smf[(size_t)p * NX + i] = v;
+            }
         }
         __syncthreads();
         fft2_forward_dif(smf, NX, nb, planX, twX, tid, FFTD_THREADS);
         // separate the two real rows: Xa[k] = (Z[k] + conj Z[-k]) / 2, Xb[k] = (Z[k] - conj Z[-k]) / (2i)
         float2* Zp = Z + ((size_t)slot * C + c) * half * NY;
+#pragma unroll 2
         for (int idx = tid; idx < nb * half; idx += FFTD_THREADS) {
-            const int kx = fast_div(idx, nb, 1.0f / (float)nb);
+            const int kx = fast_div(idx, nb, inv_nb);
             const int p = idx - kx * nb;
             const int ja = j0 + 2 * p;
             if (ja >= NY) continue;
@@ -156,14 +210,15 @@ k_fft_rows_fwd(const float* __restrict__ img, float2* __restrict__ Z, const ImgK
             }
         }
         __syncthreads();
-        (void)inv_half;
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // P2: columns.  Work item = (slot, block of CB columns); loops over the C planes of the image.
-//   shared memory: data[CB][NY] float2 | Hs[CB][NY] float | Hn[NY] float (Nyquist, block 0)
+//   shared memory: data[CB][NY] float2 | Hs[CB][NY] float | Hn[NY], Hb[NY] float (block 0:
+//                  Nyquist response, then the two mixing coefficients of column 0)
 //                  | R[CB+1][13] float2 | mbarrier
+//   Leaves r = DFT(swap(Y)) in Z: the inverse transform is swap(r), P3 swaps while loading.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(FFTD_THREADS)
 k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int* __restrict__ list,
@@ -174,7 +229,8 @@ k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int
     float2* data = reinterpret_cast<float2*>(smraw);
     float* Hs = reinterpret_cast<float*>(data + (size_t)CB * NY);
     float* Hn = Hs + (size_t)CB * NY;
-    float2* Rk = reinterpret_cast<float2*>(Hn + NY);                  // [(CB + 1)][13]
+    float* Hb = Hn + NY;
+    float2* Rk = reinterpret_cast<float2*>(Hb + NY);                  // [(CB + 1)][13]
     uint64_t* bar = reinterpret_cast<uint64_t*>(Rk + (CB + 1) * 13 + 1);
     bar = reinterpret_cast<uint64_t*>(((uintptr_t)bar + 7) & ~(uintptr_t)7);
     const int tid = threadIdx.x;
@@ -195,16 +251,26 @@ k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int
         const int kx0 = cb * CB;
         const int ncol = min(CB, half - kx0);
 
+        // kick off the first plane's columns while the transfer function is being built
+        {
+            float2* Zc = Z + (((size_t)slot * C + 0) * half + kx0) * NY;
+            if (tid == 0) {
+                fence_async_smem();
+                mbar_expect_tx(bar, (uint32_t)((size_t)ncol * NY * sizeof(float2)));
+                for (int col = 0; col < ncol; ++col)
+                    bulk_g2s(data + (size_t)col * NY, Zc + (size_t)col * NY, (uint32_t)(NY * sizeof(float2)), bar);
+            }
+        }
         // R[col][dy] = sum_dx K[dy][dx] exp(-2 pi i kx dx / NX), dy = 0..12 (R[-dy] = conj R[dy]);
         // entry CB is the Nyquist column kx = NX / 2 (needed by the block that holds kx = 0)
         for (int idx = tid; idx < (CB + 1) * 13; idx += FFTD_THREADS) {
             const int col = idx / 13, dy = idx - col * 13;
-            int kx = (col < CB) ? kx0 + col : half;
+            const int kx = (col < CB) ? kx0 + col : half;
             float2 acc = make_float2(0.f, 0.f);
             if (col < ncol || (col == CB && cb == 0)) {
                 for (int dx = -PB_PAD; dx <= PB_PAD; ++dx) {
                     const float kv = __ldg(&K->k[(dy + PB_PAD) * PB_KS + dx + PB_PAD]);
-                    int t = (int)(((long long)kx * (dx + NX)) % NX);
+                    const int t = (int)(((long long)kx * (dx + NX)) % NX);
                     const float2 e = __ldg(twX + t);
                     acc.x = fmaf(kv, e.x, acc.x);
                     acc.y = fmaf(kv, e.y, acc.y);
@@ -213,7 +279,7 @@ k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int
             Rk[idx] = acc;
         }
         __syncthreads();
-        // Hs[col][slot] = scale * P(K^(ky(slot), kx))
+        // Hs[col][slot] = scale * P(K^(ky(slot), kx)),  K^ = R[0].x + 2 sum_dy Re(R[dy] e^{-i phi dy})
         for (int idx = tid; idx < (ncol + (cb == 0 ? 1 : 0)) * NY; idx += FFTD_THREADS) {
             int col = fast_div(idx, NY, inv_ny);
             const int s = idx - col * NY;
@@ -221,67 +287,66 @@ k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int
             if (nyq) col = CB;
             const int ky = __ldg(freqY + s);
             const float2* R = Rk + col * 13;
-            float kh = R[0].x;
+            float2 e[PB_PAD];
             int t = 0;
-#pragma unroll 4
-            for (int dy = 1; dy <= PB_PAD; ++dy) {
+#pragma unroll
+            for (int dy = 0; dy < PB_PAD; ++dy) {
                 t += ky;
                 if (t >= NY) t -= NY;
-                const float2 e = __ldg(twY + t);            // (cos, -sin)(2 pi ky dy / NY)
-                kh = fmaf(2.0f * R[dy].x, e.x, kh);
-                kh = fmaf(-2.0f * R[dy].y, e.y, kh);
+                e[dy] = __ldg(twY + t);                     // (cos, -sin)(2 pi ky (dy + 1) / NY)
             }
+            float k0 = 0.f, k1 = 0.f;
+#pragma unroll
+            for (int dy = 0; dy < PB_PAD; dy += 2) {
+                k0 = fmaf(R[dy + 1].x, e[dy].x, k0);
+                k0 = fmaf(-R[dy + 1].y, e[dy].y, k0);
+                k1 = fmaf(R[dy + 2].x, e[dy + 1].x, k1);
+                k1 = fmaf(-R[dy + 2].y, e[dy + 1].y, k1);
+            }
+            const float kh = fmaf(2.0f, k0 + k1, R[0].x);
             const float h = fmaf(fmaf(fmaf(a3, kh, a2), kh, a1), kh, b0) * scale;
             if (nyq) Hn[s] = h; else Hs[(size_t)col * NY + s] = h;
         }
         __syncthreads();
+        if (cb == 0) {
+            // column 0 carries DC (real part) and Nyquist (imaginary part) of two real spectra:
+            // Y[k] = A Z[k] + B conj Z[-k], A = (H0 + Hn) / 2, B = (H0 - Hn) / 2; it is filtered by a
+            // separate pass below, so its fused multiplier becomes 1
+            for (int s = tid; s < NY; s += FFTD_THREADS) {
+                const float h0 = Hs[s], hn = Hn[s];
+                Hn[s] = 0.5f * (h0 + hn);
+                Hb[s] = 0.5f * (h0 - hn);
+                Hs[s] = 1.0f;
+            }
+            __syncthreads();
+        }
 
         for (int c = 0; c < C; ++c) {
             float2* Zc = Z + (((size_t)slot * C + c) * half + kx0) * NY;
-            const uint32_t bytes = (uint32_t)((size_t)ncol * NY * sizeof(float2));
-            if (tid == 0) {
+            if (c > 0 && tid == 0) {
                 fence_async_smem();
-                mbar_expect_tx(bar, bytes);
+                mbar_expect_tx(bar, (uint32_t)((size_t)ncol * NY * sizeof(float2)));
                 for (int col = 0; col < ncol; ++col)
                     bulk_g2s(data + (size_t)col * NY, Zc + (size_t)col * NY, (uint32_t)(NY * sizeof(float2)), bar);
             }
             mbar_wait(bar, phase);
             phase ^= 1;
             fft2_forward_dif(data, NY, ncol, planY, twY, tid, FFTD_THREADS);
-            // multiply by H and swap re/im (inverse by forward transform)
             if (cb == 0) {
-                // column 0 carries DC (real part) and Nyquist (imaginary part) of two real spectra:
-                // Y[k] = (H0 + Hn)/2 Z[k] + (H0 - Hn)/2 conj Z[-k]; the pair {k, -k} goes to one thread
+                // the pair {k, -k} of column 0 goes to one thread (in place, no hazard)
                 for (int ky = tid; ky <= NY / 2; ky += FFTD_THREADS) {
                     const int s1 = __ldg(slotY + ky);
                     const int s2 = __ldg(slotY + (NY - ky) % NY);
                     const float2 z1 = data[s1], z2 = data[s2];
-                    const float A1 = 0.5f * (Hs[s1] + Hn[s1]), B1 = 0.5f * (Hs[s1] - Hn[s1]);
-                    const float A2 = 0.5f * (Hs[s2] + Hn[s2]), B2 = 0.5f * (Hs[s2] - Hn[s2]);
-                    const float2 y1 = make_float2(A1 * z1.x + B1 * z2.x, A1 * z1.y - B1 * z2.y);
-                    const float2 y2 = make_float2(A2 * z2.x + B2 * z1.x, A2 * z2.y - B2 * z1.y);
-                    data[s1] = make_float2(y1.y, y1.x);
-                    if (s2 != s1) data[s2] = make_float2(y2.y, y2.x);
+                    const float A1 = Hn[s1], B1 = Hb[s1], A2 = Hn[s2], B2 = Hb[s2];
+                    data[s1] = make_float2(A1 * z1.x + B1 * z2.x, A1 * z1.y - B1 * z2.y);
+                    if (s2 != s1) data[s2] = make_float2(A2 * z2.x + B2 * z1.x, A2 * z2.y - B2 * z1.y);
                 }
-                for (int idx = NY + tid; idx < ncol * NY; idx += FFTD_THREADS) {
-                    const float h = Hs[idx];
-                    const float2 z = data[idx];
-                    data[idx] = make_float2(h * z.y, h * z.x);
-                }
-            } else {
-                for (int idx = tid; idx < ncol * NY; idx += FFTD_THREADS) {
-                    const float h = Hs[idx];
-                    const float2 z = data[idx];
-                    data[idx] = make_float2(h * z.y, h * z.x);
-                }
+                __syncthreads();
             }
-            __syncthreads();
-            fft2_forward_dit(data, NY, ncol, planY, twY, tid, FFTD_THREADS);
-            // result r = DFT(swap(Y)); the inverse transform is swap(r): swap back while storing
-            for (int idx = tid; idx < ncol * NY; idx += FFTD_THREADS) {
-                const float2 z = data[idx];
-                data[idx] = make_float2(z.y, z.x);
-            }
+            // inverse-direction transform with the multiplication by H (and the re/im swap) folded
+            // into its first stage
+            fft2_forward_dit(data, NY, ncol, planY, twY, tid, FFTD_THREADS, Hs, 2);
             fence_async_smem();
             __syncthreads();
             if (tid == 0) {
@@ -309,7 +374,7 @@ k_fft_rows_inv(const float2* __restrict__ Z, float* __restrict__ out, const ImgK
     const int total = count[0] * per_img;
     const size_t plane = (size_t)H * W;
     const int half = NX >> 1;
-    const float inv_w = 1.0f / (float)W;
+    const float inv_nb = 1.0f / (float)nb;
 
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
         const int slot = w / per_img;
@@ -322,17 +387,20 @@ k_fft_rows_inv(const float2* __restrict__ Z, float* __restrict__ out, const ImgK
         // rows of the extended image that are output rows: [3 pad, H + 3 pad)
         if (j0 + 2 * nb <= 3 * pad || j0 >= H + 3 * pad) continue;
         const float2* Zp = Z + ((size_t)slot * C + c) * half * NY;
+#pragma unroll 2
         for (int idx = tid; idx < nb * half; idx += FFTD_THREADS) {
-            const int kx = fast_div(idx, nb, 1.0f / (float)nb);
+            const int kx = fast_div(idx, nb, inv_nb);
             const int p = idx - kx * nb;
             const int ja = j0 + 2 * p;
+            // P2 leaves the spectra re/im swapped
             float2 xa = make_float2(0.f, 0.f), xb = make_float2(0.f, 0.f);
             if (ja + 1 < NY) {
                 const float4 v = __ldg(reinterpret_cast<const float4*>(Zp + (size_t)kx * NY + ja));
-                xa = make_float2(v.x, v.y);
-                xb = make_float2(v.z, v.w);
+                xa = make_float2(v.y, v.x);
+                xb = make_float2(v.w, v.z);
             } else if (ja < NY) {
-                xa = __ldg(Zp + (size_t)kx * NY + ja);
+                const float2 v = __ldg(Zp + (size_t)kx * NY + ja);
+                xa = make_float2(v.y, v.x);
             }
             float2* row = smf + (size_t)p * NX;
             // Z[k] = Xa[k] + i Xb[k], Z[-k] = conj Xa[k] + i conj Xb[k]; stored swapped (re <-> im)
@@ -348,13 +416,35 @@ k_fft_rows_inv(const float2* __restrict__ Z, float* __restrict__ out, const ImgK
         fft2_forward_dit(smf, NX, nb, planX, twX, tid, FFTD_THREADS);
         // r = DFT(swap(Z)): row a = r.y, row b = r.x (the 1/(NX NY) scale is inside H)
         float* dst = out + ((size_t)im * C + c) * plane;
-        for (int idx = tid; idx < nb * W; idx += FFTD_THREADS) {
-            const int p = fast_div(idx, W, inv_w);
-            const int x = idx - p * W;
-            const float2 z = smf[(size_t)p * NX + x + 3 * pad];
-            const int ya = j0 + 2 * p - 3 * pad;
-            if (ya >= 0 && ya < H) dst[(size_t)ya * W + x] = fminf(fmaxf(z.y, 0.0f), 1.0f);
-            if (ya + 1 >= 0 && ya + 1 < H) dst[(size_t)(ya + 1) * W + x] = fminf(fmaxf(z.x, 0.0f), 1.0f);
+        const int x_off = 3 * pad;
+        if (((W | x_off) & 3) == 0) {
+            const int w4 = W >> 2;
+            const float inv_w4 = 1.0f / (float)w4;
+            for (int idx = tid; idx < nb * w4; idx += FFTD_THREADS) {
+                const int p = fast_div(idx, w4, inv_w4);
+                const int x = (idx - p * w4) << 2;
+                const float4* sp = reinterpret_cast<const float4*>(smf + (size_t)p * NX + x_off + x);
+                const float4 u0 = sp[0], u1 = sp[1];
+                const int ya = j0 + 2 * p - 3 * pad;
+                if (ya >= 0 && ya < H)
+                    *reinterpret_cast<float4*>(dst + (size_t)ya * W + x) =
+                        make_float4(fminf(fmaxf(u0.y, 0.f), 1.f), fminf(fmaxf(u0.w, 0.f), 1.f),
+                                    fminf(fmaxf(u1.y, 0.f), 1.f), fminf(fmaxf(u1.w, 0.f), 1.f));
+                if (ya + 1 >= 0 && ya + 1 < H)
+                    *reinterpret_cast<float4*>(dst + (size_t)(ya + 1) * W + x) =
+                        make_float4(fminf(fmaxf(u0.x, 0.f), 1.f), fminf(fmaxf(u0.z, 0.f), 1.f),
+                                    fminf(fmaxf(u1.x, 0.f), 1.f), fminf(fmaxf(u1.z, 0.f), 1.f));
+            }
+        } else {
+            const float inv_w = 1.0f / (float)W;
+            for (int idx = tid; idx < nb * W; idx += FFTD_THREADS) {
+                const int p = fast_div(idx, W, inv_w);
+                const int x = idx - p * W;
+                const float2 z = smf[(size_t)p * NX + x + x_off];
+                const int ya = j0 + 2 * p - 3 * pad;
+                if (ya >= 0 && ya < H) dst[(size_t)ya * W + x] = fminf(fmaxf(z.y, 0.0f), 1.0f);
+                if (ya + 1 >= 0 && ya + 1 < H) dst[(size_t)(ya + 1) * W + x] = fminf(fmaxf(z.x, 0.0f), 1.0f);
+            }
         }
         __syncthreads();
     }
@@ -362,17 +452,23 @@ k_fft_rows_inv(const float2* __restrict__ Z, float* __restrict__ out, const ImgK
 
 // ---- host side ------------------------------------------------------------------------------
 
-// smallest even length >= n that the fft2 core does in <= 3 stages (<= 4 if none within 8 %)
+// Torus length for n samples: the even m in [n, 1.1 n] with the cheapest plan, cost = m x
+// fft2_plan_cost -- three conflict-free stages beat four, and pure powers of two (whose last
+// stage is 8- or 16-way bank conflicted) lose to their neighbours.
 int fft_engine_length(int n) {
     Fft2Plan p;
-    int fallback = 0;
-    for (int m = n + (n & 1); m < 2 * n + 64; m += 2) {
+    int best = 0;
+    double best_cost = 1e300;
+    const int hi = n + n / 10 + 16;
+    for (int m = n + (n & 1); m <= hi; m += 2) {
         if (make_fft2_plan(m, &p) != 0) continue;
-        if (p.ns <= 3) return (fallback && (double)m > 1.08 * n) ? fallback : m;
-        if (p.ns <= 4 && !fallback) fallback = m;
-        if (fallback && (double)m > 1.08 * n) return fallback;
+        const double cost = (double)m * fft2_plan_cost(p);
+        if (cost < best_cost) {
+            best_cost = cost;
+            best = m;
+        }
     }
-    return fallback;
+    return best;
 }
 
 static int rows_nb(int NX) {
@@ -382,7 +478,7 @@ static int rows_nb(int NX) {
     return nb;
 }
 static int cols_cb(int NY) {
-    int cb = (int)((100 * 1024) / ((size_t)NY * 12));
+    int cb = (int)((64 * 1024) / ((size_t)NY * 12));
     if (cb < 1) cb = 1;
     if (cb > 8) cb = 8;
     return cb;
@@ -392,7 +488,7 @@ bool fft_engine_supported(int H, int W, int pad) {
     const int NX = fft_engine_length(W + 6 * pad), NY = fft_engine_length(H + 6 * pad);
     if (NX <= 0 || NY <= 0) return false;
     const size_t lim = PB_SMEM_MAX - 4096;
-    return (size_t)NX * sizeof(float2) <= lim && (size_t)NY * 12 + 4 * NY + 512 <= lim;
+    return (size_t)NX * sizeof(float2) <= lim && (size_t)NY * 12 + 8 * NY + 512 <= lim;
 }
 
 size_t fft_engine_workspace(int B, int C, int H, int W, int pad, FftEngineLayout* L) {
@@ -445,7 +541,7 @@ int launch_deconv_fft(const float* img, float* out, const ImgKernel* kern, const
     const int NX = T.NX, NY = T.NY;
     const int nb = rows_nb(NX), CB = cols_cb(NY);
     const size_t smem_rows = (size_t)nb * NX * sizeof(float2);
-    const size_t smem_cols = (size_t)CB * NY * 12 + (size_t)NY * 4 + (size_t)(CB + 1) * 13 * 8 + 64;
+    const size_t smem_cols = (size_t)CB * NY * 12 + (size_t)NY * 8 + (size_t)(CB + 1) * 13 * 8 + 64;
     PB_CUDA_TRY(cudaFuncSetAttribute(k_fft_rows_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
     PB_CUDA_TRY(cudaFuncSetAttribute(k_fft_rows_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
     PB_CUDA_TRY(cudaFuncSetAttribute(k_fft_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));

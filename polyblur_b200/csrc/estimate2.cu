@@ -28,12 +28,8 @@
 namespace pb {
 
 // cos / sin of torch.linspace(0, pi, 7) exactly as torch (float32) evaluates them
-// (blur_estimation.py:127-129); same bit patterns as estimate.cu (no relocatable device code,
-// so every translation unit carries its own copy).
-static __constant__ float c_cos7[7] = {0x1.000000p+0f, 0x1.bb67aep-1f, 0x1.fffffep-2f, -0x1.777a5cp-25f,
-                                       -0x1.000002p-1f, -0x1.bb67aep-1f, -0x1.000000p+0f};
-static __constant__ float c_sin7[7] = {0x0.0p+0f, 0x1.000000p-1f, 0x1.bb67aep-1f, 0x1.000000p+0f,
-                                       0x1.bb67aep-1f, 0x1.000002p-1f, -0x1.777a5cp-24f};
+// (blur_estimation.py:127-129) are spelled as immediates inside k_cols2 (same bit patterns as
+// estimate.cu).
 
 // omega[p] = angular frequency (filters.py:175-181 rounding) of the bin held by slot p after
 // the DIF transform of length plan.n.
@@ -179,18 +175,30 @@ k_cols2(const float* __restrict__ plane_in, const float* __restrict__ gx, float*
     const float inv_nb = 1.0f / (float)nb;
     const bool vec2 = (W & 1) == 0;
 
-    for (int idx = tid; idx < H * nb; idx += THREADS) {
-        const int y = fast_div(idx, nb, inv_nb);
-        const int p = idx - y * nb;
-        const int x = x0 + 2 * p;
-        float2 g = make_float2(0.f, 0.f);
-        if (vec2) {
-            if (x < W) g = __ldg(reinterpret_cast<const float2*>(src + (size_t)y * W + x));
-        } else {
-            if (x < W) g.x = __ldg(src + (size_t)y * W + x);
-            if (x + 1 < W) g.y = __ldg(src + (size_t)y * W + x + 1);
+    for (int base = tid; base < H * nb; base += 4 * THREADS) {
+        float2 g[4];
+        int off[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = base + u * THREADS;
+            g[u] = make_float2(0.f, 0.f);
+            off[u] = -1;
+            if (idx < H * nb) {
+                const int y = fast_div(idx, nb, inv_nb);
+                const int p = idx - y * nb;
+                const int x = x0 + 2 * p;
+                if (vec2) {
+                    if (x < W) g[u] = __ldg(reinterpret_cast<const float2*>(src + (size_t)y * W + x));
+                } else {
+                    if (x < W) g[u].x = __ldg(src + (size_t)y * W + x);
+                    if (x + 1 < W) g[u].y = __ldg(src + (size_t)y * W + x + 1);
+                }
+                off[u] = p * stride + y;
+            }
         }
-        sm2[(size_t)p * stride + y] = g;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (off[u] >= 0) sm2[off[u]] = g[u];
     }
     __syncthreads();
     fft2_forward_dif(sm2, stride, nb, plan, tw, tid, THREADS);
@@ -215,6 +223,11 @@ k_cols2(const float* __restrict__ plane_in, const float* __restrict__ gx, float*
         return;
     }
 
+    // cos / sin of the 7 angles as immediates (same bit patterns as c_cos7 / c_sin7 above)
+    const float cs7[7] = {0x1.000000p+0f, 0x1.bb67aep-1f, 0x1.fffffep-2f, -0x1.777a5cp-25f,
+                          -0x1.000002p-1f, -0x1.bb67aep-1f, -0x1.000000p+0f};
+    const float sn7[7] = {0x0.0p+0f, 0x1.000000p-1f, 0x1.bb67aep-1f, 0x1.000000p+0f,
+                          0x1.bb67aep-1f, 0x1.000002p-1f, -0x1.777a5cp-24f};
     float m[7];
 #pragma unroll
     for (int j = 0; j < 7; ++j) m[j] = 0.0f;
@@ -252,7 +265,7 @@ k_cols2(const float* __restrict__ plane_in, const float* __restrict__ gx, float*
             if (discard_saturation && gr[h] > 0.99f) continue;
 #pragma unroll
             for (int j = 0; j < 7; ++j) {
-                const float v = __fsub_rn(__fmul_rn(c_cos7[j], gxv[h]), __fmul_rn(c_sin7[j], gyv[h]));
+                const float v = __fsub_rn(__fmul_rn(cs7[j], gxv[h]), __fmul_rn(sn7[j], gyv[h]));
                 m[j] = fmaxf(m[j], fabsf(v));
             }
         }

@@ -21,6 +21,9 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <mutex>
+#include <unordered_map>
+#include <utility>
 
 #if defined(__CUDACC__)
 #define PB_HD __host__ __device__ __forceinline__
@@ -267,7 +270,7 @@ PB_HD void fft2_dif_stage(float2* x, int n, int stride, int nb, int L, const flo
 //   v[q] = x[b + j + q M] W_L^{j q};  V = DFT_R(v);  x[b + j + m M] = V[m]
 template <int R>
 PB_HD void fft2_dit_stage(float2* x, int n, int stride, int nb, int L, const float2* __restrict__ tw, int tid,
-                           int nthr, const float* __restrict__ premul = nullptr) {
+                           int nthr, const float* premul = nullptr, int premode = 1) {
     const int M = L / R;
     const int bps = n / R;
     const int tws = n / L;
@@ -285,13 +288,15 @@ PB_HD void fft2_dit_stage(float2* x, int n, int stride, int nb, int L, const flo
 #pragma unroll
             for (int q = 1; q < R; ++q) v[q] = p[q];
             if (premul) {
-                // spectral-derivative multiplier folded into the first inverse stage:
-                // y = i w z, then the re/im swap of the inverse-by-forward trick -> (w z.x, -w z.y)
-                const float* pm = premul + blk * L;
+                // multiplier folded into the first inverse-direction stage, together with the
+                // re/im swap of the inverse-by-forward trick:
+                //   mode 1 (spectral derivative, one table for all sequences): y = i w z -> (w z.x, -w z.y)
+                //   mode 2 (real transfer function, one table per sequence):   y = h z   -> (h z.y,  h z.x)
+                const float* pm = premul + blk * L + (premode == 2 ? f * n : 0);
 #pragma unroll
                 for (int q = 0; q < R; ++q) {
-                    const float w = PB_LDG(pm + q);
-                    v[q] = make_float2(w * v[q].x, -w * v[q].y);
+                    const float w = premode == 2 ? pm[q] : PB_LDG(pm + q);
+                    v[q] = premode == 2 ? make_float2(w * v[q].y, w * v[q].x) : make_float2(w * v[q].x, -w * v[q].y);
                 }
             }
         } else {
@@ -347,13 +352,13 @@ PB_HD void fft2_forward_dif(float2* x, int stride, int nb, const Fft2Plan& plan,
 // Forward-sign DFT, scrambled order in -> natural order out (inverse transform through the
 // swap trick: IDFT(y) = swap(DFT(swap(y))) / n, the swaps are folded into the caller's code).
 PB_HD void fft2_forward_dit(float2* x, int stride, int nb, const Fft2Plan& plan, const float2* __restrict__ tw,
-                            int tid, int nthr, const float* __restrict__ premul = nullptr) {
+                            int tid, int nthr, const float* premul = nullptr, int premode = 1) {
     int L = 1;
     for (int s = plan.ns - 1; s >= 0; --s) {
         const int R = plan.radix[s];
         L *= R;
         PB_FFT2_DISPATCH(fft2_dit_stage, R, x, plan.n, stride, nb, L, tw, tid, nthr,
-                         (s == plan.ns - 1) ? premul : nullptr);
+                         (s == plan.ns - 1) ? premul : nullptr, premode);
         PB_FFT2_SYNC();
     }
 }
@@ -384,42 +389,136 @@ PB_HD int fft2_slot_of_freq(int k, const Fft2Plan& plan) {
     return p;
 }
 
-// Host: factor n into radices <= 16 with the fewest stages (ties: smaller largest radix), DIF
-// order = descending.  Returns 0 on success, -1 if n has a prime factor > 13 or needs more
-// than PB_FFT2_MAX_STAGES stages.
+// Average shared-memory conflict degree of one in-place stage: a half warp (64-bit accesses are
+// served 16 lanes at a time) touches x[blk L + j + m M] for 16 consecutive butterflies.
+inline double fft2_stage_conflicts(int n, int R, int M, int L) {
+    const int bps = n / R;
+    double tot = 0;
+    int cnt = 0;
+    for (int t0 = 0; t0 < bps && t0 < 512; t0 += 16) {
+        for (int m = 0; m < R; ++m) {
+            int hits[16] = {0};
+            int worst = 0;
+            for (int t = t0; t < t0 + 16 && t < bps; ++t) {
+                const int blk = t / M, j = t - blk * M;
+                const int bank = (blk * L + j + m * M) & 15;
+                if (++hits[bank] > worst) worst = hits[bank];
+            }
+            tot += worst;
+            ++cnt;
+        }
+    }
+    return cnt ? tot / cnt : 1.0;
+}
+
+// Host: factor n into radices <= 16 with the fewest stages, then order them so that the
+// strided late stages (small M) conflict least in shared memory -- in practice an odd radix
+// goes last.  Returns 0 on success, -1 if n has a prime factor > 13 or needs more than
+// PB_FFT2_MAX_STAGES stages.  (Not cached here: callers plan once per API call at most; api.cu
+// keeps a small cache.)
+inline int make_fft2_plan_uncached(int n, Fft2Plan* plan);
 inline int make_fft2_plan(int n, Fft2Plan* plan) {
+    // small cache: the search below costs ~0.1-1 ms and API calls repeat the same lengths
+    static std::mutex mu;
+    static std::unordered_map<int, std::pair<int, Fft2Plan>> cache;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = cache.find(n);
+        if (it != cache.end()) {
+            *plan = it->second.second;
+            return it->second.first;
+        }
+    }
+    Fft2Plan p;
+    const int rc = make_fft2_plan_uncached(n, &p);
+    std::lock_guard<std::mutex> lock(mu);
+    cache[n] = std::make_pair(rc, p);
+    *plan = p;
+    return rc;
+}
+inline int make_fft2_plan_uncached(int n, Fft2Plan* plan) {
     if (n < 1) return -1;
     plan->n = n;
     plan->ns = 0;
     if (n == 1) return 0;
     static const int cand[] = {16, 15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2};
-    // depth-first search for the minimum number of stages (n <= 2^24 keeps this tiny)
-    int best[PB_FFT2_MAX_STAGES], bestn = PB_FFT2_MAX_STAGES + 1, bestmax = 99;
+    struct Best {
+        int ns;
+        double score;
+        int radix[PB_FFT2_MAX_STAGES];
+    } best;
+    best.ns = PB_FFT2_MAX_STAGES + 1;
+    best.score = 1e30;
     int cur[PB_FFT2_MAX_STAGES];
     struct Rec {
-        static void go(int m, int depth, int start, int curmax, int* cur, int* best, int& bestn, int& bestmax) {
-            if (m == 1) {
-                if (depth < bestn || (depth == bestn && curmax < bestmax)) {
-                    bestn = depth;
-                    bestmax = curmax;
-                    for (int i = 0; i < depth; ++i) best[i] = cur[i];
+        static void score_perms(int n, int* a, int k, int depth, Best& best) {
+            if (k == depth) {
+                double sc = 0;
+                int L = n;
+                for (int s = 0; s < depth; ++s) {
+                    sc += fft2_stage_conflicts(n, a[s], L / a[s], L);
+                    L /= a[s];
+                }
+                sc -= 1e-3 * a[0];       // ties: the largest radix first
+                if (depth < best.ns || (depth == best.ns && sc < best.score)) {
+                    best.ns = depth;
+                    best.score = sc;
+                    for (int i = 0; i < depth; ++i) best.radix[i] = a[i];
                 }
                 return;
             }
-            if (depth >= PB_FFT2_MAX_STAGES || depth + 1 > bestn) return;
-            for (int ci = start; ci < 15; ++ci) {       // non-increasing radices: canonical order
+            for (int i = k; i < depth; ++i) {
+                bool dup = false;
+                for (int q = k; q < i; ++q) dup = dup || a[q] == a[i];
+                if (dup) continue;
+                int t = a[k]; a[k] = a[i]; a[i] = t;
+                score_perms(n, a, k + 1, depth, best);
+                t = a[k]; a[k] = a[i]; a[i] = t;
+            }
+        }
+        static void go(int n, int m, int depth, int start, int* cur, Best& best) {
+            if (m == 1) {
+                if (depth <= best.ns) {
+                    int a[PB_FFT2_MAX_STAGES];
+                    for (int i = 0; i < depth; ++i) a[i] = cur[i];
+                    score_perms(n, a, 0, depth, best);
+                }
+                return;
+            }
+            if (depth >= PB_FFT2_MAX_STAGES || depth + 1 > best.ns) return;
+            for (int ci = start; ci < 15; ++ci) {       // non-increasing radices: each multiset once
                 const int r = cand[ci];
                 if (m % r) continue;
                 cur[depth] = r;
-                go(m / r, depth + 1, ci, curmax > r ? curmax : r, cur, best, bestn, bestmax);
+                go(n, m / r, depth + 1, ci, cur, best);
             }
         }
     };
-    Rec::go(n, 0, 0, 0, cur, best, bestn, bestmax);
-    if (bestn > PB_FFT2_MAX_STAGES) return -1;
-    plan->ns = bestn;
-    for (int i = 0; i < bestn; ++i) plan->radix[i] = best[i];
+    Rec::go(n, n, 0, 0, cur, best);
+    if (best.ns > PB_FFT2_MAX_STAGES) return -1;
+    plan->ns = best.ns;
+    for (int i = 0; i < best.ns; ++i) plan->radix[i] = best.radix[i];
     return 0;
+}
+
+// Sum over the stages of the average shared-memory conflict degree (>= ns; lower is better).
+inline double fft2_plan_score(const Fft2Plan& plan) {
+    double sc = 0;
+    int L = plan.n;
+    for (int s = 0; s < plan.ns; ++s) {
+        sc += fft2_stage_conflicts(plan.n, plan.radix[s], L / plan.radix[s], L);
+        L /= plan.radix[s];
+    }
+    return sc;
+}
+
+// Rough per-element cost of a plan in "shared-memory passes": conflict degree plus arithmetic
+// (real operations per element of each register butterfly / 16); used to choose torus lengths.
+inline double fft2_plan_cost(const Fft2Plan& plan) {
+    static const double flops[17] = {0, 0, 2, 5.3, 4, 8, 9, 13, 6.5, 11, 10, 88, 9, 104, 15, 13, 9};
+    double c = fft2_plan_score(plan);
+    for (int s = 0; s < plan.ns; ++s) c += flops[plan.radix[s]] / 16.0;
+    return c;
 }
 
 }  // namespace pb

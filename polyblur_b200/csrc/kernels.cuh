@@ -80,7 +80,7 @@ int launch_deconv_fft(const float* img, float* out, const ImgKernel* kern, const
                       float b0, cudaStream_t stream);
 
 // deconv.cu
-int launch_deconv_spatial(const float* img, float* out, const ImgKernel* kern, int B, int C, int H, int W,
-                          float a3, float a2, float a1, float b0, int only_engine, cudaStream_t stream);
+int launch_deconv_spatial(const float* img, float* out, const ImgKernel* kern, const int* list, const int* count,
+                          int B, int C, int H, int W, float a3, float a2, float a1, float b0, cudaStream_t stream);
 
 }  // namespace pb
