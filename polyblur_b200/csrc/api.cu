@@ -158,19 +158,23 @@ static int prepare_tables(char* ws, const Workspace& L, int H, int W, Tables* t,
     }
     t->twH = reinterpret_cast<float2*>(ws + L.off_twH);
     t->twW = reinterpret_cast<float2*>(ws + L.off_twW);
-    int rc = launch_twiddles(t->twH, H, stream);
-    if (rc) return rc;
-    if ((rc = launch_twiddles(t->twW, W, stream))) return rc;
+    int rc;
     t->fast = fft2_supported(H, W);
     t->omH = reinterpret_cast<float*>(ws + L.off_omH);
     t->omW = reinterpret_cast<float*>(ws + L.off_omW);
     if (t->fast) {
+        // the fft2 core reads per-stage twiddle tables (< n entries each): they take the place of
+        // the master tables of the any-length core
         make_fft2_plan(H, &t->planH2);
         make_fft2_plan(W, &t->planW2);
+        if ((rc = launch_fft2_stage_tw(t->twH, t->planH2, stream))) return rc;
+        if ((rc = launch_fft2_stage_tw(t->twW, t->planW2, stream))) return rc;
         if ((rc = launch_fft2_omega(t->omH, t->planH2, stream))) return rc;
         if ((rc = launch_fft2_omega(t->omW, t->planW2, stream))) return rc;
+        return PB_OK;
     }
-    return PB_OK;
+    if ((rc = launch_twiddles(t->twH, H, stream))) return rc;
+    return launch_twiddles(t->twW, W, stream);
 }
 
 static void poly_coeffs(double alpha, double beta, float* o) {

@@ -25,6 +25,8 @@
 //
 // HBM bytes per pixel-channel: P1 4 read + ~4.4 written, P2 ~4.4 + ~4.4, P3 ~4.4 read + 4
 // written = ~26 B against 8 B algorithmic; independent of the blur.
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace pb {
@@ -223,8 +225,8 @@ k_fft_rows_fwd(const float* __restrict__ img, float2* __restrict__ Z, const ImgK
 __global__ void __launch_bounds__(FFTD_THREADS)
 k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int* __restrict__ list,
            const int* __restrict__ count, int C, int NX, int NY, int CB, Fft2Plan planY,
-           const float2* __restrict__ twX, const float2* __restrict__ twY, const int* __restrict__ freqY,
-           const int* __restrict__ slotY, float a3, float a2, float a1, float b0) {
+           const float2* __restrict__ twX, const float2* __restrict__ stwY, const int* __restrict__ slotY,
+           float a3, float a2, float a1, float b0) {
     extern __shared__ __align__(16) unsigned char smraw[];
     float2* data = reinterpret_cast<float2*>(smraw);
     float* Hs = reinterpret_cast<float*>(data + (size_t)CB * NY);
@@ -251,16 +253,6 @@ k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int
         const int kx0 = cb * CB;
         const int ncol = min(CB, half - kx0);
 
-        // kick off the first plane's columns while the transfer function is being built
-        {
-            float2* Zc = Z + (((size_t)slot * C + 0) * half + kx0) * NY;
-            if (tid == 0) {
-                fence_async_smem();
-                mbar_expect_tx(bar, (uint32_t)((size_t)ncol * NY * sizeof(float2)));
-                for (int col = 0; col < ncol; ++col)
-                    bulk_g2s(data + (size_t)col * NY, Zc + (size_t)col * NY, (uint32_t)(NY * sizeof(float2)), bar);
-            }
-        }
         // R[col][dy] = sum_dx K[dy][dx] exp(-2 pi i kx dx / NX), dy = 0..12 (R[-dy] = conj R[dy]);
         // entry CB is the Nyquist column kx = NX / 2 (needed by the block that holds kx = 0)
         for (int idx = tid; idx < (CB + 1) * 13; idx += FFTD_THREADS) {
@@ -278,34 +270,36 @@ k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int
             }
             Rk[idx] = acc;
         }
+        // K^(ky, kx) = sum_dy R[dy] exp(-2 pi i ky dy / NY) is the length-NY DFT of the sparse
+        // sequence r[dy mod NY] = R[dy]; it is real, so two columns share one complex transform
+        // (r_A + i r_B -> K^_A + i K^_B), run by the same DIF core: the result arrives in slot order.
+        const int ncolh = ncol + (cb == 0 ? 1 : 0);            // + the Nyquist column
+        const int nseq = (ncolh + 1) >> 1;
+        for (int idx = tid; idx < nseq * NY; idx += FFTD_THREADS) data[idx] = make_float2(0.f, 0.f);
         __syncthreads();
-        // Hs[col][slot] = scale * P(K^(ky(slot), kx)),  K^ = R[0].x + 2 sum_dy Re(R[dy] e^{-i phi dy})
-        for (int idx = tid; idx < (ncol + (cb == 0 ? 1 : 0)) * NY; idx += FFTD_THREADS) {
-            int col = fast_div(idx, NY, inv_ny);
+        for (int idx = tid; idx < nseq * PB_KS; idx += FFTD_THREADS) {
+            const int q = idx / PB_KS, d = idx - q * PB_KS - PB_PAD;
+            const int ca = 2 * q, cb2 = 2 * q + 1;
+            const int ad = d < 0 ? -d : d;
+            float2 ra = Rk[(ca < ncol ? ca : CB) * 13 + ad];
+            float2 rb = make_float2(0.f, 0.f);
+            if (cb2 < ncolh) rb = Rk[(cb2 < ncol ? cb2 : CB) * 13 + ad];
+            if (d < 0) {
+                ra.y = -ra.y;
+                rb.y = -rb.y;
+            }
+            data[(size_t)q * NY + (d < 0 ? d + NY : d)] = make_float2(ra.x - rb.y, ra.y + rb.x);
+        }
+        __syncthreads();
+        fft2_forward_dif(data, NY, nseq, planY, stwY, tid, FFTD_THREADS);
+        // Hs[col][slot] = scale * P(K^)
+        for (int idx = tid; idx < ncolh * NY; idx += FFTD_THREADS) {
+            const int col = fast_div(idx, NY, inv_ny);
             const int s = idx - col * NY;
-            const bool nyq = (col == ncol);
-            if (nyq) col = CB;
-            const int ky = __ldg(freqY + s);
-            const float2* R = Rk + col * 13;
-            float2 e[PB_PAD];
-            int t = 0;
-#pragma unroll
-            for (int dy = 0; dy < PB_PAD; ++dy) {
-                t += ky;
-                if (t >= NY) t -= NY;
-                e[dy] = __ldg(twY + t);                     // (cos, -sin)(2 pi ky (dy + 1) / NY)
-            }
-            float k0 = 0.f, k1 = 0.f;
-#pragma unroll
-            for (int dy = 0; dy < PB_PAD; dy += 2) {
-                k0 = fmaf(R[dy + 1].x, e[dy].x, k0);
-                k0 = fmaf(-R[dy + 1].y, e[dy].y, k0);
-                k1 = fmaf(R[dy + 2].x, e[dy + 1].x, k1);
-                k1 = fmaf(-R[dy + 2].y, e[dy + 1].y, k1);
-            }
-            const float kh = fmaf(2.0f, k0 + k1, R[0].x);
+            const float2 z = data[(size_t)(col >> 1) * NY + s];
+            const float kh = (col & 1) ? z.y : z.x;
             const float h = fmaf(fmaf(fmaf(a3, kh, a2), kh, a1), kh, b0) * scale;
-            if (nyq) Hn[s] = h; else Hs[(size_t)col * NY + s] = h;
+            if (col == ncol) Hn[s] = h; else Hs[(size_t)col * NY + s] = h;
         }
         __syncthreads();
         if (cb == 0) {
@@ -323,7 +317,7 @@ k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int
 
         for (int c = 0; c < C; ++c) {
             float2* Zc = Z + (((size_t)slot * C + c) * half + kx0) * NY;
-            if (c > 0 && tid == 0) {
+            if (tid == 0) {
                 fence_async_smem();
                 mbar_expect_tx(bar, (uint32_t)((size_t)ncol * NY * sizeof(float2)));
                 for (int col = 0; col < ncol; ++col)
@@ -331,7 +325,7 @@ k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int
             }
             mbar_wait(bar, phase);
             phase ^= 1;
-            fft2_forward_dif(data, NY, ncol, planY, twY, tid, FFTD_THREADS);
+            fft2_forward_dif(data, NY, ncol, planY, stwY, tid, FFTD_THREADS);
             if (cb == 0) {
                 // the pair {k, -k} of column 0 goes to one thread (in place, no hazard)
                 for (int ky = tid; ky <= NY / 2; ky += FFTD_THREADS) {
@@ -346,7 +340,7 @@ k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int
             }
             // inverse-direction transform with the multiplication by H (and the re/im swap) folded
             // into its first stage
-            fft2_forward_dit(data, NY, ncol, planY, twY, tid, FFTD_THREADS, Hs, 2);
+            fft2_forward_dit(data, NY, ncol, planY, stwY, tid, FFTD_THREADS, Hs, 2);
             fence_async_smem();
             __syncthreads();
             if (tid == 0) {
@@ -471,13 +465,20 @@ int fft_engine_length(int n) {
     return best;
 }
 
+// tuning knobs (environment overrides are for experiments only)
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
 static int rows_nb(int NX) {
+    if (env_int("PB_FFT_NB", 0) > 0) return env_int("PB_FFT_NB", 0);
     int nb = (int)((64 * 1024) / ((size_t)NX * sizeof(float2)));
     if (nb < 1) nb = 1;
     if (nb > 8) nb = 8;
     return nb;
 }
 static int cols_cb(int NY) {
+    if (env_int("PB_FFT_CB", 0) > 0) return env_int("PB_FFT_CB", 0);
     int cb = (int)((64 * 1024) / ((size_t)NY * 12));
     if (cb < 1) cb = 1;
     if (cb > 8) cb = 8;
@@ -503,6 +504,8 @@ size_t fft_engine_workspace(int B, int C, int H, int W, int pad, FftEngineLayout
     };
     l.off_twX = take((size_t)l.NX * sizeof(float2));
     l.off_twY = take((size_t)l.NY * sizeof(float2));
+    l.off_stwX = take((size_t)l.NX * sizeof(float2));
+    l.off_stwY = take((size_t)l.NY * sizeof(float2));
     l.off_slotX = take((size_t)l.NX * sizeof(int));
     l.off_slotY = take((size_t)l.NY * sizeof(int));
     l.off_freqY = take((size_t)l.NY * sizeof(int));
@@ -521,6 +524,8 @@ int fft_engine_prepare(char* base, const FftEngineLayout& L, FftEngineTables* T,
     }
     T->twX = reinterpret_cast<float2*>(base + L.off_twX);
     T->twY = reinterpret_cast<float2*>(base + L.off_twY);
+    T->stwX = reinterpret_cast<float2*>(base + L.off_stwX);
+    T->stwY = reinterpret_cast<float2*>(base + L.off_stwY);
     T->slotX = reinterpret_cast<int*>(base + L.off_slotX);
     T->slotY = reinterpret_cast<int*>(base + L.off_slotY);
     T->freqY = reinterpret_cast<int*>(base + L.off_freqY);
@@ -528,6 +533,8 @@ int fft_engine_prepare(char* base, const FftEngineLayout& L, FftEngineTables* T,
     int rc;
     if ((rc = launch_twiddles(T->twX, L.NX, stream))) return rc;
     if ((rc = launch_twiddles(T->twY, L.NY, stream))) return rc;
+    if ((rc = launch_fft2_stage_tw(T->stwX, T->planX, stream))) return rc;
+    if ((rc = launch_fft2_stage_tw(T->stwY, T->planY, stream))) return rc;
     ProfScope prof(PROF_SETUP, stream);
     k_fft2_perm<<<(L.NX + 255) / 256, 256, 0, stream>>>(T->slotX, nullptr, T->planX);
     k_fft2_perm<<<(L.NY + 255) / 256, 256, 0, stream>>>(T->slotY, T->freqY, T->planY);
@@ -553,19 +560,19 @@ int launch_deconv_fft(const float* img, float* out, const ImgKernel* kern, const
     {
         ProfScope prof(PROF_FFT_ROWS_FWD, stream);
         k_fft_rows_fwd<<<grid_rows, FFTD_THREADS, smem_rows, stream>>>(img, T.Z, kern, list, count, C, H, W, NX, NY,
-                                                                       nb, T.planX, T.twX, T.slotX);
+                                                                       nb, T.planX, T.stwX, T.slotX);
         PB_LAUNCH_CHECK("k_fft_rows_fwd");
     }
     {
         ProfScope prof(PROF_FFT_COLS, stream);
         k_fft_cols<<<grid_cols, FFTD_THREADS, smem_cols, stream>>>(T.Z, kern, list, count, C, NX, NY, CB, T.planY,
-                                                                   T.twX, T.twY, T.freqY, T.slotY, a3, a2, a1, b0);
+                                                                   T.twX, T.stwY, T.slotY, a3, a2, a1, b0);
         PB_LAUNCH_CHECK("k_fft_cols");
     }
     {
         ProfScope prof(PROF_FFT_ROWS_INV, stream);
         k_fft_rows_inv<<<grid_rows, FFTD_THREADS, smem_rows, stream>>>(T.Z, out, kern, list, count, C, H, W, NX, NY,
-                                                                       nb, T.planX, T.twX, T.slotX);
+                                                                       nb, T.planX, T.stwX, T.slotX);
         PB_LAUNCH_CHECK("k_fft_rows_inv");
     }
     return PB_OK;

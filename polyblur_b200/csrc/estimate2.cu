@@ -38,6 +38,12 @@ __global__ void k_fft2_omega(float* __restrict__ omega, Fft2Plan plan) {
     if (p < plan.n) omega[p] = bin_omega(fft2_freq_of_slot(p, plan), plan.n);
 }
 
+// stage-twiddle table of a plan (fft2.cuh), float64 sincospi rounded once
+__global__ void k_fft2_stage_tw(float2* __restrict__ stw, Fft2Plan plan) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < plan.tw_total) stw[i] = fft2_stage_twiddle(i, plan);
+}
+
 #define R2_THREADS 256
 
 template <bool EST>
@@ -285,6 +291,13 @@ k_cols2(const float* __restrict__ plane_in, const float* __restrict__ gx, float*
 }
 
 // ---- host side ------------------------------------------------------------------------------
+
+int launch_fft2_stage_tw(float2* stw, const Fft2Plan& plan, cudaStream_t stream) {
+    ProfScope prof(PROF_SETUP, stream);
+    k_fft2_stage_tw<<<(plan.tw_total + 255) / 256, 256, 0, stream>>>(stw, plan);
+    PB_LAUNCH_CHECK("k_fft2_stage_tw");
+    return PB_OK;
+}
 
 int launch_fft2_omega(float* omega, const Fft2Plan& plan, cudaStream_t stream) {
     ProfScope prof(PROF_SETUP, stream);

@@ -20,6 +20,7 @@
 // compute_polynomial_fft (polyblur/deblurring.py:141-169).
 #pragma once
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
 #include <mutex>
 #include <unordered_map>
@@ -46,6 +47,11 @@ struct Fft2Plan {
     int n;
     int ns;
     int radix[PB_FFT2_MAX_STAGES];   // DIF order: radix[0] is applied at sub-length n
+    // Stage twiddles live in one table, q-major per stage so that the lanes of a warp (consecutive
+    // j) read consecutive entries:  stw[tw_off[s] + (q - 1) M_s + j] = exp(-2 pi i j q / L_s),
+    // q = 1..R_s-1, j < M_s = L_s / R_s  (no entries for a stage with M_s = 1).
+    int tw_off[PB_FFT2_MAX_STAGES];
+    int tw_total;
 };
 
 // ---- small complex helpers ---------------------------------------------------------------
@@ -237,11 +243,10 @@ PB_HD int fast_div(int a, int d, float inv) {
 // ---- one DIF stage: sub-length L, radix R, in place -----------------------------------------
 //   v[m] = x[b + j + m M];  V = DFT_R(v);  x[b + j + q M] = V[q] W_L^{j q},   M = L / R
 template <int R>
-PB_HD void fft2_dif_stage(float2* x, int n, int stride, int nb, int L, const float2* __restrict__ tw, int tid,
+PB_HD void fft2_dif_stage(float2* x, int n, int stride, int nb, int L, const float2* __restrict__ stw, int tid,
                            int nthr) {
     const int M = L / R;
     const int bps = n / R;                 // butterflies per sequence
-    const int tws = n / L;
     const float inv_bps = 1.0f / (float)bps, inv_M = 1.0f / (float)M;
     const int total = nb * bps;
     for (int idx = tid; idx < total; idx += nthr) {
@@ -259,9 +264,8 @@ PB_HD void fft2_dif_stage(float2* x, int n, int stride, int nb, int L, const flo
 #pragma unroll
             for (int q = 1; q < R; ++q) p[q] = v[q];
         } else {
-            const int t1 = j * tws;
 #pragma unroll
-            for (int q = 1; q < R; ++q) p[q * M] = c_mul(v[q], PB_LDG(tw + q * t1));
+            for (int q = 1; q < R; ++q) p[q * M] = c_mul(v[q], PB_LDG(stw + (q - 1) * M + j));
         }
     }
 }
@@ -269,11 +273,10 @@ PB_HD void fft2_dif_stage(float2* x, int n, int stride, int nb, int L, const flo
 // ---- one DIT stage (the transpose of the DIF stage) -------------------------------------------
 //   v[q] = x[b + j + q M] W_L^{j q};  V = DFT_R(v);  x[b + j + m M] = V[m]
 template <int R>
-PB_HD void fft2_dit_stage(float2* x, int n, int stride, int nb, int L, const float2* __restrict__ tw, int tid,
+PB_HD void fft2_dit_stage(float2* x, int n, int stride, int nb, int L, const float2* __restrict__ stw, int tid,
                            int nthr, const float* premul = nullptr, int premode = 1) {
     const int M = L / R;
     const int bps = n / R;
-    const int tws = n / L;
     const float inv_bps = 1.0f / (float)bps, inv_M = 1.0f / (float)M;
     const int total = nb * bps;
     for (int idx = tid; idx < total; idx += nthr) {
@@ -300,9 +303,8 @@ PB_HD void fft2_dit_stage(float2* x, int n, int stride, int nb, int L, const flo
                 }
             }
         } else {
-            const int t1 = j * tws;
 #pragma unroll
-            for (int q = 1; q < R; ++q) v[q] = c_mul(p[q * M], PB_LDG(tw + q * t1));
+            for (int q = 1; q < R; ++q) v[q] = c_mul(p[q * M], PB_LDG(stw + (q - 1) * M + j));
         }
         Dft<R>::run(v);
 #pragma unroll
@@ -343,7 +345,7 @@ PB_HD void fft2_forward_dif(float2* x, int stride, int nb, const Fft2Plan& plan,
     int L = plan.n;
     for (int s = 0; s < plan.ns; ++s) {
         const int R = plan.radix[s];
-        PB_FFT2_DISPATCH(fft2_dif_stage, R, x, plan.n, stride, nb, L, tw, tid, nthr);
+        PB_FFT2_DISPATCH(fft2_dif_stage, R, x, plan.n, stride, nb, L, tw + plan.tw_off[s], tid, nthr);
         PB_FFT2_SYNC();
         L /= R;
     }
@@ -357,7 +359,7 @@ PB_HD void fft2_forward_dit(float2* x, int stride, int nb, const Fft2Plan& plan,
     for (int s = plan.ns - 1; s >= 0; --s) {
         const int R = plan.radix[s];
         L *= R;
-        PB_FFT2_DISPATCH(fft2_dit_stage, R, x, plan.n, stride, nb, L, tw, tid, nthr,
+        PB_FFT2_DISPATCH(fft2_dit_stage, R, x, plan.n, stride, nb, L, tw + plan.tw_off[s], tid, nthr,
                          (s == plan.ns - 1) ? premul : nullptr, premode);
         PB_FFT2_SYNC();
     }
@@ -416,6 +418,43 @@ inline double fft2_stage_conflicts(int n, int R, int M, int L) {
 // goes last.  Returns 0 on success, -1 if n has a prime factor > 13 or needs more than
 // PB_FFT2_MAX_STAGES stages.  (Not cached here: callers plan once per API call at most; api.cu
 // keeps a small cache.)
+// fills tw_off / tw_total from n and the radices
+inline void fft2_plan_offsets(Fft2Plan* plan) {
+    int off = 0, L = plan->n;
+    for (int s = 0; s < PB_FFT2_MAX_STAGES; ++s) plan->tw_off[s] = 0;
+    for (int s = 0; s < plan->ns; ++s) {
+        const int M = L / plan->radix[s];
+        plan->tw_off[s] = off;
+        if (M > 1) off += (plan->radix[s] - 1) * M;
+        L = M;
+    }
+    plan->tw_total = off > 0 ? off : 1;
+}
+
+// Entry i of the stage-twiddle table (host or device), computed in float64 and rounded once.
+PB_HD float2 fft2_stage_twiddle(int i, const Fft2Plan& plan) {
+    int L = plan.n;
+    for (int s = 0; s < plan.ns; ++s) {
+        const int R = plan.radix[s], M = L / R;
+        const int cnt = (M > 1) ? (R - 1) * M : 0;
+        if (i >= plan.tw_off[s] && i < plan.tw_off[s] + cnt) {
+            const int e = i - plan.tw_off[s];
+            const int q = e / M + 1, j = e - (q - 1) * M;
+            const long long t = ((long long)j * q) % L;
+            double sn, cs;
+#if defined(__CUDA_ARCH__)
+            sincospi(-2.0 * (double)t / (double)L, &sn, &cs);
+#else
+            sn = sin(-2.0 * 3.14159265358979323846 * (double)t / (double)L);
+            cs = cos(-2.0 * 3.14159265358979323846 * (double)t / (double)L);
+#endif
+            return make_float2((float)cs, (float)sn);
+        }
+        L = M;
+    }
+    return make_float2(1.0f, 0.0f);
+}
+
 inline int make_fft2_plan_uncached(int n, Fft2Plan* plan);
 inline int make_fft2_plan(int n, Fft2Plan* plan) {
     // small cache: the search below costs ~0.1-1 ms and API calls repeat the same lengths
@@ -440,6 +479,7 @@ inline int make_fft2_plan_uncached(int n, Fft2Plan* plan) {
     if (n < 1) return -1;
     plan->n = n;
     plan->ns = 0;
+    fft2_plan_offsets(plan);
     if (n == 1) return 0;
     static const int cand[] = {16, 15, 14, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2};
     struct Best {
@@ -498,6 +538,7 @@ inline int make_fft2_plan_uncached(int n, Fft2Plan* plan) {
     if (best.ns > PB_FFT2_MAX_STAGES) return -1;
     plan->ns = best.ns;
     for (int i = 0; i < best.ns; ++i) plan->radix[i] = best.radix[i];
+    fft2_plan_offsets(plan);
     return 0;
 }
 

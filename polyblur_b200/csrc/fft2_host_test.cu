@@ -21,11 +21,8 @@ int main(int argc, char** argv) {
         }
         long long prod = 1;
         for (int s = 0; s < plan.ns; ++s) prod *= plan.radix[s];
-        std::vector<float2> tw(n);
-        for (int k = 0; k < n; ++k) {
-            double ang = -2.0 * M_PI * (double)k / (double)n;
-            tw[k] = make_float2((float)cos(ang), (float)sin(ang));
-        }
+        std::vector<float2> tw(plan.tw_total);
+        for (int k = 0; k < plan.tw_total; ++k) tw[k] = fft2_stage_twiddle(k, plan);
         const int nb = 2;
         const int stride = n + 3;
         std::vector<float2> x(nb * stride), x0;

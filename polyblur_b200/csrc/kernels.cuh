@@ -47,6 +47,7 @@ int launch_params(const unsigned* stats, ImgKernel* kern, float* est, const floa
 // estimate2.cu (fast path: lengths with prime factors <= 13)
 bool fft2_supported(int H, int W);
 int launch_fft2_omega(float* omega, const Fft2Plan& plan, cudaStream_t stream);
+int launch_fft2_stage_tw(float2* stw, const Fft2Plan& plan, cudaStream_t stream);
 int launch_rows2(bool est, const float* img, float* gray, float* gx, unsigned* stats, int nimg, int C,
                  int H, int W, const Fft2Plan& planW, const float2* twW, const float* omegaW,
                  cudaStream_t stream);
@@ -62,12 +63,13 @@ int launch_deconv_narrow(int cls, const float* img, float* out, const ImgKernel*
 // deconv_fft.cu (blur-independent on-chip FFT engine)
 struct FftEngineLayout {
     int NX, NY;
-    size_t off_twX, off_twY, off_slotX, off_slotY, off_freqY, off_Z, total;
+    size_t off_twX, off_twY, off_stwX, off_stwY, off_slotX, off_slotY, off_freqY, off_Z, total;
 };
 struct FftEngineTables {
     int NX, NY;
     Fft2Plan planX, planY;
-    float2 *twX, *twY;
+    float2 *twX, *twY;       // master tables exp(-2 pi i k / N) (kernel spectrum)
+    float2 *stwX, *stwY;     // stage-twiddle tables of the two plans
     int *slotX, *slotY, *freqY;
     float2* Z;
 };
