@@ -312,11 +312,14 @@ PB_HD void fft2_dit_stage(float2* x, int n, int stride, int nb, int L, const flo
     }
 }
 
+// Barrier between stages: the whole CTA cooperates on the sequences (WARP = false), or one warp
+// owns them and only needs a warp-level barrier (WARP = true: warps of a CTA run decoupled).
+template <bool WARP>
+PB_HD void fft2_sync() {
 #if defined(__CUDA_ARCH__)
-#define PB_FFT2_SYNC() __syncthreads()
-#else
-#define PB_FFT2_SYNC() ((void)0)
+    if (WARP) __syncwarp(); else __syncthreads();
 #endif
+}
 
 #define PB_FFT2_DISPATCH(FN, R_, ...)                         \
     switch (R_) {                                             \
@@ -340,19 +343,21 @@ PB_HD void fft2_dit_stage(float2* x, int n, int stride, int nb, int L, const flo
 // Forward DFT, natural order in -> scrambled order out.  The caller has made its writes to x
 // visible (barrier) before the call; a barrier has been executed after the last stage.
 // On the host (unit tests) the caller loops tid over [0, nthr) per stage via fft2_*_stage.
+template <bool WARP = false>
 PB_HD void fft2_forward_dif(float2* x, int stride, int nb, const Fft2Plan& plan, const float2* __restrict__ tw,
                             int tid, int nthr) {
     int L = plan.n;
     for (int s = 0; s < plan.ns; ++s) {
         const int R = plan.radix[s];
         PB_FFT2_DISPATCH(fft2_dif_stage, R, x, plan.n, stride, nb, L, tw + plan.tw_off[s], tid, nthr);
-        PB_FFT2_SYNC();
+        fft2_sync<WARP>();
         L /= R;
     }
 }
 
 // Forward-sign DFT, scrambled order in -> natural order out (inverse transform through the
 // swap trick: IDFT(y) = swap(DFT(swap(y))) / n, the swaps are folded into the caller's code).
+template <bool WARP = false>
 PB_HD void fft2_forward_dit(float2* x, int stride, int nb, const Fft2Plan& plan, const float2* __restrict__ tw,
                             int tid, int nthr, const float* premul = nullptr, int premode = 1) {
     int L = 1;
@@ -361,7 +366,7 @@ PB_HD void fft2_forward_dit(float2* x, int stride, int nb, const Fft2Plan& plan,
         L *= R;
         PB_FFT2_DISPATCH(fft2_dit_stage, R, x, plan.n, stride, nb, L, tw + plan.tw_off[s], tid, nthr,
                          (s == plan.ns - 1) ? premul : nullptr, premode);
-        PB_FFT2_SYNC();
+        fft2_sync<WARP>();
     }
 }
 
