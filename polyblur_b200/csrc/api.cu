@@ -85,6 +85,8 @@ int make_fft_plan(int n, FftPlan* plan) {
 // ---- workspace layout -------------------------------------------------------------------------
 struct Workspace {
     size_t off_stats, off_kern, off_cls, off_twH, off_twW, off_omH, off_omW, off_gray, off_gy, off_tmp, off_fft, total;
+    // optional stages (allocated only when their flag is set)
+    size_t off_smooth, off_rf, off_padA, off_padB, off_et, off_g0x, off_g0y, off_ox, off_nm;
     bool has_fft;
     FftEngineLayout fft;
 };
@@ -92,7 +94,8 @@ struct Workspace {
 // Radius (max |tap offset|) from which AUTO hands an image to the FFT engine.
 #define PB_FFT_RADIUS_MIN 4
 
-static Workspace layout(int B, int C, int H, int W, int n_iter, int ksize = PB_KS, int engine = PB_ENGINE_AUTO) {
+static Workspace layout(int B, int C, int H, int W, int n_iter, int ksize = PB_KS, int engine = PB_ENGINE_AUTO,
+                        uint32_t flags = 0) {
     Workspace w;
     size_t o = 0;
     auto take = [&](size_t bytes) {
@@ -115,6 +118,18 @@ static Workspace layout(int B, int C, int H, int W, int n_iter, int ksize = PB_K
     w.has_fft = engine != PB_ENGINE_SPATIAL && fft_engine_supported(H, W, ksize / 2);
     w.off_fft = o;
     if (w.has_fft) take(fft_engine_workspace(B, C, H, W, ksize / 2, &w.fft));
+    const size_t img_bytes = (size_t)B * C * plane * sizeof(float);
+    const int pad = ksize / 2;
+    const size_t padded_bytes = (size_t)B * C * (H + 2 * pad) * (W + 2 * pad) * sizeof(float);
+    w.off_smooth = take((flags & (PB_FLAG_PREFILTER | PB_FLAG_PREFILTER_RF)) ? img_bytes : 0);
+    w.off_rf = take((flags & PB_FLAG_PREFILTER_RF) ? rf_workspace_bytes(B, H, W) : 0);
+    w.off_padA = take((flags & PB_FLAG_EDGETAPER) ? padded_bytes : 0);
+    w.off_padB = take((flags & PB_FLAG_EDGETAPER) ? padded_bytes : 0);
+    w.off_et = take((flags & PB_FLAG_EDGETAPER) ? edgetaper_scratch_bytes(B, H + 2 * pad, W + 2 * pad) : 0);
+    w.off_g0x = take((flags & PB_FLAG_REMOVE_HALO) ? img_bytes : 0);
+    w.off_g0y = take((flags & PB_FLAG_REMOVE_HALO) ? img_bytes : 0);
+    w.off_ox = take((flags & PB_FLAG_REMOVE_HALO) ? img_bytes : 0);
+    w.off_nm = take((flags & PB_FLAG_REMOVE_HALO) ? (size_t)B * C * (64 + 1) * sizeof(float) : 0);
     w.total = o;
     return w;
 }
@@ -212,22 +227,48 @@ static int estimate_into(const float* img, int B, int C, int H, int W, double c,
                          (float)(c * c), (float)(b * b), tap_thr, engine, fft_radius_min, cls, stream);
 }
 
+// filters.fourier_gradients of a stack of planes; gx and / or gy may be NULL.
+static int gradients_into(const float* planes, float* gx, float* gy, int nplanes, int H, int W, const Tables& T,
+                          cudaStream_t stream) {
+    int rc;
+    if (T.fast) {
+        if (gx && (rc = launch_rows2(false, planes, nullptr, gx, nullptr, nplanes, 1, H, W, T.planW2, T.twW, T.omW, stream)))
+            return rc;
+        if (gy && (rc = launch_cols2(false, planes, nullptr, gy, nullptr, nplanes, H, W, T.planH2, T.twH, T.omH, 0, stream)))
+            return rc;
+        return PB_OK;
+    }
+    if (gy && (rc = launch_cols(false, planes, nullptr, gy, nullptr, nplanes, 1, H, W, T.planH, T.twH, stream))) return rc;
+    if (gx && (rc = launch_rows(false, planes, nullptr, gx, nullptr, nplanes, H, W, T.planW, T.twW, 0, stream))) return rc;
+    return PB_OK;
+}
+
+static SrcGeom default_geom(int H, int W) {
+    SrcGeom g;
+    g.Hin = H;
+    g.Win = W;
+    g.off = 0;
+    g.pad = -1;
+    g.clamp_out = 1;
+    return g;
+}
+
 // Runs every deconvolution engine over its class of images (lists filled by k_params).
 static int deconv_all(const float* img, float* out, int B, int C, int H, int W, const float* coef, char* ws,
-                      const Workspace& L, const FftEngineTables* F, cudaStream_t stream) {
+                      const Workspace& L, const FftEngineTables* F, const SrcGeom& G, cudaStream_t stream) {
     const ImgKernel* kern = reinterpret_cast<const ImgKernel*>(ws + L.off_kern);
     const int* cls = reinterpret_cast<const int*>(ws + L.off_cls);
     int rc;
     for (int k = PB_CLS_N11; k <= PB_CLS_N22; ++k)
         if ((rc = launch_deconv_narrow(k, img, out, kern, cls + PB_CLS_COUNT_STRIDE + k * B, cls + k, B, C, H, W,
-                                       coef[0], coef[1], coef[2], coef[3], stream)))
+                                       coef[0], coef[1], coef[2], coef[3], G, stream)))
             return rc;
     if ((rc = launch_deconv_spatial(img, out, kern, cls + PB_CLS_COUNT_STRIDE + PB_CLS_TILED * B, cls + PB_CLS_TILED,
-                                    B, C, H, W, coef[0], coef[1], coef[2], coef[3], stream)))
+                                    B, C, H, W, coef[0], coef[1], coef[2], coef[3], G, stream)))
         return rc;
     if (F)
         return launch_deconv_fft(img, out, kern, cls + PB_CLS_COUNT_STRIDE + PB_CLS_FFT * B, cls + PB_CLS_FFT, B, C,
-                                 H, W, *F, coef[0], coef[1], coef[2], coef[3], stream);
+                                 H, W, *F, coef[0], coef[1], coef[2], coef[3], G, stream);
     return PB_OK;
 }
 
@@ -275,7 +316,8 @@ int pb_fft_plan(int n, int* radices) {
 
 size_t pb_workspace_bytes(int B, int C, int H, int W, const pb_params* p) {
     if (B < 1 || C < 1 || H < 1 || W < 1) return 0;
-    return layout(B, C, H, W, p ? p->n_iter : 1, p ? p->ker_size : PB_KS, p ? p->engine : PB_ENGINE_AUTO).total;
+    return layout(B, C, H, W, p ? p->n_iter : 1, p ? p->ker_size : PB_KS, p ? p->engine : PB_ENGINE_AUTO,
+                  p ? p->flags : 0).total;
 }
 
 static int validate_params(const pb_params* p) {
@@ -295,10 +337,9 @@ static int validate_params(const pb_params* p) {
         set_error("q > 0 (quantile normalisation) is not built yet");
         return PB_ERR_UNSUPPORTED;
     }
-    const uint32_t unsupported = PB_FLAG_REMOVE_HALO | PB_FLAG_EDGETAPER | PB_FLAG_PREFILTER | PB_FLAG_PREFILTER_RF;
-    if (p->flags & unsupported) {
-        set_error("flags 0x%x: remove_halo / edgetaper / prefilter are not built yet", p->flags & unsupported);
-        return PB_ERR_UNSUPPORTED;
+    if ((p->flags & PB_FLAG_PREFILTER) && (p->flags & PB_FLAG_PREFILTER_RF)) {
+        set_error("choose one prefilter: PB_FLAG_PREFILTER (bilateral) or PB_FLAG_PREFILTER_RF");
+        return PB_ERR_ARG;
     }
     return PB_OK;
 }
@@ -318,7 +359,7 @@ int pb_polyblur_f32(const float* in, float* out, int B, int C, int H, int W, con
         PB_CUDA_TRY(cudaMemcpyAsync(out, in, bytes, cudaMemcpyDeviceToDevice, stream));
         return PB_OK;
     }
-    const Workspace L = layout(B, C, H, W, p->n_iter, p->ker_size, p->engine);
+    const Workspace L = layout(B, C, H, W, p->n_iter, p->ker_size, p->engine, p->flags);
     if ((rc = check_ws(workspace, workspace_bytes, L.total))) return rc;
     if (p->engine == PB_ENGINE_FFT && !L.has_fft) {
         set_error("the FFT engine does not support %d x %d (ker_size %d)", H, W, p->ker_size);
@@ -334,6 +375,24 @@ int pb_polyblur_f32(const float* in, float* out, int B, int C, int H, int W, con
     poly_coeffs(p->alpha, p->beta, coef);
     const float thr = p->tap_rel_threshold > 0 ? p->tap_rel_threshold : 1e-8f;
     float* tmp = reinterpret_cast<float*>(ws + L.off_tmp);
+    const bool prefilter = (p->flags & (PB_FLAG_PREFILTER | PB_FLAG_PREFILTER_RF)) != 0;
+    const bool halo = (p->flags & PB_FLAG_REMOVE_HALO) != 0;
+    const bool taper = (p->flags & PB_FLAG_EDGETAPER) != 0;
+    const int pad = p->ker_size / 2;
+    const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+    const int planes = B * C;
+    const size_t plane = (size_t)H * W;
+    float* smooth = reinterpret_cast<float*>(ws + L.off_smooth);
+    float* g0x = reinterpret_cast<float*>(ws + L.off_g0x);
+    float* g0y = reinterpret_cast<float*>(ws + L.off_g0y);
+    float* ox = reinterpret_cast<float*>(ws + L.off_ox);
+    float* nM = reinterpret_cast<float*>(ws + L.off_nm);
+    const ImgKernel* kern = reinterpret_cast<const ImgKernel*>(ws + L.off_kern);
+    if (halo) {
+        // grad_img of the ORIGINAL input, all channels, once (deblurring.py:61) and its energy per plane
+        if ((rc = gradients_into(in, g0x, g0y, planes, H, W, T, stream))) return rc;
+        if ((rc = launch_halo_norm(g0x, g0y, nM + planes, nM, planes, plane, stream))) return rc;
+    }
     const float* cur = in;
     for (int it = 0; it < p->n_iter; ++it) {
         float* dst = ((p->n_iter - 1 - it) & 1) ? tmp : out;
@@ -341,7 +400,46 @@ int pb_polyblur_f32(const float* in, float* out, int B, int C, int H, int W, con
         if ((rc = estimate_into(cur, B, C, H, W, p->c, p->b, p->flags, est, ws, L, T, p->ker_size, thr, p->engine,
                                 L.has_fft ? PB_FFT_RADIUS_MIN : (1 << 30), stream)))
             return rc;
-        if ((rc = deconv_all(cur, dst, B, C, H, W, coef, ws, L, L.has_fft ? &F : nullptr, stream))) return rc;
+        // [prefiltering] deconvolve the smooth component only (deblurring.py:80-84)
+        const float* src = cur;
+        if (prefilter) {
+            if (p->flags & PB_FLAG_PREFILTER_RF) {
+                if ((rc = launch_recursive_filter(cur, nullptr, smooth, B, C, H, W, p->sigma_s, p->sigma_r, 1,
+                                                  ws + L.off_rf, stream)))
+                    return rc;
+            } else if ((rc = launch_bilateral(cur, smooth, planes, H, W, 5.0f, 0.1f, stream))) {
+                return rc;
+            }
+            src = smooth;
+        }
+        // [edgetaping] taper the explicitly padded image; the engines then read that padded plane
+        SrcGeom G = default_geom(H, W);
+        const float* dec_in = src;
+        if (taper) {
+            float* padA = reinterpret_cast<float*>(ws + L.off_padA);
+            float* padB = reinterpret_cast<float*>(ws + L.off_padB);
+            float *v = nullptr, *tapered = nullptr;
+            if ((rc = launch_pad_replicate(src, padA, padB, planes, H, W, pad, stream))) return rc;
+            if ((rc = launch_edgetaper_weights(kern, ws + L.off_et, B, Hp, Wp,
+                                               (p->flags & PB_FLAG_EDGETAPER_BATCHMAX) ? 1 : 0, &v, stream)))
+                return rc;
+            if ((rc = launch_edgetaper_passes(padA, padB, kern, v, B, C, Hp, Wp, 3, &tapered, stream))) return rc;
+            G.Hin = Hp;
+            G.Win = Wp;
+            G.off = pad;
+            G.pad = 0;
+            dec_in = tapered;
+        }
+        G.clamp_out = halo ? 0 : 1;
+        if ((rc = deconv_all(dec_in, dst, B, C, H, W, coef, ws, L, L.has_fft ? &F : nullptr, G, stream))) return rc;
+        if (halo) {
+            // halo_masking (deblurring.py:193-208): only d imout / dx is needed (M uses gy*gy, :174)
+            if ((rc = gradients_into(dst, ox, nullptr, planes, H, W, T, stream))) return rc;
+            if ((rc = launch_halo_apply(dst, dec_in, (size_t)G.Hin * G.Win, G.Win, G.off, g0x, g0y, ox, nM, planes, H, W,
+                                        stream)))
+                return rc;
+        }
+        if (prefilter && (rc = launch_residual_add(dst, cur, smooth, (size_t)planes * plane, stream))) return rc;
         cur = dst;
     }
     return PB_OK;
@@ -432,7 +530,7 @@ int pb_deconv_f32(const float* img, float* out, int B, int C, int H, int W, cons
         return rc;
     float coef[4];
     poly_coeffs(alpha, beta, coef);
-    return deconv_all(img, out, B, C, H, W, coef, ws, L, L.has_fft ? &F : nullptr, stream);
+    return deconv_all(img, out, B, C, H, W, coef, ws, L, L.has_fft ? &F : nullptr, default_geom(H, W), stream);
 }
 
 int pb_profile_begin(void) {
@@ -465,21 +563,61 @@ int pb_profile_end(float* ms_per_class, int* launches_per_class, int max_classes
 
 const char* pb_profile_class_name(int i) { return (i >= 0 && i < PROF_NCLASSES) ? kProfNames[i] : ""; }
 
-int pb_edgetaper_f32(const float*, float*, int, int, int, int, const float*, int, int, uint32_t, void*, size_t,
-                     void*) {
-    set_error("pb_edgetaper_f32 is not built yet");
-    return PB_ERR_UNSUPPORTED;
+int pb_edgetaper_f32(const float* img, float* out, int B, int C, int H, int W, const float* kernel, int ksize,
+                     int n_tapers, uint32_t flags, void* workspace, size_t workspace_bytes, void* stream_) {
+    // img / out are the already padded images (H, W = padded sizes), like edgetaper.edgetaper
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc;
+    if ((rc = check_shape(B, C, H, W))) return rc;
+    if (!img || !out || !kernel || img == out || ksize < 1 || ksize > PB_KS || !(ksize & 1) || n_tapers < 0) {
+        set_error("bad arguments to pb_edgetaper_f32");
+        return PB_ERR_ARG;
+    }
+    const size_t img_bytes = (size_t)B * C * H * W * sizeof(float);
+    const size_t o_kern = 0;
+    const size_t o_et = align_up((size_t)B * sizeof(ImgKernel), 256);
+    const size_t o_tmp = o_et + align_up(edgetaper_scratch_bytes(B, H, W), 256);
+    if ((rc = check_ws(workspace, workspace_bytes, o_tmp + img_bytes))) return rc;
+    char* ws = static_cast<char*>(workspace);
+    ImgKernel* kern = reinterpret_cast<ImgKernel*>(ws + o_kern);
+    float* tmp = reinterpret_cast<float*>(ws + o_tmp);
+    if ((rc = launch_params(nullptr, kern, nullptr, nullptr, nullptr, nullptr, kernel, nullptr, 2, B, ksize, 0.f, 0.f,
+                            1e-8f, PB_ENGINE_SPATIAL, 1 << 30, nullptr, stream)))
+        return rc;
+    float *v = nullptr, *res = nullptr;
+    if ((rc = launch_edgetaper_weights(kern, ws + o_et, B, H, W, (flags & PB_FLAG_EDGETAPER_BATCHMAX) ? 1 : 0, &v,
+                                       stream)))
+        return rc;
+    // ping-pong so that the last pass lands in `out`
+    PB_CUDA_TRY(cudaMemcpyAsync((n_tapers & 1) ? tmp : out, img, img_bytes, cudaMemcpyDeviceToDevice, stream));
+    if (n_tapers == 0) return PB_OK;
+    return launch_edgetaper_passes((n_tapers & 1) ? tmp : out, (n_tapers & 1) ? out : tmp, kern, v, B, C, H, W, n_tapers,
+                                   &res, stream);
 }
 
-int pb_bilateral_f32(const float*, float*, int, int, int, int, float, float, void*) {
-    set_error("pb_bilateral_f32 is not built yet");
-    return PB_ERR_UNSUPPORTED;
+int pb_bilateral_f32(const float* img, float* out, int B, int C, int H, int W, float sigma_spatial,
+                     float sigma_color, void* stream_) {
+    int rc;
+    if ((rc = check_shape(B, C, H, W))) return rc;
+    if (!img || !out || img == out) {
+        set_error("img/out must be distinct non-null device pointers");
+        return PB_ERR_ARG;
+    }
+    return launch_bilateral(img, out, B * C, H, W, sigma_spatial, sigma_color, (cudaStream_t)stream_);
 }
 
-int pb_recursive_filter_f32(const float*, const float*, float*, int, int, int, int, float, float, int, void*,
-                            size_t, void*) {
-    set_error("pb_recursive_filter_f32 is not built yet");
-    return PB_ERR_UNSUPPORTED;
+int pb_recursive_filter_f32(const float* img, const float* joint, float* out, int B, int C, int H, int W,
+                            float sigma_s, float sigma_r, int num_iterations, void* workspace,
+                            size_t workspace_bytes, void* stream_) {
+    int rc;
+    if ((rc = check_shape(B, C, H, W))) return rc;
+    if (!img || !out || img == out || num_iterations < 1) {
+        set_error("bad arguments to pb_recursive_filter_f32");
+        return PB_ERR_ARG;
+    }
+    if ((rc = check_ws(workspace, workspace_bytes, rf_workspace_bytes(B, H, W)))) return rc;
+    return launch_recursive_filter(img, joint, out, B, C, H, W, (double)sigma_s, (double)sigma_r, num_iterations,
+                                   workspace, (cudaStream_t)stream_);
 }
 
 }  // extern "C"

@@ -89,6 +89,21 @@ __device__ __forceinline__ int torus_src(int padded, int n, int pad) {
     return min(max(m, 0), n - 1);
 }
 
+// Where a deconvolution engine reads its input from.  Default: the (H, W) image itself, replicate
+// padded by the kernel half-size on the fly (pad < 0 = take ksize / 2 of the image's kernel record).
+// Edgetaper mode: an explicitly padded (Hin, Win) = (H + 2P, W + 2P) plane that already holds the
+// tapered padded image -- the torus is then pure wrap-around (pad = 0) and image pixel (y, x)
+// lives at (y + off, x + off).
+struct SrcGeom {
+    int Hin, Win;
+    int off;
+    int pad;
+    int clamp_out;     // clamp the result to [0,1] (off when halo masking post-processes it)
+};
+__device__ __forceinline__ int geom_src(int coord, int n_in, int off, int pad) {
+    return torus_src(coord + off + pad, n_in, pad);
+}
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 }  // namespace pb

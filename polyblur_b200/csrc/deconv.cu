@@ -36,7 +36,8 @@ __device__ __forceinline__ void conv_stage(const float* __restrict__ in, int in_
                                            float* __restrict__ outb, int out_stride, int RH, int RW,
                                            int hy, const DeconvSmem& S, const float* __restrict__ P,
                                            int p_stride, int poff_y, int poff_x, float cK, float cP,
-                                           float* __restrict__ gout, int gy0, int gx0, int H, int W) {
+                                           float* __restrict__ gout, int gy0, int gx0, int H, int W,
+                                           int clamp_out) {
     const int nsx = RW >> 2;
     const int nstrips = RH * nsx;
     for (int s = threadIdx.x; s < nstrips; s += blockDim.x) {
@@ -89,7 +90,7 @@ __device__ __forceinline__ void conv_stage(const float* __restrict__ in, int in_
                 const float v[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    if (gx0 + xo + j < W) g[j] = fminf(fmaxf(v[j], 0.0f), 1.0f);
+                    if (gx0 + xo + j < W) g[j] = clamp_out ? fminf(fmaxf(v[j], 0.0f), 1.0f) : v[j];
             }
         } else {
             *reinterpret_cast<float4*>(outb + yo * out_stride + xo) = r;
@@ -100,23 +101,23 @@ __device__ __forceinline__ void conv_stage(const float* __restrict__ in, int in_
 template <int HX>
 __device__ __forceinline__ void horner_tile(float* P, float* O1, float* O2, int hy, const DeconvSmem& S,
                                             float a3, float a2, float a1, float b0, float* gout,
-                                            int gy0, int gx0, int H, int W) {
+                                            int gy0, int gx0, int H, int W, int clamp_out) {
     const int PW = DT_W + 6 * HX, W1 = DT_W + 4 * HX, W2 = DT_W + 2 * HX;
     conv_stage<HX, false>(P, PW, O1, W1, DT_H + 4 * hy, W1, hy, S, P, PW, hy, HX, a3, a2,
-                          nullptr, 0, 0, 0, 0);
+                          nullptr, 0, 0, 0, 0, 0);
     __syncthreads();
     conv_stage<HX, false>(O1, W1, O2, W2, DT_H + 2 * hy, W2, hy, S, P, PW, 2 * hy, 2 * HX, 1.0f, a1,
-                          nullptr, 0, 0, 0, 0);
+                          nullptr, 0, 0, 0, 0, 0);
     __syncthreads();
     conv_stage<HX, true>(O2, W2, nullptr, 0, DT_H, DT_W, hy, S, P, PW, 3 * hy, 3 * HX, 1.0f, b0,
-                         gout, gy0, gx0, H, W);
+                         gout, gy0, gx0, H, W, clamp_out);
 }
 
 __global__ void __launch_bounds__(DC_THREADS, 1)
 k_deconv_spatial(const float* __restrict__ img, float* __restrict__ out,
                  const ImgKernel* __restrict__ kern, const int* __restrict__ list,
                  const int* __restrict__ count, int C, int H, int W,
-                 float a3, float a2, float a1, float b0) {
+                 float a3, float a2, float a1, float b0, SrcGeom G) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DeconvSmem& S = *reinterpret_cast<DeconvSmem*>(smem_raw);
     float* bufs = reinterpret_cast<float*>(smem_raw + sizeof(DeconvSmem));
@@ -135,7 +136,7 @@ k_deconv_spatial(const float* __restrict__ img, float* __restrict__ out,
         const int im = list[slot];
         const ImgKernel* K = kern + im;
         const int r = K->radius;
-        const int pad = K->ksize / 2;
+        const int pad = G.pad >= 0 ? G.pad : K->ksize / 2;
         const int hy = r;
         int HX = (r + 3) & ~3;
         if (HX == 0) HX = 4;
@@ -147,32 +148,33 @@ k_deconv_spatial(const float* __restrict__ img, float* __restrict__ out,
         }
         const int gx0 = txi * DT_W, gy0 = tyi * DT_H;
         const int PW = DT_W + 6 * HX, PH = DT_H + 6 * hy;
-        for (int i = threadIdx.x; i < PW; i += blockDim.x) S.srcx[i] = torus_src(gx0 + pad + i - 3 * HX, W, pad);
-        for (int i = threadIdx.x; i < PH; i += blockDim.x) S.srcy[i] = torus_src(gy0 + pad + i - 3 * hy, H, pad);
+        for (int i = threadIdx.x; i < PW; i += blockDim.x) S.srcx[i] = geom_src(gx0 + i - 3 * HX, G.Win, G.off, pad);
+        for (int i = threadIdx.x; i < PH; i += blockDim.x) S.srcy[i] = geom_src(gy0 + i - 3 * hy, G.Hin, G.off, pad);
         __syncthreads();
 
         float* P = bufs;
         float* O1 = P + PH * PW;
         float* O2 = O1 + (DT_H + 4 * hy) * (DT_W + 4 * HX);
         const size_t pl = ((size_t)im * C + c) * H * W;
-        const float* plane = img + pl;
+        const float* plane = img + ((size_t)im * C + c) * (size_t)G.Hin * G.Win;
         for (int i = threadIdx.x; i < PH * PW; i += blockDim.x) {
             const int ly = i / PW, lx = i - ly * PW;
-            P[i] = __ldg(plane + (size_t)S.srcy[ly] * W + S.srcx[lx]);
+            P[i] = __ldg(plane + (size_t)S.srcy[ly] * G.Win + S.srcx[lx]);
         }
         __syncthreads();
         float* gout = out + pl;
         switch (HX) {
-            case 4: horner_tile<4>(P, O1, O2, hy, S, a3, a2, a1, b0, gout, gy0, gx0, H, W); break;
-            case 8: horner_tile<8>(P, O1, O2, hy, S, a3, a2, a1, b0, gout, gy0, gx0, H, W); break;
-            default: horner_tile<12>(P, O1, O2, hy, S, a3, a2, a1, b0, gout, gy0, gx0, H, W); break;
+            case 4: horner_tile<4>(P, O1, O2, hy, S, a3, a2, a1, b0, gout, gy0, gx0, H, W, G.clamp_out); break;
+            case 8: horner_tile<8>(P, O1, O2, hy, S, a3, a2, a1, b0, gout, gy0, gx0, H, W, G.clamp_out); break;
+            default: horner_tile<12>(P, O1, O2, hy, S, a3, a2, a1, b0, gout, gy0, gx0, H, W, G.clamp_out); break;
         }
         __syncthreads();
     }
 }
 
 int launch_deconv_spatial(const float* img, float* out, const ImgKernel* kern, const int* list, const int* count,
-                          int B, int C, int H, int W, float a3, float a2, float a1, float b0, cudaStream_t stream) {
+                          int B, int C, int H, int W, float a3, float a2, float a1, float b0, const SrcGeom& G,
+                          cudaStream_t stream) {
     const int ext = DT_W + 6 * PB_PAD;
     const size_t smem = sizeof(DeconvSmem) +
                         sizeof(float) * ((size_t)ext * ext + (size_t)(DT_W + 4 * PB_PAD) * (DT_H + 4 * PB_PAD) +
@@ -181,7 +183,7 @@ int launch_deconv_spatial(const float* img, float* out, const ImgKernel* kern, c
     const long long items = (long long)B * C * ((W + DT_W - 1) / DT_W) * ((H + DT_H - 1) / DT_H);
     const int grid = (int)(items < 4LL * PB_NUM_SMS ? items : 4LL * PB_NUM_SMS);   // persistent, 1 CTA / SM resident
     ProfScope prof(PROF_DECONV_SPATIAL, stream);
-    k_deconv_spatial<<<grid, DC_THREADS, smem, stream>>>(img, out, kern, list, count, C, H, W, a3, a2, a1, b0);
+    k_deconv_spatial<<<grid, DC_THREADS, smem, stream>>>(img, out, kern, list, count, C, H, W, a3, a2, a1, b0, G);
     PB_LAUNCH_CHECK("k_deconv_spatial");
     return PB_OK;
 }

@@ -81,11 +81,13 @@ __global__ void k_fft2_perm(int* __restrict__ slot_of_freq, int* __restrict__ fr
 #define FFTD_THREADS 256
 
 // extended coordinate (any torus of length >= n + 6 pad) -> source index, or -1 for the zero fill
-__device__ __forceinline__ int ext_src(int i, int n, int pad) {
-    if (i >= n + 6 * pad) return -1;
-    const int X = i - 3 * pad;                   // image coordinate of this extended sample
-    if (X >= 0 && X < n) return X;
-    return torus_src(X + pad, n, pad);           // padded coordinate = image coordinate + pad
+//   n = image length, ext = 3 x kernel half-size (reach of the composite filter), and the source
+//   geometry (n_in, off, pad) of SrcGeom: replicate pad on the fly, or an explicitly padded plane.
+__device__ __forceinline__ int ext_src(int i, int n, int ext, int n_in, int off, int pad) {
+    if (i >= n + 2 * ext) return -1;
+    const int X = i - ext;                       // image coordinate of this extended sample
+    if (pad > 0 && X >= 0 && X < n) return X + off;
+    return geom_src(X, n_in, off, pad);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -94,7 +96,7 @@ __device__ __forceinline__ int ext_src(int i, int n, int pad) {
 __global__ void __launch_bounds__(FFTD_THREADS)
 k_fft_rows_fwd(const float* __restrict__ img, float2* __restrict__ Z, const ImgKernel* __restrict__ kern,
                const int* __restrict__ list, const int* __restrict__ count, int C, int H, int W, int NX, int NY,
-               int nb, Fft2Plan planX, const float2* __restrict__ twX, const int* __restrict__ slotX) {
+               int nb, Fft2Plan planX, const float2* __restrict__ twX, const int* __restrict__ slotX, SrcGeom G) {
     extern __shared__ __align__(16) float2 smf[];
     __shared__ int rowsrc[32];
     const int tid = threadIdx.x;
@@ -111,14 +113,17 @@ k_fft_rows_fwd(const float* __restrict__ img, float2* __restrict__ Z, const ImgK
         const int c = r / blocks_per_plane;
         const int rb = r - c * blocks_per_plane;
         const int im = list[slot];
-        const int pad = kern[im].ksize >> 1;
-        const float* src = img + ((size_t)im * C + c) * plane;
+        const int kpad = kern[im].ksize >> 1;
+        const int pad = G.pad >= 0 ? G.pad : kpad;
+        const int ext = 3 * kpad;
+        const float* src = img + ((size_t)im * C + c) * (size_t)G.Hin * G.Win;
+        const int Ws = G.Win;
         const int j0 = rb * 2 * nb;
-        if (tid < 2 * nb) rowsrc[tid] = (j0 + tid < NY) ? ext_src(j0 + tid, H, pad) : -1;
+        if (tid < 2 * nb) rowsrc[tid] = (j0 + tid < NY) ? ext_src(j0 + tid, H, ext, G.Hin, G.off, pad) : -1;
         __syncthreads();
 
-        const int x_off = 3 * pad;
-        if (((W | x_off) & 3) == 0) {
+        const int x_off = ext;
+        if (((W | x_off | Ws | G.off) & 3) == 0) {
             // interior columns: image column x lives at extended column x + 3 pad; 128-bit loads of
             // both rows of a pair, four pairs of loads in flight per thread
             const int w4 = W >> 2;
@@ -136,8 +141,8 @@ k_fft_rows_fwd(const float* __restrict__ img, float2* __restrict__ Z, const ImgK
                         const int p = fast_div(idx, w4, inv_w4);
                         const int x = (idx - p * w4) << 2;
                         const int sa = rowsrc[2 * p], sb = rowsrc[2 * p + 1];
-                        if (sa >= 0) va[u] = __ldg(reinterpret_cast<const float4*>(src + (size_t)sa * W + x));
-                        if (sb >= 0) vb[u] = __ldg(reinterpret_cast<const float4*>(src + (size_t)sb * W + x));
+                        if (sa >= 0) va[u] = __ldg(reinterpret_cast<const float4*>(src + (size_t)sa * Ws + x + G.off));
+                        if (sb >= 0) vb[u] = __ldg(reinterpret_cast<const float4*>(src + (size_t)sb * Ws + x + G.off));
                         off[u] = p * NX + x_off + x;
                     }
                 }
@@ -157,12 +162,12 @@ k_fft_rows_fwd(const float* __restrict__ img, float2* __restrict__ Z, const ImgK
                 const int p = fast_div(idx, nbord, inv_nbord);
                 const int e = idx - p * nbord;
                 const int i = e < x_off ? e : W + e;
-                const int sx = ext_src(i, W, pad);
+                const int sx = ext_src(i, W, ext, G.Win, G.off, pad);
                 float2 v = make_float2(0.f, 0.f);
                 if (sx >= 0) {
                     const int sa = rowsrc[2 * p], sb = rowsrc[2 * p + 1];
-                    if (sa >= 0) v.x = __ldg(src + (size_t)sa * W + sx);
-                    if (sb >= 0) v.y = __ldg(src + (size_t)sb * W + sx);
+                    if (sa >= 0) v.x = __ldg(src + (size_t)sa * Ws + sx);
+                    if (sb >= 0) v.y = __ldg(src + (size_t)sb * Ws + sx);
                 }
                 smf[(size_t)p * NX + i] = v;
             }
@@ -171,12 +176,12 @@ k_fft_rows_fwd(const float* __restrict__ img, float2* __restrict__ Z, const ImgK
             for (int idx = tid; idx < nb * NX; idx += FFTD_THREADS) {
                 const int p = fast_div(idx, NX, inv_nx);
                 const int i = idx - p * NX;
-                const int sx = ext_src(i, W, pad);
+                const int sx = ext_src(i, W, ext, G.Win, G.off, pad);
                 float2 v = make_float2(0.f, 0.f);
                 if (sx >= 0) {
                     const int sa = rowsrc[2 * p], sb = rowsrc[2 * p + 1];
-                    if (sa >= 0) v.x = __ldg(src + (size_t)sa * W + sx);
-                    if (sb >= 0) v.y = __ldg(src + (size_t)sb * W + sx);
+                    if (sa >= 0) v.x = __ldg(src + (size_t)sa * Ws + sx);
+                    if (sb >= 0) v.y = __ldg(src + (size_t)sb * Ws + sx);
                 }
                 smf[(size_t)p * NX + i] = v;
             }
@@ -360,7 +365,8 @@ k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int
 __global__ void __launch_bounds__(FFTD_THREADS)
 k_fft_rows_inv(const float2* __restrict__ Z, float* __restrict__ out, const ImgKernel* __restrict__ kern,
                const int* __restrict__ list, const int* __restrict__ count, int C, int H, int W, int NX, int NY,
-               int nb, Fft2Plan planX, const float2* __restrict__ twX, const int* __restrict__ slotX) {
+               int nb, Fft2Plan planX, const float2* __restrict__ twX, const int* __restrict__ slotX,
+               int clamp_out) {
     extern __shared__ __align__(16) float2 smf[];
     const int tid = threadIdx.x;
     const int blocks_per_plane = (NY / 2 + nb - 1) / nb;
@@ -369,6 +375,7 @@ k_fft_rows_inv(const float2* __restrict__ Z, float* __restrict__ out, const ImgK
     const size_t plane = (size_t)H * W;
     const int half = NX >> 1;
     const float inv_nb = 1.0f / (float)nb;
+    const float lo = clamp_out ? 0.0f : -INFINITY, hi = clamp_out ? 1.0f : INFINITY;
 
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
         const int slot = w / per_img;
@@ -376,10 +383,10 @@ k_fft_rows_inv(const float2* __restrict__ Z, float* __restrict__ out, const ImgK
         const int c = r / blocks_per_plane;
         const int rb = r - c * blocks_per_plane;
         const int im = list[slot];
-        const int pad = kern[im].ksize >> 1;
+        const int ext = 3 * (kern[im].ksize >> 1);
         const int j0 = rb * 2 * nb;
-        // rows of the extended image that are output rows: [3 pad, H + 3 pad)
-        if (j0 + 2 * nb <= 3 * pad || j0 >= H + 3 * pad) continue;
+        // rows of the extended image that are output rows: [ext, H + ext)
+        if (j0 + 2 * nb <= ext || j0 >= H + ext) continue;
         const float2* Zp = Z + ((size_t)slot * C + c) * half * NY;
 #pragma unroll 2
         for (int idx = tid; idx < nb * half; idx += FFTD_THREADS) {
@@ -410,7 +417,7 @@ k_fft_rows_inv(const float2* __restrict__ Z, float* __restrict__ out, const ImgK
         fft2_forward_dit(smf, NX, nb, planX, twX, tid, FFTD_THREADS);
         // r = DFT(swap(Z)): row a = r.y, row b = r.x (the 1/(NX NY) scale is inside H)
         float* dst = out + ((size_t)im * C + c) * plane;
-        const int x_off = 3 * pad;
+        const int x_off = ext;
         if (((W | x_off) & 3) == 0) {
             const int w4 = W >> 2;
             const float inv_w4 = 1.0f / (float)w4;
@@ -419,15 +426,15 @@ k_fft_rows_inv(const float2* __restrict__ Z, float* __restrict__ out, const ImgK
                 const int x = (idx - p * w4) << 2;
                 const float4* sp = reinterpret_cast<const float4*>(smf + (size_t)p * NX + x_off + x);
                 const float4 u0 = sp[0], u1 = sp[1];
-                const int ya = j0 + 2 * p - 3 * pad;
+                const int ya = j0 + 2 * p - ext;
                 if (ya >= 0 && ya < H)
                     *reinterpret_cast<float4*>(dst + (size_t)ya * W + x) =
-                        make_float4(fminf(fmaxf(u0.y, 0.f), 1.f), fminf(fmaxf(u0.w, 0.f), 1.f),
-                                    fminf(fmaxf(u1.y, 0.f), 1.f), fminf(fmaxf(u1.w, 0.f), 1.f));
+                        make_float4(fminf(fmaxf(u0.y, lo), hi), fminf(fmaxf(u0.w, lo), hi),
+                                    fminf(fmaxf(u1.y, lo), hi), fminf(fmaxf(u1.w, lo), hi));
                 if (ya + 1 >= 0 && ya + 1 < H)
                     *reinterpret_cast<float4*>(dst + (size_t)(ya + 1) * W + x) =
-                        make_float4(fminf(fmaxf(u0.x, 0.f), 1.f), fminf(fmaxf(u0.z, 0.f), 1.f),
-                                    fminf(fmaxf(u1.x, 0.f), 1.f), fminf(fmaxf(u1.z, 0.f), 1.f));
+                        make_float4(fminf(fmaxf(u0.x, lo), hi), fminf(fmaxf(u0.z, lo), hi),
+                                    fminf(fmaxf(u1.x, lo), hi), fminf(fmaxf(u1.z, lo), hi));
             }
         } else {
             const float inv_w = 1.0f / (float)W;
@@ -435,9 +442,9 @@ k_fft_rows_inv(const float2* __restrict__ Z, float* __restrict__ out, const ImgK
                 const int p = fast_div(idx, W, inv_w);
                 const int x = idx - p * W;
                 const float2 z = smf[(size_t)p * NX + x + x_off];
-                const int ya = j0 + 2 * p - 3 * pad;
-                if (ya >= 0 && ya < H) dst[(size_t)ya * W + x] = fminf(fmaxf(z.y, 0.0f), 1.0f);
-                if (ya + 1 >= 0 && ya + 1 < H) dst[(size_t)(ya + 1) * W + x] = fminf(fmaxf(z.x, 0.0f), 1.0f);
+                const int ya = j0 + 2 * p - ext;
+                if (ya >= 0 && ya < H) dst[(size_t)ya * W + x] = fminf(fmaxf(z.y, lo), hi);
+                if (ya + 1 >= 0 && ya + 1 < H) dst[(size_t)(ya + 1) * W + x] = fminf(fmaxf(z.x, lo), hi);
             }
         }
         __syncthreads();
@@ -544,7 +551,7 @@ int fft_engine_prepare(char* base, const FftEngineLayout& L, FftEngineTables* T,
 
 int launch_deconv_fft(const float* img, float* out, const ImgKernel* kern, const int* list, const int* count,
                       int B, int C, int H, int W, const FftEngineTables& T, float a3, float a2, float a1,
-                      float b0, cudaStream_t stream) {
+                      float b0, const SrcGeom& G, cudaStream_t stream) {
     const int NX = T.NX, NY = T.NY;
     const int nb = rows_nb(NX), CB = cols_cb(NY);
     const size_t smem_rows = (size_t)nb * NX * sizeof(float2);
@@ -560,7 +567,7 @@ int launch_deconv_fft(const float* img, float* out, const ImgKernel* kern, const
     {
         ProfScope prof(PROF_FFT_ROWS_FWD, stream);
         k_fft_rows_fwd<<<grid_rows, FFTD_THREADS, smem_rows, stream>>>(img, T.Z, kern, list, count, C, H, W, NX, NY,
-                                                                       nb, T.planX, T.stwX, T.slotX);
+                                                                       nb, T.planX, T.stwX, T.slotX, G);
         PB_LAUNCH_CHECK("k_fft_rows_fwd");
     }
     {
@@ -572,7 +579,7 @@ int launch_deconv_fft(const float* img, float* out, const ImgKernel* kern, const
     {
         ProfScope prof(PROF_FFT_ROWS_INV, stream);
         k_fft_rows_inv<<<grid_rows, FFTD_THREADS, smem_rows, stream>>>(T.Z, out, kern, list, count, C, H, W, NX, NY,
-                                                                       nb, T.planX, T.stwX, T.slotX);
+                                                                       nb, T.planX, T.stwX, T.slotX, G.clamp_out);
         PB_LAUNCH_CHECK("k_fft_rows_inv");
     }
     return PB_OK;

@@ -38,7 +38,7 @@ template <int RX, int RY>
 __global__ void __launch_bounds__(NARROW_THREADS)
 k_deconv_narrow(const float* __restrict__ img, float* __restrict__ out, const ImgKernel* __restrict__ kern,
                 const int* __restrict__ list, const int* __restrict__ count, int C, int H, int W, int TH,
-                float a3, float a2, float a1, float b0) {
+                float a3, float a2, float a1, float b0, SrcGeom G) {
     using Cfg = NarrowCfg<RX, RY>;
     constexpr int HL = Cfg::HL, VW = Cfg::VW, NW = Cfg::NW, D = Cfg::D, PW = Cfg::PW;
     constexpr unsigned FULL = 0xffffffffu;
@@ -60,7 +60,7 @@ k_deconv_narrow(const float* __restrict__ img, float* __restrict__ out, const Im
         const int tx = r - ty * tilesX;
         const int im = list[slot];
         const ImgKernel* K = kern + im;
-        const int pad = K->ksize >> 1;
+        const int pad = G.pad >= 0 ? G.pad : (K->ksize >> 1);
 
         float wk[NW][2 * RX + 1];
 #pragma unroll
@@ -69,26 +69,26 @@ k_deconv_narrow(const float* __restrict__ img, float* __restrict__ out, const Im
             for (int dx = 0; dx < 2 * RX + 1; ++dx)
                 wk[dy][dx] = __ldg(&K->k[(dy - RY + PB_PAD) * PB_KS + (dx - RX + PB_PAD)]);
 
-        const float* src = img + ((size_t)im * C + c) * plane;
+        const float* src = img + ((size_t)im * C + c) * (size_t)G.Hin * G.Win;
         float* dst = out + ((size_t)im * C + c) * plane;
         const int y0 = ty * TH;
         const int rows = min(TH, H - y0);
         const int nsteps = rows + 6 * RY;
         const int cx0 = tx * VW - 4 * HL;
         const int cx = cx0 + 4 * lane;
-        const bool fastx = (cx0 >= 0) && (cx0 + 128 <= W) && ((W & 3) == 0);
+        const bool fastx = (cx0 + G.off >= 0) && (cx0 + G.off + 128 <= G.Win) && (((G.Win | G.off) & 3) == 0);
         int sx[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) sx[i] = torus_src(cx + i + pad, W, pad);
+        for (int i = 0; i < 4; ++i) sx[i] = geom_src(cx + i, G.Win, G.off, pad);
 
         // Row j of the tile's input window (rows past the end repeat the last one: their results
         // are never stored, and an unconditional load keeps the row loop free of branches).
         auto load_row = [&](int j) -> float4 {
-            const int sy = torus_src(y0 - 3 * RY + min(j, nsteps - 1) + pad, H, pad);
-            const float* rp = src + (size_t)sy * W;
+            const int sy = geom_src(y0 - 3 * RY + min(j, nsteps - 1), G.Hin, G.off, pad);
+            const float* rp = src + (size_t)sy * G.Win;
             float4 v;
             if (fastx) {
-                v = __ldg(reinterpret_cast<const float4*>(rp + cx));
+                v = __ldg(reinterpret_cast<const float4*>(rp + cx + G.off));
             } else {
                 v.x = __ldg(rp + sx[0]);
                 v.y = __ldg(rp + sx[1]);
@@ -173,7 +173,10 @@ k_deconv_narrow(const float* __restrict__ img, float* __restrict__ out, const Im
                     if (lane_ok && yo >= 0 && yo < rows) {
                         float o[4];
 #pragma unroll
-                        for (int cc = 0; cc < 4; ++cc) o[cc] = fminf(fmaxf(acc[cc] + Q[s3][cc], 0.0f), 1.0f);
+                        for (int cc = 0; cc < 4; ++cc) {
+                            o[cc] = acc[cc] + Q[s3][cc];
+                            if (G.clamp_out) o[cc] = fminf(fmaxf(o[cc], 0.0f), 1.0f);
+                        }
                         float* g = dst + (size_t)(y0 + yo) * W + cx;
                         if (vec_ok) {
                             *reinterpret_cast<float4*>(g) = make_float4(o[0], o[1], o[2], o[3]);
@@ -193,7 +196,8 @@ k_deconv_narrow(const float* __restrict__ img, float* __restrict__ out, const Im
 
 template <int RX, int RY>
 static int launch_one(const float* img, float* out, const ImgKernel* kern, const int* list, const int* count,
-                      int B, int C, int H, int W, float a3, float a2, float a1, float b0, cudaStream_t stream) {
+                      int B, int C, int H, int W, float a3, float a2, float a1, float b0, const SrcGeom& G,
+                      cudaStream_t stream) {
     using Cfg = NarrowCfg<RX, RY>;
     // tile height: tall tiles amortise the 6 RY warm-up rows; keep >= ~8 waves of warps
     int TH = 120;
@@ -204,17 +208,17 @@ static int launch_one(const float* img, float* out, const ImgKernel* kern, const
     int grid = (int)(want < (long long)PB_NUM_SMS * 8 ? want : (long long)PB_NUM_SMS * 8);
     if (grid < 1) grid = 1;
     k_deconv_narrow<RX, RY><<<grid, NARROW_THREADS, 0, stream>>>(img, out, kern, list, count, C, H, W, TH, a3, a2,
-                                                                 a1, b0);
+                                                                 a1, b0, G);
     PB_LAUNCH_CHECK("k_deconv_narrow");
     return PB_OK;
 }
 
 int launch_deconv_narrow(int cls, const float* img, float* out, const ImgKernel* kern, const int* list,
                          const int* count, int B, int C, int H, int W, float a3, float a2, float a1, float b0,
-                         cudaStream_t stream) {
+                         const SrcGeom& G, cudaStream_t stream) {
     ProfScope prof(PROF_DECONV_NARROW, stream);
-    if (cls == PB_CLS_N11) return launch_one<1, 1>(img, out, kern, list, count, B, C, H, W, a3, a2, a1, b0, stream);
-    return launch_one<2, 2>(img, out, kern, list, count, B, C, H, W, a3, a2, a1, b0, stream);
+    if (cls == PB_CLS_N11) return launch_one<1, 1>(img, out, kern, list, count, B, C, H, W, a3, a2, a1, b0, G, stream);
+    return launch_one<2, 2>(img, out, kern, list, count, B, C, H, W, a3, a2, a1, b0, G, stream);
 }
 
 }  // namespace pb

@@ -55,10 +55,30 @@ int launch_cols2(bool est, const float* plane_in, const float* gx, float* gy, un
                  int H, int W, const Fft2Plan& planH, const float2* twH, const float* omegaH,
                  int discard_saturation, cudaStream_t stream);
 
+// stages.cu (optional stages: prefilters, halo masking, edgetaper)
+int launch_bilateral(const float* img, float* out, int planes, int H, int W, float sigma_spatial,
+                     float sigma_color, cudaStream_t stream);
+size_t rf_workspace_bytes(int B, int H, int W);
+int launch_recursive_filter(const float* in, const float* joint, float* out, int B, int C, int H, int W,
+                            double sigma_s, double sigma_r, int num_iterations, void* ws, cudaStream_t stream);
+int launch_residual_add(float* dec, const float* cur, const float* smooth, size_t n, cudaStream_t stream);
+int launch_halo_norm(const float* gx, const float* gy, float* partial, float* nM, int planes, size_t plane,
+                     cudaStream_t stream);
+int launch_halo_apply(float* imout, const float* img, size_t img_plane, int img_pitch, int img_off, const float* gx,
+                      const float* gy, const float* ox, const float* nM, int planes, int H, int W,
+                      cudaStream_t stream);
+size_t edgetaper_scratch_bytes(int B, int Hp, int Wp);
+int launch_edgetaper_weights(const ImgKernel* kern, void* scratch, int B, int Hp, int Wp, int batch_max,
+                             float** v_out, cudaStream_t stream);
+int launch_pad_replicate(const float* img, float* a, float* b, int planes, int H, int W, int pad,
+                         cudaStream_t stream);
+int launch_edgetaper_passes(float* a, float* b, const ImgKernel* kern, const float* v, int B, int C, int Hp, int Wp,
+                            int n_tapers, float** result, cudaStream_t stream);
+
 // deconv_narrow.cu
 int launch_deconv_narrow(int cls, const float* img, float* out, const ImgKernel* kern, const int* list,
                          const int* count, int B, int C, int H, int W, float a3, float a2, float a1, float b0,
-                         cudaStream_t stream);
+                         const SrcGeom& G, cudaStream_t stream);
 
 // deconv_fft.cu (blur-independent on-chip FFT engine)
 struct FftEngineLayout {
@@ -79,10 +99,11 @@ size_t fft_engine_workspace(int B, int C, int H, int W, int pad, FftEngineLayout
 int fft_engine_prepare(char* base, const FftEngineLayout& L, FftEngineTables* T, cudaStream_t stream);
 int launch_deconv_fft(const float* img, float* out, const ImgKernel* kern, const int* list, const int* count,
                       int B, int C, int H, int W, const FftEngineTables& T, float a3, float a2, float a1,
-                      float b0, cudaStream_t stream);
+                      float b0, const SrcGeom& G, cudaStream_t stream);
 
 // deconv.cu
 int launch_deconv_spatial(const float* img, float* out, const ImgKernel* kern, const int* list, const int* count,
-                          int B, int C, int H, int W, float a3, float a2, float a1, float b0, cudaStream_t stream);
+                          int B, int C, int H, int W, float a3, float a2, float a1, float b0, const SrcGeom& G,
+                          cudaStream_t stream);
 
 }  // namespace pb

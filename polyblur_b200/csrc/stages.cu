@@ -1,0 +1,490 @@
+// Optional stages of the Polyblur loop, all on the device:
+//   bilateral prefilter        filters.bilateral_filter            polyblur/filters.py:107-148
+//   domain-transform RF        domain_transform.recursive_filter   polyblur/domain_transform.py:6-85
+//   prefilter residual         impred = deconv(smooth) + (impred - smooth), clip   deblurring.py:80-88
+//   halo masking               deblurring.halo_masking             polyblur/deblurring.py:173-208
+//   edgetaper                  edgetaper.edgetaper                 polyblur/edgetaper.py:10-33
+#include "kernels.cuh"
+
+namespace pb {
+
+// ---------------------------------------------------------------------------------------------
+// 5x5 bilateral filter, per-channel range weight, replicate border (filters.py:107-148):
+//   F = exp(-(S - I)^2 / (2 sc^2)) * exp(-(dx^2 + dy^2) / (2 ss^2));  out = sum F S / (sum F + 1e-5)
+// One thread per pixel-channel; the 5x5 window comes through L1.  Row sums are formed first and
+// then accumulated, like the reference's loop over kernel rows.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_bilateral(const float* __restrict__ img, float* __restrict__ out, int H, int W, float var2_spatial,
+            float var2_color) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= W || y >= H) return;
+    const size_t pl = (size_t)blockIdx.z * H * W;
+    const float* p = img + pl;
+    const float I = __ldg(p + (size_t)y * W + x);
+    float J = 0.f, Wt = 0.f;
+#pragma unroll
+    for (int dy = -2; dy <= 2; ++dy) {
+        const int yy = min(max(y + dy, 0), H - 1);
+        float jr = 0.f, wr = 0.f;
+#pragma unroll
+        for (int dx = -2; dx <= 2; ++dx) {
+            const int xx = min(max(x + dx, 0), W - 1);
+            const float S = __ldg(p + (size_t)yy * W + xx);
+            const float d = __fsub_rn(S, I);
+            const float gw = expf(-(float)(dx * dx + dy * dy) / var2_spatial);
+            const float F = __fmul_rn(expf(__fdiv_rn(-__fmul_rn(d, d), var2_color)), gw);
+            jr = __fadd_rn(jr, __fmul_rn(F, S));
+            wr = __fadd_rn(wr, F);
+        }
+        J = __fadd_rn(J, jr);
+        Wt = __fadd_rn(Wt, wr);
+    }
+    out[pl + (size_t)y * W + x] = __fdiv_rn(J, __fadd_rn(Wt, 1e-5f));
+}
+
+int launch_bilateral(const float* img, float* out, int planes, int H, int W, float sigma_spatial,
+                     float sigma_color, cudaStream_t stream) {
+    if (planes > 65535) {
+        set_error("B*C = %d exceeds the grid z limit", planes);
+        return PB_ERR_ARG;
+    }
+    dim3 grid((W + 31) / 32, (H + 7) / 8, planes);
+    ProfScope prof(PROF_OTHER, stream);
+    k_bilateral<<<grid, 256, 0, stream>>>(img, out, H, W, 2.0f * sigma_spatial * sigma_spatial,
+                                         2.0f * sigma_color * sigma_color);
+    PB_LAUNCH_CHECK("k_bilateral");
+    return PB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Domain-transform recursive filter (domain_transform.py:6-85).
+//   k_rf_weights : Vh = a^(1 + s dIdx), Vv = a^(1 + s dIdy), dId* = L1 over channels of the forward
+//                  differences of the joint image (0 at the first column / row)        (:27-38,55,59)
+//   k_rf_rows    : per row and channel, left->right then right->left first-order recurrence (:78-83).
+//                  One warp per row: every lane owns a contiguous chunk, composes its affine map,
+//                  a warp-shuffle scan gives each lane its carry-in, and the lane then replays the
+//                  reference's own update formula on its chunk.
+//   k_rf_cols    : the same recurrence down the columns, one thread per column (coalesced).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_rf_weights(const float* __restrict__ joint, float* __restrict__ Vh, float* __restrict__ Vv, int C, int H, int W,
+             float a, float ratio) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= W || y >= H) return;
+    const size_t plane = (size_t)H * W;
+    const float* J = joint + (size_t)blockIdx.z * C * plane;
+    float dx = 0.f, dy = 0.f;
+    for (int c = 0; c < C; ++c) {
+        const float v = __ldg(J + c * plane + (size_t)y * W + x);
+        if (x > 0) dx = __fadd_rn(dx, fabsf(__fsub_rn(v, __ldg(J + c * plane + (size_t)y * W + x - 1))));
+        if (y > 0) dy = __fadd_rn(dy, fabsf(__fsub_rn(v, __ldg(J + c * plane + (size_t)(y - 1) * W + x))));
+    }
+    const size_t o = (size_t)blockIdx.z * plane + (size_t)y * W + x;
+    Vh[o] = powf(a, __fadd_rn(1.0f, __fmul_rn(ratio, dx)));
+    Vv[o] = powf(a, __fadd_rn(1.0f, __fmul_rn(ratio, dy)));
+}
+
+#define RF_ROW_WARPS 4
+
+__global__ void __launch_bounds__(RF_ROW_WARPS * 32)
+k_rf_rows(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ Vh, int C, int H, int W,
+          int chunk, int rows_total) {
+    extern __shared__ float rfs[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cs = chunk | 1;                           // odd stride: lanes hit different banks
+    float* Vs = rfs + (size_t)warp * 2 * 32 * cs;
+    float* Fs = Vs + 32 * cs;
+    const int row = blockIdx.x * RF_ROW_WARPS + warp;    // (image, y)
+    if (row >= rows_total) return;
+    const int b = row / H, y = row - b * H;
+    const size_t plane = (size_t)H * W;
+    const float* vrow = Vh + (size_t)b * plane + (size_t)y * W;
+    for (int x = lane; x < W; x += 32) Vs[(x / chunk) * cs + (x % chunk)] = __ldg(vrow + x);
+    const int x0 = lane * chunk, x1 = min(x0 + chunk, W);
+    for (int c = 0; c < C; ++c) {
+        const float* frow = in + ((size_t)b * C + c) * plane + (size_t)y * W;
+        float* orow = out + ((size_t)b * C + c) * plane + (size_t)y * W;
+        __syncwarp();
+        for (int x = lane; x < W; x += 32) Fs[(x / chunk) * cs + (x % chunk)] = __ldg(frow + x);
+        __syncwarp();
+        float* f = Fs + lane * cs;
+        const float* v = Vs + lane * cs;
+        // ---- left -> right:  F[i] += V[i] (F[i-1] - F[i]),  i >= 1
+        float A = 1.f, Bc = 0.f;
+        for (int x = x0; x < x1; ++x) {
+            const float a = (x == 0) ? 0.f : v[x - x0];
+            const float bb = (x == 0) ? f[0] : (1.f - a) * f[x - x0];
+            A = a * A;
+            Bc = fmaf(a, Bc, bb);
+        }
+        // inclusive scan of the affine maps over the lanes
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float Ap = __shfl_up_sync(0xffffffffu, A, o);
+            const float Bp = __shfl_up_sync(0xffffffffu, Bc, o);
+            if (lane >= o) {
+                Bc = fmaf(A, Bp, Bc);
+                A = A * Ap;
+            }
+        }
+        float carry = __shfl_up_sync(0xffffffffu, Bc, 1);      // value at the end of the previous chunk
+        for (int x = x0; x < x1; ++x) {
+            float cur = f[x - x0];
+            if (x > 0) cur = __fadd_rn(cur, __fmul_rn(v[x - x0], __fsub_rn(carry, cur)));
+            f[x - x0] = cur;
+            carry = cur;
+        }
+        __syncwarp();
+        // ---- right -> left:  F[i] += V[i+1] (F[i+1] - F[i]),  i <= W-2
+        A = 1.f;
+        Bc = 0.f;
+        for (int x = x1 - 1; x >= x0; --x) {
+            const bool last = (x == W - 1);
+            const float a = last ? 0.f : ((x + 1 < x1) ? v[x + 1 - x0] : Vs[(lane + 1) * cs]);
+            const float bb = last ? f[x - x0] : (1.f - a) * f[x - x0];
+            A = a * A;
+            Bc = fmaf(a, Bc, bb);
+        }
+        const bool active = x0 < W;
+        if (!active) {
+            A = 1.f;
+            Bc = 0.f;
+        }
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float An = __shfl_down_sync(0xffffffffu, A, o);
+            const float Bn = __shfl_down_sync(0xffffffffu, Bc, o);
+            if (lane + o < 32) {
+                Bc = fmaf(A, Bn, Bc);
+                A = A * An;
+            }
+        }
+        carry = __shfl_down_sync(0xffffffffu, Bc, 1);          // value at the start of the next chunk
+        for (int x = x1 - 1; x >= x0; --x) {
+            float cur = f[x - x0];
+            if (x < W - 1) {
+                const float a = (x + 1 < x1) ? v[x + 1 - x0] : Vs[(lane + 1) * cs];
+                cur = __fadd_rn(cur, __fmul_rn(a, __fsub_rn(carry, cur)));
+            }
+            f[x - x0] = cur;
+            carry = cur;
+        }
+        __syncwarp();
+        for (int x = lane; x < W; x += 32) orow[x] = Fs[(x / chunk) * cs + (x % chunk)];
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_rf_cols(float* __restrict__ img, const float* __restrict__ Vv, int C, int H, int W) {
+    const int x = blockIdx.x * 128 + threadIdx.x;
+    if (x >= W) return;
+    const int pl = blockIdx.y;                           // image * C + channel
+    const size_t plane = (size_t)H * W;
+    float* f = img + (size_t)pl * plane + x;
+    const float* v = Vv + (size_t)(pl / C) * plane + x;
+    float prev = f[0];
+    for (int y = 1; y < H; ++y) {
+        float cur = f[(size_t)y * W];
+        cur = __fadd_rn(cur, __fmul_rn(__ldg(v + (size_t)y * W), __fsub_rn(prev, cur)));
+        f[(size_t)y * W] = cur;
+        prev = cur;
+    }
+    for (int y = H - 2; y >= 0; --y) {
+        float cur = f[(size_t)y * W];
+        cur = __fadd_rn(cur, __fmul_rn(__ldg(v + (size_t)(y + 1) * W), __fsub_rn(prev, cur)));
+        f[(size_t)y * W] = cur;
+        prev = cur;
+    }
+}
+
+size_t rf_workspace_bytes(int B, int H, int W) { return 2 * align_up((size_t)B * H * W * sizeof(float), 256); }
+
+// in -> out (may not alias), joint = guide image or NULL (= in); ws holds Vh, Vv.
+int launch_recursive_filter(const float* in, const float* joint, float* out, int B, int C, int H, int W,
+                            double sigma_s, double sigma_r, int num_iterations, void* ws, cudaStream_t stream) {
+    if (B * C > 65535 || B > 65535) {
+        set_error("batch too large for the recursive filter grids");
+        return PB_ERR_ARG;
+    }
+    const size_t plane = (size_t)H * W;
+    float* Vh = static_cast<float*>(ws);
+    float* Vv = reinterpret_cast<float*>(static_cast<char*>(ws) + align_up((size_t)B * plane * sizeof(float), 256));
+    const int chunk = (W + 31) / 32;
+    const size_t smem = (size_t)RF_ROW_WARPS * 2 * 32 * (chunk | 1) * sizeof(float);
+    if (smem > PB_SMEM_MAX - 1024) {
+        set_error("row of %d pixels does not fit the recursive filter's shared memory", W);
+        return PB_ERR_UNSUPPORTED;
+    }
+    PB_CUDA_TRY(cudaFuncSetAttribute(k_rf_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope prof(PROF_OTHER, stream);
+    const float* cur = in;
+    for (int i = 0; i < num_iterations; ++i) {
+        // sigma_H_i and the feedback coefficient in Python doubles (domain_transform.py:50-53)
+        const double sigma_i = sigma_s * sqrt(3.0) * pow(2.0, (double)(num_iterations - (i + 1))) /
+                               sqrt(pow(4.0, (double)num_iterations) - 1.0);
+        const float a = (float)exp(-sqrt(2.0) / sigma_i);
+        dim3 gw((W + 31) / 32, (H + 7) / 8, B);
+        k_rf_weights<<<gw, 256, 0, stream>>>(joint ? joint : in, Vh, Vv, C, H, W, a, (float)(sigma_s / sigma_r));
+        const int rows_total = B * H;
+        k_rf_rows<<<(rows_total + RF_ROW_WARPS - 1) / RF_ROW_WARPS, RF_ROW_WARPS * 32, smem, stream>>>(
+            cur, out, Vh, C, H, W, chunk, rows_total);
+        dim3 gc((W + 127) / 128, B * C);
+        k_rf_cols<<<gc, 128, 0, stream>>>(out, Vv, C, H, W);
+        cur = out;
+    }
+    PB_LAUNCH_CHECK("recursive filter");
+    return PB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Elementwise epilogues.
+// ---------------------------------------------------------------------------------------------
+// impred = clip(deconv(smooth) + (impred - smooth), 0, 1)          (deblurring.py:80-88)
+__global__ void k_residual_add(float* __restrict__ dec, const float* __restrict__ cur, const float* __restrict__ smooth,
+                               size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const float noise = __fsub_rn(cur[i], smooth[i]);
+        dec[i] = fminf(fmaxf(__fadd_rn(dec[i], noise), 0.0f), 1.0f);
+    }
+}
+
+int launch_residual_add(float* dec, const float* cur, const float* smooth, size_t n, cudaStream_t stream) {
+    ProfScope prof(PROF_OTHER, stream);
+    k_residual_add<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(dec, cur, smooth, n);
+    PB_LAUNCH_CHECK("k_residual_add");
+    return PB_OK;
+}
+
+// nM[plane] = sum over pixels of gx^2 + gy^2, deterministic two-stage sum (deblurring.py:181,204)
+#define HALO_PARTS 64
+__global__ void __launch_bounds__(256)
+k_halo_norm_partial(const float* __restrict__ gx, const float* __restrict__ gy, float* __restrict__ partial,
+                    size_t plane) {
+    __shared__ float red[8];
+    const float* a = gx + (size_t)blockIdx.y * plane;
+    const float* b = gy + (size_t)blockIdx.y * plane;
+    const size_t per = (plane + HALO_PARTS - 1) / HALO_PARTS;
+    const size_t i0 = (size_t)blockIdx.x * per, i1 = i0 + per < plane ? i0 + per : plane;
+    float s = 0.f;
+    for (size_t i = i0 + threadIdx.x; i < i1; i += 256) s += a[i] * a[i] + b[i] * b[i];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        partial[blockIdx.y * HALO_PARTS + blockIdx.x] = t;
+    }
+}
+__global__ void k_halo_norm_final(const float* __restrict__ partial, float* __restrict__ nM, int planes) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < planes) {
+        float t = 0.f;
+        for (int i = 0; i < HALO_PARTS; ++i) t += partial[p * HALO_PARTS + i];
+        nM[p] = t;
+    }
+}
+
+int launch_halo_norm(const float* gx, const float* gy, float* partial, float* nM, int planes, size_t plane,
+                     cudaStream_t stream) {
+    if (planes > 65535) {
+        set_error("B*C = %d exceeds the grid y limit", planes);
+        return PB_ERR_ARG;
+    }
+    ProfScope prof(PROF_OTHER, stream);
+    k_halo_norm_partial<<<dim3(HALO_PARTS, planes), 256, 0, stream>>>(gx, gy, partial, plane);
+    k_halo_norm_final<<<(planes + 127) / 128, 128, 0, stream>>>(partial, nM, planes);
+    PB_LAUNCH_CHECK("k_halo_norm");
+    return PB_OK;
+}
+
+// out = clamp(imout + max(M / (nM + M), 0) (img - imout)),  M = -gx ox - gy gy  (sic, deblurring.py:174)
+// `img` is the (possibly tapered) current image: plane pitch / row pitch / offset given explicitly.
+__global__ void __launch_bounds__(256)
+k_halo_apply(float* __restrict__ imout, const float* __restrict__ img, size_t img_plane, int img_pitch, int img_off,
+             const float* __restrict__ gx, const float* __restrict__ gy, const float* __restrict__ ox,
+             const float* __restrict__ nM, int H, int W) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= W || y >= H) return;
+    const size_t i = (size_t)blockIdx.z * H * W + (size_t)y * W + x;
+    const float cur = img[(size_t)blockIdx.z * img_plane + (size_t)(y + img_off) * img_pitch + x + img_off];
+    const float M = __fadd_rn(__fmul_rn(-gx[i], ox[i]), __fmul_rn(-gy[i], gy[i]));
+    const float z = fmaxf(__fdiv_rn(M, __fadd_rn(nM[blockIdx.z], M)), 0.0f);
+    const float o = imout[i];
+    imout[i] = fminf(fmaxf(__fadd_rn(o, __fmul_rn(z, __fsub_rn(cur, o))), 0.0f), 1.0f);
+}
+
+int launch_halo_apply(float* imout, const float* img, size_t img_plane, int img_pitch, int img_off, const float* gx,
+                      const float* gy, const float* ox, const float* nM, int planes, int H, int W,
+                      cudaStream_t stream) {
+    dim3 grid((W + 31) / 32, (H + 7) / 8, planes);
+    ProfScope prof(PROF_OTHER, stream);
+    k_halo_apply<<<grid, 256, 0, stream>>>(imout, img, img_plane, img_pitch, img_off, gx, gy, ox, nM, H, W);
+    PB_LAUNCH_CHECK("k_halo_apply");
+    return PB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Edgetaper (edgetaper.py:10-33) on the replicate-padded image, method='fft' semantics:
+//   alpha = v1 (x) v2,  v = 1 - z / max z,  z = circular autocorrelation (period n - 1) of the
+//   kernel's row / column sums, last sample repeated;  3 x  p <- alpha p + (1 - alpha) (K (*) p)
+//   with the circular correlation on the padded torus.  alpha = 1 away from the border band, so
+//   the 625-tap sum is only evaluated where alpha < 1.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_pad_replicate(const float* __restrict__ img, float* __restrict__ a, float* __restrict__ b, int H,
+                                int W, int pad) {
+    const int Wp = W + 2 * pad, Hp = H + 2 * pad;
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= Wp || y >= Hp) return;
+    const float v = __ldg(img + (size_t)blockIdx.z * H * W + (size_t)min(max(y - pad, 0), H - 1) * W +
+                          min(max(x - pad, 0), W - 1));
+    const size_t o = (size_t)blockIdx.z * Hp * Wp + (size_t)y * Wp + x;
+    a[o] = v;
+    b[o] = v;
+}
+
+// per image: zl[0..48] = linear autocorrelation lags -24..24 of the row sums, zl[49..97] of the column
+// sums; zmax[2 im], zmax[2 im + 1] = lag-0 values (the maxima).
+__global__ void __launch_bounds__(128)
+k_et_autocorr(const ImgKernel* __restrict__ kern, float* __restrict__ zl, float* __restrict__ zmax) {
+    __shared__ float rh[PB_KS], rw[PB_KS];
+    const ImgKernel* K = kern + blockIdx.x;
+    const int t = threadIdx.x;
+    if (t < PB_KS) {
+        float s = 0.f, u = 0.f;
+        for (int i = 0; i < PB_KS; ++i) {
+            s += K->k[t * PB_KS + i];       // sum over columns: projection indexed by row
+            u += K->k[i * PB_KS + t];       // sum over rows: projection indexed by column
+        }
+        rh[t] = s;
+        rw[t] = u;
+    }
+    __syncthreads();
+    if (t < 2 * (2 * PB_KS - 1)) {
+        const int which = t / (2 * PB_KS - 1);
+        const int d = t % (2 * PB_KS - 1) - (PB_KS - 1);
+        const float* r = which ? rw : rh;
+        float s = 0.f;
+        for (int i = 0; i < PB_KS; ++i) {
+            const int j = i + d;
+            if (j >= 0 && j < PB_KS) s += r[i] * r[j];
+        }
+        zl[(size_t)blockIdx.x * 98 + t] = s;
+        if (d == 0) zmax[2 * blockIdx.x + which] = s;
+    }
+}
+
+// v1[im][y], y < Hp and v2[im][x], x < Wp (stored back to back: Hp + Wp floats per image)
+__global__ void __launch_bounds__(256)
+k_et_weights(const float* __restrict__ zl, const float* __restrict__ zmax, float* __restrict__ v, int B, int Hp,
+             int Wp, int batch_max) {
+    const int im = blockIdx.y;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= Hp + Wp) return;
+    const int which = i >= Hp;
+    const int n = which ? Wp : Hp;
+    int m = which ? i - Hp : i;
+    if (m == n - 1) m = 0;                                  // z = cat(z, z[0])
+    const int period = n - 1;
+    float z = 0.f;
+    if (period >= 1) {
+        for (int d = -(PB_KS - 1); d <= PB_KS - 1; ++d)
+            if (pmod(d - m, period) == 0) z += zl[(size_t)im * 98 + which * 49 + d + PB_KS - 1];
+    }
+    float mx = zmax[2 * im + which];
+    if (batch_max)
+        for (int b = 0; b < B; ++b) mx = fmaxf(mx, zmax[2 * b + which]);
+    v[(size_t)im * (Hp + Wp) + i] = __fsub_rn(1.0f, __fdiv_rn(z, mx));
+}
+
+__global__ void __launch_bounds__(256)
+k_et_pass(const float* __restrict__ src, float* __restrict__ dst, const ImgKernel* __restrict__ kern,
+          const float* __restrict__ v, int C, int Hp, int Wp) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= Wp || y >= Hp) return;
+    const int im = blockIdx.z / C;
+    const float* vv = v + (size_t)im * (Hp + Wp);
+    const float alpha = __fmul_rn(vv[y], vv[Hp + x]);
+    const size_t pl = (size_t)blockIdx.z * Hp * Wp;
+    const float p = src[pl + (size_t)y * Wp + x];
+    float o = p;
+    if (alpha != 1.0f) {
+        const ImgKernel* K = kern + im;
+        float acc = 0.f;
+        for (int dy = -PB_PAD; dy <= PB_PAD; ++dy) {
+            const int lo = K->lo[dy + PB_PAD], hi = K->hi[dy + PB_PAD];
+            if (lo > hi) continue;
+            const float* row = src + pl + (size_t)pmod(y + dy, Hp) * Wp;
+            float r = 0.f;
+            for (int t = lo; t <= hi; ++t) r = fmaf(K->k[(dy + PB_PAD) * PB_KS + t], row[pmod(x + t - PB_PAD, Wp)], r);
+            acc += r;
+        }
+        o = __fadd_rn(__fmul_rn(alpha, p), __fmul_rn(__fsub_rn(1.0f, alpha), acc));
+    }
+    dst[pl + (size_t)y * Wp + x] = o;
+}
+
+size_t edgetaper_scratch_bytes(int B, int Hp, int Wp) {
+    return align_up((size_t)B * 98 * sizeof(float), 256) + align_up((size_t)B * 2 * sizeof(float), 256) +
+           align_up((size_t)B * (Hp + Wp) * sizeof(float), 256);
+}
+
+// Builds the taper weights of every image (needs the kernel records) -> v in scratch.
+int launch_edgetaper_weights(const ImgKernel* kern, void* scratch, int B, int Hp, int Wp, int batch_max,
+                             float** v_out, cudaStream_t stream) {
+    char* s = static_cast<char*>(scratch);
+    float* zl = reinterpret_cast<float*>(s);
+    float* zmax = reinterpret_cast<float*>(s + align_up((size_t)B * 98 * sizeof(float), 256));
+    float* v = reinterpret_cast<float*>(s + align_up((size_t)B * 98 * sizeof(float), 256) +
+                                        align_up((size_t)B * 2 * sizeof(float), 256));
+    if (B > 65535) {
+        set_error("batch too large for the edgetaper grids");
+        return PB_ERR_ARG;
+    }
+    ProfScope prof(PROF_OTHER, stream);
+    k_et_autocorr<<<B, 128, 0, stream>>>(kern, zl, zmax);
+    k_et_weights<<<dim3((Hp + Wp + 255) / 256, B), 256, 0, stream>>>(zl, zmax, v, B, Hp, Wp, batch_max);
+    PB_LAUNCH_CHECK("edgetaper weights");
+    *v_out = v;
+    return PB_OK;
+}
+
+int launch_pad_replicate(const float* img, float* a, float* b, int planes, int H, int W, int pad,
+                         cudaStream_t stream) {
+    if (planes > 65535) {
+        set_error("B*C = %d exceeds the grid z limit", planes);
+        return PB_ERR_ARG;
+    }
+    dim3 grid((W + 2 * pad + 31) / 32, (H + 2 * pad + 7) / 8, planes);
+    ProfScope prof(PROF_OTHER, stream);
+    k_pad_replicate<<<grid, 256, 0, stream>>>(img, a, b, H, W, pad);
+    PB_LAUNCH_CHECK("k_pad_replicate");
+    return PB_OK;
+}
+
+// n_tapers passes ping-ponging between a and b (both hold the padded image on entry); returns the
+// buffer that holds the result.
+int launch_edgetaper_passes(float* a, float* b, const ImgKernel* kern, const float* v, int B, int C, int Hp, int Wp,
+                            int n_tapers, float** result, cudaStream_t stream) {
+    dim3 grid((Wp + 31) / 32, (Hp + 7) / 8, B * C);
+    ProfScope prof(PROF_OTHER, stream);
+    float *src = a, *dst = b;
+    for (int i = 0; i < n_tapers; ++i) {
+        k_et_pass<<<grid, 256, 0, stream>>>(src, dst, kern, v, C, Hp, Wp);
+        float* t = src;
+        src = dst;
+        dst = t;
+    }
+    PB_LAUNCH_CHECK("k_et_pass");
+    *result = src;
+    return PB_OK;
+}
+
+}  // namespace pb

@@ -38,6 +38,20 @@ def fourier_gradients(images: torch.Tensor):
     return gx.to(src), gy.to(src)
 
 
+def bilateral_filter(I, ksize=5, sigma_spatial=5.0, sigma_color=0.1):
+    """5x5 bilateral filter with per-channel range weights (polyblur/filters.py:107-148)."""
+    if ksize != 5:
+        raise NotImplementedError("only the reference's 5x5 window is built")
+    x, dev, src = _prep(I, "bilateral_filter")
+    B, C, H, W = x.shape
+    with torch.cuda.device(dev):
+        out = torch.empty_like(x)
+        rc = _lib.lib().pb_bilateral_f32(x.data_ptr(), out.data_ptr(), B, C, H, W, float(sigma_spatial),
+                                         float(sigma_color), _lib.stream_ptr(dev))
+        _lib.check(rc, "pb_bilateral_f32")
+    return out.to(src)
+
+
 def gaussian_filter(sigma, theta, shift=np.array([0.0, 0.0]), k_size=np.array([15, 15])):
     """NumPy generator of a generalised 2-D Gaussian kernel (polyblur/filters.py:198-234);
     used by the CLI's synthetic degradation, not on the GPU path."""

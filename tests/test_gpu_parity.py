@@ -255,3 +255,55 @@ def test_end_to_end_engines_agree_with_oracle(pb, engine):
     ref = po.polyblur_deblurring(x, n_iter=3, alpha=6, beta=1)
     out = pb.polyblur_deblurring(cu(x), n_iter=3, alpha=6, beta=1, engine=engine)
     assert maxabs(out.cpu().numpy(), ref) < TOL_E2E
+
+
+# ---------------------------------------------------------------------------------------------
+# optional stages: golden vectors from the live reference + the oracle
+# ---------------------------------------------------------------------------------------------
+def test_prefilters_golden(pb):
+    op = load("options.npz")
+    x = cu(op["in"])
+    assert maxabs(pb.filters.bilateral_filter(x).cpu().numpy(), op["bilateral"]) < 2e-6
+    assert maxabs(pb.domain_transform.recursive_filter(x, 2.0, 0.8, 1).cpu().numpy(), op["rf_s2_r0.8_n1"]) < 2e-6
+    assert maxabs(pb.domain_transform.recursive_filter(x, 60, 0.4, 3).cpu().numpy(), op["rf_s60_r0.4_n3"]) < 5e-6
+    padded = np.pad(op["in"], ((0, 0), (0, 0), (12, 12), (12, 12)), mode="edge")
+    got = pb.edgetaper.edgetaper(cu(padded), cu(op["edgetaper/k"]))
+    assert maxabs(got.cpu().numpy(), op["edgetaper/out"]) < 3e-6
+
+
+@pytest.mark.parametrize("shape", [(1, 3, 97, 131), (2, 1, 33, 700), (1, 2, 500, 37)])
+def test_prefilters_vs_oracle(pb, shape):
+    rng = np.random.default_rng(3)
+    x = rng.random(shape, dtype=np.float32)
+    x = np.clip(x * 0.3 + np.round(x) * 0.6, 0, 1).astype(np.float32)      # edges + texture
+    assert maxabs(pb.filters.bilateral_filter(cu(x)).cpu().numpy(), po.bilateral_filter(x)) < 2e-6
+    for (ss, sr, n) in ((2.0, 0.8, 1), (12.0, 0.3, 2), (60, 0.4, 3)):
+        ref = po.recursive_filter(x, ss, sr, n, dtype=np.float64)
+        got = pb.domain_transform.recursive_filter(cu(x), ss, sr, n)
+        assert maxabs(got.cpu().numpy(), ref) < 5e-6, (ss, sr, n)
+    j = rng.random(shape, dtype=np.float32)
+    ref = po.recursive_filter(x, 8.0, 0.5, 2, joint_image=j, dtype=np.float64)
+    got = pb.domain_transform.recursive_filter(cu(x), 8.0, 0.5, 2, joint_image=cu(j))
+    assert maxabs(got.cpu().numpy(), ref) < 5e-6
+
+
+OPTION_CASES = [("remove_halo", dict(remove_halo=True)), ("edgetaping", dict(edgetaping=True)),
+                ("prefiltering", dict(prefiltering=True)),
+                ("all_q0", dict(remove_halo=True, edgetaping=True, prefiltering=True, discard_saturation=True))]
+
+
+@pytest.mark.parametrize("engine", [0, ENGINE_SPATIAL, ENGINE_FFT])
+@pytest.mark.parametrize("key,kw", OPTION_CASES)
+def test_options_golden(pb, key, kw, engine):
+    op = load("options.npz")
+    y = pb.polyblur_deblurring(cu(op["in"]), n_iter=2, alpha=6, beta=1, engine=engine, **kw)
+    assert maxabs(y.cpu().numpy(), op[key]) < TOL_E2E
+
+
+@pytest.mark.parametrize("kw", [dict(prefiltering=True, prefilter="rf"), dict(edgetaping=True, remove_halo=True),
+                                dict(prefiltering=True, edgetaping=True)])
+def test_options_vs_oracle_larger(pb, kw):
+    x = mosaic(2, 3, 150, 210, seed=8, sigma=(1.6, 0.9), theta_deg=70.0)
+    ref = po.polyblur_deblurring(x, n_iter=2, alpha=6, beta=1, **kw)
+    out = pb.polyblur_deblurring(cu(x), n_iter=2, alpha=6, beta=1, **kw)
+    assert maxabs(out.cpu().numpy(), ref) < TOL_E2E
