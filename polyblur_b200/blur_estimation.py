@@ -12,12 +12,14 @@ def estimate_parameters(imgc: torch.Tensor, c=0.362, b=0.464, q=0.0, discard_sat
     (blur_estimation.py:59-70): dict of (B,7) mags, (B,) theta_deg, sigma, rho, m_normal, m_ortho.
 
     Note the reference's own default is q=1e-4; the Polyblur loop always passes q
-    explicitly (deblurring.py:71-74).  q > 0 is not built yet.
+    explicitly (deblurring.py:71-74).  q > 0 = quantile range normalisation (radix select on
+    the device, csrc/quantile.cu).
     """
     x, dev, src = _prep(imgc, "gaussian_blur_estimation")
     B, C, H, W = x.shape
     with torch.cuda.device(dev):
         p = _lib.default_params()
+        p.q = float(q)
         ws = _lib.workspace(B, C, H, W, p, dev)
         est = torch.empty(B, _lib.PB_EST_STRIDE, dtype=torch.float32, device=dev)
         flags = _lib.FLAG_DISCARD_SATURATION if discard_saturation else 0

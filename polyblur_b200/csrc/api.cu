@@ -86,7 +86,7 @@ int make_fft_plan(int n, FftPlan* plan) {
 struct Workspace {
     size_t off_stats, off_kern, off_cls, off_twH, off_twW, off_omH, off_omW, off_gray, off_gy, off_tmp, off_fft, total;
     // optional stages (allocated only when their flag is set)
-    size_t off_smooth, off_rf, off_padA, off_padB, off_et, off_g0x, off_g0y, off_ox, off_nm;
+    size_t off_smooth, off_rf, off_padA, off_padB, off_et, off_g0x, off_g0y, off_ox, off_nm, off_ghat, off_q;
     bool has_fft;
     FftEngineLayout fft;
 };
@@ -95,7 +95,7 @@ struct Workspace {
 #define PB_FFT_RADIUS_MIN 4
 
 static Workspace layout(int B, int C, int H, int W, int n_iter, int ksize = PB_KS, int engine = PB_ENGINE_AUTO,
-                        uint32_t flags = 0) {
+                        uint32_t flags = 0, double q = 0.0) {
     Workspace w;
     size_t o = 0;
     auto take = [&](size_t bytes) {
@@ -130,6 +130,8 @@ static Workspace layout(int B, int C, int H, int W, int n_iter, int ksize = PB_K
     w.off_g0y = take((flags & PB_FLAG_REMOVE_HALO) ? img_bytes : 0);
     w.off_ox = take((flags & PB_FLAG_REMOVE_HALO) ? img_bytes : 0);
     w.off_nm = take((flags & PB_FLAG_REMOVE_HALO) ? (size_t)B * C * (64 + 1) * sizeof(float) : 0);
+    w.off_ghat = take(q > 0 ? (size_t)B * plane * sizeof(float) : 0);
+    w.off_q = take(q > 0 ? quantile_workspace_bytes(B) : 0);
     w.total = o;
     return w;
 }
@@ -200,7 +202,7 @@ static void poly_coeffs(double alpha, double beta, float* o) {
     o[3] = (float)beta;
 }
 
-static int estimate_into(const float* img, int B, int C, int H, int W, double c, double b, uint32_t flags,
+static int estimate_into(const float* img, int B, int C, int H, int W, double c, double b, double q, uint32_t flags,
                          float* est, char* ws, const Workspace& L, const Tables& T, int ksize,
                          float tap_thr, int engine, int fft_radius_min, cudaStream_t stream) {
     unsigned* stats = reinterpret_cast<unsigned*>(ws + L.off_stats);
@@ -210,11 +212,29 @@ static int estimate_into(const float* img, int B, int C, int H, int W, double c,
     int* cls = reinterpret_cast<int*>(ws + L.off_cls);
     int rc;
     if ((rc = launch_init_stats(stats, B, stream))) return rc;
+    if (q > 0) {
+        // quantile normalisation: un-normalised gray -> quantiles -> the rows kernel normalises while
+        // loading and writes the normalised plane (its min / max are then 0 and 1, so k_params'
+        // division by the range is the identity); needs the fft2 path
+        if (!T.fast) {
+            set_error("q > 0 needs image sides whose prime factors are <= 13 (got %d x %d)", H, W);
+            return PB_ERR_UNSUPPORTED;
+        }
+        float* ghat = reinterpret_cast<float*>(ws + L.off_ghat);
+        float* qrange = nullptr;
+        if ((rc = launch_quantile_range(img, gray, B, C, H, W, q, ws + L.off_q, &qrange, stream))) return rc;
+        if ((rc = launch_rows2(true, gray, ghat, gy, stats, B, 1, H, W, T.planW2, T.twW, T.omW, qrange, stream))) return rc;
+        if ((rc = launch_cols2(true, ghat, gy, nullptr, stats, B, H, W, T.planH2, T.twH, T.omH,
+                               (flags & PB_FLAG_DISCARD_SATURATION) ? 1 : 0, gray, stream)))
+            return rc;
+        return launch_params(stats, kern, est, nullptr, nullptr, nullptr, nullptr, nullptr, 0, B, ksize,
+                             (float)(c * c), (float)(b * b), tap_thr, engine, fft_radius_min, cls, stream);
+    }
     if (T.fast) {
         // rows first (fully coalesced read of the iterate), `gy` holds d g / d x here
-        if ((rc = launch_rows2(true, img, gray, gy, stats, B, C, H, W, T.planW2, T.twW, T.omW, stream))) return rc;
+        if ((rc = launch_rows2(true, img, gray, gy, stats, B, C, H, W, T.planW2, T.twW, T.omW, nullptr, stream))) return rc;
         if ((rc = launch_cols2(true, gray, gy, nullptr, stats, B, H, W, T.planH2, T.twH, T.omH,
-                               (flags & PB_FLAG_DISCARD_SATURATION) ? 1 : 0, stream)))
+                               (flags & PB_FLAG_DISCARD_SATURATION) ? 1 : 0, nullptr, stream)))
             return rc;
         return launch_params(stats, kern, est, nullptr, nullptr, nullptr, nullptr, nullptr, 0, B, ksize,
                              (float)(c * c), (float)(b * b), tap_thr, engine, fft_radius_min, cls, stream);
@@ -232,9 +252,9 @@ static int gradients_into(const float* planes, float* gx, float* gy, int nplanes
                           cudaStream_t stream) {
     int rc;
     if (T.fast) {
-        if (gx && (rc = launch_rows2(false, planes, nullptr, gx, nullptr, nplanes, 1, H, W, T.planW2, T.twW, T.omW, stream)))
+        if (gx && (rc = launch_rows2(false, planes, nullptr, gx, nullptr, nplanes, 1, H, W, T.planW2, T.twW, T.omW, nullptr, stream)))
             return rc;
-        if (gy && (rc = launch_cols2(false, planes, nullptr, gy, nullptr, nplanes, H, W, T.planH2, T.twH, T.omH, 0, stream)))
+        if (gy && (rc = launch_cols2(false, planes, nullptr, gy, nullptr, nplanes, H, W, T.planH2, T.twH, T.omH, 0, nullptr, stream)))
             return rc;
         return PB_OK;
     }
@@ -317,7 +337,7 @@ int pb_fft_plan(int n, int* radices) {
 size_t pb_workspace_bytes(int B, int C, int H, int W, const pb_params* p) {
     if (B < 1 || C < 1 || H < 1 || W < 1) return 0;
     return layout(B, C, H, W, p ? p->n_iter : 1, p ? p->ker_size : PB_KS, p ? p->engine : PB_ENGINE_AUTO,
-                  p ? p->flags : 0).total;
+                  p ? p->flags : 0, p ? p->q : 0.0).total;
 }
 
 static int validate_params(const pb_params* p) {
@@ -333,9 +353,9 @@ static int validate_params(const pb_params* p) {
         set_error("ker_size must be odd and <= %d (got %d)", PB_KSIZE_MAX, p->ker_size);
         return PB_ERR_ARG;
     }
-    if (p->q != 0.0) {
-        set_error("q > 0 (quantile normalisation) is not built yet");
-        return PB_ERR_UNSUPPORTED;
+    if (p->q < 0.0 || p->q >= 0.5) {
+        set_error("q must be in [0, 0.5)");
+        return PB_ERR_ARG;
     }
     if ((p->flags & PB_FLAG_PREFILTER) && (p->flags & PB_FLAG_PREFILTER_RF)) {
         set_error("choose one prefilter: PB_FLAG_PREFILTER (bilateral) or PB_FLAG_PREFILTER_RF");
@@ -359,7 +379,7 @@ int pb_polyblur_f32(const float* in, float* out, int B, int C, int H, int W, con
         PB_CUDA_TRY(cudaMemcpyAsync(out, in, bytes, cudaMemcpyDeviceToDevice, stream));
         return PB_OK;
     }
-    const Workspace L = layout(B, C, H, W, p->n_iter, p->ker_size, p->engine, p->flags);
+    const Workspace L = layout(B, C, H, W, p->n_iter, p->ker_size, p->engine, p->flags, p->q);
     if ((rc = check_ws(workspace, workspace_bytes, L.total))) return rc;
     if (p->engine == PB_ENGINE_FFT && !L.has_fft) {
         set_error("the FFT engine does not support %d x %d (ker_size %d)", H, W, p->ker_size);
@@ -397,7 +417,7 @@ int pb_polyblur_f32(const float* in, float* out, int B, int C, int H, int W, con
     for (int it = 0; it < p->n_iter; ++it) {
         float* dst = ((p->n_iter - 1 - it) & 1) ? tmp : out;
         float* est = est_out ? est_out + (size_t)it * B * PB_EST_STRIDE : nullptr;
-        if ((rc = estimate_into(cur, B, C, H, W, p->c, p->b, p->flags, est, ws, L, T, p->ker_size, thr, p->engine,
+        if ((rc = estimate_into(cur, B, C, H, W, p->c, p->b, p->q, p->flags, est, ws, L, T, p->ker_size, thr, p->engine,
                                 L.has_fft ? PB_FFT_RADIUS_MIN : (1 << 30), stream)))
             return rc;
         // [prefiltering] deconvolve the smooth component only (deblurring.py:80-84)
@@ -460,9 +480,9 @@ int pb_fourier_gradients_f32(const float* img, float* gx, float* gy, int B, int 
     Tables T;
     if ((rc = prepare_tables(ws, L, H, W, &T, stream))) return rc;
     if (T.fast) {
-        if ((rc = launch_rows2(false, img, nullptr, gx, nullptr, B * C, 1, H, W, T.planW2, T.twW, T.omW, stream)))
+        if ((rc = launch_rows2(false, img, nullptr, gx, nullptr, B * C, 1, H, W, T.planW2, T.twW, T.omW, nullptr, stream)))
             return rc;
-        return launch_cols2(false, img, nullptr, gy, nullptr, B * C, H, W, T.planH2, T.twH, T.omH, 0, stream);
+        return launch_cols2(false, img, nullptr, gy, nullptr, B * C, H, W, T.planH2, T.twH, T.omH, 0, nullptr, stream);
     }
     if ((rc = launch_cols(false, img, nullptr, gy, nullptr, B * C, 1, H, W, T.planH, T.twH, stream))) return rc;
     return launch_rows(false, img, nullptr, gx, nullptr, B * C, H, W, T.planW, T.twW, 0, stream);
@@ -477,17 +497,17 @@ int pb_estimate_f32(const float* img, int B, int C, int H, int W, double c, doub
         set_error("null pointer");
         return PB_ERR_ARG;
     }
-    if (q != 0.0) {
-        set_error("q > 0 (quantile normalisation) is not built yet");
-        return PB_ERR_UNSUPPORTED;
+    if (q < 0.0 || q >= 0.5) {
+        set_error("q must be in [0, 0.5)");
+        return PB_ERR_ARG;
     }
-    const Workspace L = layout(B, C, H, W, 1);
+    const Workspace L = layout(B, C, H, W, 1, PB_KS, PB_ENGINE_SPATIAL, 0, q);
     if ((rc = check_ws(workspace, workspace_bytes, L.total))) return rc;
     char* ws = static_cast<char*>(workspace);
     Tables T;
     if ((rc = upload_constants(stream))) return rc;
     if ((rc = prepare_tables(ws, L, H, W, &T, stream))) return rc;
-    return estimate_into(img, B, C, H, W, c, b, flags, est, ws, L, T, PB_KS, 1e-8f, PB_ENGINE_SPATIAL, 1 << 30, stream);
+    return estimate_into(img, B, C, H, W, c, b, q, flags, est, ws, L, T, PB_KS, 1e-8f, PB_ENGINE_SPATIAL, 1 << 30, stream);
 }
 
 int pb_make_kernel_f32(const float* theta, const float* sigma, const float* rho, int B, int ksize,

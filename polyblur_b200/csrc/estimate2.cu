@@ -50,7 +50,7 @@ template <bool EST>
 __global__ void __launch_bounds__(R2_THREADS)
 k_rows2(const float* __restrict__ img, float* __restrict__ gray, float* __restrict__ gx,
         unsigned* __restrict__ stats, int C, int H, int W, int nb, Fft2Plan plan,
-        const float2* __restrict__ tw, const float* __restrict__ omega) {
+        const float2* __restrict__ tw, const float* __restrict__ omega, const float* __restrict__ qrange) {
     extern __shared__ __align__(16) float2 sm2[];
     const int tid = threadIdx.x;
     const int y0 = blockIdx.x * 2 * nb;
@@ -59,6 +59,12 @@ k_rows2(const float* __restrict__ img, float* __restrict__ gray, float* __restri
     const float* src = img + (size_t)im * (EST ? C : 1) * plane;
     const float fC = (float)C;
     float lmin = INFINITY, lmax = -INFINITY;
+    // q > 0: the input is the gray plane and is range-normalised with the quantiles while loading:
+    // clamp_((x - lo) / (hi - lo), 0, 1)  (blur_estimation.py:92-93, 102-105)
+    const bool qn = EST && qrange != nullptr;
+    const float qlo = qn ? qrange[2 * im] : 0.f;
+    const float qden = qn ? __fsub_rn(qrange[2 * im + 1], qlo) : 1.f;
+#define PB_QNORM(v) fminf(fmaxf(__fdiv_rn(__fsub_rn((v), qlo), qden), 0.0f), 1.0f)
 
     if ((W & 3) == 0) {
         const int w4 = W >> 2;
@@ -88,6 +94,7 @@ k_rows2(const float* __restrict__ img, float* __restrict__ gray, float* __restri
                             g[h].z = __fdiv_rn(g[h].z, fC);
                             g[h].w = __fdiv_rn(g[h].w, fC);
                         }
+                        if (qn) g[h] = make_float4(PB_QNORM(g[h].x), PB_QNORM(g[h].y), PB_QNORM(g[h].z), PB_QNORM(g[h].w));
                         *reinterpret_cast<float4*>(gray + (size_t)im * plane + (size_t)y * W + x) = g[h];
                         lmin = fminf(lmin, fminf(fminf(g[h].x, g[h].y), fminf(g[h].z, g[h].w)));
                         lmax = fmaxf(lmax, fmaxf(fmaxf(g[h].x, g[h].y), fmaxf(g[h].z, g[h].w)));
@@ -114,6 +121,7 @@ k_rows2(const float* __restrict__ img, float* __restrict__ gray, float* __restri
                     if (EST) {
                         for (int c = 1; c < C; ++c) g[h] = __fadd_rn(g[h], __ldg(q + (size_t)c * plane));
                         if (C > 1) g[h] = __fdiv_rn(g[h], fC);
+                        if (qn) g[h] = PB_QNORM(g[h]);
                         gray[(size_t)im * plane + (size_t)y * W + x] = g[h];
                         lmin = fminf(lmin, g[h]);
                         lmax = fmaxf(lmax, g[h]);
@@ -123,6 +131,7 @@ k_rows2(const float* __restrict__ img, float* __restrict__ gray, float* __restri
             sm2[(size_t)p * W + x] = make_float2(g[0], g[1]);
         }
     }
+#undef PB_QNORM
     __syncthreads();
     fft2_forward_dif(sm2, W, nb, plan, tw, tid, R2_THREADS);
     fft2_forward_dit(sm2, W, nb, plan, tw, tid, R2_THREADS, omega);
@@ -170,7 +179,8 @@ template <bool EST, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 k_cols2(const float* __restrict__ plane_in, const float* __restrict__ gx, float* __restrict__ gy,
         unsigned* __restrict__ stats, int H, int W, int nb, int stride, Fft2Plan plan,
-        const float2* __restrict__ tw, const float* __restrict__ omega, int discard_saturation) {
+        const float2* __restrict__ tw, const float* __restrict__ omega, int discard_saturation,
+        const float* __restrict__ mask_src) {
     extern __shared__ __align__(16) float2 sm2[];
     __shared__ float red[THREADS / 32][8];
     const int tid = threadIdx.x;
@@ -238,6 +248,8 @@ k_cols2(const float* __restrict__ plane_in, const float* __restrict__ gx, float*
 #pragma unroll
     for (int j = 0; j < 7; ++j) m[j] = 0.0f;
     const float* gxp = gx + (size_t)im * plane;
+    // saturation mask: un-normalised gray > 0.99 (blur_estimation.py:59, 83-88)
+    const float* msk = (mask_src ? mask_src : plane_in) + (size_t)im * plane;
     for (int idx = tid; idx < H * nb; idx += THREADS) {
         const int y = fast_div(idx, nb, inv_nb);
         const int p = idx - y * nb;
@@ -252,7 +264,7 @@ k_cols2(const float* __restrict__ plane_in, const float* __restrict__ gx, float*
             gxv[0] = t.x;
             gxv[1] = t.y;
             if (discard_saturation) {
-                const float2 s = __ldg(reinterpret_cast<const float2*>(src + (size_t)y * W + x));
+                const float2 s = __ldg(reinterpret_cast<const float2*>(msk + (size_t)y * W + x));
                 gr[0] = s.x;
                 gr[1] = s.y;
             }
@@ -260,14 +272,13 @@ k_cols2(const float* __restrict__ plane_in, const float* __restrict__ gx, float*
             gxv[0] = __ldg(gxp + (size_t)y * W + x);
             if (x + 1 < W) gxv[1] = __ldg(gxp + (size_t)y * W + x + 1);
             if (discard_saturation) {
-                gr[0] = __ldg(src + (size_t)y * W + x);
-                if (x + 1 < W) gr[1] = __ldg(src + (size_t)y * W + x + 1);
+                gr[0] = __ldg(msk + (size_t)y * W + x);
+                if (x + 1 < W) gr[1] = __ldg(msk + (size_t)y * W + x + 1);
             }
         }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             if (x + h >= W) continue;
-            // get_saturation_mask (blur_estimation.py:83-88): un-normalised gray > 0.99
             if (discard_saturation && gr[h] > 0.99f) continue;
 #pragma unroll
             for (int j = 0; j < 7; ++j) {
@@ -335,7 +346,7 @@ bool fft2_supported(int H, int W) {
 
 int launch_rows2(bool est, const float* img, float* gray, float* gx, unsigned* stats, int nimg, int C,
                  int H, int W, const Fft2Plan& planW, const float2* twW, const float* omegaW,
-                 cudaStream_t stream) {
+                 const float* qrange, cudaStream_t stream) {
     int nb = pairs_for(W, 8, 64 * 1024);
     const int pairs_total = (H + 1) / 2;
     if (nb > pairs_total) nb = pairs_total;
@@ -345,10 +356,11 @@ int launch_rows2(bool est, const float* img, float* gray, float* gx, unsigned* s
     int rc;
     if (est) {
         if ((rc = set_smem2(k_rows2<true>, smem))) return rc;
-        k_rows2<true><<<grid, R2_THREADS, smem, stream>>>(img, gray, gx, stats, C, H, W, nb, planW, twW, omegaW);
+        k_rows2<true><<<grid, R2_THREADS, smem, stream>>>(img, gray, gx, stats, C, H, W, nb, planW, twW, omegaW, qrange);
     } else {
         if ((rc = set_smem2(k_rows2<false>, smem))) return rc;
-        k_rows2<false><<<grid, R2_THREADS, smem, stream>>>(img, gray, gx, stats, 1, H, W, nb, planW, twW, omegaW);
+        k_rows2<false><<<grid, R2_THREADS, smem, stream>>>(img, gray, gx, stats, 1, H, W, nb, planW, twW, omegaW,
+                                                           nullptr);
     }
     PB_LAUNCH_CHECK("k_rows2");
     return PB_OK;
@@ -356,7 +368,7 @@ int launch_rows2(bool est, const float* img, float* gray, float* gx, unsigned* s
 
 int launch_cols2(bool est, const float* plane_in, const float* gx, float* gy, unsigned* stats, int nimg,
                  int H, int W, const Fft2Plan& planH, const float2* twH, const float* omegaH,
-                 int discard_saturation, cudaStream_t stream) {
+                 int discard_saturation, const float* mask_src, cudaStream_t stream) {
     // 8 pairs = 16 columns = 64-byte row segments; fall back to fewer when H is very long
     int nb = pairs_for(H, 8, 200 * 1024);
     const int pairs_total = (W + 1) / 2;
@@ -371,7 +383,7 @@ int launch_cols2(bool est, const float* plane_in, const float* gx, float* gy, un
     do {                                                                                               \
         if ((rc = set_smem2(k_cols2<E, T>, smem))) return rc;                                          \
         k_cols2<E, T><<<grid, T, smem, stream>>>(plane_in, gx, gy, stats, H, W, nb, stride, planH, twH, \
-                                                 omegaH, discard_saturation);                          \
+                                                 omegaH, discard_saturation, mask_src);                \
     } while (0)
     if (est) {
         if (big) PB_LAUNCH_COLS2(true, 512); else PB_LAUNCH_COLS2(true, 256);

@@ -50,10 +50,15 @@ int launch_fft2_omega(float* omega, const Fft2Plan& plan, cudaStream_t stream);
 int launch_fft2_stage_tw(float2* stw, const Fft2Plan& plan, cudaStream_t stream);
 int launch_rows2(bool est, const float* img, float* gray, float* gx, unsigned* stats, int nimg, int C,
                  int H, int W, const Fft2Plan& planW, const float2* twW, const float* omegaW,
-                 cudaStream_t stream);
+                 const float* qrange, cudaStream_t stream);
 int launch_cols2(bool est, const float* plane_in, const float* gx, float* gy, unsigned* stats, int nimg,
                  int H, int W, const Fft2Plan& planH, const float2* twH, const float* omegaH,
-                 int discard_saturation, cudaStream_t stream);
+                 int discard_saturation, const float* mask_src, cudaStream_t stream);
+
+// quantile.cu (q > 0 range normalisation)
+size_t quantile_workspace_bytes(int B);
+int launch_quantile_range(const float* img, float* gray, int B, int C, int H, int W, double q, void* ws,
+                          float** qrange_out, cudaStream_t stream);
 
 // stages.cu (optional stages: prefilters, halo masking, edgetaper)
 int launch_bilateral(const float* img, float* out, int planes, int H, int W, float sigma_spatial,

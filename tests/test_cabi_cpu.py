@@ -72,9 +72,20 @@ def test_workspace_and_errors_without_gpu(lib):
     # argument validation happens before any CUDA call
     rc = lib.lib().pb_polyblur_f32(None, None, 1, 3, 8, 8, ctypes.byref(p), None, 0, None, None)
     assert rc == lib.PB_ERR_ARG and "in/out" in lib.last_error()
-    p.q = 0.01
+    # option validation: q outside [0, 0.5), both prefilters at once
+    p.q = 0.7
     rc = lib.lib().pb_polyblur_f32(None, None, 1, 3, 8, 8, ctypes.byref(p), None, 0, None, None)
-    assert rc == lib.PB_ERR_UNSUPPORTED
+    assert rc == lib.PB_ERR_ARG and "q must be" in lib.last_error()
+    p.q = 0.0
+    p.flags = lib.FLAG_PREFILTER | lib.FLAG_PREFILTER_RF
+    rc = lib.lib().pb_polyblur_f32(None, None, 1, 3, 8, 8, ctypes.byref(p), None, 0, None, None)
+    assert rc == lib.PB_ERR_ARG
+    # optional stages grow the workspace only when asked for
+    p.flags = 0
+    base = lib.lib().pb_workspace_bytes(4, 3, 120, 160, ctypes.byref(p))
+    p.flags = lib.FLAG_REMOVE_HALO | lib.FLAG_EDGETAPER | lib.FLAG_PREFILTER_RF
+    p.q = 1e-3
+    assert lib.lib().pb_workspace_bytes(4, 3, 120, 160, ctypes.byref(p)) > base + 6 * 4 * 3 * 120 * 160 * 4
 
 
 def test_no_cpu_fallback():

@@ -307,3 +307,25 @@ def test_options_vs_oracle_larger(pb, kw):
     ref = po.polyblur_deblurring(x, n_iter=2, alpha=6, beta=1, **kw)
     out = pb.polyblur_deblurring(cu(x), n_iter=2, alpha=6, beta=1, **kw)
     assert maxabs(out.cpu().numpy(), ref) < TOL_E2E
+
+
+def test_quantile_normalisation_golden(pb):
+    op = load("options.npz")
+    x = cu(op["in"][:1])
+    y = pb.polyblur_deblurring(x, n_iter=2, alpha=6, beta=1, q=1e-2)
+    assert maxabs(y.cpu().numpy(), op["q1e-2_b1"]) < TOL_E2E
+    y = pb.polyblur_deblurring(x, n_iter=2, alpha=6, beta=1, q=1e-2, remove_halo=True, edgetaping=True,
+                               prefiltering=True, discard_saturation=True)
+    assert maxabs(y.cpu().numpy(), op["all_b1"]) < TOL_E2E
+
+
+@pytest.mark.parametrize("q", [1e-4, 1e-2, 0.2])
+def test_quantile_estimates_vs_oracle(pb, q):
+    x = mosaic(3, 3, 180, 250, seed=12, sigma=(2.0, 1.0), theta_deg=20.0)
+    x[1] = np.clip(x[1] * 1.3 - 0.1, 0, 1)            # saturated pixels at both ends
+    tr = []
+    po.gaussian_blur_estimation(x, c=0.352, b=0.768, q=q, trace=tr)
+    e = pb.blur_estimation.estimate_parameters(cu(x), c=0.352, b=0.768, q=q)
+    np.testing.assert_allclose(e["mags"].cpu().numpy(), tr[0]["mags"], rtol=3e-5, atol=3e-6)
+    assert np.array_equal(e["theta_deg"].cpu().numpy().astype(np.int64), tr[0]["theta_deg"])
+    np.testing.assert_allclose(e["sigma"].cpu().numpy(), tr[0]["sigma"], rtol=1e-4)
