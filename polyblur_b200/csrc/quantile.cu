@@ -130,7 +130,7 @@ int launch_quantile_range(const float* img, float* gray, int B, int C, int H, in
     unsigned* hist = reinterpret_cast<unsigned*>(base + align_up((size_t)B * sizeof(QState), 256));
     float* qrange = reinterpret_cast<float*>(base + align_up((size_t)B * sizeof(QState), 256) +
                                              align_up((size_t)B * Q_TARGETS * Q_BINS * sizeof(unsigned), 256));
-    // ranks exactly as torch.quantile / the oracle: pos = fl32(q) * fl32(n - 1), floor, ceil, fraction in fp32
+    // ranks exactly as torch.quantile forms them: pos = fl32(q) * fl32(n - 1), floor, ceil, fraction in fp32
     auto ranks = [&](double qq, unsigned* lo, unsigned* hi, float* frac) {
         const float pos = (float)qq * (float)(plane - 1);
         const float fl = floorf(pos);
