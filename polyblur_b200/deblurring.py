@@ -105,6 +105,8 @@ def polyblur_deblurring(img, n_iter=1, c=0.352, b=0.768, alpha=2, beta=3, sigma_
     dev = _lib.require_cuda(x)
     src_device = x.device
     xd = x.detach()
+    if not xd.is_cuda and not flag_numpy and not return_estimates and xd.shape[0] >= 2:
+        return _polyblur_host_pipelined(xd, p, dev)
     if not xd.is_cuda and not flag_numpy:
         xd = xd.pin_memory() if not xd.is_pinned() and xd.numel() > (1 << 20) else xd
     xd = xd.to(dev, non_blocking=True).contiguous()
@@ -121,6 +123,59 @@ def polyblur_deblurring(img, n_iter=1, c=0.352, b=0.768, alpha=2, beta=3, sigma_
     if return_estimates:
         return out, est.to(src_device)
     return out
+
+
+def _polyblur_host_pipelined(x: torch.Tensor, p: "_lib.PbParams", dev: torch.device, max_chunks: int = 8):
+    """CPU tensor in -> CPU tensor out with the PCIe transfers hidden behind the kernels.
+
+    Images are independent, so the batch is cut into chunks that flow through three streams:
+    host->device copy of chunk k+1, the Polyblur kernels of chunk k and the device->host copy of
+    chunk k-1 run concurrently (the link is full duplex).  Results are identical to the one-shot
+    path; the only host synchronisation is the final one."""
+    B = x.shape[0]
+    x = x.contiguous()
+    if not x.is_pinned():
+        x = x.pin_memory()
+    n_chunks = min(max_chunks, B)
+    bounds = [(B * k) // n_chunks for k in range(n_chunks + 1)]
+    host = torch.empty(x.shape, dtype=torch.float32, pin_memory=True)
+    with torch.cuda.device(dev):
+        s_in, s_run, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        start = torch.cuda.current_stream(dev).record_event()
+        for st in (s_in, s_run, s_out):
+            st.wait_event(start)
+        biggest = max(b - a for a, b in zip(bounds, bounds[1:]))
+        Cn, H, W = x.shape[1:]
+        # two device input / output buffers (double buffering); one workspace, reused in stream order
+        xin = [torch.empty(biggest, Cn, H, W, dtype=torch.float32, device=dev) for _ in range(2)]
+        yout = [torch.empty(biggest, Cn, H, W, dtype=torch.float32, device=dev) for _ in range(2)]
+        ws = _lib.workspace(biggest, Cn, H, W, p, dev)
+        free_in = [None, None]      # event: the kernels that read xin[i] are done
+        free_out = [None, None]     # event: the copy that read yout[i] is done
+        for k, (a, b) in enumerate(zip(bounds, bounds[1:])):
+            i = k & 1
+            n = b - a
+            with torch.cuda.stream(s_in):
+                if free_in[i] is not None:
+                    s_in.wait_event(free_in[i])
+                xin[i][:n].copy_(x[a:b], non_blocking=True)
+                loaded = s_in.record_event()
+            with torch.cuda.stream(s_run):
+                s_run.wait_event(loaded)
+                if free_out[i] is not None:
+                    s_run.wait_event(free_out[i])
+                rc = _lib.lib().pb_polyblur_f32(xin[i].data_ptr(), yout[i].data_ptr(), n, Cn, H, W, C.byref(p),
+                                                ws.data_ptr(), ws.numel(), None, s_run.cuda_stream)
+                _lib.check(rc, "pb_polyblur_f32")
+                done = s_run.record_event()
+                free_in[i] = done
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(done)
+                host[a:b].copy_(yout[i][:n], non_blocking=True)
+                free_out[i] = s_out.record_event()
+        s_out.synchronize()
+        s_run.synchronize()
+    return host
 
 
 def inverse_filtering_rank3(img, kernel, alpha=2, b=4, correlate=False, remove_halo=False,
@@ -162,8 +217,12 @@ class PolyblurDeblurring(nn.Module):
     """nn.Module wrapper with the reference's constructor and forward signature
     (polyblur/deblurring.py:250-347).  No parameters, no buffers.
 
-    ``patch_decomposition=True`` raises NameError in the reference; here it
-    raises NotImplementedError until the patch path is built.
+    ``patch_decomposition=True`` (spatially varying blur: every patch gets its own estimate,
+    Kaiser-window overlap-add, deblurring.py:269-340) raises NameError in the reference
+    (``handling_saturation`` is undefined) and its overlap-add indexing is only
+    right for an image batch of 1.  Here the intended flow is implemented for any batch: patches
+    are cut on the device, deblurred ``batch_size`` patch positions at a time by the CUDA engine,
+    and blended on the device.
     """
 
     def __init__(self, patch_decomposition=False, patch_size=400, patch_overlap=0.25, batch_size=1):
@@ -177,13 +236,75 @@ class PolyblurDeblurring(nn.Module):
                 sigma_r=0.4, q=0.0, n_angles=6, n_interpolated_angles=30, remove_halo=False,
                 edgetaping=False, prefiltering=False, discard_saturation=False, multichannel_kernel=False,
                 method='fft', device=None):
-        if self.patch_decomposition:
-            raise NotImplementedError("patch_decomposition is not built yet (it raises NameError in the reference)")
+        kw = dict(n_iter=n_iter, c=c, b=b, alpha=alpha, beta=beta, ker_size=ker_size, sigma_s=sigma_s,
+                  sigma_r=sigma_r, remove_halo=remove_halo, edgetaping=edgetaping, prefiltering=prefiltering,
+                  discard_saturation=discard_saturation, multichannel_kernel=multichannel_kernel, method=method,
+                  q=q, n_angles=n_angles, n_interpolated_angles=n_interpolated_angles)
         if device is not None and isinstance(images, torch.Tensor):
             images = images.to(device)
-        return polyblur_deblurring(images, n_iter=n_iter, c=c, b=b, alpha=alpha, beta=beta, ker_size=ker_size,
-                                   sigma_s=sigma_s, sigma_r=sigma_r, remove_halo=remove_halo,
-                                   edgetaping=edgetaping, prefiltering=prefiltering,
-                                   discard_saturation=discard_saturation,
-                                   multichannel_kernel=multichannel_kernel, method=method, q=q,
-                                   n_angles=n_angles, n_interpolated_angles=n_interpolated_angles)
+        if not self.patch_decomposition:
+            return polyblur_deblurring(images, **kw)
+        if not isinstance(images, torch.Tensor) or images.ndim != 4:
+            raise ValueError("patch decomposition expects a (B,C,H,W) tensor")
+        if images.dtype != torch.float32:
+            raise TypeError(f"float32 only (got {images.dtype}), like the reference")
+        src_device = images.device
+        dev = _lib.require_cuda(images)
+        x = images.detach().to(dev)
+        ph, pw = self.patch_size
+        # even dimensions (:273-279), replicate pad to a whole number of steps (:282-287)
+        h, w = x.shape[-2:]
+        if h % 2 == 1:
+            x = x[..., :-1, :]
+            h -= 1
+        if w % 2 == 1:
+            x = x[..., :, :-1]
+            w -= 1
+        step_h = int(ph * (1 - self.patch_overlap))
+        step_w = int(pw * (1 - self.patch_overlap))
+        new_h = int(np.ceil((h - ph) / step_h) * step_h) + ph
+        new_w = int(np.ceil((w - pw) / step_w) * step_w) + pw
+        padded = self.pad_with_new_size(x, (new_h, new_w), mode='replicate')
+        H2, W2 = padded.shape[-2:]
+        coords = [(i0, j0) for i0 in range(0, H2 - ph + 1, step_h) for j0 in range(0, W2 - pw + 1, step_w)]
+        window = self.build_window((ph, pw), 'kaiser').to(dev)[None, None]
+        restored = torch.zeros_like(padded)
+        window_sum = torch.zeros(1, 1, H2, W2, device=dev)
+        nimg = x.shape[0]
+        for m in range(0, len(coords), max(1, self.batch_size)):
+            chunk = coords[m:m + max(1, self.batch_size)]
+            patches = torch.cat([padded[..., i0:i0 + ph, j0:j0 + pw] for (i0, j0) in chunk], dim=0).contiguous()
+            out = polyblur_deblurring(patches, **kw)
+            for n, (i0, j0) in enumerate(chunk):
+                restored[..., i0:i0 + ph, j0:j0 + pw] += out[n * nimg:(n + 1) * nimg] * window
+                window_sum[..., i0:i0 + ph, j0:j0 + pw] += window
+        restored = (restored / (window_sum + 1e-8)).clamp(0.0, 1.0)
+        restored = self.crop_with_old_size(restored, (h, w))
+        return restored.contiguous().to(src_device)
+
+    def build_window(self, image_size, window_type='kaiser'):
+        """Separable 2-D window (deblurring.py:349-366)."""
+        H, W = image_size
+        makers = {'kaiser': lambda n: torch.kaiser_window(n, beta=5, periodic=True),
+                  'hann': lambda n: torch.hann_window(n, periodic=True),
+                  'hamming': lambda n: torch.hamming_window(n, periodic=True),
+                  'bartlett': lambda n: torch.bartlett_window(n, periodic=True)}
+        if window_type not in makers:
+            raise ValueError(f"window {window_type!r} not implemented")
+        return makers[window_type](H).unsqueeze(-1) * makers[window_type](W).unsqueeze(0)
+
+    def pad_with_new_size(self, img, new_size, mode='constant'):
+        """Centre pad to new_size (deblurring.py:368-377)."""
+        h, w = img.shape[-2:]
+        new_h, new_w = new_size
+        padding = [int(np.floor((new_w - w) / 2)), int(np.ceil((new_w - w) / 2)),
+                   int(np.floor((new_h - h) / 2)), int(np.ceil((new_h - h) / 2))]
+        return torch.nn.functional.pad(img, padding, mode=mode)
+
+    def crop_with_old_size(self, img, old_size):
+        """Inverse of pad_with_new_size (deblurring.py:379-394)."""
+        h, w = img.shape[-2:]
+        old_h, old_w = old_size
+        left, right = int(np.floor((w - old_w) / 2)), int(np.ceil((w - old_w) / 2))
+        top, bottom = int(np.floor((h - old_h) / 2)), int(np.ceil((h - old_h) / 2))
+        return img[..., top:h - bottom, left:w - right]

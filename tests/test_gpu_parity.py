@@ -329,3 +329,31 @@ def test_quantile_estimates_vs_oracle(pb, q):
     np.testing.assert_allclose(e["mags"].cpu().numpy(), tr[0]["mags"], rtol=3e-5, atol=3e-6)
     assert np.array_equal(e["theta_deg"].cpu().numpy().astype(np.int64), tr[0]["theta_deg"])
     np.testing.assert_allclose(e["sigma"].cpu().numpy(), tr[0]["sigma"], rtol=1e-4)
+
+
+def test_patch_decomposition_vs_oracle(pb):
+    """The intended patch flow of PolyblurDeblurring.forward (deblurring.py:269-340; broken
+    upstream): per-patch estimates, Kaiser overlap-add, any image batch."""
+    x = mosaic(2, 3, 151, 200, seed=21, sigma=(1.8, 0.9), theta_deg=35.0)        # odd height -> made even
+    mod = pb.PolyblurDeblurring(patch_decomposition=True, patch_size=64, patch_overlap=0.25, batch_size=3)
+    got = mod(cu(x), n_iter=2, alpha=6, beta=1, b=0.768).cpu().numpy()
+    # numpy restatement with the CPU oracle per patch
+    xe = x[..., :150, :]
+    ph = pw = 64
+    st = int(ph * 0.75)
+    new_h = int(np.ceil((150 - ph) / st) * st) + ph
+    new_w = int(np.ceil((200 - pw) / st) * st) + pw
+    pt, pl = (new_h - 150) // 2, (new_w - 200) // 2
+    padded = np.pad(xe, ((0, 0), (0, 0), (pt, new_h - 150 - pt), (pl, new_w - 200 - pl)), mode="edge")
+    win = (torch.kaiser_window(ph, beta=5, periodic=True)[:, None] *
+           torch.kaiser_window(pw, beta=5, periodic=True)[None, :]).numpy()
+    acc = np.zeros_like(padded)
+    wsum = np.zeros(padded.shape[-2:], np.float32)
+    for i0 in range(0, new_h - ph + 1, st):
+        for j0 in range(0, new_w - pw + 1, st):
+            r = po.polyblur_deblurring(padded[..., i0:i0 + ph, j0:j0 + pw], n_iter=2, alpha=6, beta=1, b=0.768)
+            acc[..., i0:i0 + ph, j0:j0 + pw] += r * win
+            wsum[i0:i0 + ph, j0:j0 + pw] += win
+    ref = np.clip(acc / (wsum + 1e-8), 0, 1)[..., pt:pt + 150, pl:pl + 200]
+    assert got.shape == ref.shape
+    assert maxabs(got, ref) < 2e-5
