@@ -12,7 +12,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpolyblur_sm100.so")
+# PB_LIB_PATH selects another build of the same library (kernel tuning experiments only)
+LIB_PATH = os.environ.get("PB_LIB_PATH") or os.path.join(_HERE, "libpolyblur_sm100.so")
 
 PB_EST_STRIDE = 12
 PB_OK, PB_ERR_ARG, PB_ERR_WORKSPACE, PB_ERR_CUDA, PB_ERR_UNSUPPORTED = 0, -1, -2, -3, -4

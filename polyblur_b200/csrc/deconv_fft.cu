@@ -79,6 +79,9 @@ __global__ void k_fft2_perm(int* __restrict__ slot_of_freq, int* __restrict__ fr
 }
 
 #define FFTD_THREADS 256
+#ifndef PB_FFTD_MINB
+#define PB_FFTD_MINB 3      // resident CTAs per SM (see estimate2.cu)
+#endif
 
 // extended coordinate (any torus of length >= n + 6 pad) -> source index, or -1 for the zero fill
 //   n = image length, ext = 3 x kernel half-size (reach of the composite filter), and the source
@@ -93,7 +96,7 @@ __device__ __forceinline__ int ext_src(int i, int n, int ext, int n_in, int off,
 // ---------------------------------------------------------------------------------------------
 // P1: rows forward.  Work item = (slot in the FFT class list, channel, block of nb row pairs).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(FFTD_THREADS)
+__global__ void __launch_bounds__(FFTD_THREADS, PB_FFTD_MINB)
 k_fft_rows_fwd(const float* __restrict__ img, float2* __restrict__ Z, const ImgKernel* __restrict__ kern,
                const int* __restrict__ list, const int* __restrict__ count, int C, int H, int W, int NX, int NY,
                int nb, Fft2Plan planX, const float2* __restrict__ twX, const int* __restrict__ slotX, SrcGeom G) {
@@ -227,7 +230,7 @@ k_fft_rows_fwd(const float* __restrict__ img, float2* __restrict__ Z, const ImgK
 //                  | R[CB+1][13] float2 | mbarrier
 //   Leaves r = DFT(swap(Y)) in Z: the inverse transform is swap(r), P3 swaps while loading.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(FFTD_THREADS)
+__global__ void __launch_bounds__(FFTD_THREADS, PB_FFTD_MINB)
 k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int* __restrict__ list,
            const int* __restrict__ count, int C, int NX, int NY, int CB, Fft2Plan planY,
            const float2* __restrict__ twX, const float2* __restrict__ stwY, const int* __restrict__ slotY,
@@ -362,7 +365,7 @@ k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int
 // ---------------------------------------------------------------------------------------------
 // P3: rows inverse.  Work item = (slot, channel, block of nb row pairs that hold output rows).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(FFTD_THREADS)
+__global__ void __launch_bounds__(FFTD_THREADS, PB_FFTD_MINB)
 k_fft_rows_inv(const float2* __restrict__ Z, float* __restrict__ out, const ImgKernel* __restrict__ kern,
                const int* __restrict__ list, const int* __restrict__ count, int C, int H, int W, int NX, int NY,
                int nb, Fft2Plan planX, const float2* __restrict__ twX, const int* __restrict__ slotX,

@@ -33,9 +33,12 @@ struct NarrowCfg {
 };
 
 #define NARROW_THREADS 128
+#ifndef PB_NARROW_MINB
+#define PB_NARROW_MINB 4    // 3x3 kernel: 4 CTAs x 4 warps at <= 128 registers
+#endif
 
 template <int RX, int RY>
-__global__ void __launch_bounds__(NARROW_THREADS)
+__global__ void __launch_bounds__(NARROW_THREADS, (RX == 1 ? PB_NARROW_MINB : 1))
 k_deconv_narrow(const float* __restrict__ img, float* __restrict__ out, const ImgKernel* __restrict__ kern,
                 const int* __restrict__ list, const int* __restrict__ count, int C, int H, int W, int TH,
                 float a3, float a2, float a1, float b0, SrcGeom G) {

@@ -45,9 +45,14 @@ __global__ void k_fft2_stage_tw(float2* __restrict__ stw, Fft2Plan plan) {
 }
 
 #define R2_THREADS 256
+// resident CTAs per SM the register allocation aims for (3 x 256 threads at <= 85 registers;
+// measured: 2 CTAs at 128 registers is 2x slower, 4 CTAs do not fit the shared memory)
+#ifndef PB_R2_MINB
+#define PB_R2_MINB 3
+#endif
 
 template <bool EST>
-__global__ void __launch_bounds__(R2_THREADS)
+__global__ void __launch_bounds__(R2_THREADS, PB_R2_MINB)
 k_rows2(const float* __restrict__ img, float* __restrict__ gray, float* __restrict__ gx,
         unsigned* __restrict__ stats, int C, int H, int W, int nb, Fft2Plan plan,
         const float2* __restrict__ tw, const float* __restrict__ omega, const float* __restrict__ qrange) {
@@ -176,7 +181,7 @@ k_rows2(const float* __restrict__ img, float* __restrict__ gray, float* __restri
 }
 
 template <bool EST, int THREADS>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, (THREADS == 256 ? PB_R2_MINB : 1))
 k_cols2(const float* __restrict__ plane_in, const float* __restrict__ gx, float* __restrict__ gy,
         unsigned* __restrict__ stats, int H, int W, int nb, int stride, Fft2Plan plan,
         const float2* __restrict__ tw, const float* __restrict__ omega, int discard_saturation,
