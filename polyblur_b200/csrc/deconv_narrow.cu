@@ -23,12 +23,16 @@
 
 namespace pb {
 
+#ifndef PB_NARROW_PF
+#define PB_NARROW_PF 2       // window periods of prefetch for the 3x3 kernel
+#endif
+
 template <int RX, int RY>
 struct NarrowCfg {
     static constexpr int HL = (3 * RX + 3) / 4;       // halo lanes per side
     static constexpr int VW = 128 - 8 * HL;           // valid output columns per warp
     static constexpr int NW = 2 * RY + 1;             // rows in a rolling window
-    static constexpr int D = NW * (RY == 1 ? 2 : 1);  // prefetch distance (rows) = unroll period
+    static constexpr int D = NW * (RY == 1 ? PB_NARROW_PF : 1);  // prefetch distance (rows) = unroll period
     static constexpr int PW = 4 + 2 * RX;             // row segment a lane sees
 };
 
@@ -86,8 +90,14 @@ k_deconv_narrow(const float* __restrict__ img, float* __restrict__ out, const Im
 
         // Row j of the tile's input window (rows past the end repeat the last one: their results
         // are never stored, and an unconditional load keeps the row loop free of branches).
+        // Row j of the tile's input window (rows past the end repeat the last one: their results
+        // are never stored, and an unconditional load keeps the row loop free of branches).  Tiles
+        // whose window lies inside the source plane skip the torus map.
+        const int ytop = y0 - 3 * RY + G.off;
+        const bool rows_inside = ytop >= 0 && ytop + nsteps <= G.Hin;
         auto load_row = [&](int j) -> float4 {
-            const int sy = geom_src(y0 - 3 * RY + min(j, nsteps - 1), G.Hin, G.off, pad);
+            const int jj = min(j, nsteps - 1);
+            const int sy = rows_inside ? ytop + jj : geom_src(y0 - 3 * RY + jj, G.Hin, G.off, pad);
             const float* rp = src + (size_t)sy * G.Win;
             float4 v;
             if (fastx) {

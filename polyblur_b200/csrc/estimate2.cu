@@ -74,24 +74,56 @@ k_rows2(const float* __restrict__ img, float* __restrict__ gray, float* __restri
     if ((W & 3) == 0) {
         const int w4 = W >> 2;
         const float inv_w4 = 1.0f / (float)w4;
-        for (int idx = tid; idx < nb * w4; idx += R2_THREADS) {
-            const int p = fast_div(idx, w4, inv_w4);
-            const int x = (idx - p * w4) << 2;
-            float4 g[2];
+        // two row pairs per trip, every 128-bit load of the trip (2 rows x up to 3 channels x 2)
+        // issued before the first use
+        constexpr int CU = 3;                                   // channels unrolled for loads in flight
+        for (int base = tid; base < nb * w4; base += 2 * R2_THREADS) {
+            float4 t[2][2][CU];
+            int pp[2], xx[2];
+            bool ok[2][2];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int y = y0 + 2 * p + h;
-                g[h] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (y < H) {
-                    const float* q = src + (size_t)y * W + x;
-                    g[h] = __ldg(reinterpret_cast<const float4*>(q));
-                    if (EST) {
-                        for (int c = 1; c < C; ++c) {
-                            const float4 t = __ldg(reinterpret_cast<const float4*>(q + (size_t)c * plane));
-                            g[h].x = __fadd_rn(g[h].x, t.x);
-                            g[h].y = __fadd_rn(g[h].y, t.y);
-                            g[h].z = __fadd_rn(g[h].z, t.z);
-                            g[h].w = __fadd_rn(g[h].w, t.w);
+            for (int u = 0; u < 2; ++u) {
+                const int idx = base + u * R2_THREADS;
+                const bool live = idx < nb * w4;
+                pp[u] = live ? fast_div(idx, w4, inv_w4) : 0;
+                xx[u] = live ? (idx - pp[u] * w4) << 2 : 0;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int y = y0 + 2 * pp[u] + h;
+                    ok[u][h] = live && y < H;
+                    const float* q = src + (size_t)y * W + xx[u];
+#pragma unroll
+                    for (int c = 0; c < CU; ++c) {
+                        t[u][h][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (ok[u][h] && c < (EST ? C : 1))
+                            t[u][h][c] = __ldg(reinterpret_cast<const float4*>(q + (size_t)c * plane));
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (base + u * R2_THREADS >= nb * w4) continue;
+                float4 g[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    g[h] = t[u][h][0];
+                    if (EST && ok[u][h]) {
+                        const int y = y0 + 2 * pp[u] + h;
+#pragma unroll
+                        for (int c = 1; c < CU; ++c) {
+                            if (c < C) {
+                                g[h].x = __fadd_rn(g[h].x, t[u][h][c].x);
+                                g[h].y = __fadd_rn(g[h].y, t[u][h][c].y);
+                                g[h].z = __fadd_rn(g[h].z, t[u][h][c].z);
+                                g[h].w = __fadd_rn(g[h].w, t[u][h][c].w);
+                            }
+                        }
+                        for (int c = CU; c < C; ++c) {      // more than 3 channels: plain loop
+                            const float4 v = __ldg(reinterpret_cast<const float4*>(src + (size_t)c * plane + (size_t)y * W + xx[u]));
+                            g[h].x = __fadd_rn(g[h].x, v.x);
+                            g[h].y = __fadd_rn(g[h].y, v.y);
+                            g[h].z = __fadd_rn(g[h].z, v.z);
+                            g[h].w = __fadd_rn(g[h].w, v.w);
                         }
                         if (C > 1) {
                             g[h].x = __fdiv_rn(g[h].x, fC);
@@ -100,15 +132,15 @@ k_rows2(const float* __restrict__ img, float* __restrict__ gray, float* __restri
                             g[h].w = __fdiv_rn(g[h].w, fC);
                         }
                         if (qn) g[h] = make_float4(PB_QNORM(g[h].x), PB_QNORM(g[h].y), PB_QNORM(g[h].z), PB_QNORM(g[h].w));
-                        *reinterpret_cast<float4*>(gray + (size_t)im * plane + (size_t)y * W + x) = g[h];
+                        *reinterpret_cast<float4*>(gray + (size_t)im * plane + (size_t)y * W + xx[u]) = g[h];
                         lmin = fminf(lmin, fminf(fminf(g[h].x, g[h].y), fminf(g[h].z, g[h].w)));
                         lmax = fmaxf(lmax, fmaxf(fmaxf(g[h].x, g[h].y), fmaxf(g[h].z, g[h].w)));
                     }
                 }
+                float4* d = reinterpret_cast<float4*>(sm2 + (size_t)pp[u] * W + xx[u]);
+                d[0] = make_float4(g[0].x, g[1].x, g[0].y, g[1].y);
+                d[1] = make_float4(g[0].z, g[1].z, g[0].w, g[1].w);
             }
-            float4* d = reinterpret_cast<float4*>(sm2 + (size_t)p * W + x);
-            d[0] = make_float4(g[0].x, g[1].x, g[0].y, g[1].y);
-            d[1] = make_float4(g[0].z, g[1].z, g[0].w, g[1].w);
         }
     } else {
         const float inv_w = 1.0f / (float)W;
@@ -255,6 +287,7 @@ k_cols2(const float* __restrict__ plane_in, const float* __restrict__ gx, float*
     const float* gxp = gx + (size_t)im * plane;
     // saturation mask: un-normalised gray > 0.99 (blur_estimation.py:59, 83-88)
     const float* msk = (mask_src ? mask_src : plane_in) + (size_t)im * plane;
+#pragma unroll 4
     for (int idx = tid; idx < H * nb; idx += THREADS) {
         const int y = fast_div(idx, nb, inv_nb);
         const int p = idx - y * nb;
