@@ -89,8 +89,6 @@ k_deconv_narrow(const float* __restrict__ img, float* __restrict__ out, const Im
         for (int i = 0; i < 4; ++i) sx[i] = geom_src(cx + i, G.Win, G.off, pad);
 
         // Row j of the tile's input window (rows past the end repeat the last one: their results
-        // are never stored, and an unconditional load keeps the row loop free of branches).
-        // Row j of the tile's input window (rows past the end repeat the last one: their results
         // are never stored, and an unconditional load keeps the row loop free of branches).  Tiles
         // whose window lies inside the source plane skip the torus map.
         const int ytop = y0 - 3 * RY + G.off;
@@ -114,6 +112,10 @@ k_deconv_narrow(const float* __restrict__ img, float* __restrict__ out, const Im
         float4 pre[D];
 #pragma unroll
         for (int u = 0; u < D; ++u) pre[u] = load_row(u);
+        // interior tiles (no torus map in either direction): the prefetch pointer just walks down
+        const bool walk = rows_inside && fastx;
+        const float* pl = src + (size_t)(walk ? ytop + D : 0) * G.Win + cx + G.off;
+        float* gs = dst + (size_t)y0 * W + cx;               // output row pointer, advanced once rows start
 
         float P[NW][PW], O1[NW][PW], O2[NW][PW], Q[NW][4];
 #pragma unroll
@@ -151,7 +153,12 @@ k_deconv_narrow(const float* __restrict__ img, float* __restrict__ out, const Im
             for (int u = 0; u < D; ++u) {
                 const int j = jb + u;
                 const float4 v = pre[u];
-                pre[u] = load_row(j + D);
+                if (walk) {
+                    if (j + D < nsteps) pre[u] = __ldg(reinterpret_cast<const float4*>(pl));
+                    pl += G.Win;
+                } else {
+                    pre[u] = load_row(j + D);
+                }
                 const int s0 = u % NW;                           // slot of input row j
                 P[s0][RX + 0] = v.x;
                 P[s0][RX + 1] = v.y;
@@ -174,7 +181,7 @@ k_deconv_narrow(const float* __restrict__ img, float* __restrict__ out, const Im
                     for (int cc = 0; cc < 4; ++cc) {
                         const float pv = P[s2][RX + cc];
                         O2[s2][RX + cc] = fmaf(a1, pv, acc[cc]);
-                        Q[s2][cc] = b0 * pv;
+                        Q[s2][cc] = pv;                          // b p is added by the last stage
                     }
                     NARROW_HALO(O2[s2]);
                 }
@@ -187,10 +194,10 @@ k_deconv_narrow(const float* __restrict__ img, float* __restrict__ out, const Im
                         float o[4];
 #pragma unroll
                         for (int cc = 0; cc < 4; ++cc) {
-                            o[cc] = acc[cc] + Q[s3][cc];
+                            o[cc] = fmaf(b0, Q[s3][cc], acc[cc]);
                             if (G.clamp_out) o[cc] = fminf(fmaxf(o[cc], 0.0f), 1.0f);
                         }
-                        float* g = dst + (size_t)(y0 + yo) * W + cx;
+                        float* g = gs;
                         if (vec_ok) {
                             *reinterpret_cast<float4*>(g) = make_float4(o[0], o[1], o[2], o[3]);
                         } else {
@@ -199,6 +206,7 @@ k_deconv_narrow(const float* __restrict__ img, float* __restrict__ out, const Im
                                 if (cx + cc < W) g[cc] = o[cc];
                         }
                     }
+                    if (yo >= 0) gs += W;
                 }
             }
         }
