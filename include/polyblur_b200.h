@@ -155,6 +155,14 @@ PB_API int pb_recursive_filter_f32(const float* img, const float* joint, float* 
                             int W, float sigma_s, float sigma_r, int num_iterations,
                             void* workspace, size_t workspace_bytes, void* stream);
 
+/* Domain-transform normalized convolution: the reference's native prototype
+ * normalized_convolution(I, sigma_s, sigma_r, num_iterations) (polyblur/domain_transform/NC.cpp:143-204,
+ * exported at :210), here for any batch size and channel count.
+ * Needs 2 * B*H*W*4 + 2 * B*C*H*W*4 bytes of workspace (+ 256-byte alignment slack per block). */
+PB_API int pb_normalized_convolution_f32(const float* img, float* out, int B, int C, int H, int W, float sigma_s,
+                                  float sigma_r, int num_iterations, void* workspace,
+                                  size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

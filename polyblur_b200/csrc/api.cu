@@ -640,4 +640,18 @@ int pb_recursive_filter_f32(const float* img, const float* joint, float* out, in
                                    workspace, (cudaStream_t)stream_);
 }
 
+int pb_normalized_convolution_f32(const float* img, float* out, int B, int C, int H, int W, float sigma_s,
+                                  float sigma_r, int num_iterations, void* workspace, size_t workspace_bytes,
+                                  void* stream_) {
+    int rc;
+    if ((rc = check_shape(B, C, H, W))) return rc;
+    if (!img || !out || img == out || num_iterations < 1) {
+        set_error("bad arguments to pb_normalized_convolution_f32");
+        return PB_ERR_ARG;
+    }
+    if ((rc = check_ws(workspace, workspace_bytes, nc_workspace_bytes(B, C, H, W)))) return rc;
+    return launch_normalized_convolution(img, out, B, C, H, W, (double)sigma_s, (double)sigma_r, num_iterations,
+                                         workspace, (cudaStream_t)stream_);
+}
+
 }  // extern "C"

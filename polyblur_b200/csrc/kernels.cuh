@@ -80,6 +80,11 @@ int launch_pad_replicate(const float* img, float* a, float* b, int planes, int H
 int launch_edgetaper_passes(float* a, float* b, const ImgKernel* kern, const float* v, int B, int C, int Hp, int Wp,
                             int n_tapers, float** result, cudaStream_t stream);
 
+// nc.cu (domain-transform normalized convolution)
+size_t nc_workspace_bytes(int B, int C, int H, int W);
+int launch_normalized_convolution(const float* img, float* out, int B, int C, int H, int W, double sigma_s,
+                                  double sigma_r, int num_iterations, void* ws, cudaStream_t stream);
+
 // deconv_narrow.cu
 int launch_deconv_narrow(int cls, const float* img, float* out, const ImgKernel* kern, const int* list,
                          const int* count, int B, int C, int H, int W, float a3, float a2, float a1, float b0,

@@ -30,3 +30,19 @@ def recursive_filter(I, sigma_s=60, sigma_r=0.4, num_iterations=3, joint_image=N
                                                 ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
         _lib.check(rc, "pb_recursive_filter_f32")
     return out.to(src)
+
+
+def normalized_convolution(I, sigma_s=60, sigma_r=0.4, num_iterations=3):
+    """Edge-aware smoothing with the normalized convolution (box filter in the transformed
+    domain): the reference's native prototype polyblur/domain_transform/NC.cpp:143-204, which
+    only handles one 3-channel image; any batch and channel count here."""
+    x, dev, src = _prep(I, "normalized_convolution")
+    B, C, H, W = x.shape
+    with torch.cuda.device(dev):
+        ws = torch.empty(2 * (B * H * W * 4 + 256) + 2 * (B * C * H * W * 4 + 256), dtype=torch.uint8, device=dev)
+        out = torch.empty_like(x)
+        rc = _lib.lib().pb_normalized_convolution_f32(x.data_ptr(), out.data_ptr(), B, C, H, W, float(sigma_s),
+                                                      float(sigma_r), int(num_iterations), ws.data_ptr(),
+                                                      ws.numel(), _lib.stream_ptr(dev))
+        _lib.check(rc, "pb_normalized_convolution_f32")
+    return out.to(src)

@@ -357,3 +357,16 @@ def test_patch_decomposition_vs_oracle(pb):
     ref = np.clip(acc / (wsum + 1e-8), 0, 1)[..., pt:pt + 150, pl:pl + 200]
     assert got.shape == ref.shape
     assert maxabs(got, ref) < 2e-5
+
+
+@pytest.mark.parametrize("shape,ss,sr,n", [((1, 3, 40, 56), 60, 0.4, 3), ((2, 3, 33, 71), 8.0, 0.5, 2),
+                                           ((1, 1, 64, 64), 2.0, 0.8, 1), ((2, 2, 50, 37), 20.0, 0.3, 1)])
+def test_normalized_convolution_vs_oracle(pb, shape, ss, sr, n):
+    """NC.cpp restatement (searchsorted form); sequential fp32 running sums on both
+    sides, so the window indices agree and the result is compared tightly."""
+    rng = np.random.default_rng(17)
+    x = rng.random(shape, dtype=np.float32)
+    x = np.clip(0.4 * x + 0.5 * np.round(x), 0, 1).astype(np.float32)
+    ref = po.normalized_convolution(x, ss, sr, n)
+    got = pb.domain_transform.normalized_convolution(cu(x), ss, sr, n).cpu().numpy()
+    assert maxabs(got, ref) < 5e-6

@@ -1,0 +1,80 @@
+#!/usr/bin/env python
+"""Condenses an Nsight Compute report (.ncu-rep, read with `ncu -i ... --page raw --csv`) into the
+per-launch table committed under profiles/ and, optionally, the DRAM traffic per kernel group that
+bench.py reports as roofline.traffic.
+
+    python tools/ncu_summary.py gpurun_out/x.ncu-rep profiles/r01_x.md [--traffic KEY profiles/roofline_traffic.json]
+"""
+import csv
+import json
+import subprocess
+import sys
+
+COLS = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram_rd"), ("dram__bytes_write.sum", "dram_wr"),
+        ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram%"),
+        ("l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex%"),
+        ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue%"),
+        ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps%"),
+        ("launch__registers_per_thread", "regs"), ("launch__shared_mem_per_block_dynamic", "smem/CTA"),
+        ("launch__grid_size", "grid"), ("smsp__inst_executed.sum", "warp_inst")]
+GROUPS = {"estimate": ("k_rows", "k_cols", "k_params"),
+          "deconvolution": ("k_deconv_narrow", "k_deconv_spatial", "k_fft_rows_fwd", "k_fft_cols", "k_fft_rows_inv")}
+
+
+def to_bytes(v, unit):
+    m = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    return float(v.replace(",", "")) * m.get(unit, 1)
+
+
+def main():
+    rep, out = sys.argv[1], sys.argv[2]
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, body = rows[0], rows[1], rows[2:]
+    idx = {h: i for i, h in enumerate(hdr)}
+    lines = ["| # | kernel | " + " | ".join(n for _, n in COLS) + " |", "|---|---|" + "---|" * len(COLS)]
+    traffic = {}
+    for n, r in enumerate(body):
+        name = r[idx["Kernel Name"]].split("(")[0].replace("void ", "").replace("pb::", "")
+        cells = []
+        for key, _ in COLS:
+            if key not in idx:
+                cells.append("-")
+                continue
+            v, u = r[idx[key]], units[idx[key]]
+            try:
+                f = float(v.replace(",", ""))
+                cells.append(f"{f:.4g} {u}".strip())
+            except ValueError:
+                cells.append(v)
+        lines.append(f"| {n} | `{name}` | " + " | ".join(cells) + " |")
+        by = to_bytes(r[idx["dram__bytes_read.sum"]], units[idx["dram__bytes_read.sum"]]) + \
+            to_bytes(r[idx["dram__bytes_write.sum"]], units[idx["dram__bytes_write.sum"]])
+        for g, members in GROUPS.items():
+            if any(name.startswith(m) for m in members):
+                traffic.setdefault(g, []).append((name, by))
+    with open(out, "w") as f:
+        f.write(f"Source: `{rep}` (`ncu --set full --clock-control none`; per-launch, cold-ish caches, serialised).\n\n")
+        f.write("\n".join(lines) + "\n")
+    if "--traffic" in sys.argv:
+        i = sys.argv.index("--traffic")
+        key_suffix, path = sys.argv[i + 1], sys.argv[i + 2]
+        try:
+            cur = json.load(open(path))
+        except Exception:
+            cur = {}
+        for g, items in traffic.items():
+            # one "launch" of a group = one Polyblur iteration: distinct kernels once each
+            seen, total = set(), 0.0
+            for name, by in items:
+                if name in seen:
+                    continue
+                seen.add(name)
+                total += by
+            cur[f"{g}:{key_suffix}"] = total
+        json.dump(cur, open(path, "w"), indent=1, sort_keys=True)
+    print("wrote", out)
+
+
+if __name__ == "__main__":
+    main()
