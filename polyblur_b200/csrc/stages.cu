@@ -17,31 +17,57 @@ namespace pb {
 __global__ void __launch_bounds__(256)
 k_bilateral(const float* __restrict__ img, float* __restrict__ out, int H, int W, float var2_spatial,
             float var2_color) {
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    __shared__ float gw[25];
+    if (threadIdx.x < 25) {
+        const int dy = threadIdx.x / 5 - 2, dx = threadIdx.x % 5 - 2;
+        gw[threadIdx.x] = expf(-(float)(dx * dx + dy * dy) / var2_spatial);      // (filters.py:110-112)
+    }
+    __syncthreads();
+    // one thread = 4 adjacent pixels of one row: the 5 x 8 window is loaded once
+    const int x0 = (blockIdx.x * 32 + (threadIdx.x & 31)) * 4;
     const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (x >= W || y >= H) return;
+    if (x0 >= W || y >= H) return;
     const size_t pl = (size_t)blockIdx.z * H * W;
     const float* p = img + pl;
-    const float I = __ldg(p + (size_t)y * W + x);
-    float J = 0.f, Wt = 0.f;
+    const float nic = -1.0f / var2_color;
+    float win[5][8];
 #pragma unroll
-    for (int dy = -2; dy <= 2; ++dy) {
-        const int yy = min(max(y + dy, 0), H - 1);
-        float jr = 0.f, wr = 0.f;
+    for (int dy = 0; dy < 5; ++dy) {
+        const float* row = p + (size_t)min(max(y + dy - 2, 0), H - 1) * W;
 #pragma unroll
-        for (int dx = -2; dx <= 2; ++dx) {
-            const int xx = min(max(x + dx, 0), W - 1);
-            const float S = __ldg(p + (size_t)yy * W + xx);
-            const float d = __fsub_rn(S, I);
-            const float gw = expf(-(float)(dx * dx + dy * dy) / var2_spatial);
-            const float F = __fmul_rn(expf(__fdiv_rn(-__fmul_rn(d, d), var2_color)), gw);
-            jr = __fadd_rn(jr, __fmul_rn(F, S));
-            wr = __fadd_rn(wr, F);
-        }
-        J = __fadd_rn(J, jr);
-        Wt = __fadd_rn(Wt, wr);
+        for (int i = 0; i < 8; ++i) win[dy][i] = __ldg(row + min(max(x0 + i - 2, 0), W - 1));
     }
-    out[pl + (size_t)y * W + x] = __fdiv_rn(J, __fadd_rn(Wt, 1e-5f));
+    float o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float I = win[2][k + 2];
+        float J = 0.f, Wt = 0.f;
+#pragma unroll
+        for (int dy = 0; dy < 5; ++dy) {
+            float jr = 0.f, wr = 0.f;
+#pragma unroll
+            for (int dx = 0; dx < 5; ++dx) {
+                const float S = win[dy][k + dx];
+                const float d = __fsub_rn(S, I);
+                // exp(-(d d) / var2) * gw: the hardware exponential is accurate to ~1e-7 relative for
+                // the arguments that matter (weights that are not negligible)
+                const float F = __fmul_rn(__expf(__fmul_rn(__fmul_rn(d, d), nic)), gw[dy * 5 + dx]);
+                jr = __fadd_rn(jr, __fmul_rn(F, S));
+                wr = __fadd_rn(wr, F);
+            }
+            J = __fadd_rn(J, jr);
+            Wt = __fadd_rn(Wt, wr);
+        }
+        o[k] = __fdiv_rn(J, __fadd_rn(Wt, 1e-5f));
+    }
+    float* g = out + pl + (size_t)y * W + x0;
+    if (((W & 3) == 0) && x0 + 3 < W) {
+        *reinterpret_cast<float4*>(g) = make_float4(o[0], o[1], o[2], o[3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (x0 + k < W) g[k] = o[k];
+    }
 }
 
 int launch_bilateral(const float* img, float* out, int planes, int H, int W, float sigma_spatial,
@@ -50,7 +76,7 @@ int launch_bilateral(const float* img, float* out, int planes, int H, int W, flo
         set_error("B*C = %d exceeds the grid z limit", planes);
         return PB_ERR_ARG;
     }
-    dim3 grid((W + 31) / 32, (H + 7) / 8, planes);
+    dim3 grid((W + 127) / 128, (H + 7) / 8, planes);
     ProfScope prof(PROF_OTHER, stream);
     k_bilateral<<<grid, 256, 0, stream>>>(img, out, H, W, 2.0f * sigma_spatial * sigma_spatial,
                                          2.0f * sigma_color * sigma_color);
@@ -62,10 +88,8 @@ int launch_bilateral(const float* img, float* out, int planes, int H, int W, flo
 // Domain-transform recursive filter (domain_transform.py:6-85).
 //   k_rf_weights : Vh = a^(1 + s dIdx), Vv = a^(1 + s dIdy), dId* = L1 over channels of the forward
 //                  differences of the joint image (0 at the first column / row)        (:27-38,55,59)
-//   k_rf_rows    : per row and channel, left->right then right->left first-order recurrence (:78-83).
-//                  One warp per row: every lane owns a contiguous chunk, composes its affine map,
-//                  a warp-shuffle scan gives each lane its carry-in, and the lane then replays the
-//                  reference's own update formula on its chunk.
+//   k_rf_rows    : per row and channel, left->right then right->left first-order recurrence (:78-83),
+//                  one lane per row, tiles transposed through shared memory.
 //   k_rf_cols    : the same recurrence down the columns, one thread per column (coalesced).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -87,96 +111,101 @@ k_rf_weights(const float* __restrict__ joint, float* __restrict__ Vh, float* __r
     Vv[o] = powf(a, __fadd_rn(1.0f, __fmul_rn(ratio, dy)));
 }
 
+// One warp = 32 consecutive rows of one plane, lane = row.  The rows are walked in tiles of 32
+// columns: the tile of F and of V is transposed through shared memory (coalesced 128-byte global
+// accesses, conflict-free 33-float pitch), every lane runs the reference's update on its row's 32
+// samples with the carry in a register, and the tile is written back.  Left -> right sweep, then
+// right -> left.
 #define RF_ROW_WARPS 4
 
 __global__ void __launch_bounds__(RF_ROW_WARPS * 32)
-k_rf_rows(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ Vh, int C, int H, int W,
-          int chunk, int rows_total) {
-    extern __shared__ float rfs[];
+k_rf_rows(const float* in, float* out, const float* __restrict__ Vh, int C, int H, int W,
+          int groups_per_plane, int groups_total) {   // in may alias out (iterations >= 2)
+    __shared__ float tf[RF_ROW_WARPS][32][33];
+    __shared__ float tv[RF_ROW_WARPS][32][33];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int cs = chunk | 1;                           // odd stride: lanes hit different banks
-    float* Vs = rfs + (size_t)warp * 2 * 32 * cs;
-    float* Fs = Vs + 32 * cs;
-    const int row = blockIdx.x * RF_ROW_WARPS + warp;    // (image, y)
-    if (row >= rows_total) return;
-    const int b = row / H, y = row - b * H;
+    const int grp = blockIdx.x * RF_ROW_WARPS + warp;
+    if (grp >= groups_total) return;
+    const int pl = grp / groups_per_plane;               // image * C + channel
+    const int y0 = (grp - pl * groups_per_plane) * 32;
     const size_t plane = (size_t)H * W;
-    const float* vrow = Vh + (size_t)b * plane + (size_t)y * W;
-    for (int x = lane; x < W; x += 32) Vs[(x / chunk) * cs + (x % chunk)] = __ldg(vrow + x);
-    const int x0 = lane * chunk, x1 = min(x0 + chunk, W);
-    for (int c = 0; c < C; ++c) {
-        const float* frow = in + ((size_t)b * C + c) * plane + (size_t)y * W;
-        float* orow = out + ((size_t)b * C + c) * plane + (size_t)y * W;
+    const float* f_in = in + (size_t)pl * plane;
+    float* f_out = out + (size_t)pl * plane;
+    const float* v = Vh + (size_t)(pl / C) * plane;
+    float (*F)[33] = tf[warp];
+    float (*V)[33] = tv[warp];
+    const int nrows = min(32, H - y0);
+    const int ntiles = (W + 31) / 32;
+    // tile load: 8 rows of F and V in flight per lane before the first shared-memory store
+#define RF_LOAD_TILE(SRC)                                                           \
+    for (int r0 = 0; r0 < nrows; r0 += 8) {                                         \
+        float a_[8], b_[8];                                                         \
+        const int x = x0 + lane;                                                    \
+        _Pragma("unroll") for (int u = 0; u < 8; ++u) {                             \
+            const int r = min(r0 + u, nrows - 1);                                   \
+            const size_t o = (size_t)(y0 + r) * W + min(x, W - 1);                  \
+            a_[u] = (SRC)[o];                                                       \
+            b_[u] = __ldg(v + o);                                                   \
+        }                                                                           \
+        _Pragma("unroll") for (int u = 0; u < 8; ++u) {                             \
+            if (r0 + u < nrows) {                                                   \
+                F[r0 + u][lane] = a_[u];                                            \
+                V[r0 + u][lane] = b_[u];                                            \
+            }                                                                       \
+        }                                                                           \
+    }
+    // ---- left -> right:  F[x] += V[x] (F[x-1] - F[x]),  x >= 1
+    float carry = 0.f;
+    for (int t = 0; t < ntiles; ++t) {
+        const int x0 = t * 32;
+        RF_LOAD_TILE(f_in);
         __syncwarp();
-        for (int x = lane; x < W; x += 32) Fs[(x / chunk) * cs + (x % chunk)] = __ldg(frow + x);
-        __syncwarp();
-        float* f = Fs + lane * cs;
-        const float* v = Vs + lane * cs;
-        // ---- left -> right:  F[i] += V[i] (F[i-1] - F[i]),  i >= 1
-        float A = 1.f, Bc = 0.f;
-        for (int x = x0; x < x1; ++x) {
-            const float a = (x == 0) ? 0.f : v[x - x0];
-            const float bb = (x == 0) ? f[0] : (1.f - a) * f[x - x0];
-            A = a * A;
-            Bc = fmaf(a, Bc, bb);
-        }
-        // inclusive scan of the affine maps over the lanes
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const float Ap = __shfl_up_sync(0xffffffffu, A, o);
-            const float Bp = __shfl_up_sync(0xffffffffu, Bc, o);
-            if (lane >= o) {
-                Bc = fmaf(A, Bp, Bc);
-                A = A * Ap;
+        if (lane < nrows) {
+            const int n = min(32, W - x0);
+#pragma unroll 8
+            for (int i = 0; i < n; ++i) {
+                float cur = F[lane][i];
+                if (x0 + i > 0) cur = __fadd_rn(cur, __fmul_rn(V[lane][i], __fsub_rn(carry, cur)));
+                F[lane][i] = cur;
+                carry = cur;
             }
         }
-        float carry = __shfl_up_sync(0xffffffffu, Bc, 1);      // value at the end of the previous chunk
-        for (int x = x0; x < x1; ++x) {
-            float cur = f[x - x0];
-            if (x > 0) cur = __fadd_rn(cur, __fmul_rn(v[x - x0], __fsub_rn(carry, cur)));
-            f[x - x0] = cur;
-            carry = cur;
+        __syncwarp();
+        for (int r = 0; r < nrows; ++r) {
+            const int x = x0 + lane;
+            if (x < W) f_out[(size_t)(y0 + r) * W + x] = F[r][lane];
         }
         __syncwarp();
-        // ---- right -> left:  F[i] += V[i+1] (F[i+1] - F[i]),  i <= W-2
-        A = 1.f;
-        Bc = 0.f;
-        for (int x = x1 - 1; x >= x0; --x) {
-            const bool last = (x == W - 1);
-            const float a = last ? 0.f : ((x + 1 < x1) ? v[x + 1 - x0] : Vs[(lane + 1) * cs]);
-            const float bb = last ? f[x - x0] : (1.f - a) * f[x - x0];
-            A = a * A;
-            Bc = fmaf(a, Bc, bb);
-        }
-        const bool active = x0 < W;
-        if (!active) {
-            A = 1.f;
-            Bc = 0.f;
-        }
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const float An = __shfl_down_sync(0xffffffffu, A, o);
-            const float Bn = __shfl_down_sync(0xffffffffu, Bc, o);
-            if (lane + o < 32) {
-                Bc = fmaf(A, Bn, Bc);
-                A = A * An;
+    }
+    // ---- right -> left:  F[x] += V[x+1] (F[x+1] - F[x]),  x <= W-2   (reads the sweep above back)
+    float vnext = 0.f;                                    // V[x+1] of the sample just processed
+    for (int t = ntiles - 1; t >= 0; --t) {
+        const int x0 = t * 32;
+        RF_LOAD_TILE(f_out);
+        __syncwarp();
+        if (lane < nrows) {
+            const int n = min(32, W - x0);
+#pragma unroll 8
+            for (int i = n - 1; i >= 0; --i) {
+                float cur = F[lane][i];
+                if (x0 + i < W - 1) cur = __fadd_rn(cur, __fmul_rn(vnext, __fsub_rn(carry, cur)));
+                F[lane][i] = cur;
+                carry = cur;
+                vnext = V[lane][i];
             }
-        }
-        carry = __shfl_down_sync(0xffffffffu, Bc, 1);          // value at the start of the next chunk
-        for (int x = x1 - 1; x >= x0; --x) {
-            float cur = f[x - x0];
-            if (x < W - 1) {
-                const float a = (x + 1 < x1) ? v[x + 1 - x0] : Vs[(lane + 1) * cs];
-                cur = __fadd_rn(cur, __fmul_rn(a, __fsub_rn(carry, cur)));
-            }
-            f[x - x0] = cur;
-            carry = cur;
         }
         __syncwarp();
-        for (int x = lane; x < W; x += 32) orow[x] = Fs[(x / chunk) * cs + (x % chunk)];
+        for (int r = 0; r < nrows; ++r) {
+            const int x = x0 + lane;
+            if (x < W) f_out[(size_t)(y0 + r) * W + x] = F[r][lane];
+        }
+        __syncwarp();
     }
 }
 
+#undef RF_LOAD_TILE
+
+// the same recurrence down the columns, one thread per column (coalesced); loads run 8 rows ahead
 __global__ void __launch_bounds__(128)
 k_rf_cols(float* __restrict__ img, const float* __restrict__ Vv, int C, int H, int W) {
     const int x = blockIdx.x * 128 + threadIdx.x;
@@ -185,18 +214,42 @@ k_rf_cols(float* __restrict__ img, const float* __restrict__ Vv, int C, int H, i
     const size_t plane = (size_t)H * W;
     float* f = img + (size_t)pl * plane + x;
     const float* v = Vv + (size_t)(pl / C) * plane + x;
+    constexpr int U = 8;
     float prev = f[0];
-    for (int y = 1; y < H; ++y) {
-        float cur = f[(size_t)y * W];
-        cur = __fadd_rn(cur, __fmul_rn(__ldg(v + (size_t)y * W), __fsub_rn(prev, cur)));
-        f[(size_t)y * W] = cur;
-        prev = cur;
+    for (int y0 = 1; y0 < H; y0 += U) {
+        float cf[U], cv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int y = min(y0 + u, H - 1);
+            cf[u] = f[(size_t)y * W];
+            cv[u] = __ldg(v + (size_t)y * W);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (y0 + u < H) {
+                const float cur = __fadd_rn(cf[u], __fmul_rn(cv[u], __fsub_rn(prev, cf[u])));
+                f[(size_t)(y0 + u) * W] = cur;
+                prev = cur;
+            }
+        }
     }
-    for (int y = H - 2; y >= 0; --y) {
-        float cur = f[(size_t)y * W];
-        cur = __fadd_rn(cur, __fmul_rn(__ldg(v + (size_t)(y + 1) * W), __fsub_rn(prev, cur)));
-        f[(size_t)y * W] = cur;
-        prev = cur;
+    // bottom -> top: F[y] += V[y+1] (F[y+1] - F[y])
+    for (int y0 = H - 2; y0 >= 0; y0 -= U) {
+        float cf[U], cv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int y = max(y0 - u, 0);
+            cf[u] = f[(size_t)y * W];
+            cv[u] = __ldg(v + (size_t)(y + 1) * W);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (y0 - u >= 0) {
+                const float cur = __fadd_rn(cf[u], __fmul_rn(cv[u], __fsub_rn(prev, cf[u])));
+                f[(size_t)(y0 - u) * W] = cur;
+                prev = cur;
+            }
+        }
     }
 }
 
@@ -212,13 +265,6 @@ int launch_recursive_filter(const float* in, const float* joint, float* out, int
     const size_t plane = (size_t)H * W;
     float* Vh = static_cast<float*>(ws);
     float* Vv = reinterpret_cast<float*>(static_cast<char*>(ws) + align_up((size_t)B * plane * sizeof(float), 256));
-    const int chunk = (W + 31) / 32;
-    const size_t smem = (size_t)RF_ROW_WARPS * 2 * 32 * (chunk | 1) * sizeof(float);
-    if (smem > PB_SMEM_MAX - 1024) {
-        set_error("row of %d pixels does not fit the recursive filter's shared memory", W);
-        return PB_ERR_UNSUPPORTED;
-    }
-    PB_CUDA_TRY(cudaFuncSetAttribute(k_rf_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ProfScope prof(PROF_OTHER, stream);
     const float* cur = in;
     for (int i = 0; i < num_iterations; ++i) {
@@ -228,9 +274,10 @@ int launch_recursive_filter(const float* in, const float* joint, float* out, int
         const float a = (float)exp(-sqrt(2.0) / sigma_i);
         dim3 gw((W + 31) / 32, (H + 7) / 8, B);
         k_rf_weights<<<gw, 256, 0, stream>>>(joint ? joint : in, Vh, Vv, C, H, W, a, (float)(sigma_s / sigma_r));
-        const int rows_total = B * H;
-        k_rf_rows<<<(rows_total + RF_ROW_WARPS - 1) / RF_ROW_WARPS, RF_ROW_WARPS * 32, smem, stream>>>(
-            cur, out, Vh, C, H, W, chunk, rows_total);
+        const int groups_per_plane = (H + 31) / 32;
+        const int groups_total = B * C * groups_per_plane;
+        k_rf_rows<<<(groups_total + RF_ROW_WARPS - 1) / RF_ROW_WARPS, RF_ROW_WARPS * 32, 0, stream>>>(
+            cur, out, Vh, C, H, W, groups_per_plane, groups_total);
         dim3 gc((W + 127) / 128, B * C);
         k_rf_cols<<<gc, 128, 0, stream>>>(out, Vv, C, H, W);
         cur = out;
