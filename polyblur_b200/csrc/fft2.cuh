@@ -370,6 +370,110 @@ PB_HD void fft2_forward_dit(float2* x, int stride, int nb, const Fft2Plan& plan,
     }
 }
 
+// ---- fused first / last stages ---------------------------------------------------------------
+// The first DIF stage (sub-length n) reads every sample exactly once and the last DIT stage
+// (sub-length n) writes every sample exactly once, in both cases at x[j + m M] with j running
+// over consecutive threads.  Handing those two stages a source / sink functor lets a kernel feed
+// the transform straight from global memory and write its result straight back, without a
+// separate load or store pass through shared memory:
+//     float2 Src::operator()(int f, int i)            sample i of sequence f
+//     void   Dst::operator()(int f, int i, float2 v)  result i of sequence f
+template <int R, class Src>
+PB_HD void fft2_dif_first(float2* x, int n, int stride, int nb, const float2* __restrict__ stw, int tid, int nthr,
+                          Src& src) {
+    const int M = n / R;                   // L = n: one block per sequence, j = butterfly index
+    const float inv_M = 1.0f / (float)M;
+    const int total = nb * M;
+    for (int idx = tid; idx < total; idx += nthr) {
+        const int f = fast_div(idx, M, inv_M);
+        const int j = idx - f * M;
+        float2* p = x + f * stride + j;
+        float2 v[R];
+#pragma unroll
+        for (int m = 0; m < R; ++m) v[m] = src(f, j + m * M);
+        Dft<R>::run(v);
+        p[0] = v[0];
+        if (M == 1) {
+#pragma unroll
+            for (int q = 1; q < R; ++q) p[q] = v[q];
+        } else {
+#pragma unroll
+            for (int q = 1; q < R; ++q) p[q * M] = c_mul(v[q], PB_LDG(stw + (q - 1) * M + j));
+        }
+    }
+}
+
+template <int R, class Dst>
+PB_HD void fft2_dit_last(const float2* x, int n, int stride, int nb, const float2* __restrict__ stw, int tid,
+                         int nthr, Dst& dst) {
+    const int M = n / R;
+    const float inv_M = 1.0f / (float)M;
+    const int total = nb * M;
+    for (int idx = tid; idx < total; idx += nthr) {
+        const int f = fast_div(idx, M, inv_M);
+        const int j = idx - f * M;
+        const float2* p = x + f * stride + j;
+        float2 v[R];
+        v[0] = p[0];
+#pragma unroll
+        for (int q = 1; q < R; ++q) v[q] = c_mul(p[q * M], PB_LDG(stw + (q - 1) * M + j));
+        Dft<R>::run(v);
+#pragma unroll
+        for (int m = 0; m < R; ++m) dst(f, j + m * M, v[m]);
+    }
+}
+
+#define PB_FFT2_DISPATCH2(FN, R_, T_, ...)                    \
+    switch (R_) {                                             \
+        case 2: FN<2, T_>(__VA_ARGS__); break;                \
+        case 3: FN<3, T_>(__VA_ARGS__); break;                \
+        case 4: FN<4, T_>(__VA_ARGS__); break;                \
+        case 5: FN<5, T_>(__VA_ARGS__); break;                \
+        case 6: FN<6, T_>(__VA_ARGS__); break;                \
+        case 7: FN<7, T_>(__VA_ARGS__); break;                \
+        case 8: FN<8, T_>(__VA_ARGS__); break;                \
+        case 9: FN<9, T_>(__VA_ARGS__); break;                \
+        case 10: FN<10, T_>(__VA_ARGS__); break;              \
+        case 11: FN<11, T_>(__VA_ARGS__); break;              \
+        case 12: FN<12, T_>(__VA_ARGS__); break;              \
+        case 13: FN<13, T_>(__VA_ARGS__); break;              \
+        case 14: FN<14, T_>(__VA_ARGS__); break;              \
+        case 15: FN<15, T_>(__VA_ARGS__); break;              \
+        default: FN<16, T_>(__VA_ARGS__); break;              \
+    }
+
+// Forward DIF transform fed by `src` (needs plan.ns >= 2: the fused stage must have M > 1 so that
+// the multiplier-folding first inverse stage stays a separate one).  No barrier is needed before
+// the call; a barrier has been executed after the last stage.
+template <class Src, bool WARP = false>
+PB_HD void fft2_forward_dif_from(float2* x, int stride, int nb, const Fft2Plan& plan, const float2* __restrict__ tw,
+                                 int tid, int nthr, Src& src) {
+    PB_FFT2_DISPATCH2(fft2_dif_first, plan.radix[0], Src, x, plan.n, stride, nb, tw + plan.tw_off[0], tid, nthr, src);
+    fft2_sync<WARP>();
+    int L = plan.n / plan.radix[0];
+    for (int s = 1; s < plan.ns; ++s) {
+        const int R = plan.radix[s];
+        PB_FFT2_DISPATCH(fft2_dif_stage, R, x, plan.n, stride, nb, L, tw + plan.tw_off[s], tid, nthr);
+        fft2_sync<WARP>();
+        L /= R;
+    }
+}
+
+// Inverse-direction (DIT) transform whose last stage hands its results to `dst` (plan.ns >= 2).
+template <class Dst, bool WARP = false>
+PB_HD void fft2_forward_dit_to(float2* x, int stride, int nb, const Fft2Plan& plan, const float2* __restrict__ tw,
+                               int tid, int nthr, Dst& dst, const float* premul = nullptr, int premode = 1) {
+    int L = 1;
+    for (int s = plan.ns - 1; s >= 1; --s) {
+        const int R = plan.radix[s];
+        L *= R;
+        PB_FFT2_DISPATCH(fft2_dit_stage, R, x, plan.n, stride, nb, L, tw + plan.tw_off[s], tid, nthr,
+                         (s == plan.ns - 1) ? premul : nullptr, premode);
+        fft2_sync<WARP>();
+    }
+    PB_FFT2_DISPATCH2(fft2_dit_last, plan.radix[0], Dst, x, plan.n, stride, nb, tw + plan.tw_off[0], tid, nthr, dst);
+}
+
 // Frequency index k held by slot p after the DIF transform:
 //   p = q_1 M_1 + q_2 M_2 + ... + q_s,  M_i = n / (R_1 ... R_i);   k = q_1 + R_1 (q_2 + R_2 (q_3 + ...))
 PB_HD int fft2_freq_of_slot(int p, const Fft2Plan& plan) {

@@ -10,6 +10,17 @@
 
 using namespace pb;
 
+struct ArraySrc {
+    const float2* a;
+    int stride;
+    float2 operator()(int f, int i) const { return a[f * stride + i]; }
+};
+struct ArrayDst {
+    float2* a;
+    int stride;
+    void operator()(int f, int i, float2 v) const { a[f * stride + i] = v; }
+};
+
 int main(int argc, char** argv) {
     int worst = 0;
     for (int a = 1; a < argc; ++a) {
@@ -54,6 +65,20 @@ int main(int argc, char** argv) {
             if (i % stride >= n) continue;
             rt = fmax(rt, fabs(x[i].y / n - x0[i].x));
             rt = fmax(rt, fabs(x[i].x / n - x0[i].y));
+        }
+        // the same round trip through the fused first / last stages (source / sink functors)
+        if (plan.ns >= 2) {
+            std::vector<float2> work(nb * stride), res(nb * stride), swapped(nb * stride);
+            ArraySrc src{x0.data(), stride};
+            fft2_forward_dif_from(work.data(), stride, nb, plan, tw.data(), 0, 1, src);
+            for (auto& v : work) v = make_float2(v.y, v.x);
+            ArrayDst dst{res.data(), stride};
+            fft2_forward_dit_to(work.data(), stride, nb, plan, tw.data(), 0, 1, dst);
+            for (int i = 0; i < nb * stride; ++i) {
+                if (i % stride >= n) continue;
+                rt = fmax(rt, fabs(res[i].y / n - x0[i].x));
+                rt = fmax(rt, fabs(res[i].x / n - x0[i].y));
+            }
         }
         printf("%d %d %.3e %.3e %d", n, plan.ns, err / (mag > 0 ? mag : 1), rt, perm_ok ? 1 : 0);
         for (int s = 0; s < plan.ns; ++s) printf(" r%d", plan.radix[s]);
