@@ -370,3 +370,21 @@ def test_normalized_convolution_vs_oracle(pb, shape, ss, sr, n):
     ref = po.normalized_convolution(x, ss, sr, n)
     got = pb.domain_transform.normalized_convolution(cu(x), ss, sr, n).cpu().numpy()
     assert maxabs(got, ref) < 5e-6
+
+
+@pytest.mark.parametrize("kind", ["mosaic", "white"])
+def test_full_hd_image_vs_oracle(pb, kind):
+    """One image of BASELINE config 2's shape (3 x 1080 x 1920) end to end against the CPU oracle:
+    the mosaic goes through the FFT engine (2016 x 1152 torus), white noise through the 3 x 3
+    register kernel.  Same tolerance as the small cases."""
+    from polyblur_b200 import synthetic
+    x = synthetic.make(kind, 1, 3, 1080, 1920).numpy()
+    tr = []
+    ref = po.polyblur_deblurring(x, n_iter=3, alpha=6, beta=1, trace=tr)
+    out, est = pb.polyblur_deblurring(cu(x), n_iter=3, alpha=6, beta=1, return_estimates=True)
+    est = est.cpu().numpy()
+    if kind == "mosaic":
+        assert np.array_equal(est[..., 7].astype(np.int64), np.stack([t["theta_deg"] for t in tr]))
+    np.testing.assert_allclose(est[..., 8], np.stack([t["sigma"] for t in tr]), rtol=5e-5)
+    np.testing.assert_allclose(est[..., 9], np.stack([t["rho"] for t in tr]), rtol=5e-5)
+    assert maxabs(out.cpu().numpy(), ref) < TOL_E2E
