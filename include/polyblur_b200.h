@@ -141,6 +141,14 @@ PB_API int pb_deconv_f32(const float* img, float* out, int B, int C, int H, int 
                   const float* kernel, int ksize, double alpha, double beta, int engine,
                   void* workspace, size_t workspace_bytes, void* stream);
 
+/* deblurring.inverse_filtering_rank3 with its optional stages (deblurring.py:211-239):
+ * flags = PB_FLAG_EDGETAPER (do_edgetaper, + PB_FLAG_EDGETAPER_BATCHMAX) | PB_FLAG_REMOVE_HALO;
+ * grad_x / grad_y = grad_img of the reference (device, (B,C,H,W)) or both NULL = gradients of img.
+ * Workspace: pb_workspace_bytes with the same flags / ker_size / engine in pb_params. */
+PB_API int pb_deconv_ex_f32(const float* img, float* out, int B, int C, int H, int W, const float* kernel,
+                     int ksize, double alpha, double beta, int engine, uint32_t flags, const float* grad_x,
+                     const float* grad_y, void* workspace, size_t workspace_bytes, void* stream);
+
 /* edgetaper.edgetaper (edgetaper.py:26-33) on an already padded image. */
 PB_API int pb_edgetaper_f32(const float* img, float* out, int B, int C, int H, int W,
                      const float* kernel, int ksize, int n_tapers, uint32_t flags,

@@ -62,6 +62,8 @@ _SIGS = {
     "pb_make_kernel_f32": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P, C.c_size_t, _P]),
     "pb_deconv_f32": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.c_double,
                                 C.c_double, C.c_int, _P, C.c_size_t, _P]),
+    "pb_deconv_ex_f32": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.c_double,
+                                   C.c_double, C.c_int, C.c_uint32, _P, _P, _P, C.c_size_t, _P]),
     "pb_edgetaper_f32": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.c_int,
                                    C.c_uint32, _P, C.c_size_t, _P]),
     "pb_bilateral_f32": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _P]),

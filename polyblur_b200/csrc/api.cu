@@ -292,6 +292,49 @@ static int deconv_all(const float* img, float* out, int B, int C, int H, int W, 
     return PB_OK;
 }
 
+// inverse_filtering_rank3 (deblurring.py:211-239) for the kernels k_params left in the workspace:
+// [edgetaper on the explicitly padded image] -> polynomial on the torus -> crop -> [halo masking] -> clamp.
+static int deconv_with_options(const float* src, float* dst, int B, int C, int H, int W, const float* coef, int ksize,
+                               uint32_t flags, const float* g0x, const float* g0y, const float* nM, float* ox,
+                               char* ws, const Workspace& L, const Tables& T, const FftEngineTables* F,
+                               cudaStream_t stream) {
+    const bool halo = (flags & PB_FLAG_REMOVE_HALO) != 0;
+    const bool taper = (flags & PB_FLAG_EDGETAPER) != 0;
+    const int pad = ksize / 2;
+    const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+    const int planes = B * C;
+    const ImgKernel* kern = reinterpret_cast<const ImgKernel*>(ws + L.off_kern);
+    int rc;
+    // [edgetaping] taper the explicitly padded image; the engines then read that padded plane
+    SrcGeom G = default_geom(H, W);
+    const float* dec_in = src;
+    if (taper) {
+        float* padA = reinterpret_cast<float*>(ws + L.off_padA);
+        float* padB = reinterpret_cast<float*>(ws + L.off_padB);
+        float *v = nullptr, *tapered = nullptr;
+        if ((rc = launch_pad_replicate(src, padA, padB, planes, H, W, pad, stream))) return rc;
+        if ((rc = launch_edgetaper_weights(kern, ws + L.off_et, B, Hp, Wp, (flags & PB_FLAG_EDGETAPER_BATCHMAX) ? 1 : 0,
+                                           &v, stream)))
+            return rc;
+        if ((rc = launch_edgetaper_passes(padA, padB, kern, v, B, C, Hp, Wp, 3, &tapered, stream))) return rc;
+        G.Hin = Hp;
+        G.Win = Wp;
+        G.off = pad;
+        G.pad = 0;
+        dec_in = tapered;
+    }
+    G.clamp_out = halo ? 0 : 1;
+    if ((rc = deconv_all(dec_in, dst, B, C, H, W, coef, ws, L, F, G, stream))) return rc;
+    if (halo) {
+        // halo_masking (deblurring.py:193-208): only d imout / dx is needed (M uses gy*gy, :174)
+        if ((rc = gradients_into(dst, ox, nullptr, planes, H, W, T, stream))) return rc;
+        if ((rc = launch_halo_apply(dst, dec_in, (size_t)G.Hin * G.Win, G.Win, G.off, g0x, g0y, ox, nM, planes, H, W,
+                                    stream)))
+            return rc;
+    }
+    return PB_OK;
+}
+
 }  // namespace pb
 
 using namespace pb;
@@ -432,33 +475,9 @@ int pb_polyblur_f32(const float* in, float* out, int B, int C, int H, int W, con
             }
             src = smooth;
         }
-        // [edgetaping] taper the explicitly padded image; the engines then read that padded plane
-        SrcGeom G = default_geom(H, W);
-        const float* dec_in = src;
-        if (taper) {
-            float* padA = reinterpret_cast<float*>(ws + L.off_padA);
-            float* padB = reinterpret_cast<float*>(ws + L.off_padB);
-            float *v = nullptr, *tapered = nullptr;
-            if ((rc = launch_pad_replicate(src, padA, padB, planes, H, W, pad, stream))) return rc;
-            if ((rc = launch_edgetaper_weights(kern, ws + L.off_et, B, Hp, Wp,
-                                               (p->flags & PB_FLAG_EDGETAPER_BATCHMAX) ? 1 : 0, &v, stream)))
-                return rc;
-            if ((rc = launch_edgetaper_passes(padA, padB, kern, v, B, C, Hp, Wp, 3, &tapered, stream))) return rc;
-            G.Hin = Hp;
-            G.Win = Wp;
-            G.off = pad;
-            G.pad = 0;
-            dec_in = tapered;
-        }
-        G.clamp_out = halo ? 0 : 1;
-        if ((rc = deconv_all(dec_in, dst, B, C, H, W, coef, ws, L, L.has_fft ? &F : nullptr, G, stream))) return rc;
-        if (halo) {
-            // halo_masking (deblurring.py:193-208): only d imout / dx is needed (M uses gy*gy, :174)
-            if ((rc = gradients_into(dst, ox, nullptr, planes, H, W, T, stream))) return rc;
-            if ((rc = launch_halo_apply(dst, dec_in, (size_t)G.Hin * G.Win, G.Win, G.off, g0x, g0y, ox, nM, planes, H, W,
-                                        stream)))
-                return rc;
-        }
+        if ((rc = deconv_with_options(src, dst, B, C, H, W, coef, p->ker_size, p->flags, g0x, g0y, nM, ox, ws, L, T,
+                                      L.has_fft ? &F : nullptr, stream)))
+            return rc;
         if (prefilter && (rc = launch_residual_add(dst, cur, smooth, (size_t)planes * plane, stream))) return rc;
         cur = dst;
     }
@@ -551,6 +570,58 @@ int pb_deconv_f32(const float* img, float* out, int B, int C, int H, int W, cons
     float coef[4];
     poly_coeffs(alpha, beta, coef);
     return deconv_all(img, out, B, C, H, W, coef, ws, L, L.has_fft ? &F : nullptr, default_geom(H, W), stream);
+}
+
+int pb_deconv_ex_f32(const float* img, float* out, int B, int C, int H, int W, const float* kernel, int ksize,
+                     double alpha, double beta, int engine, uint32_t flags, const float* grad_x, const float* grad_y,
+                     void* workspace, size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc;
+    if ((rc = check_shape(B, C, H, W))) return rc;
+    if (!img || !out || !kernel || img == out || ksize < 1 || ksize > PB_KS || !(ksize & 1)) {
+        set_error("bad arguments to pb_deconv_ex_f32 (ksize must be odd and <= 25)");
+        return PB_ERR_ARG;
+    }
+    if ((grad_x == nullptr) != (grad_y == nullptr)) {
+        set_error("grad_x and grad_y must be given together");
+        return PB_ERR_ARG;
+    }
+    flags &= PB_FLAG_REMOVE_HALO | PB_FLAG_EDGETAPER | PB_FLAG_EDGETAPER_BATCHMAX;
+    const Workspace L = layout(B, C, H, W, 1, ksize, engine, flags);
+    if ((rc = check_ws(workspace, workspace_bytes, L.total))) return rc;
+    if (engine == PB_ENGINE_FFT && !L.has_fft) {
+        set_error("the FFT engine does not support %d x %d (ker_size %d)", H, W, ksize);
+        return PB_ERR_UNSUPPORTED;
+    }
+    char* ws = static_cast<char*>(workspace);
+    ImgKernel* kern = reinterpret_cast<ImgKernel*>(ws + L.off_kern);
+    int* cls = reinterpret_cast<int*>(ws + L.off_cls);
+    Tables T;
+    FftEngineTables F;
+    if ((rc = prepare_tables(ws, L, H, W, &T, stream))) return rc;
+    if (L.has_fft && (rc = fft_engine_prepare(ws + L.off_fft, L.fft, &F, stream))) return rc;
+    if ((rc = launch_params(nullptr, kern, nullptr, nullptr, nullptr, nullptr, kernel, nullptr, 2, B, ksize, 0.f, 0.f,
+                            1e-8f, engine, L.has_fft ? PB_FFT_RADIUS_MIN : (1 << 30), cls, stream)))
+        return rc;
+    float* g0x = reinterpret_cast<float*>(ws + L.off_g0x);
+    float* g0y = reinterpret_cast<float*>(ws + L.off_g0y);
+    float* ox = reinterpret_cast<float*>(ws + L.off_ox);
+    float* nM = reinterpret_cast<float*>(ws + L.off_nm);
+    const float *gx = g0x, *gy = g0y;
+    if (flags & PB_FLAG_REMOVE_HALO) {
+        // grad_img defaults to the gradients of img itself (deblurring.py:200-203)
+        if (grad_x) {
+            gx = grad_x;
+            gy = grad_y;
+        } else if ((rc = gradients_into(img, g0x, g0y, B * C, H, W, T, stream))) {
+            return rc;
+        }
+        if ((rc = launch_halo_norm(gx, gy, nM + B * C, nM, B * C, (size_t)H * W, stream))) return rc;
+    }
+    float coef[4];
+    poly_coeffs(alpha, beta, coef);
+    return deconv_with_options(img, out, B, C, H, W, coef, ksize, flags, gx, gy, nM, ox, ws, L, T,
+                               L.has_fft ? &F : nullptr, stream);
 }
 
 int pb_profile_begin(void) {

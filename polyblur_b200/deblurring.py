@@ -179,14 +179,14 @@ def _polyblur_host_pipelined(x: torch.Tensor, p: "_lib.PbParams", dev: torch.dev
 
 
 def inverse_filtering_rank3(img, kernel, alpha=2, b=4, correlate=False, remove_halo=False,
-                            do_edgetaper=False, grad_img=None, method='direct', engine=_lib.ENGINE_AUTO):
-    """pad -> polynomial deconvolution on the torus -> crop -> clamp
-    (polyblur/deblurring.py:211-239), for explicit kernels (B,1,k,k) or (1,1,k,k).
+                            do_edgetaper=False, grad_img=None, method='direct', engine=_lib.ENGINE_AUTO,
+                            edgetaper_batch_max=True):
+    """pad -> [edgetaper] -> polynomial deconvolution on the torus -> crop -> [halo masking] ->
+    clamp (polyblur/deblurring.py:211-239), for explicit kernels (B,1,k,k) or (1,1,k,k).
 
-    Always the 'fft' (circular, replicate-padded) semantics.  ``correlate`` rotates the
-    kernel by 180 degrees like the reference."""
-    if remove_halo or do_edgetaper:
-        raise NotImplementedError("remove_halo / do_edgetaper are not built yet in inverse_filtering_rank3")
+    Always the 'fft' (circular, replicate-padded) semantics.  ``correlate`` rotates the kernel by
+    180 degrees like the reference; ``grad_img`` = (grad_x, grad_y) of the blurry image, computed
+    from ``img`` when None (deblurring.py:200-203)."""
     if img.dtype != torch.float32 or img.ndim != 4:
         raise TypeError("img must be a float32 (B,C,H,W) tensor")
     dev = _lib.require_cuda(img)
@@ -202,14 +202,28 @@ def inverse_filtering_rank3(img, kernel, alpha=2, b=4, correlate=False, remove_h
     if k.shape[1] != 1:
         raise NotImplementedError("one kernel per image (B,1,k,k); per-channel kernels are not supported")
     k = k.expand(B, 1, ks, ks).contiguous()
+    flags = 0
+    if remove_halo:
+        flags |= _lib.FLAG_REMOVE_HALO
+    if do_edgetaper:
+        flags |= _lib.FLAG_EDGETAPER | (_lib.FLAG_EDGETAPER_BATCHMAX if edgetaper_batch_max else 0)
+    gx = gy = None
+    if remove_halo and grad_img is not None:
+        gx = grad_img[0].detach().to(dev, torch.float32).contiguous()
+        gy = grad_img[1].detach().to(dev, torch.float32).contiguous()
+        if gx.shape != x.shape or gy.shape != x.shape:
+            raise ValueError("grad_img must hold two tensors of img's shape")
     with torch.cuda.device(dev):
         p = _lib.default_params()
+        p.flags = flags
+        p.ker_size = ks
+        p.engine = int(engine)
         ws = _lib.workspace(B, Cn, H, W, p, dev)
         out = torch.empty_like(x)
-        rc = _lib.lib().pb_deconv_f32(x.data_ptr(), out.data_ptr(), B, Cn, H, W, k.data_ptr(), ks,
-                                      float(alpha), float(b), int(engine), ws.data_ptr(), ws.numel(),
-                                      _lib.stream_ptr(dev))
-        _lib.check(rc, "pb_deconv_f32")
+        rc = _lib.lib().pb_deconv_ex_f32(x.data_ptr(), out.data_ptr(), B, Cn, H, W, k.data_ptr(), ks,
+                                         float(alpha), float(b), int(engine), flags, _lib.ptr(gx), _lib.ptr(gy),
+                                         ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
+        _lib.check(rc, "pb_deconv_ex_f32")
     return out.to(src)
 
 

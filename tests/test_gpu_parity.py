@@ -388,3 +388,20 @@ def test_full_hd_image_vs_oracle(pb, kind):
     np.testing.assert_allclose(est[..., 8], np.stack([t["sigma"] for t in tr]), rtol=5e-5)
     np.testing.assert_allclose(est[..., 9], np.stack([t["rho"] for t in tr]), rtol=5e-5)
     assert maxabs(out.cpu().numpy(), ref) < TOL_E2E
+
+
+@pytest.mark.parametrize("kw", [dict(remove_halo=True), dict(do_edgetaper=True), dict(remove_halo=True, do_edgetaper=True)])
+def test_inverse_filtering_stage_options(pb, kw):
+    """Stage-level inverse_filtering_rank3 with its optional stages against the oracle."""
+    rng = np.random.default_rng(23)
+    x = mosaic(2, 3, 90, 130, seed=5, sigma=(1.5, 0.8), theta_deg=20.0)
+    k = po.gaussian_kernel(np.array([0.4, 1.9], np.float32), np.array([1.4, 2.2], np.float32),
+                           np.array([0.7, 1.1], np.float32))
+    g = po.fourier_gradients(x) if kw.get("remove_halo") else None
+    ref = po.inverse_filtering_rank3(x, k, alpha=6, b=1, remove_halo=kw.get("remove_halo", False),
+                                     do_edgetaper=kw.get("do_edgetaper", False), grad_img=g)
+    got = pb.deblurring.inverse_filtering_rank3(cu(x), cu(k), alpha=6, b=1, **kw)
+    assert maxabs(got.cpu().numpy(), ref) < 5e-6
+    if kw.get("remove_halo"):
+        got2 = pb.deblurring.inverse_filtering_rank3(cu(x), cu(k), alpha=6, b=1, grad_img=(cu(g[0]), cu(g[1])), **kw)
+        assert maxabs(got2.cpu().numpy(), ref) < 5e-6
