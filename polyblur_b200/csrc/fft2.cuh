@@ -375,7 +375,10 @@ PB_HD void fft2_forward_dit(float2* x, int stride, int nb, const Fft2Plan& plan,
 // (sub-length n) writes every sample exactly once, in both cases at x[j + m M] with j running
 // over consecutive threads.  Handing those two stages a source / sink functor lets a kernel feed
 // the transform straight from global memory and write its result straight back, without a
-// separate load or store pass through shared memory:
+// separate load or store pass through shared memory.  (Measured on B200 for the estimator's row
+// kernel: 2.18 ms against 1.31 ms for the staged version with 128-bit loads -- the scalar accesses
+// and the extra registers cost more than the two passes saved -- so the shipped kernels stage through
+// shared memory; the fused stages stay available and unit-tested.)
 //     float2 Src::operator()(int f, int i)            sample i of sequence f
 //     void   Dst::operator()(int f, int i, float2 v)  result i of sequence f
 template <int R, class Src>
