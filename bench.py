@@ -288,6 +288,22 @@ def run_cuda(a):
                "d2h_bytes_per_step": nbytes, "ms_per_step": ms_e2e, "steps": k_e2e,
                "api": "polyblur_b200.polyblur_deblurring(pinned CPU tensor) -> CPU tensor"}
         del xh
+        # the same images as 8-bit HWC host buffers through polyblur_b200.io.deblur_uint8 (conversions on
+        # the device: 1 byte per sample over PCIe instead of 4) -- informational, not the contract's e2e
+        from polyblur_b200 import io as pbio
+        xu = (x.permute(0, 2, 3, 1) * 255).round().to(torch.uint8).contiguous().cpu().pin_memory()
+
+        def step_u8():
+            y = pbio.deblur_uint8(xu, n_iter=a.n_iter, alpha=6, beta=1, engine=a.engine)
+            assert y.device.type == "cpu" and y.dtype == torch.uint8
+
+        for _ in range(2):
+            step_u8()
+        ms_u8 = max_over_ranks(time_steps(step_u8, k_e2e, barrier))
+        e2e["uint8_io"] = {"value": pix_all / 1e6 / (ms_u8 / 1e3), "unit": "Mpix/s", "ms_per_step": ms_u8,
+                           "h2d_bytes_per_step": xu.numel(), "d2h_bytes_per_step": xu.numel(),
+                           "api": "polyblur_b200.io.deblur_uint8(pinned uint8 (B,H,W,C)) -> uint8 CPU tensor"}
+        del xu
 
     # ---- the other synthetic distribution, same measurement (kernel-only) ----------------------
     secondary = None

@@ -163,6 +163,11 @@ PB_API int pb_recursive_filter_f32(const float* img, const float* joint, float* 
                             int W, float sigma_s, float sigma_r, int num_iterations,
                             void* workspace, size_t workspace_bytes, void* stream);
 
+/* 8-bit I/O around the hot path, what main.py does on the host (main.py:80 img_as_float32, :146
+ * img_as_ubyte), fused with the layout change: (B,H,W,C) uint8 <-> (B,C,H,W) float32 in [0,1]. */
+PB_API int pb_u8hwc_to_f32nchw(const uint8_t* in, float* out, int B, int H, int W, int C, void* stream);
+PB_API int pb_f32nchw_to_u8hwc(const float* in, uint8_t* out, int B, int C, int H, int W, void* stream);
+
 /* Domain-transform normalized convolution: the reference's native prototype
  * normalized_convolution(I, sigma_s, sigma_r, num_iterations) (polyblur/domain_transform/NC.cpp:143-204,
  * exported at :210), here for any batch size and channel count.

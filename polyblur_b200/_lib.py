@@ -69,6 +69,8 @@ _SIGS = {
     "pb_bilateral_f32": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _P]),
     "pb_recursive_filter_f32": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                           C.c_float, C.c_int, _P, C.c_size_t, _P]),
+    "pb_u8hwc_to_f32nchw": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "pb_f32nchw_to_u8hwc": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "pb_normalized_convolution_f32": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                                 C.c_float, C.c_int, _P, C.c_size_t, _P]),
 }

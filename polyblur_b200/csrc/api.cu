@@ -725,4 +725,24 @@ int pb_normalized_convolution_f32(const float* img, float* out, int B, int C, in
                                          workspace, (cudaStream_t)stream_);
 }
 
+int pb_u8hwc_to_f32nchw(const uint8_t* in, float* out, int B, int H, int W, int C, void* stream_) {
+    int rc;
+    if ((rc = check_shape(B, C, H, W))) return rc;
+    if (!in || !out) {
+        set_error("null pointer");
+        return PB_ERR_ARG;
+    }
+    return launch_u8_to_f32(in, out, B, H, W, C, (cudaStream_t)stream_);
+}
+
+int pb_f32nchw_to_u8hwc(const float* in, uint8_t* out, int B, int C, int H, int W, void* stream_) {
+    int rc;
+    if ((rc = check_shape(B, C, H, W))) return rc;
+    if (!in || !out) {
+        set_error("null pointer");
+        return PB_ERR_ARG;
+    }
+    return launch_f32_to_u8(in, out, B, C, H, W, (cudaStream_t)stream_);
+}
+
 }  // extern "C"

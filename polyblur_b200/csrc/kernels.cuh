@@ -85,6 +85,10 @@ size_t nc_workspace_bytes(int B, int C, int H, int W);
 int launch_normalized_convolution(const float* img, float* out, int B, int C, int H, int W, double sigma_s,
                                   double sigma_r, int num_iterations, void* ws, cudaStream_t stream);
 
+// io.cu (8-bit HWC <-> float32 NCHW)
+int launch_u8_to_f32(const unsigned char* in, float* out, int B, int H, int W, int C, cudaStream_t stream);
+int launch_f32_to_u8(const float* in, unsigned char* out, int B, int C, int H, int W, cudaStream_t stream);
+
 // deconv_narrow.cu
 int launch_deconv_narrow(int cls, const float* img, float* out, const ImgKernel* kern, const int* list,
                          const int* count, int B, int C, int H, int W, float a3, float a2, float a1, float b0,

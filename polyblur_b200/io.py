@@ -1,0 +1,118 @@
+"""8-bit image path around the engine (what polyblur's main.py does on the host,
+main.py:80 ``img_as_float32`` and :146 ``img_as_ubyte``).
+
+    deblur_uint8(images_u8, n_iter=3, alpha=6, beta=1, ...) -> uint8 images of the same layout
+
+The conversion uint8 HWC -> float32 NCHW in [0,1] and back happens on the device, so one byte per
+sample crosses PCIe in each direction instead of four.  Host batches are pipelined over three
+streams (H2D / convert + Polyblur + convert / D2H per chunk of images).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .deblurring import _make_params
+
+
+def _convert_in(xu8: torch.Tensor, xf: torch.Tensor, stream: int) -> None:
+    B, H, W, Cn = xu8.shape
+    rc = _lib.lib().pb_u8hwc_to_f32nchw(xu8.data_ptr(), xf.data_ptr(), B, H, W, Cn, stream)
+    _lib.check(rc, "pb_u8hwc_to_f32nchw")
+
+
+def _convert_out(yf: torch.Tensor, yu8: torch.Tensor, stream: int) -> None:
+    B, Cn, H, W = yf.shape
+    rc = _lib.lib().pb_f32nchw_to_u8hwc(yf.data_ptr(), yu8.data_ptr(), B, Cn, H, W, stream)
+    _lib.check(rc, "pb_f32nchw_to_u8hwc")
+
+
+def deblur_uint8(images, n_iter=1, c=0.352, b=0.768, alpha=2, beta=3, sigma_r=0.8, sigma_s=2.0, ker_size=25,
+                 q=0.0, remove_halo=False, edgetaping=False, prefiltering=False, discard_saturation=False,
+                 max_chunks=4, **engine_kw):
+    """Polyblur on 8-bit images.  ``images``: uint8 ndarray (H,W), (H,W,C) or (B,H,W,C), or a uint8
+    torch tensor (B,H,W,C) on the CPU or on a CUDA device; the result has the same kind, layout and
+    device.  Keyword arguments as ``polyblur_deblurring``."""
+    is_np = isinstance(images, np.ndarray)
+    x = torch.from_numpy(np.ascontiguousarray(images)) if is_np else images
+    if not isinstance(x, torch.Tensor) or x.dtype != torch.uint8:
+        raise TypeError("deblur_uint8 expects uint8 images")
+    shape_in = tuple(x.shape)
+    if x.ndim == 2:
+        x = x[None, :, :, None]
+    elif x.ndim == 3:
+        x = x[None]
+    elif x.ndim != 4:
+        raise ValueError("expected (H,W), (H,W,C) or (B,H,W,C)")
+    x = x.contiguous()
+    B, H, W, Cn = x.shape
+    p = _make_params(n_iter, c, b, alpha, beta, sigma_r, sigma_s, ker_size, q, remove_halo, edgetaping,
+                     prefiltering, discard_saturation, **engine_kw)
+    dev = _lib.require_cuda(x)
+    if n_iter == 0:
+        return images
+    with torch.cuda.device(dev):
+        if x.is_cuda:
+            st = _lib.stream_ptr(dev)
+            xf = torch.empty(B, Cn, H, W, dtype=torch.float32, device=dev)
+            yf = torch.empty_like(xf)
+            out = torch.empty_like(x)
+            ws = _lib.workspace(B, Cn, H, W, p, dev)
+            _convert_in(x, xf, st)
+            rc = _lib.lib().pb_polyblur_f32(xf.data_ptr(), yf.data_ptr(), B, Cn, H, W, C.byref(p), ws.data_ptr(),
+                                            ws.numel(), None, st)
+            _lib.check(rc, "pb_polyblur_f32")
+            _convert_out(yf, out, st)
+        else:
+            out = _host_pipeline_u8(x, p, dev, max_chunks)
+    out = out.reshape(shape_in)
+    return out.numpy() if is_np else out
+
+
+def _host_pipeline_u8(x: torch.Tensor, p, dev: torch.device, max_chunks: int) -> torch.Tensor:
+    B, H, W, Cn = x.shape
+    if not x.is_pinned():
+        x = x.pin_memory()
+    host = torch.empty(x.shape, dtype=torch.uint8, pin_memory=True)
+    n_chunks = max(1, min(max_chunks, B))
+    bounds = [(B * k) // n_chunks for k in range(n_chunks + 1)]
+    biggest = max(b - a for a, b in zip(bounds, bounds[1:]))
+    s_in, s_run, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    start = torch.cuda.current_stream(dev).record_event()
+    for st in (s_in, s_run, s_out):
+        st.wait_event(start)
+    xin = [torch.empty(biggest, H, W, Cn, dtype=torch.uint8, device=dev) for _ in range(2)]
+    yout = [torch.empty(biggest, H, W, Cn, dtype=torch.uint8, device=dev) for _ in range(2)]
+    xf = torch.empty(biggest, Cn, H, W, dtype=torch.float32, device=dev)
+    yf = torch.empty_like(xf)
+    ws = _lib.workspace(biggest, Cn, H, W, p, dev)
+    free_in = [None, None]
+    free_out = [None, None]
+    for k, (a, b) in enumerate(zip(bounds, bounds[1:])):
+        i, n = k & 1, b - a
+        with torch.cuda.stream(s_in):
+            if free_in[i] is not None:
+                s_in.wait_event(free_in[i])
+            xin[i][:n].copy_(x[a:b], non_blocking=True)
+            loaded = s_in.record_event()
+        with torch.cuda.stream(s_run):
+            s_run.wait_event(loaded)
+            if free_out[i] is not None:
+                s_run.wait_event(free_out[i])
+            _convert_in(xin[i][:n], xf[:n], s_run.cuda_stream)
+            free_in[i] = s_run.record_event()
+            rc = _lib.lib().pb_polyblur_f32(xf.data_ptr(), yf.data_ptr(), n, Cn, H, W, C.byref(p), ws.data_ptr(),
+                                            ws.numel(), None, s_run.cuda_stream)
+            _lib.check(rc, "pb_polyblur_f32")
+            _convert_out(yf[:n], yout[i][:n], s_run.cuda_stream)
+            done = s_run.record_event()
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(done)
+            host[a:b].copy_(yout[i][:n], non_blocking=True)
+            free_out[i] = s_out.record_event()
+    s_out.synchronize()
+    s_run.synchronize()
+    return host

@@ -405,3 +405,27 @@ def test_inverse_filtering_stage_options(pb, kw):
     if kw.get("remove_halo"):
         got2 = pb.deblurring.inverse_filtering_rank3(cu(x), cu(k), alpha=6, b=1, grad_img=(cu(g[0]), cu(g[1])), **kw)
         assert maxabs(got2.cpu().numpy(), ref) < 5e-6
+
+
+def test_uint8_path_matches_float_path(pb, golden_dir, tmp_path):
+    """8-bit in / 8-bit out: device conversions == utils.to_float -> float path ->
+    utils.to_uint, for an ndarray, a pinned host batch (pipelined) and a CUDA tensor; CLI smoke."""
+    from PIL import Image
+    img = np.asarray(Image.open(os.path.join(golden_dir, "peacock_defocus.png")))
+    ref = pb.utils.to_uint(pb.polyblur_deblurring(pb.utils.to_float(img), n_iter=3, alpha=6, beta=1))
+    got = pb.io.deblur_uint8(img, n_iter=3, alpha=6, beta=1)
+    assert got.dtype == np.uint8 and got.shape == img.shape
+    d = np.abs(got.astype(np.int32) - ref.astype(np.int32))
+    assert d.max() <= 1 and (d > 0).mean() < 1e-3          # rounding ties only
+    batch = torch.from_numpy(np.stack([img, img[::-1].copy(), np.roll(img, 7, 1)]))
+    host = pb.io.deblur_uint8(batch, n_iter=2, alpha=6, beta=1, max_chunks=2)
+    devr = pb.io.deblur_uint8(batch.cuda(), n_iter=2, alpha=6, beta=1)
+    assert host.device.type == "cpu" and devr.is_cuda and torch.equal(host, devr.cpu())
+    assert torch.equal(host[0], torch.from_numpy(pb.io.deblur_uint8(img, n_iter=2, alpha=6, beta=1)))
+    gray = pb.io.deblur_uint8(img[..., 0].copy(), n_iter=1)
+    assert gray.shape == img.shape[:2]
+    from polyblur_b200 import main as cli
+    out = cli.main(["--impath", os.path.join(golden_dir, "peacock_defocus.png"), "--N", "3", "--alpha", "6",
+                    "--beta", "1", "--out", str(tmp_path / "restored.png")])
+    saved = np.asarray(Image.open(out))
+    assert saved.shape == img.shape and saved.dtype == np.uint8
