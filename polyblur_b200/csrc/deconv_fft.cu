@@ -65,7 +65,10 @@ __device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// Waits until the bulk stores have READ their shared-memory source (the buffer may be reused); the
+// global writes need no further ordering inside this kernel (nobody re-reads Z before the next
+// launch), and the plain wait_group would also flush the L1 (CCTL.IVALL) that caches the twiddles.
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- tables -------------------------------------------------------------------------------
