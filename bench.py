@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the other distribution")
+    ap.add_argument("--no-graph", action="store_true", help="time the eager enqueue instead of the CUDA graph replay")
     return ap.parse_args()
 
 
@@ -207,29 +208,48 @@ def run_cuda(a):
                                        False, engine=a.engine)
 
     def measure(kind, with_profile):
+        """-> x, out, ms per step (K timed steps, no profiling inside), per-kernel profile, clocks.
+
+        The headline timing replays the step as one CUDA graph (the enqueue has no host sync) unless
+        --no-graph.  The per-kernel CUDA events of the library's profiler cost ~5 % (two event records
+        per launch), so the roofline pass is a second region of K eager steps right after."""
         x = synthetic.make(kind, B, 3, H, W, first_index=first, device=dev)
         out = torch.empty_like(x)
         p = params()
+        graphed = None
+        if not a.no_graph:
+            try:
+                graphed = deblurring.GraphedPolyblur((B, 3, H, W), device=dev, n_iter=a.n_iter, alpha=6, beta=1,
+                                                     engine=a.engine)
+                graphed.x.copy_(x)
+            except Exception as exc:          # capture not possible on this stack: time the eager enqueue
+                print(f"CUDA graph capture failed ({exc}); timing the eager enqueue", file=sys.stderr)
+                graphed = None
 
-        def step():
+        def step_eager():
             deblurring.polyblur_device(x, p, out=out)
 
+        step = graphed if graphed is not None else step_eager
         for _ in range(a.warmup):
             step()
         clocks = None
         sampler = ClockSampler(local) if (rank == 0 and with_profile) else None
         if sampler:
             sampler.start()
-        if with_profile:
-            _lib.profile_begin()
         ms = time_steps(step, a.steps, barrier)
-        prof = _lib.profile_end() if with_profile else {}
         if sampler:
             clocks = sampler.stop()
         ms = max_over_ranks(ms)
-        return x, out, ms, prof, clocks
+        prof = {}
+        if with_profile:
+            step_eager()
+            _lib.profile_begin()
+            time_steps(step_eager, a.steps, barrier)
+            prof = _lib.profile_end()
+        mode = "cuda-graph replay" if graphed is not None else "eager enqueue"
+        return x, (graphed.out if graphed is not None else out), ms, prof, clocks, mode
 
-    x, out, ms, prof, clocks = measure(a.dist, True)
+    x, out, ms, prof, clocks, mode = measure(a.dist, True)
     value = pix_all / 1e6 / (ms / 1e3)
 
     # ---- roofline of the dominant kernel group (CUDA events recorded by the library around each launch)
@@ -261,6 +281,7 @@ def run_cuda(a):
         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_ms,
         "launch_definition": "one Polyblur iteration of this kernel group over the whole batch",
+        "timed_with": "per-launch CUDA events of the library's profiler over a second region of K eager steps",
         "kernel_share_of_step": dom_ms / total_prof_ms if total_prof_ms else None,
         "step": {"algorithmic_bytes": step_bytes, "achieved": step_bytes / (ms / 1e3) / 1e9,
                  "frac": step_bytes / (ms / 1e3) / 1e9 / peak},
@@ -311,7 +332,7 @@ def run_cuda(a):
         other = "white" if a.dist == "mosaic" else "mosaic"
         del x, out
         torch.cuda.empty_cache()
-        _, _, ms2, _, _ = measure(other, False)
+        _, _, ms2, _, _, _ = measure(other, False)
         secondary = {"workload": workload_name(a, other), "value": pix_all / 1e6 / (ms2 / 1e3),
                      "unit": "Mpix/s", "ms_per_step": ms2,
                      "step_roofline_frac": step_bytes / (ms2 / 1e3) / 1e9 / peak}
@@ -329,7 +350,7 @@ def run_cuda(a):
             "config": {"workload": workload_name(a, a.dist), "global_batch": B * world,
                        "parallelism": f"batch-sharded x{world}, no data-path collective",
                        "l2": f"inputs ({B * 3 * H * W * 4 / 1e6:.0f} MB per GPU) and every intermediate are larger than the 126 MB L2; no flush needed",
-                       "engine": {0: "auto", 1: "spatial", 2: "fft"}[a.engine]},
+                       "engine": {0: "auto", 1: "spatial", 2: "fft"}[a.engine], "launch": mode},
             "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu, "secondary": secondary,
         }

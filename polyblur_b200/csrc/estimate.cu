@@ -19,7 +19,11 @@ __constant__ float c_cos7[7] = {0x1.000000p+0f, 0x1.bb67aep-1f, 0x1.fffffep-2f, 
                                 -0x1.000002p-1f, -0x1.bb67aep-1f, -0x1.000000p+0f};
 __constant__ float c_sin7[7] = {0x0.0p+0f, 0x1.000000p-1f, 0x1.bb67aep-1f, 0x1.000000p+0f,
                                 0x1.bb67aep-1f, 0x1.000002p-1f, -0x1.777a5cp-24f};
-__constant__ float c_keys[30 * 7];   // filled by upload_constants()
+// (30,7) Keys interpolation weights travel as a kernel argument (840 bytes): no host->device copy in
+// the call, so the whole pb_polyblur_f32 enqueue can be captured into a CUDA graph.
+struct KeysW {
+    float w[30 * 7];
+};
 
 __global__ void k_twiddles(float2* __restrict__ tw, int n) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -201,7 +205,8 @@ __global__ void __launch_bounds__(128)
 k_params(const unsigned* __restrict__ stats, ImgKernel* __restrict__ kern, float* __restrict__ est,
          const float* __restrict__ th_in, const float* __restrict__ sg_in, const float* __restrict__ rh_in,
          const float* __restrict__ kin, float* __restrict__ kout, int mode, int ksize, float cc, float bb,
-         float tap_thr, int engine_req, int fft_radius_min, int* __restrict__ cls_buf, int list_stride) {
+         float tap_thr, int engine_req, int fft_radius_min, int* __restrict__ cls_buf, int list_stride,
+         KeysW keys) {
     __shared__ float s_par[3];
     __shared__ float s_red[4];
     __shared__ float s_k[PB_KS2];
@@ -224,7 +229,7 @@ k_params(const unsigned* __restrict__ stats, ImgKernel* __restrict__ kern, float
             int imin = 0;
             for (int i = 0; i < 30; ++i) {
                 float acc = 0.0f;
-                for (int j = 0; j < 7; ++j) acc = fmaf(c_keys[i * 7 + j], mags[j], acc);
+                for (int j = 0; j < 7; ++j) acc = fmaf(keys.w[i * 7 + j], mags[j], acc);
                 interp[i] = acc;
                 if (acc < interp[imin]) imin = i;          // first minimum (torch.argmin)
             }
@@ -399,12 +404,7 @@ static void host_keys_weights(float* w) {
 
 void keys_weights_host(float* out210) { host_keys_weights(out210); }
 
-int upload_constants(cudaStream_t stream) {
-    static float w[210];
-    host_keys_weights(w);
-    PB_CUDA_TRY(cudaMemcpyToSymbolAsync(c_keys, w, sizeof(w), 0, cudaMemcpyHostToDevice, stream));
-    return PB_OK;
-}
+int upload_constants(cudaStream_t) { return PB_OK; }   // nothing to upload any more (see KeysW)
 
 int launch_twiddles(float2* tw, int n, cudaStream_t stream) {
     ProfScope prof(PROF_SETUP, stream);
@@ -488,8 +488,14 @@ int launch_params(const unsigned* stats, ImgKernel* kern, float* est, const floa
                   float bb, float tap_thr, int engine_req, int fft_radius_min, int* cls, cudaStream_t stream) {
     ProfScope prof(PROF_PARAMS, stream);
     if (cls) PB_CUDA_TRY(cudaMemsetAsync(cls, 0, PB_CLS_COUNT_STRIDE * sizeof(int), stream));
+    static KeysW keys;
+    static bool keys_ready = false;
+    if (!keys_ready) {
+        host_keys_weights(keys.w);
+        keys_ready = true;
+    }
     k_params<<<B, 128, 0, stream>>>(stats, kern, est, th, sg, rh, kin, kout, mode, ksize, cc, bb, tap_thr,
-                                    engine_req, fft_radius_min, cls, B);
+                                    engine_req, fft_radius_min, cls, B, keys);
     PB_LAUNCH_CHECK("k_params");
     return PB_OK;
 }

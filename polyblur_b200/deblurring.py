@@ -66,6 +66,53 @@ def polyblur_device(x: torch.Tensor, p: "_lib.PbParams", out: torch.Tensor | Non
     return (out, est) if return_estimates else out
 
 
+class GraphedPolyblur:
+    """One ``pb_polyblur_f32`` enqueue for a fixed shape and parameter set, captured into a CUDA
+    graph.  The loop makes ~20 kernel launches per iteration and never synchronises the host (the
+    per-image engine choice happens on the device), so the whole call replays as one graph launch:
+    worth ~0.2-0.3 ms per call, i.e. most of the time for small images.
+
+        g = GraphedPolyblur((B, C, H, W), n_iter=3, alpha=6, beta=1)
+        y = g(x)            # copies x into the static input, replays, returns the static output
+    """
+
+    def __init__(self, shape, device=None, **kw):
+        B, Cn, H, W = shape
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.params = _make_params(kw.pop("n_iter", 1), kw.pop("c", 0.352), kw.pop("b", 0.768), kw.pop("alpha", 2),
+                                   kw.pop("beta", 3), kw.pop("sigma_r", 0.8), kw.pop("sigma_s", 2.0),
+                                   kw.pop("ker_size", 25), kw.pop("q", 0.0), kw.pop("remove_halo", False),
+                                   kw.pop("edgetaping", False), kw.pop("prefiltering", False),
+                                   kw.pop("discard_saturation", False), **kw)
+        if self.params.n_iter < 1:
+            raise ValueError("n_iter must be >= 1")
+        with torch.cuda.device(dev):
+            self.x = torch.zeros(B, Cn, H, W, dtype=torch.float32, device=dev)
+            self.out = torch.empty_like(self.x)
+            self.ws = _lib.workspace(B, Cn, H, W, self.params, dev)
+            self.x.uniform_(0, 1)                 # a non-constant image for the warm-up call
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                self._enqueue(side.cuda_stream)    # warm-up: sets kernel attributes outside the capture
+            torch.cuda.current_stream(dev).wait_stream(side)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._enqueue(torch.cuda.current_stream(dev).cuda_stream)
+
+    def _enqueue(self, stream):
+        B, Cn, H, W = self.x.shape
+        rc = _lib.lib().pb_polyblur_f32(self.x.data_ptr(), self.out.data_ptr(), B, Cn, H, W, C.byref(self.params),
+                                        self.ws.data_ptr(), self.ws.numel(), None, stream)
+        _lib.check(rc, "pb_polyblur_f32")
+
+    def __call__(self, x=None):
+        if x is not None:
+            self.x.copy_(x, non_blocking=True)
+        self.graph.replay()
+        return self.out
+
+
 def polyblur_deblurring(img, n_iter=1, c=0.352, b=0.768, alpha=2, beta=3, sigma_r=0.8, sigma_s=2.0,
                         ker_size=25, q=0.0, n_angles=6, n_interpolated_angles=30, remove_halo=False,
                         edgetaping=False, prefiltering=False, discard_saturation=False,

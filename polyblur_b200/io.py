@@ -37,7 +37,11 @@ def deblur_uint8(images, n_iter=1, c=0.352, b=0.768, alpha=2, beta=3, sigma_r=0.
     torch tensor (B,H,W,C) on the CPU or on a CUDA device; the result has the same kind, layout and
     device.  Keyword arguments as ``polyblur_deblurring``."""
     is_np = isinstance(images, np.ndarray)
-    x = torch.from_numpy(np.ascontiguousarray(images)) if is_np else images
+    if is_np:
+        arr = np.ascontiguousarray(images)
+        x = torch.from_numpy(arr if arr.flags.writeable else arr.copy())     # torch wants a writable buffer
+    else:
+        x = images
     if not isinstance(x, torch.Tensor) or x.dtype != torch.uint8:
         raise TypeError("deblur_uint8 expects uint8 images")
     shape_in = tuple(x.shape)

@@ -429,3 +429,14 @@ def test_uint8_path_matches_float_path(pb, golden_dir, tmp_path):
                     "--beta", "1", "--out", str(tmp_path / "restored.png")])
     saved = np.asarray(Image.open(out))
     assert saved.shape == img.shape and saved.dtype == np.uint8
+
+
+def test_cuda_graph_replay_is_bit_identical(pb):
+    """The whole enqueue has no host synchronisation, so it captures into a CUDA graph; the replay
+    must give exactly the eager result (also after feeding a new input)."""
+    x = cu(mosaic(2, 3, 120, 168, seed=31))
+    g = pb.GraphedPolyblur((2, 3, 120, 168), n_iter=3, alpha=6, beta=1)
+    eager = pb.polyblur_deblurring(x, n_iter=3, alpha=6, beta=1)
+    assert torch.equal(g(x), eager)
+    x2 = torch.rand_like(x)
+    assert torch.equal(g(x2), pb.polyblur_deblurring(x2, n_iter=3, alpha=6, beta=1))
