@@ -202,6 +202,19 @@ static void poly_coeffs(double alpha, double beta, float* o) {
     o[3] = (float)beta;
 }
 
+// The same polynomial in powers of D = K - I.  a3 + a2 + a1 + b = 1 for every (alpha, beta), so
+//     a3 K^3 + a2 K^2 + a1 K + b  =  I + c1 D + c2 D^2 + c3 D^3,   c1 = 3 a3 + 2 a2 + a1, c2 = 3 a3 + a2, c3 = a3.
+// The engines evaluate this form: for the near-delta kernels Polyblur meets, D (*) v is small, so the
+// Horner steps never subtract O(5) quantities that nearly cancel (the K form loses ~2 bits to that;
+// measured: 4.1e-6 -> see profiles/r01_parity_report.jsonl).  Algebraically identical.
+static void poly_coeffs_d(double alpha, double beta, float* o) {
+    const double a3 = alpha / 2 - beta + 2, a2 = 3 * beta - alpha - 6, a1 = 5 - 3 * beta + alpha / 2;
+    o[0] = (float)a3;                       // c3
+    o[1] = (float)(3 * a3 + a2);            // c2
+    o[2] = (float)(3 * a3 + 2 * a2 + a1);   // c1
+    o[3] = 1.0f;                            // identity term
+}
+
 static int estimate_into(const float* img, int B, int C, int H, int W, double c, double b, double q, uint32_t flags,
                          float* est, char* ws, const Workspace& L, const Tables& T, int ksize,
                          float tap_thr, int engine, int fft_radius_min, cudaStream_t stream) {
@@ -435,7 +448,7 @@ int pb_polyblur_f32(const float* in, float* out, int B, int C, int H, int W, con
     if ((rc = prepare_tables(ws, L, H, W, &T, stream))) return rc;
     if (L.has_fft && (rc = fft_engine_prepare(ws + L.off_fft, L.fft, &F, stream))) return rc;
     float coef[4];
-    poly_coeffs(p->alpha, p->beta, coef);
+    poly_coeffs_d(p->alpha, p->beta, coef);
     const float thr = p->tap_rel_threshold > 0 ? p->tap_rel_threshold : 1e-8f;
     float* tmp = reinterpret_cast<float*>(ws + L.off_tmp);
     const bool prefilter = (p->flags & (PB_FLAG_PREFILTER | PB_FLAG_PREFILTER_RF)) != 0;
@@ -568,7 +581,7 @@ int pb_deconv_f32(const float* img, float* out, int B, int C, int H, int W, cons
                             0.f, 0.f, 1e-8f, engine, L.has_fft ? PB_FFT_RADIUS_MIN : (1 << 30), cls, stream)))
         return rc;
     float coef[4];
-    poly_coeffs(alpha, beta, coef);
+    poly_coeffs_d(alpha, beta, coef);
     return deconv_all(img, out, B, C, H, W, coef, ws, L, L.has_fft ? &F : nullptr, default_geom(H, W), stream);
 }
 
@@ -619,7 +632,7 @@ int pb_deconv_ex_f32(const float* img, float* out, int B, int C, int H, int W, c
         if ((rc = launch_halo_norm(gx, gy, nM + B * C, nM, B * C, (size_t)H * W, stream))) return rc;
     }
     float coef[4];
-    poly_coeffs(alpha, beta, coef);
+    poly_coeffs_d(alpha, beta, coef);
     return deconv_with_options(img, out, B, C, H, W, coef, ksize, flags, gx, gy, nM, ox, ws, L, T,
                                L.has_fft ? &F : nullptr, stream);
 }

@@ -141,7 +141,9 @@ k_deconv_spatial(const float* __restrict__ img, float* __restrict__ out,
         int HX = (r + 3) & ~3;
         if (HX == 0) HX = 4;
 
-        for (int i = threadIdx.x; i < 640; i += blockDim.x) S.k[i] = (i < PB_KS2) ? K->k[i] : 0.0f;
+        // taps of D = K - I (centre tap minus one): see poly_coeffs_d in api.cu
+        for (int i = threadIdx.x; i < 640; i += blockDim.x)
+            S.k[i] = (i < PB_KS2) ? K->k[i] - (i == PB_PAD * PB_KS + PB_PAD ? 1.0f : 0.0f) : 0.0f;
         if (threadIdx.x < 32) {
             S.lo[threadIdx.x] = (threadIdx.x < PB_KS) ? K->lo[threadIdx.x] : PB_KS;
             S.hi[threadIdx.x] = (threadIdx.x < PB_KS) ? K->hi[threadIdx.x] : -1;

@@ -272,7 +272,8 @@ k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int
             float2 acc = make_float2(0.f, 0.f);
             if (col < ncol || (col == CB && cb == 0)) {
                 for (int dx = -PB_PAD; dx <= PB_PAD; ++dx) {
-                    const float kv = __ldg(&K->k[(dy + PB_PAD) * PB_KS + dx + PB_PAD]);
+                    float kv = __ldg(&K->k[(dy + PB_PAD) * PB_KS + dx + PB_PAD]);
+                    if (dy == 0 && dx == 0) kv -= 1.0f;        // spectrum of D = K - I (small where K^ ~ 1)
                     const int t = (int)(((long long)kx * (dx + NX)) % NX);
                     const float2 e = __ldg(twX + t);
                     acc.x = fmaf(kv, e.x, acc.x);
@@ -309,6 +310,7 @@ k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int
             const int s = idx - col * NY;
             const float2 z = data[(size_t)(col >> 1) * NY + s];
             const float kh = (col & 1) ? z.y : z.x;
+            // a3..b0 hold c3, c2, c1, 1 of the D = K - I form: H = 1 + D^ (c1 + D^ (c2 + c3 D^))
             const float h = fmaf(fmaf(fmaf(a3, kh, a2), kh, a1), kh, b0) * scale;
             if (col == ncol) Hn[s] = h; else Hs[(size_t)col * NY + s] = h;
         }

@@ -1,5 +1,7 @@
 // Narrow-kernel deconvolution engine: the three Horner stencils of
 //     o = a3 p;  o = K (*) o + a2 p;  o = K (*) o + a1 p;  o = K (*) o + b p
+// evaluated in the algebraically identical, better conditioned basis D = K - I
+//     o = c3 p;  o = D (*) o + c2 p;  o = D (*) o + c1 p;  o = D (*) o + p
 // (deblurring.inverse_filtering_rank3 / compute_polynomial_fft, polyblur/deblurring.py:211-239,
 // 141-169, on the replicate-padded torus of SURVEY.md A.6) kept entirely in registers for blur
 // kernels whose significant taps fit (2 RX + 1) x (2 RY + 1), RX, RY <= 2 -- what the estimator
@@ -75,6 +77,7 @@ k_deconv_narrow(const float* __restrict__ img, float* __restrict__ out, const Im
 #pragma unroll
             for (int dx = 0; dx < 2 * RX + 1; ++dx)
                 wk[dy][dx] = __ldg(&K->k[(dy - RY + PB_PAD) * PB_KS + (dx - RX + PB_PAD)]);
+        wk[RY][RX] -= 1.0f;       // D = K - I: the engines evaluate I + c1 D + c2 D^2 + c3 D^3 (api.cu)
 
         const float* src = img + ((size_t)im * C + c) * (size_t)G.Hin * G.Win;
         float* dst = out + ((size_t)im * C + c) * plane;
