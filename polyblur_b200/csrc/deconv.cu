@@ -113,7 +113,7 @@ __device__ __forceinline__ void horner_tile(float* P, float* O1, float* O2, int 
                          gout, gy0, gx0, H, W, clamp_out);
 }
 
-__global__ void __launch_bounds__(DC_THREADS, 1)
+__global__ void __launch_bounds__(DC_THREADS, 2)
 k_deconv_spatial(const float* __restrict__ img, float* __restrict__ out,
                  const ImgKernel* __restrict__ kern, const int* __restrict__ list,
                  const int* __restrict__ count, int C, int H, int W,
@@ -176,12 +176,19 @@ k_deconv_spatial(const float* __restrict__ img, float* __restrict__ out,
 
 int launch_deconv_spatial(const float* img, float* out, const ImgKernel* kern, const int* list, const int* count,
                           int B, int C, int H, int W, float a3, float a2, float a1, float b0, const SrcGeom& G,
-                          cudaStream_t stream) {
-    const int ext = DT_W + 6 * PB_PAD;
-    const size_t smem = sizeof(DeconvSmem) +
-                        sizeof(float) * ((size_t)ext * ext + (size_t)(DT_W + 4 * PB_PAD) * (DT_H + 4 * PB_PAD) +
-                                         (size_t)(DT_W + 2 * PB_PAD) * (DT_H + 2 * PB_PAD));
-    PB_CUDA_TRY(cudaFuncSetAttribute(k_deconv_spatial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                          int max_radius, cudaStream_t stream) {
+    // shared memory for the largest halo of this class (radius <= 4: 77 KB, two CTAs per SM)
+    const int r = max_radius < PB_PAD ? max_radius : PB_PAD;
+    const size_t smem_of_r = sizeof(DeconvSmem) +
+                             sizeof(float) * ((size_t)(DT_W + 6 * r) * (DT_H + 6 * r) + (size_t)(DT_W + 4 * r) * (DT_H + 4 * r) +
+                                              (size_t)(DT_W + 2 * r) * (DT_H + 2 * r));
+    const int rmax = PB_PAD;
+    const size_t smem_max = sizeof(DeconvSmem) +
+                            sizeof(float) * ((size_t)(DT_W + 6 * rmax) * (DT_H + 6 * rmax) +
+                                             (size_t)(DT_W + 4 * rmax) * (DT_H + 4 * rmax) +
+                                             (size_t)(DT_W + 2 * rmax) * (DT_H + 2 * rmax));
+    const size_t smem = smem_of_r;
+    PB_CUDA_TRY(cudaFuncSetAttribute(k_deconv_spatial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
     const long long items = (long long)B * C * ((W + DT_W - 1) / DT_W) * ((H + DT_H - 1) / DT_H);
     const int grid = (int)(items < 4LL * PB_NUM_SMS ? items : 4LL * PB_NUM_SMS);   // persistent, 1 CTA / SM resident
     ProfScope prof(PROF_DECONV_SPATIAL, stream);

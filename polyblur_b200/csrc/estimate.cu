@@ -353,7 +353,7 @@ k_params(const unsigned* __restrict__ stats, ImgKernel* __restrict__ kern, float
         else if (s_rx <= 1 && s_ry <= 1) cls = PB_CLS_N11;
         else if (s_rx <= 2 && s_ry <= 2) cls = PB_CLS_N22;
         else if (engine_req == PB_ENGINE_AUTO && s_rad >= fft_radius_min) cls = PB_CLS_FFT;
-        else cls = PB_CLS_TILED;
+        else cls = (s_rad <= 4) ? PB_CLS_TILED4 : PB_CLS_TILED;
         K->engine = (cls == PB_CLS_FFT) ? PB_ENGINE_FFT : PB_ENGINE_SPATIAL;
         K->rx = s_rx;
         K->ry = s_ry;

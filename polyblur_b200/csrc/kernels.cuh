@@ -18,9 +18,10 @@ enum ProfClass { PROF_SETUP = 0, PROF_COLS, PROF_ROWS, PROF_PARAMS, PROF_DECONV_
 // its work grid-stride from that list (an empty class costs one tiny launch, no host sync).
 #define PB_CLS_N11 0      // taps within 3 x 3: register-rolling kernel (deconv_narrow.cu)
 #define PB_CLS_N22 1      // taps within 5 x 5: register-rolling kernel
-#define PB_CLS_TILED 2    // shared-memory tiled Horner stencil (deconv.cu)
+#define PB_CLS_TILED 2    // shared-memory tiled Horner stencil (deconv.cu), radius > 4: 1 CTA / SM
 #define PB_CLS_FFT 3      // blur-independent on-chip FFT engine (deconv_fft.cu)
-#define PB_NCLS 4
+#define PB_CLS_TILED4 4   // tiled stencil, radius <= 4: half the shared memory, 2 CTAs / SM
+#define PB_NCLS 5
 #define PB_CLS_COUNT_STRIDE 16   // ints reserved for the counters in front of the lists
 struct ProfScope {
     int idx;
@@ -118,6 +119,6 @@ int launch_deconv_fft(const float* img, float* out, const ImgKernel* kern, const
 // deconv.cu
 int launch_deconv_spatial(const float* img, float* out, const ImgKernel* kern, const int* list, const int* count,
                           int B, int C, int H, int W, float a3, float a2, float a1, float b0, const SrcGeom& G,
-                          cudaStream_t stream);
+                          int max_radius, cudaStream_t stream);
 
 }  // namespace pb
