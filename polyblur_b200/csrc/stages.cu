@@ -399,7 +399,7 @@ __global__ void k_pad_replicate(const float* __restrict__ img, float* __restrict
 // per image: zl[0..48] = linear autocorrelation lags -24..24 of the row sums, zl[49..97] of the column
 // sums; zmax[2 im], zmax[2 im + 1] = lag-0 values (the maxima).
 __global__ void __launch_bounds__(128)
-k_et_autocorr(const ImgKernel* __restrict__ kern, float* __restrict__ zl, float* __restrict__ zmax) {
+k_et_autocorr(const ImgKernel* __restrict__ kern, float* __restrict__ zl, float* __restrict__ zmax, int Hp, int Wp) {
     __shared__ float rh[PB_KS], rw[PB_KS];
     const ImgKernel* K = kern + blockIdx.x;
     const int t = threadIdx.x;
@@ -409,8 +409,11 @@ k_et_autocorr(const ImgKernel* __restrict__ kern, float* __restrict__ zl, float*
             s += K->k[t * PB_KS + i];       // sum over columns: projection indexed by row
             u += K->k[i * PB_KS + t];       // sum over rows: projection indexed by column
         }
-        rh[t] = s;
-        rw[t] = u;
+        // torch.fft.fft(x, n) TRUNCATES x when n < len(x) (edgetaper.py:11,17 with n = size - 1): only
+        // matters for images one pixel high / wide, where the padded size minus one is below ker_size
+        const int first = PB_PAD - K->ksize / 2;        // the ksize x ksize kernel sits centred in the 25 x 25 grid
+        rh[t] = (t - first < Hp - 1) ? s : 0.f;
+        rw[t] = (t - first < Wp - 1) ? u : 0.f;
     }
     __syncthreads();
     if (t < 2 * (2 * PB_KS - 1)) {
@@ -496,7 +499,7 @@ int launch_edgetaper_weights(const ImgKernel* kern, void* scratch, int B, int Hp
         return PB_ERR_ARG;
     }
     ProfScope prof(PROF_OTHER, stream);
-    k_et_autocorr<<<B, 128, 0, stream>>>(kern, zl, zmax);
+    k_et_autocorr<<<B, 128, 0, stream>>>(kern, zl, zmax, Hp, Wp);
     k_et_weights<<<dim3((Hp + Wp + 255) / 256, B), 256, 0, stream>>>(zl, zmax, v, B, Hp, Wp, batch_max);
     PB_LAUNCH_CHECK("edgetaper weights");
     *v_out = v;

@@ -440,3 +440,17 @@ def test_cuda_graph_replay_is_bit_identical(pb):
     assert torch.equal(g(x), eager)
     x2 = torch.rand_like(x)
     assert torch.equal(g(x2), pb.polyblur_deblurring(x2, n_iter=3, alpha=6, beta=1))
+
+
+def test_random_shape_sweep(pb, capsys):
+    """tools/fuzz_parity.py: odd / prime / one-pixel-wide shapes, 1-4 channels, random options, against
+    the oracle.  Tiny images with beta = 4 amplify rounding noise, hence 2e-5 here (the worst of 100
+    recorded cases is 1.3e-5, profiles/r01_fuzz_parity.jsonl)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("fuzz_parity", os.path.join(os.path.dirname(G), "..", "tools", "fuzz_parity.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.main(n_cases=25, seed=3)
+    import json
+    last = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert last["failures"] == 0 and last["worst_ok_err"] < 2e-5

@@ -1,0 +1,71 @@
+#!/usr/bin/env python
+"""Random-shape parity sweep (GPU): polyblur_deblurring against the CPU oracle for odd, prime,
+tiny and non-square shapes, channel counts 1-4, both kinds of content, random options."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import polyblur_b200 as pb  # noqa: E402
+from oracle import polyblur_oracle as po  # noqa: E402
+
+
+def main(n_cases=40, seed=0):
+    rng = np.random.default_rng(seed)
+    worst = 0.0
+    fails = []
+    for case in range(n_cases):
+        B = int(rng.integers(1, 4))
+        C = int(rng.choice([1, 2, 3, 3, 3, 4]))
+        H = int(rng.choice([1, 2, 3, 5, 8, 13, 24, 37, 64, 97, 100, 131, 180, 256]))
+        W = int(rng.choice([1, 2, 4, 7, 8, 16, 25, 53, 64, 101, 120, 128, 200, 243]))
+        if H * W < 4:
+            H = 4
+        n_iter = int(rng.integers(1, 5))
+        kind = rng.choice(["noise", "blocks", "smooth"])
+        x = rng.random((B, C, H, W), dtype=np.float32)
+        if kind == "blocks":
+            x = np.repeat(np.repeat(rng.random((B, C, -(-H // 9), -(-W // 9)), dtype=np.float32), 9, -2), 9, -1)[..., :H, :W]
+            k = po.gaussian_filter_np((float(rng.uniform(0.5, 3)), float(rng.uniform(0.4, 1.5))), float(rng.uniform(0, 3)))
+            x = np.clip(po.convolve2d_fft(x, np.broadcast_to(k[None, None], (B, 1, 25, 25))), 0, 1).astype(np.float32)
+        elif kind == "smooth":
+            x = (0.5 + 0.4 * np.sin(np.linspace(0, 9, W))[None, None, None, :] * np.cos(np.linspace(0, 5, H))[None, None, :, None]
+                 + 0.05 * x).astype(np.float32)
+        x = np.ascontiguousarray(np.clip(x, 0, 1))
+        kw = {}
+        if rng.random() < 0.3:
+            kw["discard_saturation"] = True
+        if rng.random() < 0.2:
+            kw["ker_size"] = int(rng.choice([9, 15, 21]))
+        if rng.random() < 0.2:
+            kw["prefiltering"] = True
+        if rng.random() < 0.15:
+            kw["remove_halo"] = True
+        if rng.random() < 0.15:
+            kw["edgetaping"] = True
+        ab = [(6, 1), (2, 3), (2, 4)][int(rng.integers(0, 3))]
+        try:
+            with np.errstate(all="ignore"):
+                ref = po.polyblur_deblurring(x, n_iter=n_iter, alpha=ab[0], beta=ab[1], **kw)
+            out = pb.polyblur_deblurring(torch.from_numpy(x).cuda(), n_iter=n_iter, alpha=ab[0], beta=ab[1], **kw).cpu().numpy()
+            if not np.isfinite(ref).all():
+                status, err = "ref-nonfinite", float("nan")      # constant image: NaN in the reference too
+            else:
+                err = float(np.abs(out.astype(np.float64) - ref).max())
+                status = "ok" if err < 2e-5 else "MISMATCH"
+        except Exception as exc:                 # noqa: BLE001
+            status, err = f"EXC {type(exc).__name__}: {exc}", float("nan")
+        rec = {"case": case, "shape": [B, C, H, W], "n_iter": n_iter, "kind": str(kind), "ab": ab, **kw, "err": err, "status": status}
+        print(json.dumps(rec), flush=True)
+        if status == "ok":
+            worst = max(worst, err)
+        elif status != "ref-nonfinite":
+            fails.append(rec)
+    print(json.dumps({"worst_ok_err": worst, "failures": len(fails)}))
+
+
+if __name__ == "__main__":
+    main()
