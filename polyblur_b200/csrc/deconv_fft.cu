@@ -338,8 +338,8 @@ k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int
             }
             mbar_wait(bar, phase);
             phase ^= 1;
-            fft2_forward_dif(data, NY, ncol, planY, stwY, tid, FFTD_THREADS);
             if (cb == 0) {
+                fft2_forward_dif(data, NY, ncol, planY, stwY, tid, FFTD_THREADS);
                 // the pair {k, -k} of column 0 goes to one thread (in place, no hazard)
                 for (int ky = tid; ky <= NY / 2; ky += FFTD_THREADS) {
                     const int s1 = __ldg(slotY + ky);
@@ -350,10 +350,13 @@ k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int
                     if (s2 != s1) data[s2] = make_float2(A2 * z2.x + B2 * z1.x, A2 * z2.y - B2 * z1.y);
                 }
                 __syncthreads();
+                // inverse-direction transform with the multiplication by H (and the re/im swap) folded
+                // into its first stage
+                fft2_forward_dit(data, NY, ncol, planY, stwY, tid, FFTD_THREADS, Hs, 2);
+            } else {
+                // forward, multiply by H (with the re/im swap), inverse: innermost stages fused in registers
+                fft2_forward_mul_inverse(data, NY, ncol, planY, stwY, tid, FFTD_THREADS, Hs, 2);
             }
-            // inverse-direction transform with the multiplication by H (and the re/im swap) folded
-            // into its first stage
-            fft2_forward_dit(data, NY, ncol, planY, stwY, tid, FFTD_THREADS, Hs, 2);
             fence_async_smem();
             __syncthreads();
             if (tid == 0) {

@@ -170,8 +170,8 @@ k_rows2(const float* __restrict__ img, float* __restrict__ gray, float* __restri
     }
 #undef PB_QNORM
     __syncthreads();
-    fft2_forward_dif(sm2, W, nb, plan, tw, tid, R2_THREADS);
-    fft2_forward_dit(sm2, W, nb, plan, tw, tid, R2_THREADS, omega);
+    // forward, multiply by i omega, inverse -- the two innermost stages fused in registers
+    fft2_forward_mul_inverse(sm2, W, nb, plan, tw, tid, R2_THREADS, omega, 1);
     // inverse by forward transform of the swapped data: d(real part) = r.y / n, d(imag part) = r.x / n
     const float inv = 1.0f / (float)W;
     float* dst = gx + (size_t)im * plane;
@@ -254,8 +254,7 @@ k_cols2(const float* __restrict__ plane_in, const float* __restrict__ gx, float*
             if (off[u] >= 0) sm2[off[u]] = g[u];
     }
     __syncthreads();
-    fft2_forward_dif(sm2, stride, nb, plan, tw, tid, THREADS);
-    fft2_forward_dit(sm2, stride, nb, plan, tw, tid, THREADS, omega);
+    fft2_forward_mul_inverse(sm2, stride, nb, plan, tw, tid, THREADS, omega, 1);
     const float inv = 1.0f / (float)H;
 
     if (!EST) {

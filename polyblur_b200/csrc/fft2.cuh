@@ -370,6 +370,61 @@ PB_HD void fft2_forward_dit(float2* x, int stride, int nb, const Fft2Plan& plan,
     }
 }
 
+// ---- fused middle: last DIF stage + pointwise multiplier + first DIT stage -------------------------
+// Both stages have M = 1: they work on the same R contiguous slots and carry no twiddles, so when a
+// forward transform is followed by a pointwise multiplication and the inverse-direction transform
+// (spectral derivative, transfer function), one thread does  DFT_R -> multiply (+ re/im swap) -> DFT_R
+// in registers: one shared-memory round trip and one barrier less per transform pair.
+//   premode 1: y = i w z        -> (w z.x, -w z.y)   (one table for all sequences)
+//   premode 2: y = h z, swapped -> (h z.y,  h z.x)   (one table per sequence)
+template <int R>
+PB_HD void fft2_mid_stage(float2* x, int n, int stride, int nb, int tid, int nthr, const float* premul, int premode) {
+    const int bps = n / R;
+    const float inv_bps = 1.0f / (float)bps;
+    const int total = nb * bps;
+    for (int idx = tid; idx < total; idx += nthr) {
+        const int f = fast_div(idx, bps, inv_bps);
+        const int blk = idx - f * bps;
+        float2* p = x + f * stride + blk * R;
+        float2 v[R];
+#pragma unroll
+        for (int m = 0; m < R; ++m) v[m] = p[m];
+        Dft<R>::run(v);
+        const float* pm = premul + blk * R + (premode == 2 ? f * n : 0);
+#pragma unroll
+        for (int q = 0; q < R; ++q) {
+            const float w = premode == 2 ? pm[q] : PB_LDG(pm + q);
+            v[q] = premode == 2 ? make_float2(w * v[q].y, w * v[q].x) : make_float2(w * v[q].x, -w * v[q].y);
+        }
+        Dft<R>::run(v);
+#pragma unroll
+        for (int m = 0; m < R; ++m) p[m] = v[m];
+    }
+}
+
+// Forward DIF, multiply by `premul`, inverse-direction DIT, with the two innermost stages fused.
+// Same result as fft2_forward_dif followed by fft2_forward_dit(premul); needs plan.ns >= 1.
+template <bool WARP = false>
+PB_HD void fft2_forward_mul_inverse(float2* x, int stride, int nb, const Fft2Plan& plan, const float2* __restrict__ tw,
+                                    int tid, int nthr, const float* premul, int premode) {
+    int L = plan.n;
+    for (int s = 0; s < plan.ns - 1; ++s) {
+        const int R = plan.radix[s];
+        PB_FFT2_DISPATCH(fft2_dif_stage, R, x, plan.n, stride, nb, L, tw + plan.tw_off[s], tid, nthr);
+        fft2_sync<WARP>();
+        L /= R;
+    }
+    PB_FFT2_DISPATCH(fft2_mid_stage, plan.radix[plan.ns - 1], x, plan.n, stride, nb, tid, nthr, premul, premode);
+    fft2_sync<WARP>();
+    L = plan.radix[plan.ns - 1];
+    for (int s = plan.ns - 2; s >= 0; --s) {
+        const int R = plan.radix[s];
+        L *= R;
+        PB_FFT2_DISPATCH(fft2_dit_stage, R, x, plan.n, stride, nb, L, tw + plan.tw_off[s], tid, nthr, nullptr, 0);
+        fft2_sync<WARP>();
+    }
+}
+
 // ---- fused first / last stages ---------------------------------------------------------------
 // The first DIF stage (sub-length n) reads every sample exactly once and the last DIT stage
 // (sub-length n) writes every sample exactly once, in both cases at x[j + m M] with j running

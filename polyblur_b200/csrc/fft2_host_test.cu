@@ -66,6 +66,23 @@ int main(int argc, char** argv) {
             rt = fmax(rt, fabs(x[i].y / n - x0[i].x));
             rt = fmax(rt, fabs(x[i].x / n - x0[i].y));
         }
+        // forward -> multiply -> inverse with the fused middle stage against the unfused pair
+        {
+            std::vector<float> h(stride * nb + n);
+            for (size_t i = 0; i < h.size(); ++i) h[i] = 0.5f + (float)((i * 2654435761u) % 1000) / 1000.0f;
+            for (int mode = 1; mode <= 2; ++mode) {
+                std::vector<float2> a = x0, b = x0;
+                // sequences are addressed with `stride`, the per-sequence table of mode 2 with n
+                fft2_forward_dif(a.data(), stride, nb, plan, tw.data(), 0, 1);
+                fft2_forward_dit(a.data(), stride, nb, plan, tw.data(), 0, 1, h.data(), mode);
+                fft2_forward_mul_inverse(b.data(), stride, nb, plan, tw.data(), 0, 1, h.data(), mode);
+                for (int i = 0; i < nb * stride; ++i) {
+                    if (i % stride >= n) continue;
+                    rt = fmax(rt, fabs(a[i].x - b[i].x) / n);
+                    rt = fmax(rt, fabs(a[i].y - b[i].y) / n);
+                }
+            }
+        }
         // the same round trip through the fused first / last stages (source / sink functors)
         if (plan.ns >= 2) {
             std::vector<float2> work(nb * stride), res(nb * stride), swapped(nb * stride);
