@@ -254,10 +254,10 @@ def run_cuda(a):
 
     # ---- roofline of the dominant kernel group (CUDA events recorded by the library around each launch)
     # One "launch" of a group = the kernels one Polyblur iteration runs for it over the whole batch:
-    #   estimate      = k_rows + k_cols + k_params                        12 B/px/iter algorithmic
+    #   estimate      = k_rows2 + k_cols2 + k_params                        12 B/px/iter algorithmic
     #   deconvolution = the engines (narrow / tiled / FFT passes; every image goes through exactly one,
     #                   chosen on the device, so their times add up to one pass over the batch)  24 B/px/iter
-    EST = ("k_cols", "k_rows", "k_params")
+    EST = ("k_cols2", "k_rows2", "k_params")      # (k_cols / k_rows of estimate.cu for lengths with a prime factor > 13)
     DEC = ("k_deconv_narrow", "k_deconv_spatial", "k_fft_rows_fwd", "k_fft_cols", "k_fft_rows_inv")
     groups = {"estimate": sum(prof.get(k, (0.0, 0))[0] for k in EST),
               "deconvolution": sum(prof.get(k, (0.0, 0))[0] for k in DEC)}
