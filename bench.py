@@ -230,15 +230,15 @@ def run_cuda(a):
             deblurring.polyblur_device(x, p, out=out)
 
         step = graphed if graphed is not None else step_eager
-        for _ in range(a.warmup):
-            step()
+        # clocks / throttle reasons are sampled from the warm-up through the timed region to the end of
+        # the profiled pass (all under the same load; the timed region alone lasts ~0.1 s = 1 sample)
         clocks = None
         sampler = ClockSampler(local) if (rank == 0 and with_profile) else None
         if sampler:
             sampler.start()
+        for _ in range(a.warmup):
+            step()
         ms = time_steps(step, a.steps, barrier)
-        if sampler:
-            clocks = sampler.stop()
         ms = max_over_ranks(ms)
         prof = {}
         if with_profile:
@@ -246,6 +246,14 @@ def run_cuda(a):
             _lib.profile_begin()
             time_steps(step_eager, a.steps, barrier)
             prof = _lib.profile_end()
+            if sampler:
+                # keep the load on for a few more sampling periods
+                t_end = time.time() + 0.6
+                while time.time() < t_end:
+                    step()
+                    torch.cuda.synchronize()
+        if sampler:
+            clocks = sampler.stop()
         mode = "cuda-graph replay" if graphed is not None else "eager enqueue"
         return x, (graphed.out if graphed is not None else out), ms, prof, clocks, mode
 
