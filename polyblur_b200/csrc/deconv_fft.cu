@@ -27,6 +27,9 @@
 // written = ~26 B against 8 B algorithmic; independent of the blur.
 #include <cstdlib>
 
+#include <type_traits>
+
+#include "fft2_static.cuh"
 #include "kernels.cuh"
 
 namespace pb {
@@ -99,6 +102,7 @@ __device__ __forceinline__ int ext_src(int i, int n, int ext, int n_in, int off,
 // ---------------------------------------------------------------------------------------------
 // P1: rows forward.  Work item = (slot in the FFT class list, channel, block of nb row pairs).
 // ---------------------------------------------------------------------------------------------
+template <class SP>
 __global__ void __launch_bounds__(FFTD_THREADS, PB_FFTD_MINB)
 k_fft_rows_fwd(const float* __restrict__ img, float2* __restrict__ Z, const ImgKernel* __restrict__ kern,
                const int* __restrict__ list, const int* __restrict__ count, int C, int H, int W, int NX, int NY,
@@ -193,7 +197,10 @@ k_fft_rows_fwd(const float* __restrict__ img, float2* __restrict__ Z, const ImgK
             }
         }
         __syncthreads();
-        fft2_forward_dif(smf, NX, nb, planX, twX, tid, FFTD_THREADS);
+        if constexpr (std::is_same<SP, NoStaticPlan>::value)
+            fft2_forward_dif(smf, NX, nb, planX, twX, tid, FFTD_THREADS);
+        else
+            s_forward_dif<SP>(smf, NX, nb, twX, tid, FFTD_THREADS);
         // separate the two real rows: Xa[k] = (Z[k] + conj Z[-k]) / 2, Xb[k] = (Z[k] - conj Z[-k]) / (2i)
         float2* Zp = Z + ((size_t)slot * C + c) * half * NY;
 #pragma unroll 2
@@ -233,6 +240,7 @@ k_fft_rows_fwd(const float* __restrict__ img, float2* __restrict__ Z, const ImgK
 //                  | R[CB+1][13] float2 | mbarrier
 //   Leaves r = DFT(swap(Y)) in Z: the inverse transform is swap(r), P3 swaps while loading.
 // ---------------------------------------------------------------------------------------------
+template <class SP>
 __global__ void __launch_bounds__(FFTD_THREADS, PB_FFTD_MINB)
 k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int* __restrict__ list,
            const int* __restrict__ count, int C, int NX, int NY, int CB, Fft2Plan planY,
@@ -303,7 +311,10 @@ k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int
             data[(size_t)q * NY + (d < 0 ? d + NY : d)] = make_float2(ra.x - rb.y, ra.y + rb.x);
         }
         __syncthreads();
-        fft2_forward_dif(data, NY, nseq, planY, stwY, tid, FFTD_THREADS);
+        if constexpr (std::is_same<SP, NoStaticPlan>::value)
+            fft2_forward_dif(data, NY, nseq, planY, stwY, tid, FFTD_THREADS);
+        else
+            s_forward_dif<SP>(data, NY, nseq, stwY, tid, FFTD_THREADS);
         // Hs[col][slot] = scale * P(K^)
         for (int idx = tid; idx < ncolh * NY; idx += FFTD_THREADS) {
             const int col = fast_div(idx, NY, inv_ny);
@@ -355,7 +366,10 @@ k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int
                 fft2_forward_dit(data, NY, ncol, planY, stwY, tid, FFTD_THREADS, Hs, 2);
             } else {
                 // forward, multiply by H (with the re/im swap), inverse: innermost stages fused in registers
-                fft2_forward_mul_inverse(data, NY, ncol, planY, stwY, tid, FFTD_THREADS, Hs, 2);
+                if constexpr (std::is_same<SP, NoStaticPlan>::value)
+                    fft2_forward_mul_inverse(data, NY, ncol, planY, stwY, tid, FFTD_THREADS, Hs, 2);
+                else
+                    s_forward_mul_inverse<SP, 2>(data, NY, ncol, stwY, tid, FFTD_THREADS, Hs);
             }
             fence_async_smem();
             __syncthreads();
@@ -373,6 +387,7 @@ k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int
 // ---------------------------------------------------------------------------------------------
 // P3: rows inverse.  Work item = (slot, channel, block of nb row pairs that hold output rows).
 // ---------------------------------------------------------------------------------------------
+template <class SP>
 __global__ void __launch_bounds__(FFTD_THREADS, PB_FFTD_MINB)
 k_fft_rows_inv(const float2* __restrict__ Z, float* __restrict__ out, const ImgKernel* __restrict__ kern,
                const int* __restrict__ list, const int* __restrict__ count, int C, int H, int W, int NX, int NY,
@@ -425,7 +440,10 @@ k_fft_rows_inv(const float2* __restrict__ Z, float* __restrict__ out, const ImgK
             }
         }
         __syncthreads();
-        fft2_forward_dit(smf, NX, nb, planX, twX, tid, FFTD_THREADS);
+        if constexpr (std::is_same<SP, NoStaticPlan>::value)
+            fft2_forward_dit(smf, NX, nb, planX, twX, tid, FFTD_THREADS);
+        else
+            s_forward_dit<SP>(smf, NX, nb, twX, tid, FFTD_THREADS);
         // r = DFT(swap(Z)): row a = r.y, row b = r.x (the 1/(NX NY) scale is inside H)
         float* dst = out + ((size_t)im * C + c) * plane;
         const int x_off = ext;
@@ -567,32 +585,49 @@ int launch_deconv_fft(const float* img, float* out, const ImgKernel* kern, const
     const int nb = rows_nb(NX), CB = cols_cb(NY);
     const size_t smem_rows = (size_t)nb * NX * sizeof(float2);
     const size_t smem_cols = (size_t)CB * NY * 12 + (size_t)NY * 8 + (size_t)(CB + 1) * 13 * 8 + 64;
-    PB_CUDA_TRY(cudaFuncSetAttribute(k_fft_rows_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
-    PB_CUDA_TRY(cudaFuncSetAttribute(k_fft_rows_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));
-    PB_CUDA_TRY(cudaFuncSetAttribute(k_fft_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
     const long long row_items = (long long)B * C * ((NY / 2 + nb - 1) / nb);
     const long long col_items = (long long)B * ((NX / 2 + CB - 1) / CB);
     const int cap = PB_NUM_SMS * 6;
     const int grid_rows = (int)(row_items < cap ? row_items : cap);
     const int grid_cols = (int)(col_items < cap ? col_items : cap);
-    {
-        ProfScope prof(PROF_FFT_ROWS_FWD, stream);
-        k_fft_rows_fwd<<<grid_rows, FFTD_THREADS, smem_rows, stream>>>(img, T.Z, kern, list, count, C, H, W, NX, NY,
-                                                                       nb, T.planX, T.stwX, T.slotX, G);
-        PB_LAUNCH_CHECK("k_fft_rows_fwd");
+    // compile-time plans for the standard tori (1080p: 2016 x 1152, 4K: 4000 x 2304), else the run-time core
+#define PB_FFT_ROWS(SP)                                                                                          \
+    do {                                                                                                         \
+        PB_CUDA_TRY(cudaFuncSetAttribute(k_fft_rows_fwd<SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows)); \
+        PB_CUDA_TRY(cudaFuncSetAttribute(k_fft_rows_inv<SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows)); \
+        if (fwd) {                                                                                               \
+            ProfScope prof(PROF_FFT_ROWS_FWD, stream);                                                           \
+            k_fft_rows_fwd<SP><<<grid_rows, FFTD_THREADS, smem_rows, stream>>>(img, T.Z, kern, list, count, C, H, W, NX, \
+                                                                               NY, nb, T.planX, T.stwX, T.slotX, G); \
+        } else {                                                                                                 \
+            ProfScope prof(PROF_FFT_ROWS_INV, stream);                                                           \
+            k_fft_rows_inv<SP><<<grid_rows, FFTD_THREADS, smem_rows, stream>>>(T.Z, out, kern, list, count, C, H, W, NX, \
+                                                                               NY, nb, T.planX, T.stwX, T.slotX, \
+                                                                               G.clamp_out);                     \
+        }                                                                                                        \
+    } while (0)
+#define PB_FFT_COLS(SP)                                                                                          \
+    do {                                                                                                         \
+        PB_CUDA_TRY(cudaFuncSetAttribute(k_fft_cols<SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols)); \
+        ProfScope prof(PROF_FFT_COLS, stream);                                                                   \
+        k_fft_cols<SP><<<grid_cols, FFTD_THREADS, smem_cols, stream>>>(T.Z, kern, list, count, C, NX, NY, CB, T.planY, \
+                                                                       T.twX, T.stwY, T.slotY, a3, a2, a1, b0);  \
+    } while (0)
+    for (int pass = 0; pass < 3; ++pass) {
+        const bool fwd = pass == 0;
+        if (pass == 1) {
+            if (PlanY1152::matches(T.planY)) PB_FFT_COLS(PlanY1152);
+            else if (PlanY2304::matches(T.planY)) PB_FFT_COLS(PlanY2304);
+            else PB_FFT_COLS(NoStaticPlan);
+        } else {
+            if (PlanX2016::matches(T.planX)) PB_FFT_ROWS(PlanX2016);
+            else if (PlanX4000::matches(T.planX)) PB_FFT_ROWS(PlanX4000);
+            else PB_FFT_ROWS(NoStaticPlan);
+        }
     }
-    {
-        ProfScope prof(PROF_FFT_COLS, stream);
-        k_fft_cols<<<grid_cols, FFTD_THREADS, smem_cols, stream>>>(T.Z, kern, list, count, C, NX, NY, CB, T.planY,
-                                                                   T.twX, T.stwY, T.slotY, a3, a2, a1, b0);
-        PB_LAUNCH_CHECK("k_fft_cols");
-    }
-    {
-        ProfScope prof(PROF_FFT_ROWS_INV, stream);
-        k_fft_rows_inv<<<grid_rows, FFTD_THREADS, smem_rows, stream>>>(T.Z, out, kern, list, count, C, H, W, NX, NY,
-                                                                       nb, T.planX, T.stwX, T.slotX, G.clamp_out);
-        PB_LAUNCH_CHECK("k_fft_rows_inv");
-    }
+#undef PB_FFT_ROWS
+#undef PB_FFT_COLS
+    PB_LAUNCH_CHECK("fft deconvolution passes");
     return PB_OK;
 }
 

@@ -22,7 +22,10 @@
 // (algorithmic: 12).  g and gx are scratch that mostly lives in the 126 MB L2
 // when the batch is processed a few images at a time.
 #include "fft.cuh"
+#include <type_traits>
+
 #include "fft2.cuh"
+#include "fft2_static.cuh"
 #include "kernels.cuh"
 
 namespace pb {
@@ -51,7 +54,7 @@ __global__ void k_fft2_stage_tw(float2* __restrict__ stw, Fft2Plan plan) {
 #define PB_R2_MINB 3
 #endif
 
-template <bool EST>
+template <bool EST, class SP>
 __global__ void __launch_bounds__(R2_THREADS, PB_R2_MINB)
 k_rows2(const float* __restrict__ img, float* __restrict__ gray, float* __restrict__ gx,
         unsigned* __restrict__ stats, int C, int H, int W, int nb, Fft2Plan plan,
@@ -170,8 +173,12 @@ k_rows2(const float* __restrict__ img, float* __restrict__ gray, float* __restri
     }
 #undef PB_QNORM
     __syncthreads();
-    // forward, multiply by i omega, inverse -- the two innermost stages fused in registers
-    fft2_forward_mul_inverse(sm2, W, nb, plan, tw, tid, R2_THREADS, omega, 1);
+    // forward, multiply by i omega, inverse -- the two innermost stages fused in registers; SP = a
+    // compile-time plan for the standard widths (fft2_static.cuh), else the run-time core
+    if constexpr (std::is_same<SP, NoStaticPlan>::value)
+        fft2_forward_mul_inverse(sm2, W, nb, plan, tw, tid, R2_THREADS, omega, 1);
+    else
+        s_forward_mul_inverse<SP, 1>(sm2, W, nb, tw, tid, R2_THREADS, omega);
     // inverse by forward transform of the swapped data: d(real part) = r.y / n, d(imag part) = r.x / n
     const float inv = 1.0f / (float)W;
     float* dst = gx + (size_t)im * plane;
@@ -212,7 +219,7 @@ k_rows2(const float* __restrict__ img, float* __restrict__ gray, float* __restri
     }
 }
 
-template <bool EST, int THREADS>
+template <bool EST, int THREADS, class SP>
 __global__ void __launch_bounds__(THREADS, (THREADS == 256 ? PB_R2_MINB : 1))
 k_cols2(const float* __restrict__ plane_in, const float* __restrict__ gx, float* __restrict__ gy,
         unsigned* __restrict__ stats, int H, int W, int nb, int stride, Fft2Plan plan,
@@ -254,7 +261,10 @@ k_cols2(const float* __restrict__ plane_in, const float* __restrict__ gx, float*
             if (off[u] >= 0) sm2[off[u]] = g[u];
     }
     __syncthreads();
-    fft2_forward_mul_inverse(sm2, stride, nb, plan, tw, tid, THREADS, omega, 1);
+    if constexpr (std::is_same<SP, NoStaticPlan>::value)
+        fft2_forward_mul_inverse(sm2, stride, nb, plan, tw, tid, THREADS, omega, 1);
+    else
+        s_forward_mul_inverse<SP, 1>(sm2, stride, nb, tw, tid, THREADS, omega);
     const float inv = 1.0f / (float)H;
 
     if (!EST) {
@@ -391,14 +401,21 @@ int launch_rows2(bool est, const float* img, float* gray, float* gx, unsigned* s
     dim3 grid((pairs_total + nb - 1) / nb, nimg);
     ProfScope prof(PROF_ROWS, stream);
     int rc;
-    if (est) {
-        if ((rc = set_smem2(k_rows2<true>, smem))) return rc;
-        k_rows2<true><<<grid, R2_THREADS, smem, stream>>>(img, gray, gx, stats, C, H, W, nb, planW, twW, omegaW, qrange);
-    } else {
-        if ((rc = set_smem2(k_rows2<false>, smem))) return rc;
-        k_rows2<false><<<grid, R2_THREADS, smem, stream>>>(img, gray, gx, stats, 1, H, W, nb, planW, twW, omegaW,
-                                                           nullptr);
-    }
+#define PB_LAUNCH_ROWS2(E, SP)                                                                            \
+    do {                                                                                                  \
+        if ((rc = set_smem2(k_rows2<E, SP>, smem))) return rc;                                            \
+        k_rows2<E, SP><<<grid, R2_THREADS, smem, stream>>>(img, gray, gx, stats, (E) ? C : 1, H, W, nb, planW, twW, \
+                                                           omegaW, (E) ? qrange : nullptr);               \
+    } while (0)
+#define PB_LAUNCH_ROWS2_SP(SP)                                  \
+    do {                                                        \
+        if (est) PB_LAUNCH_ROWS2(true, SP); else PB_LAUNCH_ROWS2(false, SP); \
+    } while (0)
+    if (PlanW1920::matches(planW)) PB_LAUNCH_ROWS2_SP(PlanW1920);
+    else if (PlanW3840::matches(planW)) PB_LAUNCH_ROWS2_SP(PlanW3840);
+    else PB_LAUNCH_ROWS2_SP(NoStaticPlan);
+#undef PB_LAUNCH_ROWS2_SP
+#undef PB_LAUNCH_ROWS2
     PB_LAUNCH_CHECK("k_rows2");
     return PB_OK;
 }
@@ -416,17 +433,21 @@ int launch_cols2(bool est, const float* plane_in, const float* gx, float* gy, un
     ProfScope prof(PROF_COLS, stream);
     int rc;
     const bool big = smem > 72 * 1024;
-#define PB_LAUNCH_COLS2(E, T)                                                                          \
-    do {                                                                                               \
-        if ((rc = set_smem2(k_cols2<E, T>, smem))) return rc;                                          \
-        k_cols2<E, T><<<grid, T, smem, stream>>>(plane_in, gx, gy, stats, H, W, nb, stride, planH, twH, \
-                                                 omegaH, discard_saturation, mask_src);                \
+#define PB_LAUNCH_COLS2(E, T, SP)                                                                          \
+    do {                                                                                                   \
+        if ((rc = set_smem2(k_cols2<E, T, SP>, smem))) return rc;                                          \
+        k_cols2<E, T, SP><<<grid, T, smem, stream>>>(plane_in, gx, gy, stats, H, W, nb, stride, planH, twH, \
+                                                     omegaH, discard_saturation, mask_src);                \
     } while (0)
-    if (est) {
-        if (big) PB_LAUNCH_COLS2(true, 512); else PB_LAUNCH_COLS2(true, 256);
-    } else {
-        if (big) PB_LAUNCH_COLS2(false, 512); else PB_LAUNCH_COLS2(false, 256);
-    }
+#define PB_LAUNCH_COLS2_SP(T, SP)                                               \
+    do {                                                                        \
+        if (est) PB_LAUNCH_COLS2(true, T, SP); else PB_LAUNCH_COLS2(false, T, SP); \
+    } while (0)
+    if (!big && PlanH1080::matches(planH)) PB_LAUNCH_COLS2_SP(256, PlanH1080);
+    else if (big && PlanH2160::matches(planH)) PB_LAUNCH_COLS2_SP(512, PlanH2160);
+    else if (big) PB_LAUNCH_COLS2_SP(512, NoStaticPlan);
+    else PB_LAUNCH_COLS2_SP(256, NoStaticPlan);
+#undef PB_LAUNCH_COLS2_SP
 #undef PB_LAUNCH_COLS2
     PB_LAUNCH_CHECK("k_cols2");
     return PB_OK;

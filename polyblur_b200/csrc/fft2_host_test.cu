@@ -4,9 +4,10 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
-#include "fft2.cuh"
+#include "fft2_static.cuh"
 
 using namespace pb;
 
@@ -21,8 +22,56 @@ struct ArrayDst {
     void operator()(int f, int i, float2 v) const { a[f * stride + i] = v; }
 };
 
+// compile-time plans against the run-time core on the same data: must agree to rounding (same
+// operations, possibly different contraction)
+template <class P>
+int check_static() {
+    Fft2Plan plan;
+    if (make_fft2_plan(P::n, &plan) != 0 || !P::matches(plan)) {
+        printf("static %d: radix order differs from the planner\n", P::n);
+        return 1;
+    }
+    const int n = P::n, nb = 2, stride = n + 1;
+    std::vector<float2> tw(plan.tw_total);
+    for (int k = 0; k < plan.tw_total; ++k) tw[k] = fft2_stage_twiddle(k, plan);
+    std::vector<float2> a(nb * stride), b;
+    srand(n + 7);
+    for (auto& v : a) v = make_float2(rand() / (float)RAND_MAX - 0.5f, rand() / (float)RAND_MAX - 0.5f);
+    b = a;
+    std::vector<float> h(stride * nb + n);
+    for (size_t i = 0; i < h.size(); ++i) h[i] = 0.5f + (float)((i * 2654435761u) % 1000) / 1000.0f;
+    double worst = 0;
+    {
+        std::vector<float2> u = a, v = a;
+        fft2_forward_dif(u.data(), stride, nb, plan, tw.data(), 0, 1);
+        s_forward_dif<P>(v.data(), stride, nb, tw.data(), 0, 1);
+        for (size_t i = 0; i < u.size(); ++i) worst = fmax(worst, fmax(fabs(u[i].x - v[i].x), fabs(u[i].y - v[i].y)));
+        fft2_forward_dit(u.data(), stride, nb, plan, tw.data(), 0, 1);
+        s_forward_dit<P>(v.data(), stride, nb, tw.data(), 0, 1);
+        for (size_t i = 0; i < u.size(); ++i) worst = fmax(worst, fmax(fabs(u[i].x - v[i].x), fabs(u[i].y - v[i].y)) / n);
+    }
+    {
+        std::vector<float2> u = a, v = a;
+        fft2_forward_mul_inverse(u.data(), stride, nb, plan, tw.data(), 0, 1, h.data(), 1);
+        s_forward_mul_inverse<P, 1>(v.data(), stride, nb, tw.data(), 0, 1, h.data());
+        for (size_t i = 0; i < u.size(); ++i) worst = fmax(worst, fmax(fabs(u[i].x - v[i].x), fabs(u[i].y - v[i].y)) / n);
+        u = a; v = a;
+        fft2_forward_mul_inverse(u.data(), stride, nb, plan, tw.data(), 0, 1, h.data(), 2);
+        s_forward_mul_inverse<P, 2>(v.data(), stride, nb, tw.data(), 0, 1, h.data());
+        for (size_t i = 0; i < u.size(); ++i) worst = fmax(worst, fmax(fabs(u[i].x - v[i].x), fabs(u[i].y - v[i].y)) / n);
+    }
+    printf("static %d %.3e\n", n, worst);
+    return worst > 1e-5 ? 1 : 0;
+}
+
 int main(int argc, char** argv) {
     int worst = 0;
+    if (argc > 1 && std::string(argv[1]) == "static") {
+        worst |= check_static<PlanW1920>() | check_static<PlanH1080>() | check_static<PlanX2016>() |
+                 check_static<PlanY1152>() | check_static<PlanW3840>() | check_static<PlanH2160>() |
+                 check_static<PlanX4000>() | check_static<PlanY2304>();
+        return worst;
+    }
     for (int a = 1; a < argc; ++a) {
         const int n = atoi(argv[a]);
         Fft2Plan plan;
