@@ -85,6 +85,11 @@ __global__ void k_fft2_perm(int* __restrict__ slot_of_freq, int* __restrict__ fr
 }
 
 #define FFTD_THREADS 256
+// threads of the column kernel (288 = 9 warps would divide the butterfly counts of a 4-column block of
+// 1152 evenly, but its 72-register budget spills: measured equal to 256)
+#ifndef FFTC_THREADS
+#define FFTC_THREADS 256
+#endif
 #ifndef PB_FFTD_MINB
 #define PB_FFTD_MINB 3      // resident CTAs per SM (see estimate2.cu)
 #endif
@@ -241,7 +246,7 @@ k_fft_rows_fwd(const float* __restrict__ img, float2* __restrict__ Z, const ImgK
 //   Leaves r = DFT(swap(Y)) in Z: the inverse transform is swap(r), P3 swaps while loading.
 // ---------------------------------------------------------------------------------------------
 template <class SP>
-__global__ void __launch_bounds__(FFTD_THREADS, PB_FFTD_MINB)
+__global__ void __launch_bounds__(FFTC_THREADS, PB_FFTD_MINB)
 k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int* __restrict__ list,
            const int* __restrict__ count, int C, int NX, int NY, int CB, Fft2Plan planY,
            const float2* __restrict__ twX, const float2* __restrict__ stwY, const int* __restrict__ slotY,
@@ -274,7 +279,7 @@ k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int
 
         // R[col][dy] = sum_dx K[dy][dx] exp(-2 pi i kx dx / NX), dy = 0..12 (R[-dy] = conj R[dy]);
         // entry CB is the Nyquist column kx = NX / 2 (needed by the block that holds kx = 0)
-        for (int idx = tid; idx < (CB + 1) * 13; idx += FFTD_THREADS) {
+        for (int idx = tid; idx < (CB + 1) * 13; idx += FFTC_THREADS) {
             const int col = idx / 13, dy = idx - col * 13;
             const int kx = (col < CB) ? kx0 + col : half;
             float2 acc = make_float2(0.f, 0.f);
@@ -295,9 +300,9 @@ k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int
         // (r_A + i r_B -> K^_A + i K^_B), run by the same DIF core: the result arrives in slot order.
         const int ncolh = ncol + (cb == 0 ? 1 : 0);            // + the Nyquist column
         const int nseq = (ncolh + 1) >> 1;
-        for (int idx = tid; idx < nseq * NY; idx += FFTD_THREADS) data[idx] = make_float2(0.f, 0.f);
+        for (int idx = tid; idx < nseq * NY; idx += FFTC_THREADS) data[idx] = make_float2(0.f, 0.f);
         __syncthreads();
-        for (int idx = tid; idx < nseq * PB_KS; idx += FFTD_THREADS) {
+        for (int idx = tid; idx < nseq * PB_KS; idx += FFTC_THREADS) {
             const int q = idx / PB_KS, d = idx - q * PB_KS - PB_PAD;
             const int ca = 2 * q, cb2 = 2 * q + 1;
             const int ad = d < 0 ? -d : d;
@@ -312,11 +317,11 @@ k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int
         }
         __syncthreads();
         if constexpr (std::is_same<SP, NoStaticPlan>::value)
-            fft2_forward_dif(data, NY, nseq, planY, stwY, tid, FFTD_THREADS);
+            fft2_forward_dif(data, NY, nseq, planY, stwY, tid, FFTC_THREADS);
         else
-            s_forward_dif<SP>(data, NY, nseq, stwY, tid, FFTD_THREADS);
+            s_forward_dif<SP>(data, NY, nseq, stwY, tid, FFTC_THREADS);
         // Hs[col][slot] = scale * P(K^)
-        for (int idx = tid; idx < ncolh * NY; idx += FFTD_THREADS) {
+        for (int idx = tid; idx < ncolh * NY; idx += FFTC_THREADS) {
             const int col = fast_div(idx, NY, inv_ny);
             const int s = idx - col * NY;
             const float2 z = data[(size_t)(col >> 1) * NY + s];
@@ -330,7 +335,7 @@ k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int
             // column 0 carries DC (real part) and Nyquist (imaginary part) of two real spectra:
             // Y[k] = A Z[k] + B conj Z[-k], A = (H0 + Hn) / 2, B = (H0 - Hn) / 2; it is filtered by a
             // separate pass below, so its fused multiplier becomes 1
-            for (int s = tid; s < NY; s += FFTD_THREADS) {
+            for (int s = tid; s < NY; s += FFTC_THREADS) {
                 const float h0 = Hs[s], hn = Hn[s];
                 Hn[s] = 0.5f * (h0 + hn);
                 Hb[s] = 0.5f * (h0 - hn);
@@ -350,9 +355,9 @@ k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int
             mbar_wait(bar, phase);
             phase ^= 1;
             if (cb == 0) {
-                fft2_forward_dif(data, NY, ncol, planY, stwY, tid, FFTD_THREADS);
+                fft2_forward_dif(data, NY, ncol, planY, stwY, tid, FFTC_THREADS);
                 // the pair {k, -k} of column 0 goes to one thread (in place, no hazard)
-                for (int ky = tid; ky <= NY / 2; ky += FFTD_THREADS) {
+                for (int ky = tid; ky <= NY / 2; ky += FFTC_THREADS) {
                     const int s1 = __ldg(slotY + ky);
                     const int s2 = __ldg(slotY + (NY - ky) % NY);
                     const float2 z1 = data[s1], z2 = data[s2];
@@ -363,13 +368,13 @@ k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int
                 __syncthreads();
                 // inverse-direction transform with the multiplication by H (and the re/im swap) folded
                 // into its first stage
-                fft2_forward_dit(data, NY, ncol, planY, stwY, tid, FFTD_THREADS, Hs, 2);
+                fft2_forward_dit(data, NY, ncol, planY, stwY, tid, FFTC_THREADS, Hs, 2);
             } else {
                 // forward, multiply by H (with the re/im swap), inverse: innermost stages fused in registers
                 if constexpr (std::is_same<SP, NoStaticPlan>::value)
-                    fft2_forward_mul_inverse(data, NY, ncol, planY, stwY, tid, FFTD_THREADS, Hs, 2);
+                    fft2_forward_mul_inverse(data, NY, ncol, planY, stwY, tid, FFTC_THREADS, Hs, 2);
                 else
-                    s_forward_mul_inverse<SP, 2>(data, NY, ncol, stwY, tid, FFTD_THREADS, Hs);
+                    s_forward_mul_inverse<SP, 2>(data, NY, ncol, stwY, tid, FFTC_THREADS, Hs);
             }
             fence_async_smem();
             __syncthreads();
@@ -610,7 +615,7 @@ int launch_deconv_fft(const float* img, float* out, const ImgKernel* kern, const
     do {                                                                                                         \
         PB_CUDA_TRY(cudaFuncSetAttribute(k_fft_cols<SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols)); \
         ProfScope prof(PROF_FFT_COLS, stream);                                                                   \
-        k_fft_cols<SP><<<grid_cols, FFTD_THREADS, smem_cols, stream>>>(T.Z, kern, list, count, C, NX, NY, CB, T.planY, \
+        k_fft_cols<SP><<<grid_cols, FFTC_THREADS, smem_cols, stream>>>(T.Z, kern, list, count, C, NX, NY, CB, T.planY, \
                                                                        T.twX, T.stwY, T.slotY, a3, a2, a1, b0);  \
     } while (0)
     for (int pass = 0; pass < 3; ++pass) {
