@@ -208,30 +208,44 @@ k_fft_rows_fwd(const float* __restrict__ img, float2* __restrict__ Z, const ImgK
             s_forward_dif<SP>(smf, NX, nb, twX, tid, FFTD_THREADS);
         // separate the two real rows: Xa[k] = (Z[k] + conj Z[-k]) / 2, Xb[k] = (Z[k] - conj Z[-k]) / (2i)
         float2* Zp = Z + ((size_t)slot * C + c) * half * NY;
-#pragma unroll 2
-        for (int idx = tid; idx < nb * half; idx += FFTD_THREADS) {
-            const int kx = fast_div(idx, nb, inv_nb);
-            const int p = idx - kx * nb;
-            const int ja = j0 + 2 * p;
-            if (ja >= NY) continue;
-            const float2* row = smf + (size_t)p * NX;
-            float2 xa, xb;
-            if (kx == 0) {
-                const float2 z0 = row[__ldg(slotX)];
-                const float2 zn = row[__ldg(slotX + half)];
-                xa = make_float2(z0.x, zn.x);
-                xb = make_float2(z0.y, zn.y);
-            } else {
-                const float2 z1 = row[__ldg(slotX + kx)];
-                const float2 z2 = row[__ldg(slotX + NX - kx)];
-                xa = make_float2(0.5f * (z1.x + z2.x), 0.5f * (z1.y - z2.y));
-                xb = make_float2(0.5f * (z1.y + z2.y), 0.5f * (z2.x - z1.x));
+        // four (kx, pair) items per trip: slot lookups first, then the scattered shared-memory reads
+        for (int base = tid; base < nb * half; base += 4 * FFTD_THREADS) {
+            int s1[4], s2[4], pp[4], kk[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int idx = base + u * FFTD_THREADS;
+                kk[u] = -1;
+                if (idx < nb * half) {
+                    const int kx = fast_div(idx, nb, inv_nb);
+                    const int p = idx - kx * nb;
+                    if (j0 + 2 * p < NY) {
+                        kk[u] = kx;
+                        pp[u] = p;
+                        s1[u] = __ldg(slotX + kx);
+                        s2[u] = __ldg(slotX + (kx == 0 ? half : NX - kx));
+                    }
+                }
             }
-            float2* d = Zp + (size_t)kx * NY + ja;
-            if (ja + 1 < NY) {
-                *reinterpret_cast<float4*>(d) = make_float4(xa.x, xa.y, xb.x, xb.y);
-            } else {
-                d[0] = xa;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (kk[u] < 0) continue;
+                const int ja = j0 + 2 * pp[u];
+                const float2* row = smf + (size_t)pp[u] * NX;
+                const float2 z1 = row[s1[u]], z2 = row[s2[u]];
+                float2 xa, xb;
+                if (kk[u] == 0) {                    // z1 = Z[0], z2 = Z[N/2]: both spectra real there
+                    xa = make_float2(z1.x, z2.x);
+                    xb = make_float2(z1.y, z2.y);
+                } else {
+                    xa = make_float2(0.5f * (z1.x + z2.x), 0.5f * (z1.y - z2.y));
+                    xb = make_float2(0.5f * (z1.y + z2.y), 0.5f * (z2.x - z1.x));
+                }
+                float2* d = Zp + (size_t)kk[u] * NY + ja;
+                if (ja + 1 < NY) {
+                    *reinterpret_cast<float4*>(d) = make_float4(xa.x, xa.y, xb.x, xb.y);
+                } else {
+                    d[0] = xa;
+                }
             }
         }
         __syncthreads();
@@ -419,29 +433,46 @@ k_fft_rows_inv(const float2* __restrict__ Z, float* __restrict__ out, const ImgK
         // rows of the extended image that are output rows: [ext, H + ext)
         if (j0 + 2 * nb <= ext || j0 >= H + ext) continue;
         const float2* Zp = Z + ((size_t)slot * C + c) * half * NY;
-#pragma unroll 2
-        for (int idx = tid; idx < nb * half; idx += FFTD_THREADS) {
-            const int kx = fast_div(idx, nb, inv_nb);
-            const int p = idx - kx * nb;
-            const int ja = j0 + 2 * p;
-            // P2 leaves the spectra re/im swapped
-            float2 xa = make_float2(0.f, 0.f), xb = make_float2(0.f, 0.f);
-            if (ja + 1 < NY) {
-                const float4 v = __ldg(reinterpret_cast<const float4*>(Zp + (size_t)kx * NY + ja));
-                xa = make_float2(v.y, v.x);
-                xb = make_float2(v.w, v.z);
-            } else if (ja < NY) {
-                const float2 v = __ldg(Zp + (size_t)kx * NY + ja);
-                xa = make_float2(v.y, v.x);
+        // four (kx, pair) items per trip: their 128-bit spectrum loads and slot lookups are all in flight
+        // before the first is used
+        for (int base = tid; base < nb * half; base += 4 * FFTD_THREADS) {
+            float4 v[4];
+            int s1[4], s2[4], pp[4], kk[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int idx = base + u * FFTD_THREADS;
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                kk[u] = -1;
+                if (idx < nb * half) {
+                    const int kx = fast_div(idx, nb, inv_nb);
+                    const int p = idx - kx * nb;
+                    const int ja = j0 + 2 * p;
+                    kk[u] = kx;
+                    pp[u] = p;
+                    // P2 leaves the spectra re/im swapped
+                    if (ja + 1 < NY) {
+                        v[u] = __ldg(reinterpret_cast<const float4*>(Zp + (size_t)kx * NY + ja));
+                    } else if (ja < NY) {
+                        const float2 t = __ldg(Zp + (size_t)kx * NY + ja);
+                        v[u] = make_float4(t.x, t.y, 0.f, 0.f);
+                    }
+                    s1[u] = __ldg(slotX + kx);
+                    s2[u] = __ldg(slotX + (kx == 0 ? half : NX - kx));
+                }
             }
-            float2* row = smf + (size_t)p * NX;
-            // Z[k] = Xa[k] + i Xb[k], Z[-k] = conj Xa[k] + i conj Xb[k]; stored swapped (re <-> im)
-            if (kx == 0) {
-                row[__ldg(slotX)] = make_float2(xb.x, xa.x);
-                row[__ldg(slotX + half)] = make_float2(xb.y, xa.y);
-            } else {
-                row[__ldg(slotX + kx)] = make_float2(xa.y + xb.x, xa.x - xb.y);
-                row[__ldg(slotX + NX - kx)] = make_float2(xb.x - xa.y, xa.x + xb.y);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (kk[u] < 0) continue;
+                const float2 xa = make_float2(v[u].y, v[u].x), xb = make_float2(v[u].w, v[u].z);
+                float2* row = smf + (size_t)pp[u] * NX;
+                // Z[k] = Xa[k] + i Xb[k], Z[-k] = conj Xa[k] + i conj Xb[k]; stored swapped (re <-> im)
+                if (kk[u] == 0) {
+                    row[s1[u]] = make_float2(xb.x, xa.x);
+                    row[s2[u]] = make_float2(xb.y, xa.y);
+                } else {
+                    row[s1[u]] = make_float2(xa.y + xb.x, xa.x - xb.y);
+                    row[s2[u]] = make_float2(xb.x - xa.y, xa.x + xb.y);
+                }
             }
         }
         __syncthreads();
