@@ -293,21 +293,38 @@ k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int
 
         // R[col][dy] = sum_dx K[dy][dx] exp(-2 pi i kx dx / NX), dy = 0..12 (R[-dy] = conj R[dy]);
         // entry CB is the Nyquist column kx = NX / 2 (needed by the block that holds kx = 0)
-        for (int idx = tid; idx < (CB + 1) * 13; idx += FFTC_THREADS) {
+        // two threads per (col, dy): dx <= 0 and dx > 0, all loads of a thread issued together
+        for (int base = 0; base < (CB + 1) * 13 * 2; base += FFTC_THREADS) {
+            const int i2 = base + tid;
+            const int idx = i2 >> 1, part = i2 & 1;
             const int col = idx / 13, dy = idx - col * 13;
             const int kx = (col < CB) ? kx0 + col : half;
             float2 acc = make_float2(0.f, 0.f);
-            if (col < ncol || (col == CB && cb == 0)) {
-                for (int dx = -PB_PAD; dx <= PB_PAD; ++dx) {
-                    float kv = __ldg(&K->k[(dy + PB_PAD) * PB_KS + dx + PB_PAD]);
-                    if (dy == 0 && dx == 0) kv -= 1.0f;        // spectrum of D = K - I (small where K^ ~ 1)
-                    const int t = (int)(((long long)kx * (dx + NX)) % NX);
-                    const float2 e = __ldg(twX + t);
-                    acc.x = fmaf(kv, e.x, acc.x);
-                    acc.y = fmaf(kv, e.y, acc.y);
+            if (idx < (CB + 1) * 13 && (col < ncol || (col == CB && cb == 0))) {
+                const int dx0 = part ? 1 : -PB_PAD;
+                // t = kx * dx mod NX, stepped by kx (kx * NX < 2^31 for every supported length)
+                unsigned t = ((unsigned)kx * (unsigned)(dx0 + NX)) % (unsigned)NX;
+                const float* kr = &K->k[(dy + PB_PAD) * PB_KS + dx0 + PB_PAD];
+                float kv[PB_PAD + 1];
+                float2 e[PB_PAD + 1];
+#pragma unroll
+                for (int u = 0; u <= PB_PAD; ++u) {
+                    const bool on = part ? (u < PB_PAD) : true;          // 13 taps below, 12 above
+                    kv[u] = on ? __ldg(kr + u) : 0.f;
+                    e[u] = on ? __ldg(twX + t) : make_float2(0.f, 0.f);
+                    t += kx;
+                    if (t >= (unsigned)NX) t -= NX;
+                }
+                if (dy == 0 && !part) kv[PB_PAD] -= 1.0f;     // spectrum of D = K - I (small where K^ ~ 1)
+#pragma unroll
+                for (int u = 0; u <= PB_PAD; ++u) {
+                    acc.x = fmaf(kv[u], e[u].x, acc.x);
+                    acc.y = fmaf(kv[u], e[u].y, acc.y);
                 }
             }
-            Rk[idx] = acc;
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 1);
+            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 1);
+            if (!part && idx < (CB + 1) * 13) Rk[idx] = acc;
         }
         // K^(ky, kx) = sum_dy R[dy] exp(-2 pi i ky dy / NY) is the length-NY DFT of the sparse
         // sequence r[dy mod NY] = R[dy]; it is real, so two columns share one complex transform
@@ -358,14 +375,15 @@ k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int
             __syncthreads();
         }
 
+        float2* Z0 = Z + ((size_t)slot * C * half + kx0) * NY;
+        if (tid == 0) {
+            fence_async_smem();
+            mbar_expect_tx(bar, (uint32_t)((size_t)ncol * NY * sizeof(float2)));
+            for (int col = 0; col < ncol; ++col)
+                bulk_g2s(data + (size_t)col * NY, Z0 + (size_t)col * NY, (uint32_t)(NY * sizeof(float2)), bar);
+        }
         for (int c = 0; c < C; ++c) {
-            float2* Zc = Z + (((size_t)slot * C + c) * half + kx0) * NY;
-            if (tid == 0) {
-                fence_async_smem();
-                mbar_expect_tx(bar, (uint32_t)((size_t)ncol * NY * sizeof(float2)));
-                for (int col = 0; col < ncol; ++col)
-                    bulk_g2s(data + (size_t)col * NY, Zc + (size_t)col * NY, (uint32_t)(NY * sizeof(float2)), bar);
-            }
+            float2* Zc = Z0 + (size_t)c * half * NY;
             mbar_wait(bar, phase);
             phase ^= 1;
             if (cb == 0) {
@@ -397,9 +415,17 @@ k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int
                     bulk_s2g(Zc + (size_t)col * NY, data + (size_t)col * NY, (uint32_t)(NY * sizeof(float2)));
                 bulk_commit();
                 bulk_wait_all();
+                // the buffer has been read out: fetch the next plane right away, the other threads
+                // go straight to the mbarrier
+                if (c + 1 < C) {
+                    const float2* Zn = Zc + (size_t)half * NY;
+                    mbar_expect_tx(bar, (uint32_t)((size_t)ncol * NY * sizeof(float2)));
+                    for (int col = 0; col < ncol; ++col)
+                        bulk_g2s(data + (size_t)col * NY, Zn + (size_t)col * NY, (uint32_t)(NY * sizeof(float2)), bar);
+                }
             }
-            __syncthreads();
         }
+        __syncthreads();
     }
 }
 
