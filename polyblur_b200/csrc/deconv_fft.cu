@@ -118,7 +118,6 @@ k_fft_rows_fwd(const float* __restrict__ img, float2* __restrict__ Z, const ImgK
     const int blocks_per_plane = (NY / 2 + nb - 1) / nb;
     const int per_img = C * blocks_per_plane;
     const int total = count[0] * per_img;
-    const size_t plane = (size_t)H * W;
     const int half = NX >> 1;
     const float inv_nb = 1.0f / (float)nb;
 

@@ -47,7 +47,19 @@ __global__ void k_fft2_stage_tw(float2* __restrict__ stw, Fft2Plan plan) {
     if (i < plan.tw_total) stw[i] = fft2_stage_twiddle(i, plan);
 }
 
+#ifndef R2_THREADS
 #define R2_THREADS 256
+#endif
+// shared-memory budget of a row tile, threads and column pairs of a column tile (tuning hooks)
+#ifndef PB_R2_SMEM
+#define PB_R2_SMEM (64 * 1024)
+#endif
+#ifndef PB_C2_THREADS
+#define PB_C2_THREADS 256
+#endif
+#ifndef PB_C2_NB
+#define PB_C2_NB 8
+#endif
 // resident CTAs per SM the register allocation aims for (3 x 256 threads at <= 85 registers;
 // measured: 2 CTAs at 128 registers is 2x slower, 4 CTAs do not fit the shared memory)
 #ifndef PB_R2_MINB
@@ -220,7 +232,7 @@ k_rows2(const float* __restrict__ img, float* __restrict__ gray, float* __restri
 }
 
 template <bool EST, int THREADS, class SP>
-__global__ void __launch_bounds__(THREADS, (THREADS == 256 ? PB_R2_MINB : 1))
+__global__ void __launch_bounds__(THREADS, (THREADS == PB_C2_THREADS ? PB_R2_MINB : 1))
 k_cols2(const float* __restrict__ plane_in, const float* __restrict__ gx, float* __restrict__ gy,
         unsigned* __restrict__ stats, int H, int W, int nb, int stride, Fft2Plan plan,
         const float2* __restrict__ tw, const float* __restrict__ omega, int discard_saturation,
@@ -296,41 +308,53 @@ k_cols2(const float* __restrict__ plane_in, const float* __restrict__ gx, float*
     const float* gxp = gx + (size_t)im * plane;
     // saturation mask: un-normalised gray > 0.99 (blur_estimation.py:59, 83-88)
     const float* msk = (mask_src ? mask_src : plane_in) + (size_t)im * plane;
-#pragma unroll 4
-    for (int idx = tid; idx < H * nb; idx += THREADS) {
-        const int y = fast_div(idx, nb, inv_nb);
-        const int p = idx - y * nb;
-        const int x = x0 + 2 * p;
-        if (x >= W) continue;
-        const float2 z = sm2[(size_t)p * stride + y];
-        const float gyv[2] = {z.y * inv, z.x * inv};
-        float gxv[2] = {0.f, 0.f};
-        float gr[2] = {0.f, 0.f};
-        if (vec2) {
-            const float2 t = __ldg(reinterpret_cast<const float2*>(gxp + (size_t)y * W + x));
-            gxv[0] = t.x;
-            gxv[1] = t.y;
-            if (discard_saturation) {
-                const float2 s = __ldg(reinterpret_cast<const float2*>(msk + (size_t)y * W + x));
-                gr[0] = s.x;
-                gr[1] = s.y;
-            }
-        } else {
-            gxv[0] = __ldg(gxp + (size_t)y * W + x);
-            if (x + 1 < W) gxv[1] = __ldg(gxp + (size_t)y * W + x + 1);
-            if (discard_saturation) {
-                gr[0] = __ldg(msk + (size_t)y * W + x);
-                if (x + 1 < W) gr[1] = __ldg(msk + (size_t)y * W + x + 1);
+    // four pixel pairs per trip: the d/dx (and mask) loads of all four are in flight before the first use
+    for (int base = tid; base < H * nb; base += 4 * THREADS) {
+        float2 zz[4], gxx[4], grr[4];
+        int cnt[4];                      // live pixels of the pair: 0, 1 or 2
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = base + u * THREADS;
+            cnt[u] = 0;
+            gxx[u] = make_float2(0.f, 0.f);
+            grr[u] = make_float2(0.f, 0.f);
+            zz[u] = make_float2(0.f, 0.f);
+            if (idx < H * nb) {
+                const int y = fast_div(idx, nb, inv_nb);
+                const int p = idx - y * nb;
+                const int x = x0 + 2 * p;
+                if (x < W) {
+                    cnt[u] = (x + 1 < W) ? 2 : 1;
+                    const size_t o = (size_t)y * W + x;
+                    if (vec2) {
+                        gxx[u] = __ldg(reinterpret_cast<const float2*>(gxp + o));
+                        if (discard_saturation) grr[u] = __ldg(reinterpret_cast<const float2*>(msk + o));
+                    } else {
+                        gxx[u].x = __ldg(gxp + o);
+                        if (cnt[u] == 2) gxx[u].y = __ldg(gxp + o + 1);
+                        if (discard_saturation) {
+                            grr[u].x = __ldg(msk + o);
+                            if (cnt[u] == 2) grr[u].y = __ldg(msk + o + 1);
+                        }
+                    }
+                    zz[u] = sm2[(size_t)p * stride + y];
+                }
             }
         }
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            if (x + h >= W) continue;
-            if (discard_saturation && gr[h] > 0.99f) continue;
+        for (int u = 0; u < 4; ++u) {
+            const float gyv[2] = {zz[u].y * inv, zz[u].x * inv};
+            const float gxv[2] = {gxx[u].x, gxx[u].y};
+            const float gr[2] = {grr[u].x, grr[u].y};
 #pragma unroll
-            for (int j = 0; j < 7; ++j) {
-                const float v = __fsub_rn(__fmul_rn(cs7[j], gxv[h]), __fmul_rn(sn7[j], gyv[h]));
-                m[j] = fmaxf(m[j], fabsf(v));
+            for (int h = 0; h < 2; ++h) {
+                if (h >= cnt[u]) continue;
+                if (discard_saturation && gr[h] > 0.99f) continue;
+#pragma unroll
+                for (int j = 0; j < 7; ++j) {
+                    const float v = __fsub_rn(__fmul_rn(cs7[j], gxv[h]), __fmul_rn(sn7[j], gyv[h]));
+                    m[j] = fmaxf(m[j], fabsf(v));
+                }
             }
         }
     }
@@ -394,7 +418,7 @@ bool fft2_supported(int H, int W) {
 int launch_rows2(bool est, const float* img, float* gray, float* gx, unsigned* stats, int nimg, int C,
                  int H, int W, const Fft2Plan& planW, const float2* twW, const float* omegaW,
                  const float* qrange, cudaStream_t stream) {
-    int nb = pairs_for(W, 8, 64 * 1024);
+    int nb = pairs_for(W, 8, PB_R2_SMEM);
     const int pairs_total = (H + 1) / 2;
     if (nb > pairs_total) nb = pairs_total;
     const size_t smem = (size_t)nb * W * sizeof(float2);
@@ -424,7 +448,7 @@ int launch_cols2(bool est, const float* plane_in, const float* gx, float* gy, un
                  int H, int W, const Fft2Plan& planH, const float2* twH, const float* omegaH,
                  int discard_saturation, const float* mask_src, cudaStream_t stream) {
     // 8 pairs = 16 columns = 64-byte row segments; fall back to fewer when H is very long
-    int nb = pairs_for(H, 8, 200 * 1024);
+    int nb = pairs_for(H, PB_C2_NB, 200 * 1024);
     const int pairs_total = (W + 1) / 2;
     if (nb > pairs_total) nb = pairs_total;
     const int stride = H | 1;
@@ -443,10 +467,10 @@ int launch_cols2(bool est, const float* plane_in, const float* gx, float* gy, un
     do {                                                                        \
         if (est) PB_LAUNCH_COLS2(true, T, SP); else PB_LAUNCH_COLS2(false, T, SP); \
     } while (0)
-    if (!big && PlanH1080::matches(planH)) PB_LAUNCH_COLS2_SP(256, PlanH1080);
+    if (!big && PlanH1080::matches(planH)) PB_LAUNCH_COLS2_SP(PB_C2_THREADS, PlanH1080);
     else if (big && PlanH2160::matches(planH)) PB_LAUNCH_COLS2_SP(512, PlanH2160);
     else if (big) PB_LAUNCH_COLS2_SP(512, NoStaticPlan);
-    else PB_LAUNCH_COLS2_SP(256, NoStaticPlan);
+    else PB_LAUNCH_COLS2_SP(PB_C2_THREADS, NoStaticPlan);
 #undef PB_LAUNCH_COLS2_SP
 #undef PB_LAUNCH_COLS2
     PB_LAUNCH_CHECK("k_cols2");

@@ -28,8 +28,10 @@
 
 #if defined(__CUDACC__)
 #define PB_HD __host__ __device__ __forceinline__
+#define PB_HDC __host__ __device__
 #else
 #define PB_HD inline
+#define PB_HDC
 #endif
 #if defined(__CUDA_ARCH__)
 #define PB_LDG(p) __ldg(p)

@@ -14,18 +14,18 @@ template <int N_, int... RS>
 struct StaticPlan {
     static constexpr int n = N_;
     static constexpr int ns = sizeof...(RS);
-    static constexpr int R(int s) {
+    static constexpr PB_HDC int R(int s) {
         const int r[] = {RS...};
         return r[s];
     }
     // sub-length on entry to DIF stage s
-    static constexpr int L(int s) {
+    static constexpr PB_HDC int L(int s) {
         int l = N_;
         for (int i = 0; i < s; ++i) l /= R(i);
         return l;
     }
     // offset of stage s in the stage-twiddle table (same rule as fft2_plan_offsets)
-    static constexpr int tw_off(int s) {
+    static constexpr PB_HDC int tw_off(int s) {
         int off = 0, l = N_;
         for (int i = 0; i < s; ++i) {
             const int m = l / R(i);

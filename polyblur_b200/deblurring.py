@@ -172,7 +172,7 @@ def polyblur_deblurring(img, n_iter=1, c=0.352, b=0.768, alpha=2, beta=3, sigma_
     return out
 
 
-def _polyblur_host_pipelined(x: torch.Tensor, p: "_lib.PbParams", dev: torch.device, max_chunks: int = 8):
+def _polyblur_host_pipelined(x: torch.Tensor, p: "_lib.PbParams", dev: torch.device, max_chunks: int = 16):
     """CPU tensor in -> CPU tensor out with the PCIe transfers hidden behind the kernels.
 
     Images are independent, so the batch is cut into chunks that flow through three streams:
