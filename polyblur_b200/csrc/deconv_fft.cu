@@ -85,6 +85,9 @@ __global__ void k_fft2_perm(int* __restrict__ slot_of_freq, int* __restrict__ fr
 }
 
 #define FFTD_THREADS 256
+// float2 per row pair in shared memory: the sequence + 4, so that the same slot of the nb row pairs
+// of a CTA falls into different banks (the spectrum passes of P1 / P3 touch one slot of every pair)
+__host__ __device__ inline int fftd_row_stride(int NX) { return NX + 4; }
 // threads of the column kernel (288 = 9 warps would divide the butterfly counts of a 4-column block of
 // 1152 evenly, but its 72-register budget spills: measured equal to 256)
 #ifndef FFTC_THREADS
@@ -120,6 +123,7 @@ k_fft_rows_fwd(const float* __restrict__ img, float2* __restrict__ Z, const ImgK
     const int total = count[0] * per_img;
     const int half = NX >> 1;
     const float inv_nb = 1.0f / (float)nb;
+    const int RS = fftd_row_stride(NX);
 
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
         const int slot = w / per_img;
@@ -157,7 +161,7 @@ k_fft_rows_fwd(const float* __restrict__ img, float2* __restrict__ Z, const ImgK
                         const int sa = rowsrc[2 * p], sb = rowsrc[2 * p + 1];
                         if (sa >= 0) va[u] = __ldg(reinterpret_cast<const float4*>(src + (size_t)sa * Ws + x + G.off));
                         if (sb >= 0) vb[u] = __ldg(reinterpret_cast<const float4*>(src + (size_t)sb * Ws + x + G.off));
-                        off[u] = p * NX + x_off + x;
+                        off[u] = p * RS + x_off + x;
                     }
                 }
 #pragma unroll
@@ -183,7 +187,7 @@ k_fft_rows_fwd(const float* __restrict__ img, float2* __restrict__ Z, const ImgK
                     if (sa >= 0) v.x = __ldg(src + (size_t)sa * Ws + sx);
                     if (sb >= 0) v.y = __ldg(src + (size_t)sb * Ws + sx);
                 }
-                smf[(size_t)p * NX + i] = v;
+                smf[(size_t)p * RS + i] = v;
             }
         } else {
             const float inv_nx = 1.0f / (float)NX;
@@ -197,14 +201,14 @@ k_fft_rows_fwd(const float* __restrict__ img, float2* __restrict__ Z, const ImgK
                     if (sa >= 0) v.x = __ldg(src + (size_t)sa * Ws + sx);
                     if (sb >= 0) v.y = __ldg(src + (size_t)sb * Ws + sx);
                 }
-                smf[(size_t)p * NX + i] = v;
+                smf[(size_t)p * RS + i] = v;
             }
         }
         __syncthreads();
         if constexpr (std::is_same<SP, NoStaticPlan>::value)
-            fft2_forward_dif(smf, NX, nb, planX, twX, tid, FFTD_THREADS);
+            fft2_forward_dif(smf, RS, nb, planX, twX, tid, FFTD_THREADS);
         else
-            s_forward_dif<SP>(smf, NX, nb, twX, tid, FFTD_THREADS);
+            s_forward_dif<SP>(smf, RS, nb, twX, tid, FFTD_THREADS);
         // separate the two real rows: Xa[k] = (Z[k] + conj Z[-k]) / 2, Xb[k] = (Z[k] - conj Z[-k]) / (2i)
         float2* Zp = Z + ((size_t)slot * C + c) * half * NY;
         // four (kx, pair) items per trip: slot lookups first, then the scattered shared-memory reads
@@ -229,7 +233,7 @@ k_fft_rows_fwd(const float* __restrict__ img, float2* __restrict__ Z, const ImgK
             for (int u = 0; u < 4; ++u) {
                 if (kk[u] < 0) continue;
                 const int ja = j0 + 2 * pp[u];
-                const float2* row = smf + (size_t)pp[u] * NX;
+                const float2* row = smf + (size_t)pp[u] * RS;
                 const float2 z1 = row[s1[u]], z2 = row[s2[u]];
                 float2 xa, xb;
                 if (kk[u] == 0) {                    // z1 = Z[0], z2 = Z[N/2]: both spectra real there
@@ -446,6 +450,7 @@ k_fft_rows_inv(const float2* __restrict__ Z, float* __restrict__ out, const ImgK
     const int half = NX >> 1;
     const float inv_nb = 1.0f / (float)nb;
     const float lo = clamp_out ? 0.0f : -INFINITY, hi = clamp_out ? 1.0f : INFINITY;
+    const int RS = fftd_row_stride(NX);
 
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
         const int slot = w / per_img;
@@ -489,7 +494,7 @@ k_fft_rows_inv(const float2* __restrict__ Z, float* __restrict__ out, const ImgK
             for (int u = 0; u < 4; ++u) {
                 if (kk[u] < 0) continue;
                 const float2 xa = make_float2(v[u].y, v[u].x), xb = make_float2(v[u].w, v[u].z);
-                float2* row = smf + (size_t)pp[u] * NX;
+                float2* row = smf + (size_t)pp[u] * RS;
                 // Z[k] = Xa[k] + i Xb[k], Z[-k] = conj Xa[k] + i conj Xb[k]; stored swapped (re <-> im)
                 if (kk[u] == 0) {
                     row[s1[u]] = make_float2(xb.x, xa.x);
@@ -502,9 +507,9 @@ k_fft_rows_inv(const float2* __restrict__ Z, float* __restrict__ out, const ImgK
         }
         __syncthreads();
         if constexpr (std::is_same<SP, NoStaticPlan>::value)
-            fft2_forward_dit(smf, NX, nb, planX, twX, tid, FFTD_THREADS);
+            fft2_forward_dit(smf, RS, nb, planX, twX, tid, FFTD_THREADS);
         else
-            s_forward_dit<SP>(smf, NX, nb, twX, tid, FFTD_THREADS);
+            s_forward_dit<SP>(smf, RS, nb, twX, tid, FFTD_THREADS);
         // r = DFT(swap(Z)): row a = r.y, row b = r.x (the 1/(NX NY) scale is inside H)
         float* dst = out + ((size_t)im * C + c) * plane;
         const int x_off = ext;
@@ -514,7 +519,7 @@ k_fft_rows_inv(const float2* __restrict__ Z, float* __restrict__ out, const ImgK
             for (int idx = tid; idx < nb * w4; idx += FFTD_THREADS) {
                 const int p = fast_div(idx, w4, inv_w4);
                 const int x = (idx - p * w4) << 2;
-                const float4* sp = reinterpret_cast<const float4*>(smf + (size_t)p * NX + x_off + x);
+                const float4* sp = reinterpret_cast<const float4*>(smf + (size_t)p * RS + x_off + x);
                 const float4 u0 = sp[0], u1 = sp[1];
                 const int ya = j0 + 2 * p - ext;
                 if (ya >= 0 && ya < H)
@@ -531,7 +536,7 @@ k_fft_rows_inv(const float2* __restrict__ Z, float* __restrict__ out, const ImgK
             for (int idx = tid; idx < nb * W; idx += FFTD_THREADS) {
                 const int p = fast_div(idx, W, inv_w);
                 const int x = idx - p * W;
-                const float2 z = smf[(size_t)p * NX + x + x_off];
+                const float2 z = smf[(size_t)p * RS + x + x_off];
                 const int ya = j0 + 2 * p - ext;
                 if (ya >= 0 && ya < H) dst[(size_t)ya * W + x] = fminf(fmaxf(z.y, lo), hi);
                 if (ya + 1 >= 0 && ya + 1 < H) dst[(size_t)(ya + 1) * W + x] = fminf(fmaxf(z.x, lo), hi);
@@ -644,7 +649,7 @@ int launch_deconv_fft(const float* img, float* out, const ImgKernel* kern, const
                       float b0, const SrcGeom& G, cudaStream_t stream) {
     const int NX = T.NX, NY = T.NY;
     const int nb = rows_nb(NX), CB = cols_cb(NY);
-    const size_t smem_rows = (size_t)nb * NX * sizeof(float2);
+    const size_t smem_rows = (size_t)nb * fftd_row_stride(NX) * sizeof(float2);
     const size_t smem_cols = (size_t)CB * NY * 12 + (size_t)NY * 8 + (size_t)(CB + 1) * 13 * 8 + 64;
     const long long row_items = (long long)B * C * ((NY / 2 + nb - 1) / nb);
     const long long col_items = (long long)B * ((NX / 2 + CB - 1) / CB);
