@@ -400,7 +400,7 @@ static int set_smem2(KernelT kern, size_t bytes) {
 
 // sequences (pairs) per CTA: as many as fit `budget` bytes, at most max_nb, at least 1
 static int pairs_for(int n, int max_nb, size_t budget) {
-    int nb = (int)(budget / ((size_t)(n + 1) * sizeof(float2)));
+    int nb = (int)(budget / ((size_t)(n + 4) * sizeof(float2)));
     if (nb < 1) nb = 1;
     if (nb > max_nb) nb = max_nb;
     return nb;
@@ -451,7 +451,9 @@ int launch_cols2(bool est, const float* plane_in, const float* gx, float* gy, un
     int nb = pairs_for(H, PB_C2_NB, 200 * 1024);
     const int pairs_total = (W + 1) / 2;
     if (nb > pairs_total) nb = pairs_total;
-    const int stride = H | 1;
+    // float2 per column pair: >= H and = 2 (mod 4), so that the 8 pairs x 2 rows a half-warp touches in
+    // the load and reduce passes (address = pair * stride + row) fall into 16 different bank pairs
+    const int stride = H + ((2 - H) & 3);
     const size_t smem = (size_t)nb * stride * sizeof(float2);
     dim3 grid((pairs_total + nb - 1) / nb, nimg);
     ProfScope prof(PROF_COLS, stream);
