@@ -84,7 +84,9 @@ __global__ void k_fft2_perm(int* __restrict__ slot_of_freq, int* __restrict__ fr
     }
 }
 
+#ifndef FFTD_THREADS
 #define FFTD_THREADS 256
+#endif
 // float2 per row pair in shared memory: the sequence + 4, so that the same slot of the nb row pairs
 // of a CTA falls into different banks (the spectrum passes of P1 / P3 touch one slot of every pair)
 __host__ __device__ inline int fftd_row_stride(int NX) { return NX + 4; }

@@ -449,6 +449,10 @@ int launch_cols2(bool est, const float* plane_in, const float* gx, float* gy, un
                  int discard_saturation, const float* mask_src, cudaStream_t stream) {
     // 8 pairs = 16 columns = 64-byte row segments; fall back to fewer when H is very long
     int nb = pairs_for(H, PB_C2_NB, 200 * 1024);
+    // three resident CTAs of 4+ pairs (32-byte row segments) beat one big CTA of 8 (measured at H = 2160:
+    // occupancy matters more than the segment length)
+    const int nb3 = pairs_for(H, PB_C2_NB, 72 * 1024);
+    if (nb3 >= 4) nb = nb3;
     const int pairs_total = (W + 1) / 2;
     if (nb > pairs_total) nb = pairs_total;
     // float2 per column pair: >= H and = 2 (mod 4), so that the 8 pairs x 2 rows a half-warp touches in
@@ -470,7 +474,7 @@ int launch_cols2(bool est, const float* plane_in, const float* gx, float* gy, un
         if (est) PB_LAUNCH_COLS2(true, T, SP); else PB_LAUNCH_COLS2(false, T, SP); \
     } while (0)
     if (!big && PlanH1080::matches(planH)) PB_LAUNCH_COLS2_SP(PB_C2_THREADS, PlanH1080);
-    else if (big && PlanH2160::matches(planH)) PB_LAUNCH_COLS2_SP(512, PlanH2160);
+    else if (!big && PlanH2160::matches(planH)) PB_LAUNCH_COLS2_SP(PB_C2_THREADS, PlanH2160);
     else if (big) PB_LAUNCH_COLS2_SP(512, NoStaticPlan);
     else PB_LAUNCH_COLS2_SP(PB_C2_THREADS, NoStaticPlan);
 #undef PB_LAUNCH_COLS2_SP
