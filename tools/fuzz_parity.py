@@ -47,6 +47,7 @@ def main(n_cases=40, seed=0):
         if rng.random() < 0.15:
             kw["edgetaping"] = True
         ab = [(6, 1), (2, 3), (2, 4)][int(rng.integers(0, 3))]
+        extra = {}
         try:
             with np.errstate(all="ignore"):
                 ref = po.polyblur_deblurring(x, n_iter=n_iter, alpha=ab[0], beta=ab[1], **kw)
@@ -55,12 +56,21 @@ def main(n_cases=40, seed=0):
                 status, err = "ref-nonfinite", float("nan")      # constant image: NaN in the reference too
             else:
                 err = float(np.abs(out.astype(np.float64) - ref).max())
-                status = "ok" if err < 2e-5 else "MISMATCH"
+                status = "ok" if err < 1e-5 else "MISMATCH"
+                if status != "ok":
+                    # the float32 oracle carries its own rounding: arbitrate with the float64 restatement
+                    with np.errstate(all="ignore"):
+                        truth = po.polyblur_deblurring(x, n_iter=n_iter, alpha=ab[0], beta=ab[1], dtype=np.float64, **kw)
+                    extra = {"err_vs_f64": float(np.abs(out.astype(np.float64) - truth).max()),
+                             "oracle_f32_vs_f64": float(np.abs(ref.astype(np.float64) - truth).max())}
+                    if extra["err_vs_f64"] < 1e-5:
+                        status = "ok-vs-f64"
         except Exception as exc:                 # noqa: BLE001
             status, err = f"EXC {type(exc).__name__}: {exc}", float("nan")
-        rec = {"case": case, "shape": [B, C, H, W], "n_iter": n_iter, "kind": str(kind), "ab": ab, **kw, "err": err, "status": status}
+        rec = {"case": case, "shape": [B, C, H, W], "n_iter": n_iter, "kind": str(kind), "ab": ab, **kw, "err": err,
+               "status": status, **extra}
         print(json.dumps(rec), flush=True)
-        if status == "ok":
+        if status.startswith("ok"):
             worst = max(worst, err)
         elif status != "ref-nonfinite":
             fails.append(rec)
