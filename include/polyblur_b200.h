@@ -50,6 +50,7 @@ extern "C" {
 #define PB_FLAG_PREFILTER_RF       0x08u  /* domain-transform RF instead (the commented call, :107) */
 #define PB_FLAG_DISCARD_SATURATION 0x10u
 #define PB_FLAG_EDGETAPER_BATCHMAX 0x20u  /* bug-compatible batch-global max (edgetaper.py:15,21) */
+#define PB_FLAG_NO_CLAMP           0x40u  /* pb_deconv_ex_f32 only: skip the final clamp (for the backward pass) */
 
 /* deconvolution engine selection (pb_params.engine); AUTO decides per image on device */
 #define PB_ENGINE_AUTO    0
@@ -142,12 +143,24 @@ PB_API int pb_deconv_f32(const float* img, float* out, int B, int C, int H, int 
                   void* workspace, size_t workspace_bytes, void* stream);
 
 /* deblurring.inverse_filtering_rank3 with its optional stages (deblurring.py:211-239):
- * flags = PB_FLAG_EDGETAPER (do_edgetaper, + PB_FLAG_EDGETAPER_BATCHMAX) | PB_FLAG_REMOVE_HALO;
+ * flags = PB_FLAG_EDGETAPER (do_edgetaper, + PB_FLAG_EDGETAPER_BATCHMAX) | PB_FLAG_REMOVE_HALO |
+ * PB_FLAG_NO_CLAMP;
  * grad_x / grad_y = grad_img of the reference (device, (B,C,H,W)) or both NULL = gradients of img.
  * Workspace: pb_workspace_bytes with the same flags / ker_size / engine in pb_params. */
 PB_API int pb_deconv_ex_f32(const float* img, float* out, int B, int C, int H, int W, const float* kernel,
                      int ksize, double alpha, double beta, int engine, uint32_t flags, const float* grad_x,
                      const float* grad_y, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Vector-Jacobian product of deblurring.inverse_filtering_rank3 (default flags, deblurring.py:211-239)
+ * with respect to the image, the kernel held constant -- what torch.autograd computes for the
+ * reference's replicate pad -> circular polynomial filter -> crop -> clamp chain (README.md:70 claims
+ * the module differentiable): grad_img = pad^T filter^T crop^T (grad_out * pass), pass = 1 where
+ * `preclamp` (the forward result computed with PB_FLAG_NO_CLAMP, or NULL = no clamp) lies in [0,1].
+ * Workspace: pb_deconv_vjp_workspace_bytes. */
+PB_API size_t pb_deconv_vjp_workspace_bytes(int B, int C, int H, int W, int ksize, int engine);
+PB_API int pb_deconv_vjp_f32(const float* grad_out, const float* preclamp, float* grad_img, int B, int C,
+                      int H, int W, const float* kernel, int ksize, double alpha, double beta, int engine,
+                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* edgetaper.edgetaper (edgetaper.py:26-33) on an already padded image. */
 PB_API int pb_edgetaper_f32(const float* img, float* out, int B, int C, int H, int W,

@@ -23,6 +23,7 @@ FLAG_PREFILTER = 0x04
 FLAG_PREFILTER_RF = 0x08
 FLAG_DISCARD_SATURATION = 0x10
 FLAG_EDGETAPER_BATCHMAX = 0x20
+FLAG_NO_CLAMP = 0x40
 ENGINE_AUTO, ENGINE_SPATIAL, ENGINE_FFT = 0, 1, 2
 
 
@@ -64,6 +65,9 @@ _SIGS = {
                                 C.c_double, C.c_int, _P, C.c_size_t, _P]),
     "pb_deconv_ex_f32": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.c_double,
                                    C.c_double, C.c_int, C.c_uint32, _P, _P, _P, C.c_size_t, _P]),
+    "pb_deconv_vjp_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "pb_deconv_vjp_f32": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.c_double,
+                                    C.c_double, C.c_int, _P, C.c_size_t, _P]),
     "pb_edgetaper_f32": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.c_int,
                                    C.c_uint32, _P, C.c_size_t, _P]),
     "pb_bilateral_f32": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _P]),

@@ -341,7 +341,7 @@ static int deconv_with_options(const float* src, float* dst, int B, int C, int H
         G.pad = 0;
         dec_in = tapered;
     }
-    G.clamp_out = halo ? 0 : 1;
+    G.clamp_out = (halo || (flags & PB_FLAG_NO_CLAMP)) ? 0 : 1;
     if ((rc = deconv_all(dec_in, dst, B, C, H, W, coef, ws, L, F, G, stream))) return rc;
     if (halo) {
         // halo_masking (deblurring.py:193-208): only d imout / dx is needed (M uses gy*gy, :174)
@@ -604,7 +604,11 @@ int pb_deconv_ex_f32(const float* img, float* out, int B, int C, int H, int W, c
         set_error("grad_x and grad_y must be given together");
         return PB_ERR_ARG;
     }
-    flags &= PB_FLAG_REMOVE_HALO | PB_FLAG_EDGETAPER | PB_FLAG_EDGETAPER_BATCHMAX;
+    flags &= PB_FLAG_REMOVE_HALO | PB_FLAG_EDGETAPER | PB_FLAG_EDGETAPER_BATCHMAX | PB_FLAG_NO_CLAMP;
+    if ((flags & PB_FLAG_NO_CLAMP) && (flags & PB_FLAG_REMOVE_HALO)) {
+        set_error("PB_FLAG_NO_CLAMP cannot be combined with halo masking (which clamps itself)");
+        return PB_ERR_ARG;
+    }
     const Workspace L = layout(B, C, H, W, 1, ksize, engine, flags);
     if ((rc = check_ws(workspace, workspace_bytes, L.total))) return rc;
     if (engine == PB_ENGINE_FFT && !L.has_fft) {
@@ -640,6 +644,80 @@ int pb_deconv_ex_f32(const float* img, float* out, int B, int C, int H, int W, c
     poly_coeffs_d(alpha, beta, coef);
     return deconv_with_options(img, out, B, C, H, W, coef, ksize, flags, gx, gy, nM, ox, ws, L, T,
                                L.has_fft ? &F : nullptr, stream);
+}
+
+// workspace of the backward pass: the engines' workspace for a (H+2P) x (W+2P) "image", the
+// embedded gradient, the filtered plane and the rotated kernels
+struct VjpLayout {
+    Workspace eng;
+    size_t off_z, off_t, off_k, total;
+};
+static VjpLayout vjp_layout(int B, int C, int H, int W, int ksize, int engine) {
+    VjpLayout v;
+    const int pad = ksize / 2;
+    const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+    v.eng = layout(B, C, Hp, Wp, 1, ksize, engine);
+    size_t o = align_up(v.eng.total, 256);
+    const size_t plane_bytes = align_up((size_t)B * C * Hp * Wp * sizeof(float), 256);
+    v.off_z = o;
+    o += plane_bytes;
+    v.off_t = o;
+    o += plane_bytes;
+    v.off_k = o;
+    o += align_up((size_t)B * ksize * ksize * sizeof(float), 256);
+    v.total = o;
+    return v;
+}
+
+size_t pb_deconv_vjp_workspace_bytes(int B, int C, int H, int W, int ksize, int engine) {
+    if (B < 1 || C < 1 || H < 1 || W < 1 || ksize < 1 || ksize > PB_KS || !(ksize & 1)) return 0;
+    return vjp_layout(B, C, H, W, ksize, engine).total;
+}
+
+int pb_deconv_vjp_f32(const float* grad_out, const float* preclamp, float* grad_img, int B, int C, int H, int W,
+                      const float* kernel, int ksize, double alpha, double beta, int engine, void* workspace,
+                      size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc;
+    if ((rc = check_shape(B, C, H, W))) return rc;
+    if (!grad_out || !grad_img || !kernel || ksize < 1 || ksize > PB_KS || !(ksize & 1)) {
+        set_error("bad arguments to pb_deconv_vjp_f32 (ksize must be odd and <= 25)");
+        return PB_ERR_ARG;
+    }
+    const int pad = ksize / 2;
+    const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+    if ((rc = check_shape(B, C, Hp, Wp))) return rc;
+    const VjpLayout V = vjp_layout(B, C, H, W, ksize, engine);
+    if ((rc = check_ws(workspace, workspace_bytes, V.total))) return rc;
+    const Workspace& L = V.eng;
+    if (engine == PB_ENGINE_FFT && !L.has_fft) {
+        set_error("the FFT engine does not support %d x %d (ker_size %d)", Hp, Wp, ksize);
+        return PB_ERR_UNSUPPORTED;
+    }
+    char* ws = static_cast<char*>(workspace);
+    ImgKernel* kern = reinterpret_cast<ImgKernel*>(ws + L.off_kern);
+    int* cls = reinterpret_cast<int*>(ws + L.off_cls);
+    float* z = reinterpret_cast<float*>(ws + V.off_z);
+    float* t = reinterpret_cast<float*>(ws + V.off_t);
+    float* kf = reinterpret_cast<float*>(ws + V.off_k);
+    FftEngineTables F;
+    if (L.has_fft && (rc = fft_engine_prepare(ws + L.off_fft, L.fft, &F, stream))) return rc;
+    if ((rc = launch_flip_kernels(kernel, kf, B, ksize, stream))) return rc;
+    if ((rc = launch_params(nullptr, kern, nullptr, nullptr, nullptr, nullptr, kf, nullptr, 2, B, ksize, 0.f, 0.f,
+                            1e-8f, engine, L.has_fft ? PB_FFT_RADIUS_MIN : (1 << 30), cls, stream)))
+        return rc;
+    if ((rc = launch_vjp_embed(grad_out, preclamp, z, B * C, H, W, pad, stream))) return rc;
+    // the embedded plane is its own torus: pure wrap-around source, every padded position is an output
+    SrcGeom G;
+    G.Hin = Hp;
+    G.Win = Wp;
+    G.off = 0;
+    G.pad = 0;
+    G.clamp_out = 0;
+    float coef[4];
+    poly_coeffs_d(alpha, beta, coef);
+    if ((rc = deconv_all(z, t, B, C, Hp, Wp, coef, ws, L, L.has_fft ? &F : nullptr, G, stream))) return rc;
+    return launch_vjp_fold(t, grad_img, B * C, H, W, pad, stream);
 }
 
 int pb_profile_begin(void) {

@@ -76,6 +76,10 @@ int launch_halo_apply(float* imout, const float* img, size_t img_plane, int img_
 size_t edgetaper_scratch_bytes(int B, int Hp, int Wp);
 int launch_edgetaper_weights(const ImgKernel* kern, void* scratch, int B, int Hp, int Wp, int batch_max,
                              float** v_out, cudaStream_t stream);
+int launch_vjp_embed(const float* gout, const float* preclamp, float* z, int planes, int H, int W, int pad,
+                     cudaStream_t stream);
+int launch_vjp_fold(const float* t, float* gin, int planes, int H, int W, int pad, cudaStream_t stream);
+int launch_flip_kernels(const float* k, float* kf, int B, int ksize, cudaStream_t stream);
 int launch_pad_replicate(const float* img, float* a, float* b, int planes, int H, int W, int pad,
                          cudaStream_t stream);
 int launch_edgetaper_passes(float* a, float* b, const ImgKernel* kern, const float* v, int B, int C, int Hp, int Wp,

@@ -537,4 +537,84 @@ int launch_edgetaper_passes(float* a, float* b, const ImgKernel* kern, const flo
     return PB_OK;
 }
 
+// ---- vector-Jacobian product of the deconvolution with respect to the image -------------------
+// Forward (deblurring.py:211-239, default flags): y = clamp(C T R x), R = replicate pad by P
+// (utils.py:48-53), T = circular convolution with the polynomial of the blur on the (H+2P) x (W+2P)
+// torus, C = crop (utils.py:56-61).  What autograd gives for it: x~ = R^T T~ C^T (y~ . pass), pass = 1
+// where the unclamped value lies in [0, 1], T~ = the same filter with the kernel rotated by 180 degrees.
+// k_vjp_embed is C^T with the clamp mask, k_vjp_fold is R^T; T~ runs on the ordinary engines, which
+// read the embedded plane as a pure wrap-around torus (SrcGeom pad = 0).
+__global__ void k_vjp_embed(const float* __restrict__ gout, const float* __restrict__ preclamp,
+                            float* __restrict__ z, int H, int W, int pad) {
+    const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+    const int xp = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int yp = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (xp >= Wp || yp >= Hp) return;
+    const size_t pl = blockIdx.z;
+    const int x = xp - pad, y = yp - pad;
+    float v = 0.0f;
+    if (x >= 0 && x < W && y >= 0 && y < H) {
+        const size_t o = pl * (size_t)H * W + (size_t)y * W + x;
+        v = gout[o];
+        if (preclamp) {
+            const float u = preclamp[o];
+            if (!(u >= 0.0f && u <= 1.0f)) v = 0.0f;
+        }
+    }
+    z[pl * (size_t)Hp * Wp + (size_t)yp * Wp + xp] = v;
+}
+
+__global__ void k_vjp_fold(const float* __restrict__ t, float* __restrict__ gin, int H, int W, int pad) {
+    const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= W || y >= H) return;
+    const size_t pl = blockIdx.z;
+    // padded rows / columns that replicate this pixel
+    const int y0 = (y == 0) ? 0 : y + pad, y1 = (y == H - 1) ? Hp - 1 : y + pad;
+    const int x0 = (x == 0) ? 0 : x + pad, x1 = (x == W - 1) ? Wp - 1 : x + pad;
+    const float* tp = t + pl * (size_t)Hp * Wp;
+    float acc = 0.0f;
+    for (int yy = y0; yy <= y1; ++yy)
+        for (int xx = x0; xx <= x1; ++xx) acc += tp[(size_t)yy * Wp + xx];
+    gin[pl * (size_t)H * W + (size_t)y * W + x] = acc;
+}
+
+// kernel rotated by 180 degrees (the adjoint of a correlation-free convolution)
+__global__ void k_flip_kernels(const float* __restrict__ k, float* __restrict__ kf, int n_per, int total) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int b = i / n_per, e = i - b * n_per;
+    kf[i] = k[(size_t)b * n_per + (n_per - 1 - e)];
+}
+
+int launch_vjp_embed(const float* gout, const float* preclamp, float* z, int planes, int H, int W, int pad,
+                     cudaStream_t stream) {
+    if (planes > 65535) {
+        set_error("B*C = %d exceeds the grid z limit", planes);
+        return PB_ERR_ARG;
+    }
+    dim3 grid((W + 2 * pad + 31) / 32, (H + 2 * pad + 7) / 8, planes);
+    ProfScope prof(PROF_OTHER, stream);
+    k_vjp_embed<<<grid, 256, 0, stream>>>(gout, preclamp, z, H, W, pad);
+    PB_LAUNCH_CHECK("k_vjp_embed");
+    return PB_OK;
+}
+
+int launch_vjp_fold(const float* t, float* gin, int planes, int H, int W, int pad, cudaStream_t stream) {
+    dim3 grid((W + 31) / 32, (H + 7) / 8, planes);
+    ProfScope prof(PROF_OTHER, stream);
+    k_vjp_fold<<<grid, 256, 0, stream>>>(t, gin, H, W, pad);
+    PB_LAUNCH_CHECK("k_vjp_fold");
+    return PB_OK;
+}
+
+int launch_flip_kernels(const float* k, float* kf, int B, int ksize, cudaStream_t stream) {
+    const int total = B * ksize * ksize;
+    ProfScope prof(PROF_OTHER, stream);
+    k_flip_kernels<<<(total + 255) / 256, 256, 0, stream>>>(k, kf, ksize * ksize, total);
+    PB_LAUNCH_CHECK("k_flip_kernels");
+    return PB_OK;
+}
+
 }  // namespace pb

@@ -148,6 +148,16 @@ def polyblur_deblurring(img, n_iter=1, c=0.352, b=0.768, alpha=2, beta=3, sigma_
             raise TypeError(f"float32 only (got {x.dtype}), like the reference")
     if n_iter == 0:                     # the reference returns its input object (:60,:96)
         return utils.to_array(x) if flag_numpy else img
+    if not flag_numpy and x.requires_grad and torch.is_grad_enabled():
+        # differentiable path (autograd.py): gradient with respect to the image, blur estimates held constant
+        if remove_halo or edgetaping or prefiltering or return_estimates:
+            raise NotImplementedError("gradients are implemented for the default options only "
+                                      "(no remove_halo / edgetaping / prefiltering); call under torch.no_grad() "
+                                      "or detach the input")
+        from . import autograd as _autograd
+        return _autograd.polyblur_deblurring_grad(x, n_iter=n_iter, c=c, b=b, alpha=alpha, beta=beta,
+                                                  ker_size=ker_size, q=q, discard_saturation=discard_saturation,
+                                                  engine=p.engine)
 
     dev = _lib.require_cuda(x)
     src_device = x.device
@@ -236,6 +246,12 @@ def inverse_filtering_rank3(img, kernel, alpha=2, b=4, correlate=False, remove_h
     from ``img`` when None (deblurring.py:200-203)."""
     if img.dtype != torch.float32 or img.ndim != 4:
         raise TypeError("img must be a float32 (B,C,H,W) tensor")
+    if img.requires_grad and torch.is_grad_enabled():
+        if remove_halo or do_edgetaper:
+            raise NotImplementedError("gradients are implemented for the default flags only")
+        from . import autograd as _autograd
+        kk = torch.rot90(kernel, k=2, dims=(-2, -1)) if correlate else kernel
+        return _autograd.DeconvolutionFunction.apply(img, kk, alpha, b, engine)
     dev = _lib.require_cuda(img)
     src = img.device
     x = img.detach().to(dev).contiguous()

@@ -1,0 +1,109 @@
+"""GPU tests of the backward pass: the vector-Jacobian product of the deconvolution
+against torch.autograd over the live reference (tests/golden/vjp.npz, made by make_golden_vjp.py) and
+against the adjoint identity; the Polyblur loop with the blur estimates held constant.  Run with -m gpu."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+ENGINES = {"auto": 0, "spatial": 1, "fft": 2}
+
+
+@pytest.fixture(scope="module")
+def pb():
+    import polyblur_b200
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return polyblur_b200
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(G, "vjp.npz"))
+
+
+def cu(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / np.abs(b).max())
+
+
+@pytest.mark.parametrize("engine", sorted(ENGINES))
+@pytest.mark.parametrize("tag,alpha,beta", [("a6b1", 6, 1), ("a2b4", 2, 4)])
+def test_deconvolution_vjp_golden(pb, gold, tag, alpha, beta, engine):
+    """inverse_filtering_rank3 with a requires_grad image: forward and gradient against the reference's
+    autograd, a wide and a narrow kernel in one batch, part of the result clamped."""
+    x = cu(gold["deconv_x"]).requires_grad_(True)
+    k = cu(gold["deconv_kernels"])
+    y = pb.deblurring.inverse_filtering_rank3(x, k, alpha=alpha, b=beta, engine=ENGINES[engine])
+    assert y.requires_grad
+    assert np.abs(y.detach().cpu().numpy() - gold[f"deconv_{tag}_y"]).max() < 1e-5
+    (y * cu(gold["deconv_ybar"])).sum().backward()
+    ref = gold[f"deconv_{tag}_grad"]
+    assert rel(x.grad.cpu().numpy(), ref) < 2e-5
+    # the clamp mask is part of the golden: a gradient that ignored it would be far off
+    from polyblur_b200 import autograd as ag
+    nomask = ag.inverse_filtering_rank3_vjp(cu(gold["deconv_ybar"]), k, alpha, beta, preclamp=None, engine=ENGINES[engine])
+    assert rel(nomask.cpu().numpy(), ref) > 1e-2
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 5, 7), (2, 3, 33, 1), (1, 2, 1, 40), (2, 3, 97, 131), (1, 3, 300, 260)])
+@pytest.mark.parametrize("engine", ["auto", "fft"])
+def test_deconvolution_vjp_is_the_adjoint(pb, shape, engine):
+    """<A x, y> = <x, A^T y> for the unclamped operator, odd / tiny / one-pixel-wide shapes, wide kernels."""
+    from polyblur_b200 import autograd as ag
+    from oracle import polyblur_oracle as po
+    B, C, H, W = shape
+    rng = np.random.default_rng(H * 1000 + W)
+    x = cu(rng.standard_normal(shape).astype(np.float32))
+    ybar = cu(rng.standard_normal(shape).astype(np.float32))
+    ks = np.stack([po.gaussian_filter_np((float(rng.uniform(0.4, 3.0)), float(rng.uniform(0.3, 1.5))),
+                                         float(rng.uniform(0, 3))) for _ in range(B)])[:, None].astype(np.float32)
+    k = cu(ks)
+    e = ENGINES[engine]
+    Ax = ag._deconv_noclamp(x, k, 6, 1, e)
+    ATy = ag.inverse_filtering_rank3_vjp(ybar, k, 6, 1, preclamp=None, engine=e)
+    lhs = float((Ax.double() * ybar.double()).sum())
+    rhs = float((x.double() * ATy.double()).sum())
+    scale = float(Ax.double().norm() * ybar.double().norm())
+    assert abs(lhs - rhs) < 1e-5 * scale
+
+
+def test_polyblur_gradient_with_constant_estimates(pb, gold):
+    """Two iterations: forward equals the no-grad path, gradient equals autograd over the reference with its
+    estimator under no_grad (the estimates held constant); the module surface routes the same way."""
+    x0 = cu(gold["chain_x"])
+    ybar = cu(gold["chain_ybar"])
+    x = x0.clone().requires_grad_(True)
+    y = pb.polyblur_deblurring(x, n_iter=2, alpha=6, beta=1)
+    with torch.no_grad():
+        y0 = pb.polyblur_deblurring(x0, n_iter=2, alpha=6, beta=1)
+    assert float((y.detach() - y0).abs().max()) < 2e-6
+    assert np.abs(y.detach().cpu().numpy() - gold["chain_y"]).max() < 1e-5
+    (y * ybar).sum().backward()
+    assert rel(x.grad.cpu().numpy(), gold["chain_grad"]) < 1e-4
+    xm = x0.clone().requires_grad_(True)
+    ym = pb.PolyblurDeblurring()(xm, n_iter=2, c=0.352, b=0.768, alpha=6, beta=1)
+    (ym * ybar).sum().backward()
+    assert torch.equal(xm.grad, x.grad)
+    # CPU tensors: the gradient comes back on the input's device
+    xc = gold["chain_x"]
+    xc = torch.from_numpy(xc).requires_grad_(True)
+    yc = pb.polyblur_deblurring(xc, n_iter=1, alpha=6, beta=1)
+    yc.sum().backward()
+    assert xc.grad is not None and xc.grad.device.type == "cpu" and bool(torch.isfinite(xc.grad).all())
+
+
+def test_gradient_unsupported_options_raise(pb, gold):
+    x = cu(gold["chain_x"]).requires_grad_(True)
+    for kw in (dict(remove_halo=True), dict(edgetaping=True), dict(prefiltering=True)):
+        with pytest.raises(NotImplementedError):
+            pb.polyblur_deblurring(x, n_iter=1, **kw)
+    with torch.no_grad():
+        pb.polyblur_deblurring(x, n_iter=1, remove_halo=True)

@@ -390,6 +390,22 @@ def test_full_hd_image_vs_oracle(pb, kind):
     assert maxabs(out.cpu().numpy(), ref) < TOL_E2E
 
 
+def test_4k_image_vs_oracle(pb):
+    """One image of BASELINE configs 3 / 5's shape (3 x 2160 x 3840), two iterations, against the CPU
+    oracle: the compile-time plans of the 4K lengths (3840 / 2160 and the 4000 x 2304 torus of the FFT
+    engine) on the path the 4K benchmarks take."""
+    from polyblur_b200 import synthetic
+    x = synthetic.make("mosaic", 1, 3, 2160, 3840).numpy()
+    tr = []
+    ref = po.polyblur_deblurring(x, n_iter=2, alpha=6, beta=1, trace=tr)
+    out, est = pb.polyblur_deblurring(cu(x), n_iter=2, alpha=6, beta=1, return_estimates=True)
+    est = est.cpu().numpy()
+    assert np.array_equal(est[..., 7].astype(np.int64), np.stack([t["theta_deg"] for t in tr]))
+    np.testing.assert_allclose(est[..., 8], np.stack([t["sigma"] for t in tr]), rtol=5e-5)
+    np.testing.assert_allclose(est[..., 9], np.stack([t["rho"] for t in tr]), rtol=5e-5)
+    assert maxabs(out.cpu().numpy(), ref) < TOL_E2E
+
+
 @pytest.mark.parametrize("kw", [dict(remove_halo=True), dict(do_edgetaper=True), dict(remove_halo=True, do_edgetaper=True)])
 def test_inverse_filtering_stage_options(pb, kw):
     """Stage-level inverse_filtering_rank3 with its optional stages against the oracle."""
