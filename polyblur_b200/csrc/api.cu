@@ -458,9 +458,6 @@ int pb_polyblur_f32(const float* in, float* out, int B, int C, int H, int W, con
     float* tmp = reinterpret_cast<float*>(ws + L.off_tmp);
     const bool prefilter = (p->flags & (PB_FLAG_PREFILTER | PB_FLAG_PREFILTER_RF)) != 0;
     const bool halo = (p->flags & PB_FLAG_REMOVE_HALO) != 0;
-    const bool taper = (p->flags & PB_FLAG_EDGETAPER) != 0;
-    const int pad = p->ker_size / 2;
-    const int Hp = H + 2 * pad, Wp = W + 2 * pad;
     const int planes = B * C;
     const size_t plane = (size_t)H * W;
     float* smooth = reinterpret_cast<float*>(ws + L.off_smooth);
@@ -468,7 +465,6 @@ int pb_polyblur_f32(const float* in, float* out, int B, int C, int H, int W, con
     float* g0y = reinterpret_cast<float*>(ws + L.off_g0y);
     float* ox = reinterpret_cast<float*>(ws + L.off_ox);
     float* nM = reinterpret_cast<float*>(ws + L.off_nm);
-    const ImgKernel* kern = reinterpret_cast<const ImgKernel*>(ws + L.off_kern);
     if (halo) {
         // grad_img of the ORIGINAL input, all channels, once (deblurring.py:61) and its energy per plane
         if ((rc = gradients_into(in, g0x, g0y, planes, H, W, T, stream))) return rc;
