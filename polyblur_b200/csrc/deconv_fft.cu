@@ -98,6 +98,9 @@ __host__ __device__ inline int fftd_row_stride(int NX) { return NX + 4; }
 #ifndef PB_FFTD_MINB
 #define PB_FFTD_MINB 3      // resident CTAs per SM (see estimate2.cu)
 #endif
+#ifndef PB_FFTC_MINB
+#define PB_FFTC_MINB PB_FFTD_MINB
+#endif
 
 // extended coordinate (any torus of length >= n + 6 pad) -> source index, or -1 for the zero fill
 //   n = image length, ext = 3 x kernel half-size (reach of the composite filter), and the source
@@ -265,7 +268,7 @@ k_fft_rows_fwd(const float* __restrict__ img, float2* __restrict__ Z, const ImgK
 //   Leaves r = DFT(swap(Y)) in Z: the inverse transform is swap(r), P3 swaps while loading.
 // ---------------------------------------------------------------------------------------------
 template <class SP>
-__global__ void __launch_bounds__(FFTC_THREADS, PB_FFTD_MINB)
+__global__ void __launch_bounds__(FFTC_THREADS, PB_FFTC_MINB)
 k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int* __restrict__ list,
            const int* __restrict__ count, int C, int NX, int NY, int CB, Fft2Plan planY,
            const float2* __restrict__ twX, const float2* __restrict__ stwY, const int* __restrict__ slotY,
