@@ -16,7 +16,7 @@ import numpy as np
 import torch
 from torch import nn
 
-from . import _lib, utils
+from . import _lib, sharding, utils
 
 _METHODS = ("fft", "direct", "direct_separable")
 
@@ -182,7 +182,8 @@ def polyblur_deblurring(img, n_iter=1, c=0.352, b=0.768, alpha=2, beta=3, sigma_
     return out
 
 
-def _polyblur_host_pipelined(x: torch.Tensor, p: "_lib.PbParams", dev: torch.device, max_chunks: int = 16):
+def _polyblur_host_pipelined(x: torch.Tensor, p: "_lib.PbParams", dev: torch.device, max_chunks: int = 16,
+                             ramp=()):
     """CPU tensor in -> CPU tensor out with the PCIe transfers hidden behind the kernels.
 
     Images are independent, so the batch is cut into chunks that flow through three streams:
@@ -193,8 +194,13 @@ def _polyblur_host_pipelined(x: torch.Tensor, p: "_lib.PbParams", dev: torch.dev
     x = x.contiguous()
     if not x.is_pinned():
         x = x.pin_memory()
-    n_chunks = min(max_chunks, B)
-    bounds = [(B * k) // n_chunks for k in range(n_chunks + 1)]
+    # float32 over PCIe is the bottleneck (1.6 GB per 32 x 1080p step against 8 ms of kernels): many small
+    # chunks (measured with tools/e2e_probe.py: 16 uniform chunks 19.1 ms against 15.9 ms for the bare
+    # concurrent copies; smaller first / last chunks did not help)
+    sizes = sharding.pipeline_chunks(B, -(-B // max(1, min(max_chunks, B))), ramp)
+    bounds = [0]
+    for n_k in sizes:
+        bounds.append(bounds[-1] + n_k)
     host = torch.empty(x.shape, dtype=torch.float32, pin_memory=True)
     with torch.cuda.device(dev):
         s_in, s_run, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)

@@ -32,3 +32,21 @@ def gather_outputs(local: torch.Tensor, n_items: int, group=None) -> torch.Tenso
     parts = [torch.empty_like(padded) for _ in range(world)]
     dist.all_gather(parts, padded.contiguous(), group=group)
     return torch.cat([p[: b - a] for p, (a, b) in zip(parts, sizes)], 0)
+
+
+def pipeline_chunks(n_items: int, body: int, ramp=(1,)):
+    """Chunk sizes for the host <-> device pipelines (deblurring._polyblur_host_pipelined,
+    io._host_pipeline_u8): chunks of about `body` images, with the small `ramp` chunks first and, mirrored,
+    last -- the first device->host copy can start after one image has been loaded and processed, and the
+    copy left over when the last kernels finish is one image, not a whole chunk."""
+    if n_items < 1:
+        return []
+    body = max(1, int(body))
+    head, rem = [], n_items
+    for r in ramp:
+        if r <= body and rem - 2 * r >= body:
+            head.append(int(r))
+            rem -= 2 * r
+    n_mid = -(-rem // body)
+    mid = [rem // n_mid + (1 if i < rem % n_mid else 0) for i in range(n_mid)]
+    return head + mid + head[::-1]

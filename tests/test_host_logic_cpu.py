@@ -84,3 +84,16 @@ def test_cli_parser_defaults_match_reference():
     img = np.random.default_rng(2).random((40, 50, 3)).astype(np.float32)
     blurred = cli.synthetic_blur(img, 2.0, 1.0, 30.0, 0.0)
     assert blurred.shape == img.shape and abs(float(blurred.mean()) - float(img.mean())) < 1e-3
+
+
+def test_pipeline_chunks_cover_the_batch():
+    """The host pipelines' chunk schedule: every image exactly once, small chunks at both ends."""
+    from polyblur_b200.sharding import pipeline_chunks
+    for B in range(1, 70):
+        for body in (1, 2, 3, 8):
+            for ramp in ((1,), (1, 3), ()):
+                s = pipeline_chunks(B, body, ramp)
+                assert sum(s) == B and all(v > 0 for v in s)
+                assert max(s) <= body
+    assert pipeline_chunks(32, 2, (1,)) == [1] + [2] * 15 + [1]
+    assert pipeline_chunks(32, 8, (1, 3)) == [1, 3, 8, 8, 8, 3, 1]
