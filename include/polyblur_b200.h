@@ -162,6 +162,29 @@ PB_API int pb_deconv_vjp_f32(const float* grad_out, const float* preclamp, float
                       int H, int W, const float* kernel, int ksize, double alpha, double beta, int engine,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* The rest of the backward pass: what torch.autograd computes through the blur estimator
+ * (blur_estimation.py:18-79) and the kernel argument of inverse_filtering_rank3.  One workspace size
+ * serves the three calls.
+ *   pb_estimate_trace_f32: forward trace of the estimator on img: trace_f = device float[B][24]
+ *     (7 directional maxima of the normalised gray image, the sign of cos gx - sin gy at their arg-max
+ *     pixels, min, max of the gray image and how many pixels attain them), trace_pos = device
+ *     int32[B][8] (arg-max pixel y*W+x per angle).
+ *   pb_kernel_grad_f32: gradient of <grad_out, inverse_filtering_rank3(img, kernel)> with respect to
+ *     the kernel taps -> kernel_grad device float[B][ksize][ksize] (preclamp as in pb_deconv_vjp_f32).
+ *   pb_estimator_vjp_f32: given mbar = device float[B][7], the gradient with respect to the 7 maxima
+ *     (the scalar chain kernel taps -> sigma, rho -> maxima is left to the caller), ADDS the gradient
+ *     with respect to img into grad_img: arg-max scatter, transposed spectral derivative, range
+ *     normalisation (blur_estimation.py:96-134), channel mean. */
+PB_API size_t pb_backward_workspace_bytes(int B, int C, int H, int W, int ksize, int engine);
+PB_API int pb_estimate_trace_f32(const float* img, int B, int C, int H, int W, float* trace_f, int* trace_pos,
+                          void* workspace, size_t workspace_bytes, void* stream);
+PB_API int pb_kernel_grad_f32(const float* img, const float* grad_out, const float* preclamp, int B, int C,
+                       int H, int W, const float* kernel, int ksize, double alpha, double beta, int engine,
+                       float* kernel_grad, void* workspace, size_t workspace_bytes, void* stream);
+PB_API int pb_estimator_vjp_f32(const float* img, const float* mbar, const float* trace_f, const int* trace_pos,
+                         float* grad_img, int B, int C, int H, int W, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
 /* edgetaper.edgetaper (edgetaper.py:26-33) on an already padded image. */
 PB_API int pb_edgetaper_f32(const float* img, float* out, int B, int C, int H, int W,
                      const float* kernel, int ksize, int n_tapers, uint32_t flags,

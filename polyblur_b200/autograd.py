@@ -6,14 +6,20 @@ The reference is differentiable because it is written in torch ops (README.md:70
   ``deblurring.inverse_filtering_rank3`` (default flags, polyblur/deblurring.py:211-239) with respect
   to ``img`` for a given kernel: replicate pad, circular polynomial filter, crop and clamp, transposed.
   It matches torch.autograd over the reference (tests/golden/vjp.npz).
-* ``polyblur_deblurring_grad`` / ``PolyblurFunction`` -- the Polyblur loop with the blur estimate of
-  every iteration held constant (as if ``gaussian_blur_estimation`` ran under ``torch.no_grad()``).
-  The reference also differentiates through its estimator; that term is a sub-gradient through the
-  arg-max pixels of the seven directional maxima and min / max of the gray image, concentrated on the
-  rows and columns through those few pixels, and is deliberately not reproduced.
+* ``polyblur_deblurring_grad`` / ``PolyblurFunction`` -- the Polyblur loop.  With
+  ``estimate_grad=True`` (default, what the reference does) the gradient also flows through the blur
+  estimator of every iteration: kernel taps -> sigma, rho -> interpolated directional maxima -> the
+  arg-max pixels of ``|cos gx - sin gy|`` -> spectral derivative -> range normalisation (including the
+  min / max pixels) -> channel mean.  The image-sized steps run in CUDA (csrc/backward.cu:
+  ``pb_estimate_trace_f32``, ``pb_kernel_grad_f32``, ``pb_estimator_vjp_f32``); the chain of a dozen
+  scalars per image between the 25 x 25 kernel gradient and the 7 maxima is evaluated with torch autograd
+  on (B, 7) / (B, 25, 25) tensors.  ``estimate_grad=False`` holds the estimates constant (the
+  estimator under ``torch.no_grad()``), which removes the spiky rows / columns through the arg-max
+  pixels from the gradient.
 
-Only the default options are differentiable (no halo masking, edgetaper, prefilter); the kernels and
-the unclamped iterates are kept for the backward pass (n_iter extra images of memory).
+Only the default options are differentiable (no halo masking, edgetaper, prefilter, quantile
+normalisation, saturation mask); the kernels, the estimator traces and the unclamped iterates are kept
+for the backward pass (n_iter extra images of memory).
 """
 from __future__ import annotations
 
@@ -74,6 +80,92 @@ def inverse_filtering_rank3_vjp(grad_out: torch.Tensor, kernel: torch.Tensor, al
     return gin.to(src)
 
 
+def _bw_workspace(B, Cn, H, W, ks, engine, dev):
+    n = _lib.lib().pb_backward_workspace_bytes(B, Cn, H, W, int(ks), int(engine))
+    return torch.empty(n, dtype=torch.uint8, device=dev)
+
+
+def estimate_trace(x: torch.Tensor):
+    """Forward trace of the estimator (pb_estimate_trace_f32): (B,24) floats and (B,8) pixel indices."""
+    B, Cn, H, W = x.shape
+    dev = x.device
+    with torch.cuda.device(dev):
+        ws = _bw_workspace(B, Cn, H, W, 25, _lib.ENGINE_AUTO, dev)
+        tf = torch.empty(B, 24, dtype=torch.float32, device=dev)
+        tp = torch.empty(B, 8, dtype=torch.int32, device=dev)
+        rc = _lib.lib().pb_estimate_trace_f32(x.data_ptr(), B, Cn, H, W, tf.data_ptr(), tp.data_ptr(), ws.data_ptr(),
+                                              ws.numel(), _lib.stream_ptr(dev))
+        _lib.check(rc, "pb_estimate_trace_f32")
+    return tf, tp
+
+
+def kernel_grad(x: torch.Tensor, grad_out: torch.Tensor, preclamp, k: torch.Tensor, alpha, beta, engine):
+    """d <grad_out, inverse_filtering_rank3(x, k)> / d k  -> (B,1,ks,ks)  (pb_kernel_grad_f32)."""
+    B, Cn, H, W = x.shape
+    ks = k.shape[-1]
+    dev = x.device
+    with torch.cuda.device(dev):
+        ws = _bw_workspace(B, Cn, H, W, ks, engine, dev)
+        kb = torch.empty(B, 1, ks, ks, dtype=torch.float32, device=dev)
+        rc = _lib.lib().pb_kernel_grad_f32(x.data_ptr(), grad_out.data_ptr(), _lib.ptr(preclamp), B, Cn, H, W,
+                                           k.data_ptr(), ks, float(alpha), float(beta), int(engine), kb.data_ptr(),
+                                           ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
+        _lib.check(rc, "pb_kernel_grad_f32")
+    return kb
+
+
+def _keys_weights(dev) -> torch.Tensor:
+    import ctypes as C
+    buf = (C.c_float * 210)()
+    _lib.lib().pb_keys_weights(buf)
+    return torch.tensor(list(buf), dtype=torch.float32, device=dev).view(30, 7)
+
+
+def _maxima_grad(m: torch.Tensor, kbar: torch.Tensor, c: float, b: float, ks: int) -> torch.Tensor:
+    """Gradient with respect to the 7 directional maxima given the gradient with respect to the kernel taps:
+    blur_estimation.py:138-232 (Keys interpolation, arg-min direction, affine model with clamping, Gaussian
+    taps) on (B,7) tensors, differentiated by torch autograd."""
+    dev = m.device
+    W30 = _keys_weights(dev)
+    with torch.enable_grad():
+        mm = m.detach().clone().requires_grad_(True)
+        mags = mm @ W30.t()                                          # (B,30)
+        i_min = torch.argmin(mags, dim=-1, keepdim=True)
+        theta_deg = i_min * 6
+        m_n = torch.take_along_dim(mags, i_min, dim=-1)
+        i_o = ((theta_deg + 90) % 180) // 6
+        m_o = torch.take_along_dim(mags, i_o, dim=-1)
+        cc, bb = c * c, b * b
+        sigma = torch.sqrt(torch.clamp(cc / (m_n * m_n + 1e-8) - bb, min=0.09, max=16.0))
+        rho = torch.sqrt(torch.clamp(cc / (m_o * m_o + 1e-8) - bb, min=0.09, max=16.0))
+        th = -(theta_deg.float() * 3.14159274101257324 / 180.0)
+        cs, sn = torch.cos(th), torch.sin(th)
+        il1, il2 = 1.0 / (sigma * sigma), 1.0 / (rho * rho)
+        s00 = cs * cs * il1 + sn * sn * il2
+        s01 = sn * cs * (il1 - il2)
+        s11 = cs * cs * il2 + sn * sn * il1
+        t = torch.arange(ks, device=dev) - ((ks - 1) // 2)
+        X, Y = torch.meshgrid(t, t, indexing="xy")
+        X, Y = X.float()[None], Y.float()[None]
+        quad = s00[:, :, None] * X * X + 2.0 * s01[:, :, None] * X * Y + s11[:, :, None] * Y * Y
+        E = torch.exp(-0.5 * quad)
+        K = E / E.sum(dim=(-1, -2), keepdim=True)
+        (K * kbar.view(-1, ks, ks)).sum().backward()
+    return mm.grad.contiguous()
+
+
+def estimator_vjp(x: torch.Tensor, mbar: torch.Tensor, tf: torch.Tensor, tp: torch.Tensor, grad_img: torch.Tensor):
+    """Adds the gradient through the estimator into grad_img (pb_estimator_vjp_f32)."""
+    B, Cn, H, W = x.shape
+    dev = x.device
+    with torch.cuda.device(dev):
+        ws = _bw_workspace(B, Cn, H, W, 25, _lib.ENGINE_AUTO, dev)
+        rc = _lib.lib().pb_estimator_vjp_f32(x.data_ptr(), mbar.data_ptr(), tf.data_ptr(), tp.data_ptr(),
+                                             grad_img.data_ptr(), B, Cn, H, W, ws.data_ptr(), ws.numel(),
+                                             _lib.stream_ptr(dev))
+        _lib.check(rc, "pb_estimator_vjp_f32")
+
+
 class DeconvolutionFunction(torch.autograd.Function):
     """``inverse_filtering_rank3(img, kernel, alpha, b)`` with default flags, differentiable in ``img``."""
 
@@ -97,38 +189,49 @@ class DeconvolutionFunction(torch.autograd.Function):
 
 
 class PolyblurFunction(torch.autograd.Function):
-    """The Polyblur loop (polyblur/deblurring.py:68-88, default options), differentiable in the image with the
-    per-iteration blur estimates held constant."""
+    """The Polyblur loop (polyblur/deblurring.py:68-88, default options), differentiable in the image."""
 
     @staticmethod
-    def forward(ctx, img, n_iter, c, b, alpha, beta, ker_size, q, discard_saturation, engine):
+    def forward(ctx, img, n_iter, c, b, alpha, beta, ker_size, engine, estimate_grad):
         dev = _lib.require_cuda(img)
-        cur = img.detach().to(dev).contiguous()
-        saved = []
+        x0 = img.detach().to(dev).contiguous()
+        cur = x0
+        saved = [x0]
         for _ in range(int(n_iter)):
-            k = blur_estimation.gaussian_blur_estimation(cur, q=q, c=c, b=b, ker_size=ker_size,
-                                                         discard_saturation=discard_saturation)
-            v = _deconv_noclamp(cur, k.contiguous(), alpha, beta, engine)
+            k = blur_estimation.gaussian_blur_estimation(cur, q=0.0, c=c, b=b, ker_size=ker_size).contiguous()
+            v = _deconv_noclamp(cur, k, alpha, beta, engine)
             saved += [k, v]
+            if estimate_grad:
+                saved += list(estimate_trace(cur))
             cur = v.clamp(0.0, 1.0)
         ctx.save_for_backward(*saved)
-        ctx.meta = (alpha, beta, engine, img.device)
+        ctx.meta = (int(n_iter), c, b, alpha, beta, int(ker_size), engine, bool(estimate_grad), img.device)
         return cur.to(img.device)
 
     @staticmethod
     def backward(ctx, grad_out):
         saved = ctx.saved_tensors
-        alpha, beta, engine, src = ctx.meta
-        dev = saved[0].device
-        g = grad_out.detach().to(dev).contiguous()
-        for t in range(len(saved) // 2 - 1, -1, -1):
-            g = inverse_filtering_rank3_vjp(g, saved[2 * t], alpha, beta, preclamp=saved[2 * t + 1], engine=engine)
-        return (g.to(src),) + (None,) * 9
+        n_iter, c, b, alpha, beta, ks, engine, estimate_grad, src = ctx.meta
+        per = 4 if estimate_grad else 2
+        x0 = saved[0]
+        g = grad_out.detach().to(x0.device).contiguous()
+        for t in range(n_iter - 1, -1, -1):
+            rec = saved[1 + per * t: 1 + per * (t + 1)]
+            k, v = rec[0], rec[1]
+            gin = inverse_filtering_rank3_vjp(g, k, alpha, beta, preclamp=v, engine=engine)
+            if estimate_grad:
+                xt = x0 if t == 0 else saved[1 + per * (t - 1) + 1].clamp(0.0, 1.0)
+                tf, tp = rec[2], rec[3]
+                kb = kernel_grad(xt, g, v, k, alpha, beta, engine)
+                mbar = _maxima_grad(tf[:, :7], kb, float(c), float(b), ks)
+                estimator_vjp(xt, mbar, tf, tp, gin)
+            g = gin
+        return (g.to(src),) + (None,) * 8
 
 
-def polyblur_deblurring_grad(img: torch.Tensor, n_iter=1, c=0.352, b=0.768, alpha=2, beta=3, ker_size=25, q=0.0,
-                             discard_saturation=False, engine=_lib.ENGINE_AUTO) -> torch.Tensor:
+def polyblur_deblurring_grad(img: torch.Tensor, n_iter=1, c=0.352, b=0.768, alpha=2, beta=3, ker_size=25,
+                             engine=_lib.ENGINE_AUTO, estimate_grad=True) -> torch.Tensor:
     """Differentiable ``polyblur_deblurring`` for (B,C,H,W) float32 tensors (default options only)."""
     if img.dtype != torch.float32 or img.ndim != 4:
         raise TypeError("img must be a float32 (B,C,H,W) tensor")
-    return PolyblurFunction.apply(img, n_iter, c, b, alpha, beta, ker_size, q, discard_saturation, engine)
+    return PolyblurFunction.apply(img, n_iter, c, b, alpha, beta, ker_size, engine, estimate_grad)

@@ -716,6 +716,139 @@ int pb_deconv_vjp_f32(const float* grad_out, const float* preclamp, float* grad_
     return launch_vjp_fold(t, grad_img, B * C, H, W, pad, stream);
 }
 
+// ---- backward pass through the estimator and the kernel argument (backward.cu) -----------------
+struct BwLayout {
+    Workspace eng;                       // engines + tables, sized for the (H+2P) x (W+2P) frame
+    size_t off_pad, off_v, off_q[4], off_keys, off_stats, off_sums, total;
+};
+static BwLayout bw_layout(int B, int C, int H, int W, int ksize, int engine) {
+    BwLayout v;
+    const int pad = ksize / 2;
+    const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+    v.eng = layout(B, C, Hp, Wp, 1, ksize, engine);
+    size_t o = align_up(v.eng.total, 256);
+    auto take = [&](size_t bytes) {
+        size_t at = o;
+        o = align_up(o + bytes, 256);
+        return at;
+    };
+    v.off_pad = take((size_t)B * C * Hp * Wp * sizeof(float));
+    v.off_v = take((size_t)B * C * Hp * Wp * sizeof(float));
+    for (int i = 0; i < 4; ++i) v.off_q[i] = take((size_t)B * H * W * sizeof(float));
+    v.off_keys = take((size_t)B * 7 * sizeof(unsigned long long));
+    v.off_stats = take((size_t)B * 2 * sizeof(unsigned));
+    v.off_sums = take((size_t)B * 2 * sizeof(double));
+    v.total = o;
+    return v;
+}
+
+size_t pb_backward_workspace_bytes(int B, int C, int H, int W, int ksize, int engine) {
+    if (B < 1 || C < 1 || H < 1 || W < 1 || ksize < 1 || ksize > PB_KS || !(ksize & 1)) return 0;
+    return bw_layout(B, C, H, W, ksize, engine).total;
+}
+
+int pb_estimate_trace_f32(const float* img, int B, int C, int H, int W, float* trace_f, int* trace_pos,
+                          void* workspace, size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc;
+    if ((rc = check_shape(B, C, H, W))) return rc;
+    if (!img || !trace_f || !trace_pos) {
+        set_error("null pointer");
+        return PB_ERR_ARG;
+    }
+    const BwLayout V = bw_layout(B, C, H, W, PB_KS, PB_ENGINE_AUTO);
+    if ((rc = check_ws(workspace, workspace_bytes, V.total))) return rc;
+    char* ws = static_cast<char*>(workspace);
+    Tables T;
+    if ((rc = upload_constants(stream))) return rc;
+    if ((rc = prepare_tables(ws, V.eng, H, W, &T, stream))) return rc;
+    float* g = reinterpret_cast<float*>(ws + V.off_q[0]);
+    float* gn = reinterpret_cast<float*>(ws + V.off_q[1]);
+    float* gx = reinterpret_cast<float*>(ws + V.off_q[2]);
+    float* gy = reinterpret_cast<float*>(ws + V.off_q[3]);
+    unsigned* stats = reinterpret_cast<unsigned*>(ws + V.off_stats);
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(ws + V.off_keys);
+    if ((rc = launch_bw_trace(img, g, gn, stats, keys, B, C, H, W, stream))) return rc;
+    if ((rc = gradients_into(gn, gx, gy, B, H, W, T, stream))) return rc;
+    return launch_bw_dirmax(gx, gy, g, keys, stats, trace_f, trace_pos, B, H, W, stream);
+}
+
+int pb_kernel_grad_f32(const float* img, const float* grad_out, const float* preclamp, int B, int C, int H, int W,
+                       const float* kernel, int ksize, double alpha, double beta, int engine, float* kernel_grad,
+                       void* workspace, size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc;
+    if ((rc = check_shape(B, C, H, W))) return rc;
+    if (!img || !grad_out || !kernel || !kernel_grad || ksize < 1 || ksize > PB_KS || !(ksize & 1)) {
+        set_error("bad arguments to pb_kernel_grad_f32 (ksize must be odd and <= 25)");
+        return PB_ERR_ARG;
+    }
+    const int pad = ksize / 2;
+    const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+    if ((rc = check_shape(B, C, Hp, Wp))) return rc;
+    const BwLayout V = bw_layout(B, C, H, W, ksize, engine);
+    if ((rc = check_ws(workspace, workspace_bytes, V.total))) return rc;
+    const Workspace& L = V.eng;
+    if (engine == PB_ENGINE_FFT && !L.has_fft) {
+        set_error("the FFT engine does not support %d x %d (ker_size %d)", Hp, Wp, ksize);
+        return PB_ERR_UNSUPPORTED;
+    }
+    char* ws = static_cast<char*>(workspace);
+    ImgKernel* kern = reinterpret_cast<ImgKernel*>(ws + L.off_kern);
+    int* cls = reinterpret_cast<int*>(ws + L.off_cls);
+    float* xp = reinterpret_cast<float*>(ws + V.off_pad);
+    float* v = reinterpret_cast<float*>(ws + V.off_v);
+    FftEngineTables F;
+    if (L.has_fft && (rc = fft_engine_prepare(ws + L.off_fft, L.fft, &F, stream))) return rc;
+    if ((rc = launch_params(nullptr, kern, nullptr, nullptr, nullptr, nullptr, kernel, nullptr, 2, B, ksize, 0.f, 0.f,
+                            1e-8f, engine, L.has_fft ? PB_FFT_RADIUS_MIN : (1 << 30), cls, stream)))
+        return rc;
+    if ((rc = launch_pad_replicate(img, xp, xp, B * C, H, W, pad, stream))) return rc;
+    // V = dP/dK (*) pad(x) on the padded torus: dP/dD = c1 + 2 c2 D + 3 c3 D^2 in the engines' basis D = K - I
+    float coef[4], dq[4];
+    poly_coeffs_d(alpha, beta, coef);
+    dq[0] = 0.0f;
+    dq[1] = 3.0f * coef[0];
+    dq[2] = 2.0f * coef[1];
+    dq[3] = coef[2];
+    SrcGeom G;
+    G.Hin = Hp;
+    G.Win = Wp;
+    G.off = 0;
+    G.pad = 0;
+    G.clamp_out = 0;
+    if ((rc = deconv_all(xp, v, B, C, Hp, Wp, dq, ws, L, L.has_fft ? &F : nullptr, G, stream))) return rc;
+    return launch_bw_kernel_grad(grad_out, preclamp, v, kernel_grad, B, C, H, W, ksize, stream);
+}
+
+int pb_estimator_vjp_f32(const float* img, const float* mbar, const float* trace_f, const int* trace_pos,
+                         float* grad_img, int B, int C, int H, int W, void* workspace, size_t workspace_bytes,
+                         void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc;
+    if ((rc = check_shape(B, C, H, W))) return rc;
+    if (!img || !mbar || !trace_f || !trace_pos || !grad_img) {
+        set_error("null pointer");
+        return PB_ERR_ARG;
+    }
+    const BwLayout V = bw_layout(B, C, H, W, PB_KS, PB_ENGINE_AUTO);
+    if ((rc = check_ws(workspace, workspace_bytes, V.total))) return rc;
+    char* ws = static_cast<char*>(workspace);
+    Tables T;
+    if ((rc = upload_constants(stream))) return rc;
+    if ((rc = prepare_tables(ws, V.eng, H, W, &T, stream))) return rc;
+    float* sgx = reinterpret_cast<float*>(ws + V.off_q[0]);
+    float* sgy = reinterpret_cast<float*>(ws + V.off_q[1]);
+    float* dx = reinterpret_cast<float*>(ws + V.off_q[2]);
+    float* dy = reinterpret_cast<float*>(ws + V.off_q[3]);
+    double* sums = reinterpret_cast<double*>(ws + V.off_sums);
+    if ((rc = launch_bw_scatter(mbar, trace_f, trace_pos, sgx, sgy, B, H, W, stream))) return rc;
+    // D^T = -D: the sign is applied where the two planes are combined
+    if ((rc = gradients_into(sgx, dx, nullptr, B, H, W, T, stream))) return rc;
+    if ((rc = gradients_into(sgy, nullptr, dy, B, H, W, T, stream))) return rc;
+    return launch_bw_norm(dx, dy, img, trace_f, sums, grad_img, B, C, H, W, stream);
+}
+
 int pb_profile_begin(void) {
     for (auto& r : g_prof) {
         g_event_pool.push_back(r.a);

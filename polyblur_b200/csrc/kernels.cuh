@@ -76,6 +76,18 @@ int launch_halo_apply(float* imout, const float* img, size_t img_plane, int img_
 size_t edgetaper_scratch_bytes(int B, int Hp, int Wp);
 int launch_edgetaper_weights(const ImgKernel* kern, void* scratch, int B, int Hp, int Wp, int batch_max,
                              float** v_out, cudaStream_t stream);
+// backward pass through the estimator (backward.cu)
+#define PB_BW_TRACE_STRIDE 24   // per image: 7 maxima, 7 signs, min, max, #min, #max
+int launch_bw_trace(const float* img, float* g, float* gn, unsigned* stats, unsigned long long* keys, int B, int C,
+                    int H, int W, cudaStream_t stream);
+int launch_bw_dirmax(const float* gx, const float* gy, const float* g, unsigned long long* keys, const unsigned* stats,
+                     float* trace_f, int* trace_pos, int B, int H, int W, cudaStream_t stream);
+int launch_bw_kernel_grad(const float* gout, const float* preclamp, const float* V, float* kbar, int B, int C, int H,
+                          int W, int ks, cudaStream_t stream);
+int launch_bw_scatter(const float* mbar, const float* trace_f, const int* trace_pos, float* sgx, float* sgy, int B,
+                      int H, int W, cudaStream_t stream);
+int launch_bw_norm(const float* dx, const float* dy, const float* img, const float* trace_f, double* sums, float* gin,
+                   int B, int C, int H, int W, cudaStream_t stream);
 int launch_vjp_embed(const float* gout, const float* preclamp, float* z, int planes, int H, int W, int pad,
                      cudaStream_t stream);
 int launch_vjp_fold(const float* t, float* gin, int planes, int H, int W, int pad, cudaStream_t stream);

@@ -132,6 +132,7 @@ def polyblur_deblurring(img, n_iter=1, c=0.352, b=0.768, alpha=2, beta=3, sigma_
         raise ValueError("only n_angles=6 and n_interpolated_angles=30 work in the reference "
                          "(SURVEY.md Appendix B.10); other values are rejected here")
     return_estimates = bool(engine_kw.pop("return_estimates", False))
+    estimate_grad = bool(engine_kw.pop("estimate_grad", True))
     p = _make_params(n_iter, c, b, alpha, beta, sigma_r, sigma_s, ker_size, q, remove_halo, edgetaping,
                      prefiltering, discard_saturation, **engine_kw)
 
@@ -150,14 +151,13 @@ def polyblur_deblurring(img, n_iter=1, c=0.352, b=0.768, alpha=2, beta=3, sigma_
         return utils.to_array(x) if flag_numpy else img
     if not flag_numpy and x.requires_grad and torch.is_grad_enabled():
         # differentiable path (autograd.py): gradient with respect to the image, blur estimates held constant
-        if remove_halo or edgetaping or prefiltering or return_estimates:
-            raise NotImplementedError("gradients are implemented for the default options only "
-                                      "(no remove_halo / edgetaping / prefiltering); call under torch.no_grad() "
-                                      "or detach the input")
+        if remove_halo or edgetaping or prefiltering or return_estimates or q > 0 or discard_saturation:
+            raise NotImplementedError("gradients are implemented for the default options only (no remove_halo / "
+                                      "edgetaping / prefiltering / q / discard_saturation); call under "
+                                      "torch.no_grad() or detach the input")
         from . import autograd as _autograd
         return _autograd.polyblur_deblurring_grad(x, n_iter=n_iter, c=c, b=b, alpha=alpha, beta=beta,
-                                                  ker_size=ker_size, q=q, discard_saturation=discard_saturation,
-                                                  engine=p.engine)
+                                                  ker_size=ker_size, engine=p.engine, estimate_grad=estimate_grad)
 
     dev = _lib.require_cuda(x)
     src_device = x.device

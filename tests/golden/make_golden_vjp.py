@@ -7,6 +7,9 @@ Run in the build container only (needs /root/reference):
 Writes vjp.npz next to this file:
   * deconv_*: one reference ``inverse_filtering_rank3`` (method='fft') and the gradient of
     sum(y * ybar) with respect to the image, for a wide and a narrow Gaussian kernel;
+  * deconv_*_kernel_grad: the gradient of the same scalar with respect to the kernel taps;
+  * est_*: the estimator alone, gradient of <gaussian_blur_estimation(x), kbar> with respect to x
+    (image 1 has tied maxima);
   * chain_*: two Polyblur iterations in which the blur estimate of each iteration is taken from the
     reference estimator under no_grad (the estimate held constant), and the gradient with respect to the
     input; ``chain_full_grad`` is the gradient of the reference's own polyblur_deblurring, estimator in
@@ -41,6 +44,34 @@ def mosaic(B, C, H, W, seed, sigma=(2.5, 1.2), theta_deg=30.0, block=12):
     return filters.convolve2d(img, k, method="fft").clamp(0, 1).contiguous()
 
 
+def textured(B, C, H, W, seed):
+    """Blurred mosaic plus a smooth random field: along a straight mosaic edge the gradient is constant to
+    within rounding, so the arg-max pixel of a directional maximum (where autograd puts its sub-gradient)
+    would depend on the last bit of the FFT; the texture makes every maximum unique by a clear margin."""
+    g = torch.Generator().manual_seed(seed + 1000)
+    base = mosaic(B, C, H, W, seed)
+    n = torch.randn(B, C, H, W, generator=g)
+    k = torch.from_numpy(filters.gaussian_filter((3.0, 3.0), 0.0, k_size=np.array([25, 25])))[None, None].repeat(B, 1, 1, 1)
+    n = filters.convolve2d(n, k, method="fft")
+    n = n / n.abs().amax(dim=(1, 2, 3), keepdim=True)
+    return (0.1 + 0.8 * base + 0.08 * n).clamp(0, 1).contiguous()
+
+
+def unique_maxima_margin(x):
+    """Smallest relative gap between the two largest |cos gx - sin gy| over the 7 angles and the images."""
+    gray = x.mean(1, keepdim=True)
+    gn = blur_estimation.normalize(gray, q=0)
+    gx, gy = blur_estimation.compute_gradients(gn, blur_estimation.get_saturation_mask(gray, False))
+    ang = torch.linspace(0, np.pi, 7)
+    worst = 1.0
+    for b in range(x.shape[0]):
+        for j in range(7):
+            v = (torch.cos(ang[j]) * gx[b, 0] - torch.sin(ang[j]) * gy[b, 0]).abs().flatten()
+            top = torch.topk(v, 2).values
+            worst = min(worst, float((top[0] - top[1]) / top[0]))
+    return worst
+
+
 def main():
     out = {}
     g = torch.Generator().manual_seed(11)
@@ -59,14 +90,37 @@ def main():
         (gx,) = torch.autograd.grad((y * ybar).sum(), xr)
         out[f"deconv_{tag}_y"] = y.detach().numpy()
         out[f"deconv_{tag}_grad"] = gx.numpy()
+        # gradient with respect to the kernel taps of the same scalar
+        kr = kernels.clone().requires_grad_(True)
+        y = deblurring.inverse_filtering_rank3(x, kr, alpha=alpha, b=beta, method="fft")
+        (gk,) = torch.autograd.grad((y * ybar).sum(), kr)
+        out[f"deconv_{tag}_kernel_grad"] = gk.numpy()
     out["deconv_x"] = x.numpy()
     out["deconv_kernels"] = kernels.numpy()
     out["deconv_ybar"] = ybar.numpy()
 
+    # ---- the estimator alone: gradient of <kernel(x), kbar> with respect to the image ----------
+    B, C, H, W = 2, 3, 48, 60
+    x = textured(B, C, H, W, seed=9)
+    x[1, :, 5:9, 7:12] = x[1].max()          # ties at the maximum of image 1 (amax spreads its gradient)
+    print("estimator case: smallest top-2 gap of a directional maximum =", unique_maxima_margin(x))
+    assert unique_maxima_margin(x) > 1e-4
+    kbar = torch.randn(B, 1, 25, 25, generator=g)
+    xr = x.clone().requires_grad_(True)
+    k = blur_estimation.gaussian_blur_estimation(xr, q=0.0, n_angles=6, n_interpolated_angles=30, c=0.352, b=0.768,
+                                                 ker_size=25)
+    (gx,) = torch.autograd.grad((k * kbar).sum(), xr)
+    out["est_x"] = x.numpy()
+    out["est_kbar"] = kbar.numpy()
+    out["est_kernel"] = k.detach().numpy()
+    out["est_grad"] = gx.numpy()
+
     # ---- two iterations, estimate held constant ----------------------------------------------
     B, C, H, W = 2, 3, 64, 80
-    x = mosaic(B, C, H, W, seed=5)
+    x = textured(B, C, H, W, seed=5)
     ybar = torch.randn(B, C, H, W, generator=g)
+    print("chain case: smallest top-2 gap, iteration 1 =", unique_maxima_margin(x))
+    assert unique_maxima_margin(x) > 1e-4
     c, b, alpha, beta = 0.352, 0.768, 6, 1
     xr = x.clone().requires_grad_(True)
     cur = xr
@@ -78,6 +132,10 @@ def main():
         ks.append(k)
         cur = deblurring.inverse_filtering_rank3(cur, k, alpha=alpha, b=beta, method="fft")
     (gx,) = torch.autograd.grad((cur * ybar).sum(), xr)
+    with torch.no_grad():
+        x1 = deblurring.inverse_filtering_rank3(x, ks[0], alpha=alpha, b=beta, method="fft")
+    print("chain case: smallest top-2 gap, iteration 2 =", unique_maxima_margin(x1))
+    assert unique_maxima_margin(x1) > 1e-4
     out["chain_x"] = x.numpy()
     out["chain_ybar"] = ybar.numpy()
     out["chain_y"] = cur.detach().numpy()
@@ -88,6 +146,10 @@ def main():
     yf = deblurring.polyblur_deblurring(xr, n_iter=2, c=c, b=b, alpha=alpha, beta=beta)
     (gf,) = torch.autograd.grad((yf * ybar).sum(), xr)
     out["chain_full_grad"] = gf.numpy()
+    xr = x.clone().requires_grad_(True)
+    y1 = deblurring.polyblur_deblurring(xr, n_iter=1, c=c, b=b, alpha=alpha, beta=beta)
+    (g1,) = torch.autograd.grad((y1 * ybar).sum(), xr)
+    out["chain_full_grad_1iter"] = g1.numpy()
     rel = float((gf - gx).abs().max() / gx.abs().max())
     print("max |full - constant-estimate| / max |grad| =", rel)
     out["chain_full_rel_diff"] = np.float64(rel)

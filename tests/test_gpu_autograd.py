@@ -75,26 +75,58 @@ def test_deconvolution_vjp_is_the_adjoint(pb, shape, engine):
     assert abs(lhs - rhs) < 1e-5 * scale
 
 
-def test_polyblur_gradient_with_constant_estimates(pb, gold):
-    """Two iterations: forward equals the no-grad path, gradient equals autograd over the reference with its
-    estimator under no_grad (the estimates held constant); the module surface routes the same way."""
+@pytest.mark.parametrize("engine", sorted(ENGINES))
+@pytest.mark.parametrize("tag,alpha,beta", [("a6b1", 6, 1), ("a2b4", 2, 4)])
+def test_kernel_gradient_golden(pb, gold, tag, alpha, beta, engine):
+    """d <ybar, inverse_filtering_rank3(x, k)> / d k against autograd over the reference."""
+    from polyblur_b200 import autograd as ag
+    x, k, ybar = cu(gold["deconv_x"]), cu(gold["deconv_kernels"]), cu(gold["deconv_ybar"])
+    e = ENGINES[engine]
+    v = ag._deconv_noclamp(x, k, alpha, beta, e)
+    kb = ag.kernel_grad(x, ybar, v, k, alpha, beta, e)
+    assert rel(kb.cpu().numpy(), gold[f"deconv_{tag}_kernel_grad"]) < 1e-4
+
+
+def test_estimator_vjp_golden(pb, gold):
+    """Gradient of <gaussian_blur_estimation(x), kbar> with respect to x: arg-max pixels, transposed spectral
+    derivative, range normalisation with tied maxima, against autograd over the reference."""
+    from polyblur_b200 import autograd as ag
+    x, kbar = cu(gold["est_x"]), cu(gold["est_kbar"])
+    k = pb.blur_estimation.gaussian_blur_estimation(x, q=0.0, c=0.352, b=0.768)
+    assert np.abs(k.cpu().numpy() - gold["est_kernel"]).max() < 1e-6
+    tf, tp = ag.estimate_trace(x)
+    mbar = ag._maxima_grad(tf[:, :7], kbar, 0.352, 0.768, 25)
+    gin = torch.zeros_like(x)
+    ag.estimator_vjp(x, mbar, tf, tp, gin)
+    ref = gold["est_grad"]
+    assert float(np.abs(ref).max()) > 0
+    assert rel(gin.cpu().numpy(), ref) < 2e-4
+
+
+def test_polyblur_gradient(pb, gold):
+    """Two iterations.  Default (estimate_grad=True): the reference's own gradient, estimator in the graph.
+    estimate_grad=False: autograd over the reference with its estimator under no_grad.  Forward equals the
+    no-grad path either way; the module surface routes the same way."""
     x0 = cu(gold["chain_x"])
     ybar = cu(gold["chain_ybar"])
-    x = x0.clone().requires_grad_(True)
-    y = pb.polyblur_deblurring(x, n_iter=2, alpha=6, beta=1)
     with torch.no_grad():
         y0 = pb.polyblur_deblurring(x0, n_iter=2, alpha=6, beta=1)
-    assert float((y.detach() - y0).abs().max()) < 2e-6
-    assert np.abs(y.detach().cpu().numpy() - gold["chain_y"]).max() < 1e-5
-    (y * ybar).sum().backward()
-    assert rel(x.grad.cpu().numpy(), gold["chain_grad"]) < 1e-4
+    for flag, key, tol in ((True, "chain_full_grad", 5e-4), (False, "chain_grad", 1e-4)):
+        x = x0.clone().requires_grad_(True)
+        y = pb.polyblur_deblurring(x, n_iter=2, alpha=6, beta=1, estimate_grad=flag)
+        assert float((y.detach() - y0).abs().max()) < 2e-6
+        assert np.abs(y.detach().cpu().numpy() - gold["chain_y"]).max() < 1e-5
+        (y * ybar).sum().backward()
+        assert rel(x.grad.cpu().numpy(), gold[key]) < tol, key
+    x = x0.clone().requires_grad_(True)
+    (pb.polyblur_deblurring(x, n_iter=1, alpha=6, beta=1) * ybar).sum().backward()
+    assert rel(x.grad.cpu().numpy(), gold["chain_full_grad_1iter"]) < 5e-4
     xm = x0.clone().requires_grad_(True)
-    ym = pb.PolyblurDeblurring()(xm, n_iter=2, c=0.352, b=0.768, alpha=6, beta=1)
+    ym = pb.PolyblurDeblurring()(xm, n_iter=1, c=0.352, b=0.768, alpha=6, beta=1)
     (ym * ybar).sum().backward()
-    assert torch.equal(xm.grad, x.grad)
+    assert rel(xm.grad.cpu().numpy(), gold["chain_full_grad_1iter"]) < 5e-4
     # CPU tensors: the gradient comes back on the input's device
-    xc = gold["chain_x"]
-    xc = torch.from_numpy(xc).requires_grad_(True)
+    xc = torch.from_numpy(gold["chain_x"]).requires_grad_(True)
     yc = pb.polyblur_deblurring(xc, n_iter=1, alpha=6, beta=1)
     yc.sum().backward()
     assert xc.grad is not None and xc.grad.device.type == "cpu" and bool(torch.isfinite(xc.grad).all())
@@ -102,7 +134,8 @@ def test_polyblur_gradient_with_constant_estimates(pb, gold):
 
 def test_gradient_unsupported_options_raise(pb, gold):
     x = cu(gold["chain_x"]).requires_grad_(True)
-    for kw in (dict(remove_halo=True), dict(edgetaping=True), dict(prefiltering=True)):
+    for kw in (dict(remove_halo=True), dict(edgetaping=True), dict(prefiltering=True), dict(q=0.01),
+               dict(discard_saturation=True)):
         with pytest.raises(NotImplementedError):
             pb.polyblur_deblurring(x, n_iter=1, **kw)
     with torch.no_grad():

@@ -27,6 +27,9 @@ def main():
     xg = x.clone().requires_grad_(True)
     pb.polyblur_deblurring(xg, n_iter=2, alpha=6, beta=1).sum().backward()
     assert bool(torch.isfinite(xg.grad).all())
+    xg = x.clone().requires_grad_(True)
+    pb.polyblur_deblurring(xg, n_iter=2, alpha=6, beta=1, estimate_grad=False, engine=2).sum().backward()
+    assert bool(torch.isfinite(xg.grad).all())
     gx, gy = pb.filters.fourier_gradients(x)
     u8 = (x.permute(0, 2, 3, 1) * 255).round().to(torch.uint8).contiguous().cpu()
     from polyblur_b200 import io as pbio
