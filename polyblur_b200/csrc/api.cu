@@ -386,8 +386,15 @@ void pb_polynomial_coefficients(double alpha, double beta, float* out4) { poly_c
 void pb_keys_weights(float* out210) { keys_weights_host(out210); }
 
 int pb_fft_plan(int n, int* radices) {
+    // the register-radix core (fft2.cuh) runs every length whose prime factors are <= 13; the any-length
+    // Stockham core (fft.cuh) is the fallback
+    Fft2Plan p2;
+    if (n >= 2 && radices && make_fft2_plan(n, &p2) == 0) {
+        for (int i = 0; i < p2.ns; ++i) radices[i] = p2.radix[i];
+        return p2.ns;
+    }
     FftPlan p;
-    if (make_fft_plan(n, &p) != PB_OK) {
+    if (!radices || make_fft_plan(n, &p) != PB_OK) {
         set_error("cannot plan FFT of length %d", n);
         return PB_ERR_ARG;
     }

@@ -105,3 +105,28 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.replace("# oracle", ""), f"{f} mentions the oracle"
+
+
+def test_plain_c_consumer(tmp_path):
+    """The boundary is usable from plain C: tests/c/abi_smoke.c compiles against include/polyblur_b200.h with
+    gcc, dlopens the library and exercises the host-side entry points (no Python, no torch in the loop)."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = os.path.join(root, "polyblur_b200", "libpolyblur_sm100.so")
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    exe = str(tmp_path / "abi_smoke")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I" + os.path.join(root, "include"),
+                    os.path.join(root, "tests", "c", "abi_smoke.c"), "-ldl", "-lm", "-o", exe], check=True)
+    out = subprocess.run([exe, so], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert "abi smoke ok" in out.stdout
+
+
+def test_fft_plan_reports_the_register_radix_plan(lib):
+    """1080p lengths take three stages of radices <= 16 (what the kernels run), not the fallback's plan."""
+    r = (ctypes.c_int * 32)()
+    for n, want in ((1920, 3), (1080, 3), (2016, 3), (1152, 3), (3840, 3), (2160, 3)):
+        assert lib.lib().pb_fft_plan(n, r) == want
+        assert max(r[:want]) <= 16

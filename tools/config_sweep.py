@@ -53,6 +53,18 @@ def main():
         prefiltering=True, prefilter="rf")
     for kind in ("white", "mosaic"):
         run(f"C4 single 12000x9000 {kind}", synthetic.make(kind, 1, 3, 9000, 12000, device=dev), 5)
+    # forward + backward on 8 x 1080p, with and without the estimator's gradient
+    xb = synthetic.make("mosaic", 8, 3, 1080, 1920, device=dev)
+    for flag in (True, False):
+        def step():
+            xg = xb.clone().requires_grad_(True)
+            pb.polyblur_deblurring(xg, n_iter=3, alpha=6, beta=1, estimate_grad=flag).sum().backward()
+            return xg.grad
+        ms = timed(step)
+        gr = step()
+        print(json.dumps({"config": f"forward + backward 8 x 1080p mosaic n_iter=3 estimate_grad={flag}", "shape": list(xb.shape),
+                          "n_iter": 3, "ms": round(ms, 3), "Mpix_s": round(8 * 1080 * 1920 / 1e6 / (ms / 1e3), 1),
+                          "finite": bool(torch.isfinite(gr).all())}), flush=True)
 
 
 if __name__ == "__main__":
