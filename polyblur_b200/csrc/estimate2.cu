@@ -54,6 +54,9 @@ __global__ void k_fft2_stage_tw(float2* __restrict__ stw, Fft2Plan plan) {
 #ifndef PB_R2_SMEM
 #define PB_R2_SMEM (64 * 1024)
 #endif
+#ifndef PB_R2_LOAD_U
+#define PB_R2_LOAD_U 2
+#endif
 #ifndef PB_C2_THREADS
 #define PB_C2_THREADS 256
 #endif
@@ -92,12 +95,13 @@ k_rows2(const float* __restrict__ img, float* __restrict__ gray, float* __restri
         // two row pairs per trip, every 128-bit load of the trip (2 rows x up to 3 channels x 2)
         // issued before the first use
         constexpr int CU = 3;                                   // channels unrolled for loads in flight
-        for (int base = tid; base < nb * w4; base += 2 * R2_THREADS) {
-            float4 t[2][2][CU];
-            int pp[2], xx[2];
-            bool ok[2][2];
+        constexpr int LU = PB_R2_LOAD_U;                        // row-pair items per trip
+        for (int base = tid; base < nb * w4; base += LU * R2_THREADS) {
+            float4 t[LU][2][CU];
+            int pp[LU], xx[LU];
+            bool ok[LU][2];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+            for (int u = 0; u < LU; ++u) {
                 const int idx = base + u * R2_THREADS;
                 const bool live = idx < nb * w4;
                 pp[u] = live ? fast_div(idx, w4, inv_w4) : 0;
@@ -116,7 +120,7 @@ k_rows2(const float* __restrict__ img, float* __restrict__ gray, float* __restri
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+            for (int u = 0; u < LU; ++u) {
                 if (base + u * R2_THREADS >= nb * w4) continue;
                 float4 g[2];
 #pragma unroll
