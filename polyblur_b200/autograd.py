@@ -114,11 +114,18 @@ def kernel_grad(x: torch.Tensor, grad_out: torch.Tensor, preclamp, k: torch.Tens
     return kb
 
 
+_KEYS_WEIGHTS: dict = {}
+
+
 def _keys_weights(dev) -> torch.Tensor:
-    import ctypes as C
-    buf = (C.c_float * 210)()
-    _lib.lib().pb_keys_weights(buf)
-    return torch.tensor(list(buf), dtype=torch.float32, device=dev).view(30, 7)
+    """(30,7) normalised Keys weights (pb_keys_weights), uploaded once per device."""
+    key = str(dev)
+    if key not in _KEYS_WEIGHTS:
+        import ctypes as C
+        buf = (C.c_float * 210)()
+        _lib.lib().pb_keys_weights(buf)
+        _KEYS_WEIGHTS[key] = torch.tensor(list(buf), dtype=torch.float32, device=dev).view(30, 7)
+    return _KEYS_WEIGHTS[key]
 
 
 def _maxima_grad(m: torch.Tensor, kbar: torch.Tensor, c: float, b: float, ks: int) -> torch.Tensor:

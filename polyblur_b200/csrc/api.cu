@@ -743,7 +743,7 @@ static BwLayout bw_layout(int B, int C, int H, int W, int ksize, int engine) {
     v.off_v = take((size_t)B * C * Hp * Wp * sizeof(float));
     for (int i = 0; i < 4; ++i) v.off_q[i] = take((size_t)B * H * W * sizeof(float));
     v.off_keys = take((size_t)B * 7 * sizeof(unsigned long long));
-    v.off_stats = take((size_t)B * 2 * sizeof(unsigned));
+    v.off_stats = take((size_t)B * 4 * sizeof(unsigned));
     v.off_sums = take((size_t)B * 2 * sizeof(double));
     v.total = o;
     return v;

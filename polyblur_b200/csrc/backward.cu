@@ -36,8 +36,10 @@ __device__ __forceinline__ float bw_gray_of(const float* __restrict__ img, size_
 __global__ void k_bw_init(unsigned* __restrict__ stats, unsigned long long* __restrict__ keys, int B) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < B) {
-        stats[2 * i] = 0xffffffffu;
-        stats[2 * i + 1] = 0u;
+        stats[4 * i] = 0xffffffffu;          // running min (ordered encoding)
+        stats[4 * i + 1] = 0u;               // running max
+        stats[4 * i + 2] = 0u;               // pixels that attain the min
+        stats[4 * i + 3] = 0u;               // ... the max
     }
     if (i < B * 7) keys[i] = 0ull;
 }
@@ -57,8 +59,8 @@ __global__ void k_bw_gray(const float* __restrict__ img, float* __restrict__ g, 
     lmin = warp_min(lmin);
     lmax = warp_max(lmax);
     if ((threadIdx.x & 31) == 0) {
-        atomicMin(&stats[2 * b], f2ord(lmin));
-        atomicMax(&stats[2 * b + 1], f2ord(lmax));
+        atomicMin(&stats[4 * b], f2ord(lmin));
+        atomicMax(&stats[4 * b + 1], f2ord(lmax));
     }
 }
 
@@ -66,7 +68,7 @@ __global__ void k_bw_gray(const float* __restrict__ img, float* __restrict__ g, 
 __global__ void k_bw_normalize(const float* __restrict__ g, float* __restrict__ gn, const unsigned* __restrict__ stats,
                                size_t plane) {
     const int b = blockIdx.y;
-    const float mn = ord2f(stats[2 * b]), mx = ord2f(stats[2 * b + 1]);
+    const float mn = ord2f(stats[4 * b]), mx = ord2f(stats[4 * b + 1]);
     const float den = __fsub_rn(mx, mn);
     for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < plane; o += (size_t)gridDim.x * blockDim.x) {
         const float v = __fdiv_rn(__fsub_rn(g[(size_t)b * plane + o], mn), den);
@@ -75,14 +77,19 @@ __global__ void k_bw_normalize(const float* __restrict__ g, float* __restrict__ 
 }
 
 // per angle: the largest |cos gx - sin gy| and where (first pixel on ties) as one 64-bit key
-__global__ void k_bw_dirmax(const float* __restrict__ gx, const float* __restrict__ gy,
-                            unsigned long long* __restrict__ keys, size_t plane) {
+__global__ void k_bw_dirmax(const float* __restrict__ gx, const float* __restrict__ gy, const float* __restrict__ g,
+                            unsigned long long* __restrict__ keys, unsigned* __restrict__ stats, size_t plane) {
     const int b = blockIdx.y;
+    const float mn = ord2f(stats[4 * b]), mx = ord2f(stats[4 * b + 1]);
+    unsigned nmin = 0, nmax = 0;
     unsigned long long best[7];
 #pragma unroll
     for (int j = 0; j < 7; ++j) best[j] = 0ull;
     for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < plane; o += (size_t)gridDim.x * blockDim.x) {
         const float x = gx[(size_t)b * plane + o], y = gy[(size_t)b * plane + o];
+        const float gv = g[(size_t)b * plane + o];
+        nmin += (gv == mn);
+        nmax += (gv == mx);
 #pragma unroll
         for (int j = 0; j < 7; ++j) {
             const float v = fabsf(__fsub_rn(__fmul_rn(c_bw_cos7[j], x), __fmul_rn(c_bw_sin7[j], y)));
@@ -100,27 +107,20 @@ __global__ void k_bw_dirmax(const float* __restrict__ gx, const float* __restric
         }
         if ((threadIdx.x & 31) == 0) atomicMax(&keys[b * 7 + j], k);
     }
+    nmin = __reduce_add_sync(0xffffffffu, nmin);
+    nmax = __reduce_add_sync(0xffffffffu, nmax);
+    if ((threadIdx.x & 31) == 0) {
+        if (nmin) atomicAdd(&stats[4 * b + 2], nmin);
+        if (nmax) atomicAdd(&stats[4 * b + 3], nmax);
+    }
 }
 
-// one CTA per image: decode the arg-max pixels, the sign there, count the ties of min / max
+// one warp per image: decode the arg-max pixels and the sign there
 //   trace_f[b][0..6] maxima, [7..13] sign, [14] min, [15] max, [16] #min, [17] #max;  trace_pos[b][0..6] pixel
-__global__ void k_bw_finish(const float* __restrict__ gx, const float* __restrict__ gy, const float* __restrict__ g,
+__global__ void k_bw_finish(const float* __restrict__ gx, const float* __restrict__ gy,
                             const unsigned long long* __restrict__ keys, const unsigned* __restrict__ stats,
                             float* __restrict__ trace_f, int* __restrict__ trace_pos, size_t plane) {
     const int b = blockIdx.x;
-    const float mn = ord2f(stats[2 * b]), mx = ord2f(stats[2 * b + 1]);
-    __shared__ unsigned cnt[2];
-    if (threadIdx.x < 2) cnt[threadIdx.x] = 0u;
-    __syncthreads();
-    unsigned nmin = 0, nmax = 0;
-    for (size_t o = threadIdx.x; o < plane; o += blockDim.x) {
-        const float v = g[(size_t)b * plane + o];
-        nmin += (v == mn);
-        nmax += (v == mx);
-    }
-    atomicAdd(&cnt[0], nmin);
-    atomicAdd(&cnt[1], nmax);
-    __syncthreads();
     float* tf = trace_f + (size_t)b * PB_BW_TRACE_STRIDE;
     if (threadIdx.x < 7) {
         const int j = threadIdx.x;
@@ -133,24 +133,30 @@ __global__ void k_bw_finish(const float* __restrict__ gx, const float* __restric
         trace_pos[b * 8 + j] = (int)o;
     }
     if (threadIdx.x == 0) {
-        tf[14] = mn;
-        tf[15] = mx;
-        tf[16] = (float)cnt[0];
-        tf[17] = (float)cnt[1];
+        tf[14] = ord2f(stats[4 * b]);
+        tf[15] = ord2f(stats[4 * b + 1]);
+        tf[16] = (float)stats[4 * b + 2];
+        tf[17] = (float)stats[4 * b + 3];
         trace_pos[b * 8 + 7] = 0;
     }
 }
 
-// K~[b][d] += sum over one 32 x 32 tile of one plane of y~[p] V[p + pad - d]
+// K~[b][d] += sum over one 32 x 32 tile of one plane of y~[p] V[p + pad - d].
+// A thread owns a 5 x 5 block of kernel offsets and 4 rows of the tile and walks along x with a sliding
+// window of V per offset row in registers: 6 shared-memory loads per 25 FMAs.  The 8 row groups are summed
+// by warp shuffles, one global atomic per offset and tile.
 #define BW_KG_TILE 32
+#define BW_KG_OB 5
 __global__ void __launch_bounds__(256)
 k_bw_kernel_grad(const float* __restrict__ gout, const float* __restrict__ preclamp, const float* __restrict__ V,
                  float* __restrict__ kbar, int C, int H, int W, int ks) {
     extern __shared__ float smk[];
     const int pad = ks >> 1;
     const int VT = BW_KG_TILE + 2 * pad;             // V tile edge
-    float* sg = smk;                                 // [32][32]
-    float* sv = smk + BW_KG_TILE * BW_KG_TILE;       // [VT][VT + 1]
+    const int VS = VT + 1;                           // row stride of the V tile
+    constexpr int GS = BW_KG_TILE + 1;               // row stride of the gradient tile
+    float* sg = smk;                                 // [32][33]
+    float* sv = sg + BW_KG_TILE * GS;                // [VT][VT + 1]
     const int pl = blockIdx.z, b = pl / C;
     const int x0 = blockIdx.x * BW_KG_TILE, y0 = blockIdx.y * BW_KG_TILE;
     const int Hp = H + 2 * pad, Wp = W + 2 * pad;
@@ -167,26 +173,65 @@ k_bw_kernel_grad(const float* __restrict__ gout, const float* __restrict__ precl
                 if (!(u >= 0.0f && u <= 1.0f)) v = 0.0f;
             }
         }
-        sg[i] = v;
+        sg[ty * GS + tx] = v;
     }
-    // V tile: padded coordinates [y0, y0 + 32 + 2 pad) x [x0, ...): index (p + pad - d) for d in [-pad, pad]
+    // V tile: padded coordinates [y0, y0 + 32 + 2 pad) x [x0, ...); pixel p and kernel index (iy, ix) meet at
+    // tile position (ty + 2 pad - iy, tx + 2 pad - ix)
     for (int i = threadIdx.x; i < VT * VT; i += blockDim.x) {
         const int ty = i / VT, tx = i - ty * VT;
         const int yp = y0 + ty, xp = x0 + tx;
-        sv[ty * (VT + 1) + tx] = (yp < Hp && xp < Wp) ? V[(size_t)pl * Hp * Wp + (size_t)yp * Wp + xp] : 0.0f;
+        sv[ty * VS + tx] = (yp < Hp && xp < Wp) ? V[(size_t)pl * Hp * Wp + (size_t)yp * Wp + xp] : 0.0f;
     }
     __syncthreads();
-    for (int d = threadIdx.x; d < ks * ks; d += blockDim.x) {
-        const int iy = d / ks, ix = d - iy * ks;     // kernel array index; offset = index - pad
-        // p + pad - (index - pad) = p + 2 pad - index  (tile-local: row ty + 2 pad - iy)
-        const float* vrow = sv + (2 * pad - iy) * (VT + 1) + (2 * pad - ix);
-        float acc = 0.0f;
-        for (int ty = 0; ty < BW_KG_TILE; ++ty) {
-#pragma unroll 8
-            for (int tx = 0; tx < BW_KG_TILE; ++tx) acc = fmaf(sg[ty * BW_KG_TILE + tx], vrow[ty * (VT + 1) + tx], acc);
+    const int nob = (ks + BW_KG_OB - 1) / BW_KG_OB;      // offset blocks per axis
+    const int ob = threadIdx.x >> 3, rg = threadIdx.x & 7;
+    const int iy0 = (ob / nob) * BW_KG_OB, ix0 = (ob - (ob / nob) * nob) * BW_KG_OB;
+    float acc[BW_KG_OB][BW_KG_OB];
+#pragma unroll
+    for (int a = 0; a < BW_KG_OB; ++a)
+#pragma unroll
+        for (int c = 0; c < BW_KG_OB; ++c) acc[a][c] = 0.0f;
+    if (ob < nob * nob) {
+        // offsets past the kernel edge are computed on clamped addresses and dropped at the end
+        const int colbase = 2 * pad - min(ix0, ks - 1);
+        for (int r = 0; r < 4; ++r) {
+            const int ty = 4 * rg + r;
+            const float* vr[BW_KG_OB];
+            float w[BW_KG_OB][BW_KG_OB];
+#pragma unroll
+            for (int a = 0; a < BW_KG_OB; ++a) {
+                const int iy = min(iy0 + a, ks - 1);
+                vr[a] = sv + (ty + 2 * pad - iy) * VS + colbase;
+#pragma unroll
+                for (int c = 1; c < BW_KG_OB; ++c) w[a][c] = (colbase - c >= 0) ? vr[a][-c] : 0.0f;
+            }
+            const float* gr = sg + ty * GS;
+#pragma unroll          // fully: the sliding window then lives in renamed registers, no moves
+            for (int tx = 0; tx < BW_KG_TILE; ++tx) {
+                const float sgv = gr[tx];
+#pragma unroll
+                for (int a = 0; a < BW_KG_OB; ++a) {
+                    w[a][0] = vr[a][tx];
+#pragma unroll
+                    for (int c = 0; c < BW_KG_OB; ++c) acc[a][c] = fmaf(sgv, w[a][c], acc[a][c]);
+#pragma unroll
+                    for (int c = BW_KG_OB - 1; c > 0; --c) w[a][c] = w[a][c - 1];
+                }
+            }
         }
-        atomicAdd(&kbar[(size_t)b * ks * ks + d], acc);
     }
+    // the 8 row groups of an offset block sit in adjacent lanes: butterfly sum, lane 0 of the group adds to global
+#pragma unroll
+    for (int a = 0; a < BW_KG_OB; ++a)
+#pragma unroll
+        for (int c = 0; c < BW_KG_OB; ++c) {
+            float v = acc[a][c];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            if (rg == 0 && ob < nob * nob && iy0 + a < ks && ix0 + c < ks)
+                atomicAdd(&kbar[(size_t)b * ks * ks + (iy0 + a) * ks + ix0 + c], v);
+        }
 }
 
 // m~ -> sparse gradient planes at the arg-max pixels
@@ -270,12 +315,12 @@ int launch_bw_trace(const float* img, float* g, float* gn, unsigned* stats, unsi
     return PB_OK;
 }
 
-int launch_bw_dirmax(const float* gx, const float* gy, const float* g, unsigned long long* keys, const unsigned* stats,
+int launch_bw_dirmax(const float* gx, const float* gy, const float* g, unsigned long long* keys, unsigned* stats,
                      float* trace_f, int* trace_pos, int B, int H, int W, cudaStream_t stream) {
     const size_t plane = (size_t)H * W;
     ProfScope prof(PROF_OTHER, stream);
-    k_bw_dirmax<<<bw_grid(plane, B), 256, 0, stream>>>(gx, gy, keys, plane);
-    k_bw_finish<<<B, 1024, 0, stream>>>(gx, gy, g, keys, stats, trace_f, trace_pos, plane);
+    k_bw_dirmax<<<bw_grid(plane, B), 256, 0, stream>>>(gx, gy, g, keys, stats, plane);
+    k_bw_finish<<<B, 32, 0, stream>>>(gx, gy, keys, stats, trace_f, trace_pos, plane);
     PB_LAUNCH_CHECK("k_bw_dirmax / k_bw_finish");
     return PB_OK;
 }
@@ -287,7 +332,7 @@ int launch_bw_kernel_grad(const float* gout, const float* preclamp, const float*
         return PB_ERR_ARG;
     }
     const int pad = ks >> 1, VT = BW_KG_TILE + 2 * pad;
-    const size_t smem = (size_t)(BW_KG_TILE * BW_KG_TILE + VT * (VT + 1)) * sizeof(float);
+    const size_t smem = (size_t)(BW_KG_TILE * (BW_KG_TILE + 1) + VT * (VT + 1)) * sizeof(float);
     dim3 grid((W + BW_KG_TILE - 1) / BW_KG_TILE, (H + BW_KG_TILE - 1) / BW_KG_TILE, B * C);
     ProfScope prof(PROF_OTHER, stream);
     PB_CUDA_TRY(cudaMemsetAsync(kbar, 0, (size_t)B * ks * ks * sizeof(float), stream));

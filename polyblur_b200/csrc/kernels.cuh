@@ -80,7 +80,7 @@ int launch_edgetaper_weights(const ImgKernel* kern, void* scratch, int B, int Hp
 #define PB_BW_TRACE_STRIDE 24   // per image: 7 maxima, 7 signs, min, max, #min, #max
 int launch_bw_trace(const float* img, float* g, float* gn, unsigned* stats, unsigned long long* keys, int B, int C,
                     int H, int W, cudaStream_t stream);
-int launch_bw_dirmax(const float* gx, const float* gy, const float* g, unsigned long long* keys, const unsigned* stats,
+int launch_bw_dirmax(const float* gx, const float* gy, const float* g, unsigned long long* keys, unsigned* stats,
                      float* trace_f, int* trace_pos, int B, int H, int W, cudaStream_t stream);
 int launch_bw_kernel_grad(const float* gout, const float* preclamp, const float* V, float* kbar, int B, int C, int H,
                           int W, int ks, cudaStream_t stream);
