@@ -329,6 +329,9 @@ class PolyblurDeblurring(nn.Module):
             return polyblur_deblurring(images, **kw)
         if not isinstance(images, torch.Tensor) or images.ndim != 4:
             raise ValueError("patch decomposition expects a (B,C,H,W) tensor")
+        if images.requires_grad and torch.is_grad_enabled():
+            raise NotImplementedError("gradients are not implemented through the patch decomposition; call under "
+                                      "torch.no_grad() or detach the input")
         if images.dtype != torch.float32:
             raise TypeError(f"float32 only (got {images.dtype}), like the reference")
         src_device = images.device

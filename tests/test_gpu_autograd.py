@@ -138,5 +138,7 @@ def test_gradient_unsupported_options_raise(pb, gold):
                dict(discard_saturation=True)):
         with pytest.raises(NotImplementedError):
             pb.polyblur_deblurring(x, n_iter=1, **kw)
+    with pytest.raises(NotImplementedError):
+        pb.PolyblurDeblurring(patch_decomposition=True, patch_size=32)(x, n_iter=1)
     with torch.no_grad():
         pb.polyblur_deblurring(x, n_iter=1, remove_halo=True)
