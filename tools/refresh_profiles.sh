@@ -14,7 +14,9 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_r
     python bench.py --steps 1 --warmup 1 --no-graph --no-e2e --no-cpu-baseline --no-secondary > $O/ncu_mosaic.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_rows2|k_cols2|k_params|k_deconv_narrow" -s 15 -c 5 -f -o $O/prof_white32 \
     python bench.py --dist white --steps 1 --warmup 1 --no-graph --no-e2e --no-cpu-baseline --no-secondary > $O/ncu_white.log 2>&1
+if [ -z "${REFRESH_QUICK:-}" ]; then
 timeout 600 python tools/config_sweep.py > $O/config_sweep.jsonl 2> $O/config_sweep.err
 timeout 600 python tools/parity_report.py > $O/parity_report.jsonl 2> $O/parity_report.err
 timeout 900 python tools/fuzz_parity.py > $O/fuzz_parity.jsonl 2> $O/fuzz_parity.err
+fi
 ls -la $O
