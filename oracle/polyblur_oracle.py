@@ -471,6 +471,51 @@ def inverse_filtering_rank3(img, kernel, alpha=2, b=4, remove_halo=False, do_edg
     return np.clip(o, dtype(0), dtype(1)).astype(dtype)
 
 
+def inverse_filtering_rank3_vjp(img, kernel, grad_out, alpha=2, b=4, dtype=np.float64):
+    """What torch.autograd computes over the reference's inverse_filtering_rank3 (default flags,
+    deblurring.py:211-239 with utils.py:48-61 and deblurring.py:141-169) for the scalar
+    <grad_out, output>: the gradients with respect to ``img`` and to the kernel taps.
+
+    Forward: y = clamp(C T R x); R replicate pad, T circular filter with the spectrum
+    P(K^) = ((a3 K^ + a2) K^ + a1) K^ + b on the padded torus, C crop.  Backward: the clamp passes
+    the gradient where the unclamped value lies in [0, 1] (torch.clamp), C^T zero-embeds, T^T
+    multiplies by conj P(K^), R^T folds the border back (sums the padded rows / columns that
+    replicate an edge pixel).  Kernel: K~[d] = sum_p z[p] v[p - d] with v = P'(K) (*) R x, i.e. the
+    circular cross-correlation of z and v read at the kernel's offsets.
+    Returns (grad_img (B,C,H,W), grad_kernel (B,1,k,k), unclamped forward result)."""
+    dtype = np.dtype(dtype).type
+    cdt = _cdt(dtype)
+    img = np.asarray(img, dtype=dtype)
+    kernel = np.asarray(kernel, dtype=dtype)
+    ksz = kernel.shape[-1]
+    pad = ksz // 2
+    B, C, H, W = img.shape
+    xp = pad_with_kernel(img, pad)
+    Hp, Wp = xp.shape[-2:]
+    a3, a2, a1, b0 = (dtype(v) for v in polynomial_coefficients(alpha, b))
+    K = _p2o(np.broadcast_to(kernel, (B, 1, ksz, ksz)), (Hp, Wp), dtype)
+    P = ((a3 * K + a2) * K + a1) * K + b0
+    dP = (3 * a3 * K + 2 * a2) * K + a1
+    X = _fft.fft2(xp.astype(cdt), axes=(-2, -1), workers=_WORKERS)
+    pre = crop_with_kernel(_fft.ifft2(P * X, axes=(-2, -1), workers=_WORKERS).real, pad)
+    z = np.zeros((B, C, Hp, Wp), dtype=dtype)
+    z[..., pad:pad + H, pad:pad + W] = np.asarray(grad_out, dtype=dtype) * ((pre >= 0) & (pre <= 1))
+    Z = _fft.fft2(z.astype(cdt), axes=(-2, -1), workers=_WORKERS)
+    t = _fft.ifft2(np.conj(P) * Z, axes=(-2, -1), workers=_WORKERS).real
+    # R^T: interior pixels map to one padded position, edge pixels collect their replicas
+    g = t[..., pad:pad + H, :].copy()
+    g[..., 0, :] += t[..., :pad, :].sum(axis=-2)
+    g[..., H - 1, :] += t[..., pad + H:, :].sum(axis=-2)
+    gi = g[..., pad:pad + W].copy()
+    gi[..., 0] += g[..., :pad].sum(axis=-1)
+    gi[..., W - 1] += g[..., pad + W:].sum(axis=-1)
+    # kernel taps: correlation of z with v = P'(K) (*) xp at offsets d = index - pad
+    corr = _fft.ifft2(Z * np.conj(dP * X), axes=(-2, -1), workers=_WORKERS).real.sum(axis=1)
+    idx = (np.arange(ksz) - pad)
+    gk = corr[:, idx % Hp][:, :, idx % Wp][:, None]
+    return gi.astype(dtype), gk.astype(dtype), pre.astype(dtype)
+
+
 # --------------------------------------------------------------------------------------
 # optional prefilters
 # --------------------------------------------------------------------------------------

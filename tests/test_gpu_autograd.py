@@ -87,6 +87,38 @@ def test_kernel_gradient_golden(pb, gold, tag, alpha, beta, engine):
     assert rel(kb.cpu().numpy(), gold[f"deconv_{tag}_kernel_grad"]) < 1e-4
 
 
+@pytest.mark.parametrize("shape,ks", [((2, 3, 45, 77), 25), ((1, 1, 64, 31), 9), ((2, 4, 19, 120), 15),
+                                      ((1, 2, 130, 96), 25), ((1, 3, 7, 9), 9)])
+@pytest.mark.parametrize("engine", ["auto", "fft"])
+def test_deconvolution_backward_vs_oracle(pb, shape, ks, engine):
+    """Image and kernel gradients of one deconvolution against the numpy backward oracle (float64) on odd,
+    small and non-square shapes, 1-4 channels and smaller kernel supports; part of the result is clamped."""
+    from oracle import polyblur_oracle as po
+    from polyblur_b200 import autograd as ag
+    B, C, H, W = shape
+    rng = np.random.default_rng(B * 7 + H * 13 + W + ks)
+    x = np.clip(rng.random(shape, dtype=np.float32) * 1.4 - 0.2, 0, 1).astype(np.float32)
+    full = np.stack([po.gaussian_filter_np((float(rng.uniform(0.4, 2.2)), float(rng.uniform(0.3, 1.2))),
+                                           float(rng.uniform(0, 3))) for _ in range(B)])[:, None]
+    c0 = 12 - ks // 2
+    k = full[..., c0:c0 + ks, c0:c0 + ks]
+    k = (k / k.sum(axis=(-1, -2), keepdims=True)).astype(np.float32)
+    ybar = rng.standard_normal(shape).astype(np.float32)
+    _, _, pre = po.inverse_filtering_rank3_vjp(x, k, ybar, alpha=6, b=1, dtype=np.float64)
+    # pixels whose unclamped value sits within rounding of 0 or 1 may fall on either side of the clamp mask:
+    # give them no upstream gradient
+    ybar[(np.abs(pre) < 5e-6) | (np.abs(pre - 1) < 5e-6)] = 0
+    gi, gk, pre = po.inverse_filtering_rank3_vjp(x, k, ybar, alpha=6, b=1, dtype=np.float64)
+    e = ENGINES[engine]
+    xd, kd, yd = cu(x), cu(k), cu(ybar)
+    v = ag._deconv_noclamp(xd, kd, 6, 1, e)
+    assert np.abs(v.cpu().numpy() - pre).max() < 1e-5
+    got_i = ag.inverse_filtering_rank3_vjp(yd, kd, 6, 1, preclamp=v, engine=e).cpu().numpy()
+    got_k = ag.kernel_grad(xd, yd, v, kd, 6, 1, e).cpu().numpy()
+    assert rel(got_i, gi) < 2e-5
+    assert rel(got_k, gk) < 1e-4
+
+
 def test_estimator_vjp_golden(pb, gold):
     """Gradient of <gaussian_blur_estimation(x), kbar> with respect to x: arg-max pixels, transposed spectral
     derivative, range normalisation with tied maxima, against autograd over the reference."""

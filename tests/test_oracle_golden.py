@@ -163,3 +163,16 @@ def test_torch_port_matches_reference(name):
     np.testing.assert_allclose(np.stack([t["sigma"].numpy() for t in tr]), sc[f"{name}/a6b1n3/sigma"], rtol=1e-6)
     y = pt.polyblur_deblurring(x, n_iter=1, alpha=2, beta=3).numpy()
     assert maxabs(y, sc[f"{name}/a2b3n1/out"]) < 1e-6
+
+
+@pytest.mark.parametrize("tag,alpha,beta", [("a6b1", 6, 1), ("a2b4", 2, 4)])
+def test_deconvolution_backward_oracle_matches_reference_autograd(tag, alpha, beta):
+    """The numpy restatement of the backward pass (image and kernel gradients of inverse_filtering_rank3)
+    against torch.autograd over the live reference (vjp.npz, tests/golden/make_golden_vjp.py)."""
+    d = np.load(os.path.join(G, "vjp.npz"))
+    gi, gk, pre = po.inverse_filtering_rank3_vjp(d["deconv_x"], d["deconv_kernels"], d["deconv_ybar"], alpha=alpha,
+                                                 b=beta, dtype=np.float64)
+    ref_i, ref_k = d[f"deconv_{tag}_grad"], d[f"deconv_{tag}_kernel_grad"]
+    assert np.abs(np.clip(pre, 0, 1) - d[f"deconv_{tag}_y"]).max() < 5e-6
+    assert np.abs(gi - ref_i).max() < 1e-5 * np.abs(ref_i).max()
+    assert np.abs(gk - ref_k).max() < 1e-5 * np.abs(ref_k).max()
