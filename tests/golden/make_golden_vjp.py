@@ -115,6 +115,25 @@ def main():
     out["est_kernel"] = k.detach().numpy()
     out["est_grad"] = gx.numpy()
 
+    # ---- the scalar chain alone: 7 maxima -> interpolation, arg-min direction, affine model, Gaussian taps ----
+    g2 = torch.Generator().manual_seed(21)         # its own stream: the other cases keep their random draws
+    m = torch.rand(6, 7, generator=g2) * 0.25 + 0.05
+    m[0] = torch.tensor([0.30, 0.22, 0.15, 0.12, 0.16, 0.24, 0.30])
+    m[1] = m[1] * 4                               # strong gradients: sigma, rho clamp to 0.3 (zero gradient)
+    m[2] = m[2] * 0.2                             # weak gradients: clamp to 4.0
+    kb = torch.randn(6, 25, 25, generator=g2)
+    mr = m.clone().requires_grad_(True)
+    thetas = torch.linspace(0, 180, 7).unsqueeze(0)
+    interp = torch.arange(0, 180, 6.0).unsqueeze(0)
+    m_n, m_o, th = blur_estimation.find_maximal_blur_direction(mr, thetas, interp)
+    sg, rh = blur_estimation.compute_gaussian_parameters(m_n, m_o, c=0.352, b=0.768)
+    kk = blur_estimation.create_gaussian_filter(th, sg, rh, ksize=25)
+    (gm,) = torch.autograd.grad((kk[:, 0] * kb).sum(), mr)
+    out["chainrule_m"] = m.numpy()
+    out["chainrule_kbar"] = kb.numpy()
+    out["chainrule_mbar"] = gm.numpy()
+    out["chainrule_sigma_rho"] = torch.cat([sg, rh], dim=1).detach().numpy()
+
     # ---- two iterations, estimate held constant ----------------------------------------------
     B, C, H, W = 2, 3, 64, 80
     x = textured(B, C, H, W, seed=5)

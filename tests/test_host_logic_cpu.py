@@ -97,3 +97,23 @@ def test_pipeline_chunks_cover_the_batch():
                 assert max(s) <= body
     assert pipeline_chunks(32, 2, (1,)) == [1] + [2] * 15 + [1]
     assert pipeline_chunks(32, 8, (1, 3)) == [1, 3, 8, 8, 8, 3, 1]
+
+
+def test_maxima_gradient_chain_matches_reference_autograd():
+    """The host-side scalar chain of the backward pass (autograd._maxima_grad: Keys interpolation, arg-min
+    direction, affine model with clamping, Gaussian taps; blur_estimation.py:138-232) against torch.autograd
+    over the reference's own functions (vjp.npz chainrule_*), on CPU tensors."""
+    import os
+    import numpy as np
+    import torch
+    from polyblur_b200 import autograd as ag
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "vjp.npz"))
+    m, kb, ref = (torch.from_numpy(d[k]) for k in ("chainrule_m", "chainrule_kbar", "chainrule_mbar"))
+    got = ag._maxima_grad(m, kb, 0.352, 0.768, 25)
+    assert float(ref.abs().max()) > 0
+    assert float((got - ref).abs().max()) < 1e-5 * float(ref.abs().max())
+    sr = d["chainrule_sigma_rho"]
+    # image 2 sits on the upper clamp of the affine model with both sigma and rho (4.0): no gradient at all;
+    # image 1 has rho on the lower clamp (0.3) and still gets the sigma term
+    assert np.allclose(sr[2], 4.0) and float(got[2].abs().max()) == 0.0
+    assert np.isclose(sr[1, 1], 0.3) and float(got[1].abs().max()) > 0.0
