@@ -377,7 +377,9 @@ def torus_source_index(n, pad, coords):
 
 def compute_polynomial_torus(img, kernel, alpha, beta, dtype=np.float64):
     """Spatial-domain twin of :func:`compute_polynomial_fft` on the *padded* image:
-    three circular correlations on the (H',W') torus, Horner order.  O(625 H W) per
+    three circular convolutions on the (H',W') torus, Horner order: out[p] = sum_d K[d] v[p - d],
+    which is what the p2o / fft2 product computes (filters.py:255-273), also for kernels that
+    are not point-symmetric (pinned by tests/golden/round2.npz "asym/*").  O(625 H W) per
     step -- small inputs only.  Used to validate the gather map the CUDA kernel uses.
     """
     dtype = np.dtype(dtype).type
@@ -386,11 +388,11 @@ def compute_polynomial_torus(img, kernel, alpha, beta, dtype=np.float64):
     r = k.shape[-1] // 2
     a3, a2, a1, b = (dtype(v) for v in polynomial_coefficients(alpha, beta))
 
-    def corr(v):
+    def corr(v):          # circular convolution with k
         out = np.zeros_like(v)
         for dy in range(-r, r + 1):
             for dx in range(-r, r + 1):
-                out += k[:, :, dy + r, dx + r][..., None, None] * np.roll(v, (-dy, -dx), axis=(-2, -1))
+                out += k[:, :, dy + r, dx + r][..., None, None] * np.roll(v, (dy, dx), axis=(-2, -1))
         return out
 
     o = a3 * p

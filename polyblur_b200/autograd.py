@@ -174,7 +174,8 @@ def estimator_vjp(x: torch.Tensor, mbar: torch.Tensor, tf: torch.Tensor, tp: tor
 
 
 class DeconvolutionFunction(torch.autograd.Function):
-    """``inverse_filtering_rank3(img, kernel, alpha, b)`` with default flags, differentiable in ``img``."""
+    """``inverse_filtering_rank3(img, kernel, alpha, b)`` with default flags, differentiable in ``img`` and in
+    the kernel taps."""
 
     @staticmethod
     def forward(ctx, img, kernel, alpha, beta, engine):
@@ -183,16 +184,25 @@ class DeconvolutionFunction(torch.autograd.Function):
         k = kernel.detach().to(dev, torch.float32)
         k = k.expand(x.shape[0], 1, k.shape[-2], k.shape[-1]).contiguous()
         v = _deconv_noclamp(x, k, alpha, beta, engine)
-        ctx.save_for_backward(k, v)
-        ctx.meta = (alpha, beta, engine, img.device)
+        ctx.save_for_backward(x, k, v)
+        ctx.meta = (alpha, beta, engine, img.device, tuple(kernel.shape), kernel.device, kernel.dtype)
         return v.clamp(0.0, 1.0).to(img.device)
 
     @staticmethod
     def backward(ctx, grad_out):
-        k, v = ctx.saved_tensors
-        alpha, beta, engine, src = ctx.meta
-        g = inverse_filtering_rank3_vjp(grad_out.contiguous(), k, alpha, beta, preclamp=v, engine=engine)
-        return g.to(src), None, None, None, None
+        x, k, v = ctx.saved_tensors
+        alpha, beta, engine, src, kshape, kdev, kdtype = ctx.meta
+        go = grad_out.detach().to(x.device).contiguous()
+        g = gk = None
+        if ctx.needs_input_grad[0]:
+            g = inverse_filtering_rank3_vjp(go, k, alpha, beta, preclamp=v, engine=engine).to(src)
+        if ctx.needs_input_grad[1]:
+            # d <grad_out, y> / d taps (pb_kernel_grad_f32); a kernel shared by the batch collects every image's term
+            gk = kernel_grad(x, go, v, k, alpha, beta, engine)
+            if kshape[0] == 1 and gk.shape[0] != 1:
+                gk = gk.sum(dim=0, keepdim=True)
+            gk = gk.to(kdev, kdtype)
+        return g, gk, None, None, None
 
 
 class PolyblurFunction(torch.autograd.Function):

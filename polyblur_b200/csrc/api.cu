@@ -2,6 +2,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "kernels.cuh"
@@ -25,6 +26,8 @@ int check_cuda(cudaError_t e, const char* what) {
 
 // ---- profiler ------------------------------------------------------------------------------
 struct ProfRec { int cls; cudaEvent_t a, b; };
+// process-global, guarded by g_prof_mu (host threads may drive the library concurrently on their own streams)
+static std::mutex g_prof_mu;
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
 static std::vector<cudaEvent_t> g_event_pool;
@@ -44,6 +47,7 @@ static cudaEvent_t get_event() {
 }
 
 ProfScope::ProfScope(int cls, cudaStream_t s) : idx(-1), stream(s) {
+    std::lock_guard<std::mutex> lock(g_prof_mu);
     if (!g_prof_on) return;
     ProfRec r{cls, get_event(), get_event()};
     cudaEventRecord(r.a, s);
@@ -51,7 +55,9 @@ ProfScope::ProfScope(int cls, cudaStream_t s) : idx(-1), stream(s) {
     g_prof.push_back(r);
 }
 ProfScope::~ProfScope() {
-    if (idx >= 0) cudaEventRecord(g_prof[idx].b, stream);
+    if (idx < 0) return;
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    if (idx < (int)g_prof.size()) cudaEventRecord(g_prof[idx].b, stream);
 }
 
 int make_fft_plan(int n, FftPlan* plan) {
@@ -170,14 +176,15 @@ struct Tables {
     float *omH, *omW;
 };
 
-static int prepare_tables(char* ws, const Workspace& L, int H, int W, Tables* t, cudaStream_t stream) {
+// Fills the table pointers and queues the generation of the tables (launch_table_jobs runs the queue);
+// the any-length fallback core keeps its own master-twiddle launches.
+static int prepare_tables(char* ws, const Workspace& L, int H, int W, Tables* t, TableJobs* jobs, cudaStream_t stream) {
     if (make_fft_plan(H, &t->planH) || make_fft_plan(W, &t->planW)) {
         set_error("cannot plan FFT for %d x %d", H, W);
         return PB_ERR_ARG;
     }
     t->twH = reinterpret_cast<float2*>(ws + L.off_twH);
     t->twW = reinterpret_cast<float2*>(ws + L.off_twW);
-    int rc;
     t->fast = fft2_supported(H, W);
     t->omH = reinterpret_cast<float*>(ws + L.off_omH);
     t->omW = reinterpret_cast<float*>(ws + L.off_omW);
@@ -186,14 +193,16 @@ static int prepare_tables(char* ws, const Workspace& L, int H, int W, Tables* t,
         // the master tables of the any-length core
         make_fft2_plan(H, &t->planH2);
         make_fft2_plan(W, &t->planW2);
-        if ((rc = launch_fft2_stage_tw(t->twH, t->planH2, stream))) return rc;
-        if ((rc = launch_fft2_stage_tw(t->twW, t->planW2, stream))) return rc;
-        if ((rc = launch_fft2_omega(t->omH, t->planH2, stream))) return rc;
-        if ((rc = launch_fft2_omega(t->omW, t->planW2, stream))) return rc;
+        jobs->add(TJ_STAGE_TW, t->planH2.tw_total, t->twH, nullptr, &t->planH2);
+        jobs->add(TJ_STAGE_TW, t->planW2.tw_total, t->twW, nullptr, &t->planW2);
+        jobs->add(TJ_OMEGA, H, t->omH, nullptr, &t->planH2);
+        jobs->add(TJ_OMEGA, W, t->omW, nullptr, &t->planW2);
         return PB_OK;
     }
-    if ((rc = launch_twiddles(t->twH, H, stream))) return rc;
-    return launch_twiddles(t->twW, W, stream);
+    (void)stream;
+    jobs->add(TJ_TWIDDLES, H, t->twH, nullptr, nullptr);
+    jobs->add(TJ_TWIDDLES, W, t->twW, nullptr, nullptr);
+    return PB_OK;
 }
 
 static void poly_coeffs(double alpha, double beta, float* o) {
@@ -312,10 +321,13 @@ static int deconv_all(const float* img, float* out, int B, int C, int H, int W, 
 
 // inverse_filtering_rank3 (deblurring.py:211-239) for the kernels k_params left in the workspace:
 // [edgetaper on the explicitly padded image] -> polynomial on the torus -> crop -> [halo masking] -> clamp.
+// grads_of_tapered: halo masking without an explicit grad_img takes the gradients of the image it is handed
+// (deblurring.py:200-203), which inverse_filtering_rank3 has already cropped out of the padded AND tapered
+// plane (deblurring.py:237-238): g0x / g0y / nM are then filled here, after the taper.
 static int deconv_with_options(const float* src, float* dst, int B, int C, int H, int W, const float* coef, int ksize,
                                uint32_t flags, const float* g0x, const float* g0y, const float* nM, float* ox,
                                char* ws, const Workspace& L, const Tables& T, const FftEngineTables* F,
-                               cudaStream_t stream) {
+                               cudaStream_t stream, bool grads_of_tapered = false) {
     const bool halo = (flags & PB_FLAG_REMOVE_HALO) != 0;
     const bool taper = (flags & PB_FLAG_EDGETAPER) != 0;
     const int pad = ksize / 2;
@@ -340,6 +352,15 @@ static int deconv_with_options(const float* src, float* dst, int B, int C, int H
         G.off = pad;
         G.pad = 0;
         dec_in = tapered;
+        if (halo && grads_of_tapered) {
+            // dst is free until the engines write it: it holds the cropped tapered image for a moment
+            float* wx = reinterpret_cast<float*>(ws + L.off_g0x);
+            float* wy = reinterpret_cast<float*>(ws + L.off_g0y);
+            float* wn = reinterpret_cast<float*>(ws + L.off_nm);
+            if ((rc = launch_crop(tapered, dst, planes, H, W, pad, stream))) return rc;
+            if ((rc = gradients_into(dst, wx, wy, planes, H, W, T, stream))) return rc;
+            if ((rc = launch_halo_norm(wx, wy, wn + planes, wn, planes, (size_t)H * W, stream))) return rc;
+        }
     }
     G.clamp_out = (halo || (flags & PB_FLAG_NO_CLAMP)) ? 0 : 1;
     if ((rc = deconv_all(dec_in, dst, B, C, H, W, coef, ws, L, F, G, stream))) return rc;
@@ -457,8 +478,10 @@ int pb_polyblur_f32(const float* in, float* out, int B, int C, int H, int W, con
     Tables T;
     FftEngineTables F;
     if ((rc = upload_constants(stream))) return rc;
-    if ((rc = prepare_tables(ws, L, H, W, &T, stream))) return rc;
-    if (L.has_fft && (rc = fft_engine_prepare(ws + L.off_fft, L.fft, &F, stream))) return rc;
+    TableJobs jobs;
+    if ((rc = prepare_tables(ws, L, H, W, &T, &jobs, stream))) return rc;
+    if (L.has_fft && (rc = fft_engine_prepare(ws + L.off_fft, L.fft, &F, &jobs))) return rc;
+    if ((rc = launch_table_jobs(jobs, stream))) return rc;
     float coef[4];
     poly_coeffs_d(p->alpha, p->beta, coef);
     const float thr = p->tap_rel_threshold > 0 ? p->tap_rel_threshold : 1e-8f;
@@ -518,7 +541,9 @@ int pb_fourier_gradients_f32(const float* img, float* gx, float* gy, int B, int 
     if ((rc = check_ws(workspace, workspace_bytes, L.total))) return rc;
     char* ws = static_cast<char*>(workspace);
     Tables T;
-    if ((rc = prepare_tables(ws, L, H, W, &T, stream))) return rc;
+    TableJobs jobs;
+    if ((rc = prepare_tables(ws, L, H, W, &T, &jobs, stream))) return rc;
+    if ((rc = launch_table_jobs(jobs, stream))) return rc;
     if (T.fast) {
         if ((rc = launch_rows2(false, img, nullptr, gx, nullptr, B * C, 1, H, W, T.planW2, T.twW, T.omW, nullptr, stream)))
             return rc;
@@ -546,7 +571,9 @@ int pb_estimate_f32(const float* img, int B, int C, int H, int W, double c, doub
     char* ws = static_cast<char*>(workspace);
     Tables T;
     if ((rc = upload_constants(stream))) return rc;
-    if ((rc = prepare_tables(ws, L, H, W, &T, stream))) return rc;
+    TableJobs jobs;
+    if ((rc = prepare_tables(ws, L, H, W, &T, &jobs, stream))) return rc;
+    if ((rc = launch_table_jobs(jobs, stream))) return rc;
     return estimate_into(img, B, C, H, W, c, b, q, flags, est, ws, L, T, PB_KS, 1e-8f, PB_ENGINE_SPATIAL, 1 << 30, stream);
 }
 
@@ -584,7 +611,9 @@ int pb_deconv_f32(const float* img, float* out, int B, int C, int H, int W, cons
     ImgKernel* kern = reinterpret_cast<ImgKernel*>(ws + L.off_kern);
     int* cls = reinterpret_cast<int*>(ws + L.off_cls);
     FftEngineTables F;
-    if (L.has_fft && (rc = fft_engine_prepare(ws + L.off_fft, L.fft, &F, stream))) return rc;
+    TableJobs jobs;
+    if (L.has_fft && (rc = fft_engine_prepare(ws + L.off_fft, L.fft, &F, &jobs))) return rc;
+    if ((rc = launch_table_jobs(jobs, stream))) return rc;
     if ((rc = launch_params(nullptr, kern, nullptr, nullptr, nullptr, nullptr, kernel, nullptr, 2, B, ksize,
                             0.f, 0.f, 1e-8f, engine, L.has_fft ? PB_FFT_RADIUS_MIN : (1 << 30), cls, stream)))
         return rc;
@@ -623,8 +652,10 @@ int pb_deconv_ex_f32(const float* img, float* out, int B, int C, int H, int W, c
     int* cls = reinterpret_cast<int*>(ws + L.off_cls);
     Tables T;
     FftEngineTables F;
-    if ((rc = prepare_tables(ws, L, H, W, &T, stream))) return rc;
-    if (L.has_fft && (rc = fft_engine_prepare(ws + L.off_fft, L.fft, &F, stream))) return rc;
+    TableJobs jobs;
+    if ((rc = prepare_tables(ws, L, H, W, &T, &jobs, stream))) return rc;
+    if (L.has_fft && (rc = fft_engine_prepare(ws + L.off_fft, L.fft, &F, &jobs))) return rc;
+    if ((rc = launch_table_jobs(jobs, stream))) return rc;
     if ((rc = launch_params(nullptr, kern, nullptr, nullptr, nullptr, nullptr, kernel, nullptr, 2, B, ksize, 0.f, 0.f,
                             1e-8f, engine, L.has_fft ? PB_FFT_RADIUS_MIN : (1 << 30), cls, stream)))
         return rc;
@@ -633,20 +664,23 @@ int pb_deconv_ex_f32(const float* img, float* out, int B, int C, int H, int W, c
     float* ox = reinterpret_cast<float*>(ws + L.off_ox);
     float* nM = reinterpret_cast<float*>(ws + L.off_nm);
     const float *gx = g0x, *gy = g0y;
+    bool from_tapered = false;
     if (flags & PB_FLAG_REMOVE_HALO) {
         // grad_img defaults to the gradients of img itself (deblurring.py:200-203)
         if (grad_x) {
             gx = grad_x;
             gy = grad_y;
+        } else if (flags & PB_FLAG_EDGETAPER) {
+            from_tapered = true;                 // gradients of the cropped tapered image, computed after the taper
         } else if ((rc = gradients_into(img, g0x, g0y, B * C, H, W, T, stream))) {
             return rc;
         }
-        if ((rc = launch_halo_norm(gx, gy, nM + B * C, nM, B * C, (size_t)H * W, stream))) return rc;
+        if (!from_tapered && (rc = launch_halo_norm(gx, gy, nM + B * C, nM, B * C, (size_t)H * W, stream))) return rc;
     }
     float coef[4];
     poly_coeffs_d(alpha, beta, coef);
     return deconv_with_options(img, out, B, C, H, W, coef, ksize, flags, gx, gy, nM, ox, ws, L, T,
-                               L.has_fft ? &F : nullptr, stream);
+                               L.has_fft ? &F : nullptr, stream, from_tapered);
 }
 
 // workspace of the backward pass: the engines' workspace for a (H+2P) x (W+2P) "image", the
@@ -704,7 +738,9 @@ int pb_deconv_vjp_f32(const float* grad_out, const float* preclamp, float* grad_
     float* t = reinterpret_cast<float*>(ws + V.off_t);
     float* kf = reinterpret_cast<float*>(ws + V.off_k);
     FftEngineTables F;
-    if (L.has_fft && (rc = fft_engine_prepare(ws + L.off_fft, L.fft, &F, stream))) return rc;
+    TableJobs jobs;
+    if (L.has_fft && (rc = fft_engine_prepare(ws + L.off_fft, L.fft, &F, &jobs))) return rc;
+    if ((rc = launch_table_jobs(jobs, stream))) return rc;
     if ((rc = launch_flip_kernels(kernel, kf, B, ksize, stream))) return rc;
     if ((rc = launch_params(nullptr, kern, nullptr, nullptr, nullptr, nullptr, kf, nullptr, 2, B, ksize, 0.f, 0.f,
                             1e-8f, engine, L.has_fft ? PB_FFT_RADIUS_MIN : (1 << 30), cls, stream)))
@@ -768,7 +804,9 @@ int pb_estimate_trace_f32(const float* img, int B, int C, int H, int W, float* t
     char* ws = static_cast<char*>(workspace);
     Tables T;
     if ((rc = upload_constants(stream))) return rc;
-    if ((rc = prepare_tables(ws, V.eng, H, W, &T, stream))) return rc;
+    TableJobs jobs;
+    if ((rc = prepare_tables(ws, V.eng, H, W, &T, &jobs, stream))) return rc;
+    if ((rc = launch_table_jobs(jobs, stream))) return rc;
     float* g = reinterpret_cast<float*>(ws + V.off_q[0]);
     float* gn = reinterpret_cast<float*>(ws + V.off_q[1]);
     float* gx = reinterpret_cast<float*>(ws + V.off_q[2]);
@@ -806,7 +844,9 @@ int pb_kernel_grad_f32(const float* img, const float* grad_out, const float* pre
     float* xp = reinterpret_cast<float*>(ws + V.off_pad);
     float* v = reinterpret_cast<float*>(ws + V.off_v);
     FftEngineTables F;
-    if (L.has_fft && (rc = fft_engine_prepare(ws + L.off_fft, L.fft, &F, stream))) return rc;
+    TableJobs jobs;
+    if (L.has_fft && (rc = fft_engine_prepare(ws + L.off_fft, L.fft, &F, &jobs))) return rc;
+    if ((rc = launch_table_jobs(jobs, stream))) return rc;
     if ((rc = launch_params(nullptr, kern, nullptr, nullptr, nullptr, nullptr, kernel, nullptr, 2, B, ksize, 0.f, 0.f,
                             1e-8f, engine, L.has_fft ? PB_FFT_RADIUS_MIN : (1 << 30), cls, stream)))
         return rc;
@@ -843,7 +883,9 @@ int pb_estimator_vjp_f32(const float* img, const float* mbar, const float* trace
     char* ws = static_cast<char*>(workspace);
     Tables T;
     if ((rc = upload_constants(stream))) return rc;
-    if ((rc = prepare_tables(ws, V.eng, H, W, &T, stream))) return rc;
+    TableJobs jobs;
+    if ((rc = prepare_tables(ws, V.eng, H, W, &T, &jobs, stream))) return rc;
+    if ((rc = launch_table_jobs(jobs, stream))) return rc;
     float* sgx = reinterpret_cast<float*>(ws + V.off_q[0]);
     float* sgy = reinterpret_cast<float*>(ws + V.off_q[1]);
     float* dx = reinterpret_cast<float*>(ws + V.off_q[2]);
@@ -857,6 +899,7 @@ int pb_estimator_vjp_f32(const float* img, const float* mbar, const float* trace
 }
 
 int pb_profile_begin(void) {
+    std::lock_guard<std::mutex> lock(g_prof_mu);
     for (auto& r : g_prof) {
         g_event_pool.push_back(r.a);
         g_event_pool.push_back(r.b);
@@ -867,6 +910,7 @@ int pb_profile_begin(void) {
 }
 
 int pb_profile_end(float* ms_per_class, int* launches_per_class, int max_classes) {
+    std::lock_guard<std::mutex> lock(g_prof_mu);
     g_prof_on = false;
     for (int i = 0; i < max_classes; ++i) {
         if (ms_per_class) ms_per_class[i] = 0.f;

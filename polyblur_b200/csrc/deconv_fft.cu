@@ -74,16 +74,6 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// ---- tables -------------------------------------------------------------------------------
-// slot[k] = position of frequency k after the DIF transform; freq[p] = its inverse.
-__global__ void k_fft2_perm(int* __restrict__ slot_of_freq, int* __restrict__ freq_of_slot, Fft2Plan plan) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < plan.n) {
-        if (slot_of_freq) slot_of_freq[i] = fft2_slot_of_freq(i, plan);
-        if (freq_of_slot) freq_of_slot[i] = fft2_freq_of_slot(i, plan);
-    }
-}
-
 #ifndef FFTD_THREADS
 #define FFTD_THREADS 256
 #endif
@@ -622,7 +612,7 @@ size_t fft_engine_workspace(int B, int C, int H, int W, int pad, FftEngineLayout
     return o;
 }
 
-int fft_engine_prepare(char* base, const FftEngineLayout& L, FftEngineTables* T, cudaStream_t stream) {
+int fft_engine_prepare(char* base, const FftEngineLayout& L, FftEngineTables* T, TableJobs* jobs) {
     T->NX = L.NX;
     T->NY = L.NY;
     if (make_fft2_plan(L.NX, &T->planX) || make_fft2_plan(L.NY, &T->planY)) {
@@ -637,15 +627,12 @@ int fft_engine_prepare(char* base, const FftEngineLayout& L, FftEngineTables* T,
     T->slotY = reinterpret_cast<int*>(base + L.off_slotY);
     T->freqY = reinterpret_cast<int*>(base + L.off_freqY);
     T->Z = reinterpret_cast<float2*>(base + L.off_Z);
-    int rc;
-    if ((rc = launch_twiddles(T->twX, L.NX, stream))) return rc;
-    if ((rc = launch_twiddles(T->twY, L.NY, stream))) return rc;
-    if ((rc = launch_fft2_stage_tw(T->stwX, T->planX, stream))) return rc;
-    if ((rc = launch_fft2_stage_tw(T->stwY, T->planY, stream))) return rc;
-    ProfScope prof(PROF_SETUP, stream);
-    k_fft2_perm<<<(L.NX + 255) / 256, 256, 0, stream>>>(T->slotX, nullptr, T->planX);
-    k_fft2_perm<<<(L.NY + 255) / 256, 256, 0, stream>>>(T->slotY, T->freqY, T->planY);
-    PB_LAUNCH_CHECK("k_fft2_perm");
+    jobs->add(TJ_TWIDDLES, L.NX, T->twX, nullptr, nullptr);
+    jobs->add(TJ_TWIDDLES, L.NY, T->twY, nullptr, nullptr);
+    jobs->add(TJ_STAGE_TW, T->planX.tw_total, T->stwX, nullptr, &T->planX);
+    jobs->add(TJ_STAGE_TW, T->planY.tw_total, T->stwY, nullptr, &T->planY);
+    jobs->add(TJ_PERM, L.NX, T->slotX, nullptr, &T->planX);
+    jobs->add(TJ_PERM, L.NY, T->slotY, T->freqY, &T->planY);
     return PB_OK;
 }
 

@@ -293,12 +293,15 @@ k_params(const unsigned* __restrict__ stats, ImgKernel* __restrict__ kern, float
         const float total = (s_red[0] + s_red[1]) + (s_red[2] + s_red[3]);
         for (int i = tid; i < PB_KS2; i += blockDim.x) s_k[i] = __fdiv_rn(s_k[i], total);
     } else {
-        // explicit taps: (ksize x ksize) embedded in the centre of the 25x25 grid
+        // explicit taps: (ksize x ksize) embedded in the centre of the 25x25 grid, rotated by 180 degrees:
+        // the engines (and k_et_pass) evaluate sum_d k[d] x[p + d], the reference's p2o / fft2 product
+        // (filters.py:255-273, deblurring.py:141-169) is the convolution sum_d K[d] x[p - d], so k[d] = K[-d].
+        // (A Gaussian from mode 0 / 1 is point-symmetric bit for bit, so nothing changes for it.)
         for (int i = tid; i < PB_KS2; i += blockDim.x) {
             const int dy = i / PB_KS - PB_PAD, dx = i % PB_KS - PB_PAD;
             float kv = 0.0f;
             if (abs(dy) <= half && abs(dx) <= half)
-                kv = kin[(size_t)im * ksize * ksize + (dy + half) * ksize + (dx + half)];
+                kv = kin[(size_t)im * ksize * ksize + (half - dy) * ksize + (half - dx)];
             s_k[i] = kv;
         }
     }
@@ -313,6 +316,15 @@ k_params(const unsigned* __restrict__ stats, ImgKernel* __restrict__ kern, float
     kmax = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
     const float thr = tap_thr * kmax;
     for (int i = tid; i < PB_KS2; i += blockDim.x) K->k[i] = s_k[i];
+    // The FFT engine builds a real kernel spectrum from the rows dy >= 0 (deconv_fft.cu), which is only the
+    // spectrum of a point-symmetric kernel: explicit taps with K[-d] != K[d] (motion blur, shifted Gaussians)
+    // are kept on the spatial engines, whatever engine was asked for.
+    int asym = 0;
+    if (mode == 2) {
+        const float tol = kmax * 2.4e-7f;
+        for (int i = tid; i < PB_KS2 / 2; i += blockDim.x) asym |= fabsf(s_k[i] - s_k[PB_KS2 - 1 - i]) > tol;
+    }
+    asym = __syncthreads_or(asym);
     if (kout) {
         for (int i = tid; i < ksize * ksize; i += blockDim.x) {
             const int yy = i / ksize, xx = i % ksize;
@@ -349,10 +361,10 @@ k_params(const unsigned* __restrict__ stats, ImgKernel* __restrict__ kern, float
         // engine class: the FFT engine when asked for (or, on AUTO, for wide kernels), else the
         // narrowest spatial engine that holds every kept tap
         int cls;
-        if (engine_req == PB_ENGINE_FFT) cls = PB_CLS_FFT;
+        if (engine_req == PB_ENGINE_FFT && !asym) cls = PB_CLS_FFT;
         else if (s_rx <= 1 && s_ry <= 1) cls = PB_CLS_N11;
         else if (s_rx <= 2 && s_ry <= 2) cls = PB_CLS_N22;
-        else if (engine_req == PB_ENGINE_AUTO && s_rad >= fft_radius_min) cls = PB_CLS_FFT;
+        else if (engine_req == PB_ENGINE_AUTO && s_rad >= fft_radius_min && !asym) cls = PB_CLS_FFT;
         else cls = (s_rad <= 4) ? PB_CLS_TILED4 : PB_CLS_TILED;
         K->engine = (cls == PB_CLS_FFT) ? PB_ENGINE_FFT : PB_ENGINE_SPATIAL;
         K->rx = s_rx;

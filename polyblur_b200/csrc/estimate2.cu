@@ -47,6 +47,47 @@ __global__ void k_fft2_stage_tw(float2* __restrict__ stw, Fft2Plan plan) {
     if (i < plan.tw_total) stw[i] = fft2_stage_twiddle(i, plan);
 }
 
+// all tables of one API call in one launch: blockIdx.y = job
+__global__ void __launch_bounds__(256) k_table_jobs(const TableJobs jobs) {
+    const TableJob& J = jobs.job[blockIdx.y];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= J.n) return;
+    switch (J.kind) {
+        case TJ_TWIDDLES: {
+            double s, c;
+            sincospi(-2.0 * (double)i / (double)J.n, &s, &c);
+            static_cast<float2*>(J.out)[i] = make_float2((float)c, (float)s);
+            break;
+        }
+        case TJ_STAGE_TW: static_cast<float2*>(J.out)[i] = fft2_stage_twiddle(i, J.plan); break;
+        case TJ_OMEGA: static_cast<float*>(J.out)[i] = bin_omega(fft2_freq_of_slot(i, J.plan), J.plan.n); break;
+        default:
+            if (J.out) static_cast<int*>(J.out)[i] = fft2_slot_of_freq(i, J.plan);
+            if (J.out2) static_cast<int*>(J.out2)[i] = fft2_freq_of_slot(i, J.plan);
+            break;
+    }
+}
+
+void TableJobs::add(int kind, int n, void* out, void* out2, const Fft2Plan* plan) {
+    if (count >= PB_MAX_TABLE_JOBS) return;       // cannot happen: an entry point adds at most 10
+    TableJob& j = job[count++];
+    j.kind = kind;
+    j.n = n;
+    j.out = out;
+    j.out2 = out2;
+    if (plan) j.plan = *plan; else j.plan.n = n, j.plan.ns = 0;
+}
+
+int launch_table_jobs(const TableJobs& jobs, cudaStream_t stream) {
+    if (jobs.count == 0) return PB_OK;
+    int nmax = 1;
+    for (int i = 0; i < jobs.count; ++i) nmax = jobs.job[i].n > nmax ? jobs.job[i].n : nmax;
+    ProfScope prof(PROF_SETUP, stream);
+    k_table_jobs<<<dim3((nmax + 255) / 256, jobs.count), 256, 0, stream>>>(jobs);
+    PB_LAUNCH_CHECK("k_table_jobs");
+    return PB_OK;
+}
+
 #ifndef R2_THREADS
 #define R2_THREADS 256
 #endif

@@ -16,7 +16,7 @@ k_u8hwc_to_f32nchw(const unsigned char* __restrict__ in, float* __restrict__ out
     for (int c = 0; c < C; ++c) d[(size_t)c * plane] = __fdiv_rn((float)s[c], 255.0f);
 }
 
-// (B,C,H,W) float32 -> (B,H,W,C) uint8: rint(clip(x, 0, 1) * 255)  (img_as_ubyte / utils.to_uint)
+// (B,C,H,W) float32 -> (B,H,W,C) uint8: rint(clip(x, 0, 1) * 255)  (main.py:146 img_as_ubyte = utils.to_ubyte)
 __global__ void __launch_bounds__(256)
 k_f32nchw_to_u8hwc(const float* __restrict__ in, unsigned char* __restrict__ out, int C, size_t plane, size_t total) {
     const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;

@@ -519,6 +519,29 @@ int launch_pad_replicate(const float* img, float* a, float* b, int planes, int H
     return PB_OK;
 }
 
+// utils.crop_with_kernel (utils.py:56-61) of a padded stack into a dense one
+__global__ void __launch_bounds__(256)
+k_crop(const float* __restrict__ padded, float* __restrict__ out, int H, int W, int pad) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= W || y >= H) return;
+    const size_t pl = blockIdx.z;
+    const int Wp = W + 2 * pad, Hp = H + 2 * pad;
+    out[pl * (size_t)H * W + (size_t)y * W + x] = padded[pl * (size_t)Hp * Wp + (size_t)(y + pad) * Wp + x + pad];
+}
+
+int launch_crop(const float* padded, float* out, int planes, int H, int W, int pad, cudaStream_t stream) {
+    if (planes > 65535) {
+        set_error("B*C = %d exceeds the grid z limit", planes);
+        return PB_ERR_ARG;
+    }
+    dim3 grid((W + 31) / 32, (H + 7) / 8, planes);
+    ProfScope prof(PROF_OTHER, stream);
+    k_crop<<<grid, 256, 0, stream>>>(padded, out, H, W, pad);
+    PB_LAUNCH_CHECK("k_crop");
+    return PB_OK;
+}
+
 // n_tapers passes ping-ponging between a and b (both hold the padded image on entry); returns the
 // buffer that holds the result.
 int launch_edgetaper_passes(float* a, float* b, const ImgKernel* kern, const float* v, int B, int C, int Hp, int Wp,

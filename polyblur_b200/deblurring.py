@@ -162,7 +162,10 @@ def polyblur_deblurring(img, n_iter=1, c=0.352, b=0.768, alpha=2, beta=3, sigma_
     dev = _lib.require_cuda(x)
     src_device = x.device
     xd = x.detach()
-    if not xd.is_cuda and not flag_numpy and not return_estimates and xd.shape[0] >= 2:
+    # the chunked host pipeline runs one engine call per chunk; the reference's edgetaper normalises its weights by
+    # a batch-global max (edgetaper.py:15,21), which must see the whole batch, so that option takes the one-shot path
+    batch_coupled = bool(p.flags & _lib.FLAG_EDGETAPER_BATCHMAX)
+    if not xd.is_cuda and not flag_numpy and not return_estimates and xd.shape[0] >= 2 and not batch_coupled:
         return _polyblur_host_pipelined(xd, p, dev)
     if not xd.is_cuda and not flag_numpy:
         xd = xd.pin_memory() if not xd.is_pinned() and xd.numel() > (1 << 20) else xd
@@ -252,9 +255,11 @@ def inverse_filtering_rank3(img, kernel, alpha=2, b=4, correlate=False, remove_h
     from ``img`` when None (deblurring.py:200-203)."""
     if img.dtype != torch.float32 or img.ndim != 4:
         raise TypeError("img must be a float32 (B,C,H,W) tensor")
-    if img.requires_grad and torch.is_grad_enabled():
+    if (img.requires_grad or (isinstance(kernel, torch.Tensor) and kernel.requires_grad)) and torch.is_grad_enabled():
         if remove_halo or do_edgetaper:
             raise NotImplementedError("gradients are implemented for the default flags only")
+        if kernel.shape[1] != 1 or kernel.shape[-1] != kernel.shape[-2]:
+            raise NotImplementedError("one square kernel per image (B,1,k,k) or (1,1,k,k)")
         from . import autograd as _autograd
         kk = torch.rot90(kernel, k=2, dims=(-2, -1)) if correlate else kernel
         return _autograd.DeconvolutionFunction.apply(img, kk, alpha, b, engine)

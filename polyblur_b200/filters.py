@@ -7,11 +7,16 @@ import torch
 from . import _lib
 
 
-def _prep(images: torch.Tensor, what: str):
+def _prep(images: torch.Tensor, what: str, differentiable: bool = False):
     if not isinstance(images, torch.Tensor) or images.ndim != 4:
         raise ValueError(f"{what}: expected a (B,C,H,W) tensor")
     if images.dtype != torch.float32:
         raise TypeError(f"{what}: float32 only (got {images.dtype}), like the reference")
+    if images.requires_grad and torch.is_grad_enabled() and not differentiable:
+        # the reference's stage is written in differentiable torch ops; dropping the autograd history
+        # silently would hand back wrong (zero) gradients
+        raise NotImplementedError(f"{what}: no backward pass is built for this stage; call it under "
+                                  "torch.no_grad() or on a detached tensor")
     dev = _lib.require_cuda(images)
     src_device = images.device
     x = images.detach().to(dev, non_blocking=True).contiguous()
@@ -25,7 +30,9 @@ def fourier_gradients(images: torch.Tensor):
     multiply by 2*pi*f*i, ifft2.  Here: independent 1-D spectral derivatives of the rows and
     the columns, computed by the on-chip FFT kernels (csrc/estimate.cu k_rows / k_cols).
     """
-    x, dev, src = _prep(images, "fourier_gradients")
+    if isinstance(images, torch.Tensor) and images.requires_grad and torch.is_grad_enabled():
+        return _FourierGradients.apply(images)
+    x, dev, src = _prep(images, "fourier_gradients", differentiable=True)
     B, C, H, W = x.shape
     with torch.cuda.device(dev):
         p = _lib.default_params()
@@ -36,6 +43,21 @@ def fourier_gradients(images: torch.Tensor):
                                                  ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
         _lib.check(rc, "pb_fourier_gradients_f32")
     return gx.to(src), gy.to(src)
+
+
+class _FourierGradients(torch.autograd.Function):
+    """The spectral derivative is a real skew-symmetric circulant (i omega is odd), so its transpose is its
+    negative: grad_in = -(D_x gx_bar + D_y gy_bar)."""
+
+    @staticmethod
+    def forward(ctx, images):
+        return fourier_gradients(images.detach())
+
+    @staticmethod
+    def backward(ctx, gx_bar, gy_bar):
+        ax, _ = fourier_gradients(gx_bar.detach().contiguous())
+        _, by = fourier_gradients(gy_bar.detach().contiguous())
+        return -(ax + by)
 
 
 def bilateral_filter(I, ksize=5, sigma_spatial=5.0, sigma_color=0.1):

@@ -59,6 +59,12 @@ def deblur_uint8(images, n_iter=1, c=0.352, b=0.768, alpha=2, beta=3, sigma_r=0.
     if n_iter == 0:
         return images
     with torch.cuda.device(dev):
+        if not x.is_cuda and (p.flags & _lib.FLAG_EDGETAPER_BATCHMAX):
+            # batch-global edgetaper normalisation (edgetaper.py:15,21): one engine call for the whole batch
+            return_cpu = True
+            x = x.to(dev)
+        else:
+            return_cpu = False
         if x.is_cuda:
             st = _lib.stream_ptr(dev)
             xf = torch.empty(B, Cn, H, W, dtype=torch.float32, device=dev)
@@ -70,6 +76,8 @@ def deblur_uint8(images, n_iter=1, c=0.352, b=0.768, alpha=2, beta=3, sigma_r=0.
                                             ws.numel(), None, st)
             _lib.check(rc, "pb_polyblur_f32")
             _convert_out(yf, out, st)
+            if return_cpu:
+                out = out.cpu()
         else:
             out = _host_pipeline_u8(x, p, dev, max_chunks)
     out = out.reshape(shape_in)

@@ -87,7 +87,7 @@ def main(argv=None):
             x = utils.to_tensor(img).unsqueeze(0).cuda()
             with torch.no_grad():
                 y = mod(x, **kw)
-            out_u8 = utils.to_uint(utils.to_array(y))
+            out_u8 = utils.to_ubyte(utils.to_array(y))
         torch.cuda.synchronize()
         print('Restoration took %2.4f seconds' % (time.time() - start))
     out = args.out or os.path.join('results', 'restored_alpha_%d_beta_%d.png' % (args.alpha, args.beta))

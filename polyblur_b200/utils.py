@@ -35,7 +35,17 @@ def to_float(img):
 
 
 def to_uint(img):
-    """float ndarray in [0,1] -> uint8 (utils.py:41-45)."""
+    """float ndarray -> uint8 exactly like the reference's utils.to_uint (utils.py:41-45):
+    ``(255 * img).astype(np.uint8)``, i.e. TRUNCATION towards zero (0.999 -> 254), not rounding.  Input outside
+    [0,1] is clipped first (the reference's cast is undefined there).  The command line and the 8-bit pipeline use
+    :func:`to_ubyte` instead, as main.py:146 does."""
+    img = np.clip(np.asarray(img, dtype=np.float32), 0, 1)
+    return (255 * img).astype(np.uint8)
+
+
+def to_ubyte(img):
+    """float ndarray in [0,1] -> uint8 with rounding to nearest: skimage.img_as_ubyte, which the reference's
+    command line applies to the result (main.py:146); csrc/io.cu does the same on the device."""
     img = np.clip(np.asarray(img, dtype=np.float64), 0, 1)
     return np.rint(img * 255.0).astype(np.uint8)
 

@@ -356,7 +356,7 @@ def test_patch_decomposition_vs_oracle(pb):
             wsum[i0:i0 + ph, j0:j0 + pw] += win
     ref = np.clip(acc / (wsum + 1e-8), 0, 1)[..., pt:pt + 150, pl:pl + 200]
     assert got.shape == ref.shape
-    assert maxabs(got, ref) < 2e-5
+    assert maxabs(got, ref) < TOL_E2E
 
 
 @pytest.mark.parametrize("shape,ss,sr,n", [((1, 3, 40, 56), 60, 0.4, 3), ((2, 3, 33, 71), 8.0, 0.5, 2),
@@ -425,10 +425,10 @@ def test_inverse_filtering_stage_options(pb, kw):
 
 def test_uint8_path_matches_float_path(pb, golden_dir, tmp_path):
     """8-bit in / 8-bit out: device conversions == utils.to_float -> float path ->
-    utils.to_uint, for an ndarray, a pinned host batch (pipelined) and a CUDA tensor; CLI smoke."""
+    utils.to_ubyte (main.py:146 img_as_ubyte), for an ndarray, a pinned host batch (pipelined) and a CUDA tensor; CLI smoke."""
     from PIL import Image
     img = np.asarray(Image.open(os.path.join(golden_dir, "peacock_defocus.png")))
-    ref = pb.utils.to_uint(pb.polyblur_deblurring(pb.utils.to_float(img), n_iter=3, alpha=6, beta=1))
+    ref = pb.utils.to_ubyte(pb.polyblur_deblurring(pb.utils.to_float(img), n_iter=3, alpha=6, beta=1))
     got = pb.io.deblur_uint8(img, n_iter=3, alpha=6, beta=1)
     assert got.dtype == np.uint8 and got.shape == img.shape
     d = np.abs(got.astype(np.int32) - ref.astype(np.int32))
@@ -460,8 +460,9 @@ def test_cuda_graph_replay_is_bit_identical(pb):
 
 def test_random_shape_sweep(pb, capsys):
     """tools/fuzz_parity.py: odd / prime / one-pixel-wide shapes, 1-4 channels, random options, against
-    the oracle.  Tiny images with beta = 4 amplify rounding noise, hence 2e-5 here (the worst of 100
-    recorded cases is 1.3e-5, profiles/r01_fuzz_parity.jsonl)."""
+    the oracle at the north-star tolerance 1e-5.  Tiny images with beta = 4 amplify rounding noise until the
+    float32 reference itself sits ~1e-5 from the exact result; such a case is arbitrated inside the tool with
+    the float64 restatement and must be within 1e-5 of THAT (status "ok-vs-f64"), anything else is a failure."""
     import importlib.util
     spec = importlib.util.spec_from_file_location("fuzz_parity", os.path.join(os.path.dirname(G), "..", "tools", "fuzz_parity.py"))
     mod = importlib.util.module_from_spec(spec)
@@ -469,4 +470,5 @@ def test_random_shape_sweep(pb, capsys):
     mod.main(n_cases=25, seed=3)
     import json
     last = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
-    assert last["failures"] == 0 and last["worst_ok_err"] < 2e-5
+    assert last["failures"] == 0
+    assert last["worst_ok_err"] < TOL_E2E and last["worst_arbitrated_err_vs_f64"] < TOL_E2E

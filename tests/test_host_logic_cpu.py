@@ -45,7 +45,10 @@ def test_utils_match_oracle_restatement():
     assert p.shape == (2, 3, 32, 34) and np.array_equal(p.numpy(), po.pad_with_kernel(x.numpy(), 12))
     assert torch.equal(pb.utils.crop_with_kernel(p, k), x)
     u8 = (rng.random((4, 5, 3)) * 255).astype(np.uint8)
-    assert np.array_equal(pb.utils.to_uint(pb.utils.to_float(u8)), u8)
+    assert np.array_equal(pb.utils.to_ubyte(pb.utils.to_float(u8)), u8)         # main.py:146 img_as_ubyte rounds
+    f = np.array([0.0, 0.999, 1.0, 0.5, 1.7, -0.2], np.float32)
+    assert pb.utils.to_uint(f).tolist() == [0, 254, 255, 127, 255, 0]               # utils.py:41-45 truncates
+    assert pb.utils.to_ubyte(f).tolist() == [0, 255, 255, 128, 255, 0]
 
 
 def test_patch_geometry_helpers():
