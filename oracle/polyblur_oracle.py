@@ -405,7 +405,8 @@ def compute_polynomial_torus(img, kernel, alpha, beta, dtype=np.float64):
 def halo_masking(img, imout, grad_img, dtype=np.float32):
     """Bug-compatible halo masking (deblurring.py:173-208): M uses gy*gy, not gy*goy."""
     dtype = np.dtype(dtype).type
-    gx, gy = grad_img
+    # grad_img defaults to the gradients of the image it is handed (deblurring.py:200-203)
+    gx, gy = fourier_gradients(img, dtype) if grad_img is None else grad_img
     ox, oy = fourier_gradients(imout, dtype)
     M = (-gx * ox) + (-gy * gy)
     nM = np.sum(gx * gx + gy * gy, axis=(-2, -1), keepdims=True, dtype=dtype)

@@ -5,6 +5,7 @@
 * ``nc/*``     outputs of the reference's native normalized convolution, JIT-compiled from
                /root/reference/polyblur/domain_transform/NC.cpp:143-204 where it lies (B = 1, C = 3 as written
                there); pins oracle.normalized_convolution and csrc/nc.cu.
+* ``halo/*``   inverse_filtering_rank3 with remove_halo=True and grad_img=None, with and without do_edgetaper.
 * ``asym/*``   inverse_filtering_rank3 (deblurring.py:211-239, method='fft'), edgetaper (edgetaper.py:26-33) and the
                autograd gradients of the deconvolution for kernels that are NOT point-symmetric (a motion streak and a
                shifted anisotropic Gaussian): the p2o / fft2 product (filters.py:255-273) is a convolution, and
@@ -99,6 +100,16 @@ def main():
     G["asym/vjp/gx"] = xg.grad.numpy()
     G["asym/vjp/gk"] = kg.grad.numpy()
     print("vjp", float(xg.grad.abs().max()), float(kg.grad.abs().max()))
+
+    # ---- halo masking without grad_img: gradients of the image inverse_filtering_rank3 hands over, i.e. of the crop of
+    #      the padded (and, with do_edgetaper, tapered) image (deblurring.py:237-238, 200-203) ---------------------------
+    from polyblur import blur_estimation
+    kk = blur_estimation.create_gaussian_filter(torch.tensor([[0.4], [1.9]]), torch.tensor([[1.4], [2.2]]),
+                                                torch.tensor([[0.7], [1.1]]), ksize=25)
+    G["halo/k"] = kk.numpy()
+    for taper in (False, True):
+        y = deblurring.inverse_filtering_rank3(x, kk, alpha=6, b=1, remove_halo=True, do_edgetaper=taper, method="fft")
+        G[f"halo/{'taper' if taper else 'plain'}"] = y.numpy()
 
     # ---- method= is accepted and 'direct' differs upstream (B = 1 only there): record the fft result the
     #      drop-in returns for every method ----------------------------------------------------------

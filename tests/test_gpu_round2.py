@@ -107,6 +107,15 @@ def test_stage_functions_refuse_to_drop_autograd_history(pb):
     assert abs(lhs - rhs) < 1e-3 * max(1.0, abs(lhs))
 
 
+def test_halo_gradients_default_golden(pb, r2):
+    x, k = cu(r2["asym/in25"]), cu(r2["halo/k"])
+    for tag, taper in (("plain", False), ("taper", True)):
+        for engine in (ENGINE_AUTO, ENGINE_SPATIAL, ENGINE_FFT):
+            got = pb.deblurring.inverse_filtering_rank3(x, k, alpha=6, b=1, remove_halo=True, do_edgetaper=taper,
+                                                        engine=engine)
+            assert maxabs(got.cpu().numpy(), r2[f"halo/{tag}"]) < 5e-6
+
+
 def test_halo_gradients_default_to_the_tapered_crop(pb):
     """remove_halo + do_edgetaper without grad_img: the reference takes the gradients of crop(tapered padded
     image) (deblurring.py:237-238, 200-203), which differs from the input in the border band."""

@@ -51,3 +51,11 @@ def test_asymmetric_kernel_gradients_match_autograd(r2):
     gi, gk, _ = po.inverse_filtering_rank3_vjp(r2["asym/in25"], r2["asym/k25"], r2["asym/vjp/w"], alpha=6, b=1)
     assert maxabs(gi, r2["asym/vjp/gx"]) < 5e-6 * np.abs(r2["asym/vjp/gx"]).max()
     assert maxabs(gk, r2["asym/vjp/gk"]) < 5e-6 * np.abs(r2["asym/vjp/gk"]).max()
+
+
+def test_halo_masking_default_gradients(r2):
+    """remove_halo with grad_img=None: gradients of the cropped (tapered) padded image (deblurring.py:200-203, 237-238)."""
+    x, k = r2["asym/in25"], r2["halo/k"]
+    for tag, taper in (("plain", False), ("taper", True)):
+        y = po.inverse_filtering_rank3(x, k, alpha=6, b=1, remove_halo=True, do_edgetaper=taper, grad_img=None)
+        assert maxabs(y, r2[f"halo/{tag}"]) < 4e-6

@@ -3,7 +3,11 @@
 per-launch table committed under profiles/ and, optionally, the DRAM traffic per kernel group that
 bench.py reports as roofline.traffic.
 
-    python tools/ncu_summary.py gpurun_out/x.ncu-rep profiles/r01_x.md [--traffic KEY profiles/roofline_traffic.json]
+    python tools/ncu_summary.py gpurun_out/x.ncu-rep profiles/r02_x.md [--traffic KEY profiles/roofline_traffic.json]
+                                [--pipes KEY profiles/roofline_pipes.json] [--csv profiles/r02_x.csv]
+
+--pipes records, per kernel, the utilisation of the units that can bind it (DRAM, L1/shared-memory pipe, FMA pipe,
+issue slots) -- bench.py derives ``roofline.bound`` from it; --csv keeps the raw metric rows those numbers come from.
 """
 import csv
 import json
@@ -14,6 +18,12 @@ COLS = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram_rd"),
         ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram%"),
         ("l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex%"),
         ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue%"),
+        ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "fma%"),
+        ("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "alu%"),
+        ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "lsu%"),
+        ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "l2%"),
+        ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smem_wavefronts"),
+        ("derived__memory_l1_wavefronts_shared_excessive", "smem_excess"),
         ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps%"),
         ("launch__registers_per_thread", "regs"), ("launch__shared_mem_per_block_dynamic", "smem/CTA"),
         ("launch__grid_size", "grid"), ("smsp__inst_executed.sum", "warp_inst")]
@@ -73,6 +83,50 @@ def main():
                 total += by
             cur[f"{g}:{key_suffix}"] = total
         json.dump(cur, open(path, "w"), indent=1, sort_keys=True)
+    def num(r, key):
+        try:
+            return float(r[idx[key]].replace(",", ""))
+        except Exception:
+            return None
+
+    if "--pipes" in sys.argv:
+        i = sys.argv.index("--pipes")
+        key_suffix, path = sys.argv[i + 1], sys.argv[i + 2]
+        try:
+            cur = json.load(open(path))
+        except Exception:
+            cur = {}
+        seen = set()
+        for r in body:
+            name = r[idx["Kernel Name"]].split("(")[0].replace("void ", "").replace("pb::", "").split("<")[0]
+            if name in seen:
+                continue
+            seen.add(name)
+            cur[f"{name}:{key_suffix}"] = {
+                "dram_pct": num(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+                "l1tex_pct": num(r, "l1tex__throughput.avg.pct_of_peak_sustained_elapsed"),
+                "l2_pct": num(r, "lts__throughput.avg.pct_of_peak_sustained_elapsed"),
+                "fma_pipe_pct": num(r, "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+                "issue_pct": num(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                "warps_pct": num(r, "sm__warps_active.avg.pct_of_peak_sustained_active"),
+                "source": rep.split("/")[-1],
+            }
+        json.dump(cur, open(path, "w"), indent=1, sort_keys=True)
+    if "--csv" in sys.argv:
+        path = sys.argv[sys.argv.index("--csv") + 1]
+        keep = ["ID", "Kernel Name"] + [k for k, _ in COLS if k in idx] + [
+            k for k in hdr if k.startswith(("smsp__pcsamp_warps_issue_stalled", "smsp__average_warps_issue_stalled",
+                                            "l1tex__data_bank_conflicts_pipe_lsu_mem_shared", "sm__inst_executed_pipe_",
+                                            "launch__occupancy", "smsp__warp_issue_stalled")) and k.endswith(
+                                                ("ratio", ".sum", "pct_of_peak_sustained_active", "limit_registers",
+                                                 "limit_shared_mem", "limit_warps"))]
+        keep = [k for i2, k in enumerate(keep) if k in idx and k not in keep[:i2]]
+        with open(path, "w", newline="") as f:
+            w = csv.writer(f)
+            w.writerow(keep)
+            w.writerow([units[idx[k]] for k in keep])
+            for r in body:
+                w.writerow([r[idx[k]] for k in keep])
     print("wrote", out)
 
 
