@@ -34,6 +34,8 @@
 
 namespace pb {
 
+static int env_int(const char* name, int dflt);
+
 // ---- PTX wrappers: mbarrier + 1-D bulk (TMA) copies ---------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
@@ -262,7 +264,7 @@ __global__ void __launch_bounds__(FFTC_THREADS, PB_FFTC_MINB)
 k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int* __restrict__ list,
            const int* __restrict__ count, int C, int NX, int NY, int CB, Fft2Plan planY,
            const float2* __restrict__ twX, const float2* __restrict__ stwY, const int* __restrict__ slotY,
-           float a3, float a2, float a1, float b0) {
+           float a3, float a2, float a1, float b0, int first_block_only) {
     extern __shared__ __align__(16) unsigned char smraw[];
     float2* data = reinterpret_cast<float2*>(smraw);
     float* Hs = reinterpret_cast<float*>(data + (size_t)CB * NY);
@@ -273,7 +275,8 @@ k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int
     bar = reinterpret_cast<uint64_t*>(((uintptr_t)bar + 7) & ~(uintptr_t)7);
     const int tid = threadIdx.x;
     const int half = NX >> 1;
-    const int nblk = (half + CB - 1) / CB;
+    // first_block_only: just the block that holds kx = 0 (the second-generation kernel does the other columns)
+    const int nblk = first_block_only ? 1 : (half + CB - 1) / CB;
     const int total = count[0] * nblk;
     const float scale = 1.0f / ((float)NX * (float)NY);
     const float inv_ny = 1.0f / (float)NY;
@@ -541,6 +544,539 @@ k_fft_rows_inv(const float2* __restrict__ Z, float* __restrict__ out, const ImgK
     }
 }
 
+// =============================================================================================
+// Second-generation row passes (compile-time plans only): the first / last FFT stage works straight
+// from / to global memory and the Hermitian separation (P1) / rebuild (P3) happens in the registers of
+// the stage that touches the spectrum, so a row pair crosses shared memory once per inner stage only:
+//   P1: global --(stage 0 in registers)--> smem --(inner stages)--> smem --(last stage + separation)--> Z
+//   P3: Z --(rebuild + first inverse stage)--> smem --(inner stages)--> smem --(stage 0 + crop + clamp)--> out
+// (first generation: load pass, ns stages, separation pass = ns + 2 round trips, and 50 % of the warp
+// instructions of P1 / 47 % of P3 in the load / separation passes -- profiles/r02_sass_segments.md.)
+// =============================================================================================
+
+// feeds stage 0 of P1: sample e = j + m M of row pair f = (extended rows 2f, 2f + 1) of one plane
+struct RowPairSrc {
+    const float* src;      // plane
+    const int* rowsrc;     // [2 nb] source row of each extended row, -1 = zero row
+    int Ws, off, W, ext, Win, pad;
+    bool inner_interior;   // samples with 1 <= m <= R - 2 are all interior image columns
+    template <int R, int M>
+    __device__ __forceinline__ void load(int f, int j, float2 (&v)[R]) const {
+        const int sa = rowsrc[2 * f], sb = rowsrc[2 * f + 1];
+        if (inner_interior && sa >= 0 && sb >= 0) {
+            // fast path (every pair but the ones that touch the zero fill): one base pointer per row, the inner
+            // samples at immediate offsets, only the two outer ones go through the torus map
+            const float* pa = src + (size_t)sa * Ws + (j - ext + off);
+            const float* pb = src + (size_t)sb * Ws + (j - ext + off);
+#pragma unroll
+            for (int m = 1; m < R - 1; ++m) v[m] = make_float2(__ldg(pa + m * M), __ldg(pb + m * M));
+            const int s0 = ext_src(j, W, ext, Win, off, pad);
+            const int s1 = ext_src(j + (R - 1) * M, W, ext, Win, off, pad);
+            const float* ra = src + (size_t)sa * Ws;
+            const float* rb = src + (size_t)sb * Ws;
+            v[0] = s0 >= 0 ? make_float2(__ldg(ra + s0), __ldg(rb + s0)) : make_float2(0.f, 0.f);
+            v[R - 1] = s1 >= 0 ? make_float2(__ldg(ra + s1), __ldg(rb + s1)) : make_float2(0.f, 0.f);
+            return;
+        }
+        const float* ra = src + (size_t)(sa < 0 ? 0 : sa) * Ws;
+        const float* rb = src + (size_t)(sb < 0 ? 0 : sb) * Ws;
+#pragma unroll
+        for (int m = 0; m < R; ++m) {
+            const int sx = ext_src(j + m * M, W, ext, Win, off, pad);
+            float a = 0.f, b = 0.f;
+            if (sx >= 0) {
+                if (sa >= 0) a = __ldg(ra + sx);
+                if (sb >= 0) b = __ldg(rb + sx);
+            }
+            v[m] = make_float2(a, b);
+        }
+    }
+};
+
+// drains stage 0 of P3: result e = j + m M of row pair f; r = DFT(swap(Z)): row a = r.y, row b = r.x
+struct RowPairDst {
+    float* dst;            // plane
+    int W, H, ext, ya0;    // ya0 = image row of extended row 0 of this block (j0 - ext)
+    float lo, hi;
+    bool inner_interior;
+    template <int R, int M>
+    __device__ __forceinline__ void store(int f, int j, const float2 (&v)[R]) const {
+        const int ya = ya0 + 2 * f;
+        const bool oka = ya >= 0 && ya < H, okb = ya + 1 >= 0 && ya + 1 < H;
+        if (inner_interior && oka && okb) {
+            float* pa = dst + (size_t)ya * W + (j - ext);
+            float* pb = pa + W;
+#pragma unroll
+            for (int m = 1; m < R - 1; ++m) {
+                pa[m * M] = fminf(fmaxf(v[m].y, lo), hi);
+                pb[m * M] = fminf(fmaxf(v[m].x, lo), hi);
+            }
+            if (j >= ext) {
+                pa[0] = fminf(fmaxf(v[0].y, lo), hi);
+                pb[0] = fminf(fmaxf(v[0].x, lo), hi);
+            }
+            if (j + (R - 1) * M - ext < W) {
+                pa[(R - 1) * M] = fminf(fmaxf(v[R - 1].y, lo), hi);
+                pb[(R - 1) * M] = fminf(fmaxf(v[R - 1].x, lo), hi);
+            }
+            return;
+        }
+        float* pa = dst + (size_t)(oka ? ya : 0) * W;
+        float* pb = dst + (size_t)(okb ? ya + 1 : 0) * W;
+#pragma unroll
+        for (int m = 0; m < R; ++m) {
+            const int X = j + m * M - ext;
+            if (X >= 0 && X < W) {
+                if (oka) pa[X] = fminf(fmaxf(v[m].y, lo), hi);
+                if (okb) pb[X] = fminf(fmaxf(v[m].x, lo), hi);
+            }
+        }
+    }
+};
+
+// Which of {k, NX - k} is the half-spectrum column of slot q of a mirror unit's block A (k = fA + KS q, fA < KS):
+// known at compile time for every q but the one whose range straddles NX / 2.
+template <int NX, int KS>
+__device__ __forceinline__ bool unit_lower_half(int q, int kA) {
+    if (2 * KS * (q + 1) <= NX) return true;
+    if (2 * KS * q > NX) return false;
+    return 2 * kA < NX;
+}
+template <int NX, int KS>
+__device__ __forceinline__ bool unit_maybe_nyquist(int q) { return 2 * KS * q <= NX && NX < 2 * KS * (q + 1); }
+
+template <class SP, int NY>
+__global__ void __launch_bounds__(FFTD_THREADS, PB_FFTD_MINB)
+k_fft_rows_fwd2(const float* __restrict__ img, float2* __restrict__ Z, const ImgKernel* __restrict__ kern,
+                const int* __restrict__ list, const int* __restrict__ count, int C, int H, int W, int nb,
+                const float2* __restrict__ twX, const int4* __restrict__ units, SrcGeom G) {
+    constexpr int NX = SP::n, NS = SP::ns, R0 = SP::R(0), M0 = NX / R0, RL = SP::R(NS - 1), KS = NX / RL;
+    extern __shared__ __align__(16) float2 smf[];
+    __shared__ int rowsrc[32];
+    const int tid = threadIdx.x;
+    const int blocks_per_plane = (NY / 2 + nb - 1) / nb;
+    const int per_img = C * blocks_per_plane;
+    const int total = count[0] * per_img;
+    constexpr int half = NX >> 1;
+    const int RS = fftd_row_stride(NX);
+    const int nunits = units[0].x;
+
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int slot = w / per_img;
+        int r = w - slot * per_img;
+        const int c = r / blocks_per_plane;
+        const int rb = r - c * blocks_per_plane;
+        const int im = list[slot];
+        const int kpad = kern[im].ksize >> 1;
+        const int pad = G.pad >= 0 ? G.pad : kpad;
+        const int ext = 3 * kpad;
+        const int j0 = rb * 2 * nb;
+        if (tid < 2 * nb) rowsrc[tid] = (j0 + tid < NY) ? ext_src(j0 + tid, H, ext, G.Hin, G.off, pad) : -1;
+        __syncthreads();
+        RowPairSrc S;
+        S.src = img + ((size_t)im * C + c) * (size_t)G.Hin * G.Win;
+        S.rowsrc = rowsrc;
+        S.Ws = G.Win;
+        S.off = G.off;
+        S.W = W;
+        S.ext = ext;
+        S.Win = G.Win;
+        S.pad = pad;
+        S.inner_interior = (M0 >= ext) && ((R0 - 1) * M0 - ext <= W);
+        s_dif_first<R0, M0, NX>(smf, RS, nb, twX + SP::tw_off(0), tid, FFTD_THREADS, S);
+        __syncthreads();
+        SDifRun<SP, 1, NS - 2, false>::run(smf, RS, nb, twX, tid, FFTD_THREADS);
+        // last stage (M = 1) on the two blocks of a mirror unit, then
+        //   Xa[k] = (Z[k] + conj Z[-k]) / 2,  Xb[k] = (Z[k] - conj Z[-k]) / (2i)   ->  Z[plane][kx][row pair]
+        float2* Zp = Z + ((size_t)slot * C + c) * half * NY;
+        for (int idx = tid; idx < nunits * nb; idx += FFTD_THREADS) {
+            const int u = idx / nb, p = idx - u * nb;
+            const int ja = j0 + 2 * p;
+            if (ja >= NY) continue;
+            const int4 U = __ldg(units + 1 + u);
+            const float2* row = smf + (size_t)p * RS;
+            float2 va[RL], vb[RL];
+#pragma unroll
+            for (int q = 0; q < RL; ++q) va[q] = row[U.x * RL + q];
+            Dft<RL>::run(va);
+            if (U.x == 0 || U.x == U.y) {
+                // the two self-mirror blocks (block 0; the block that holds NX / 2): rare, generic code
+#pragma unroll
+                for (int q = 0; q < RL; ++q) {
+                    const int kA = U.z + KS * q;
+                    const float2 z1 = va[q];
+                    const float2 z2 = (U.x == 0) ? va[(RL - q) % RL] : va[RL - 1 - q];
+                    if (kA == 0 || 2 * kA == NX) {
+                        // DC and Nyquist are real for both rows and share column 0: (Xa, Xb) = ((dc, ny), (dc, ny))
+                        float* d = reinterpret_cast<float*>(Zp + ja) + (kA == 0 ? 0 : 1);
+                        d[0] = z1.x;
+                        if (ja + 1 < NY) d[2] = z1.y;
+                    } else if (2 * kA < NX) {
+                        const float2 xa = make_float2(0.5f * (z1.x + z2.x), 0.5f * (z1.y - z2.y));
+                        const float2 xb = make_float2(0.5f * (z1.y + z2.y), 0.5f * (z2.x - z1.x));
+                        float2* d = Zp + (size_t)kA * NY + ja;
+                        if (ja + 1 < NY) *reinterpret_cast<float4*>(d) = make_float4(xa.x, xa.y, xb.x, xb.y);
+                        else d[0] = xa;
+                    }
+                }
+                continue;
+            }
+#pragma unroll
+            for (int q = 0; q < RL; ++q) vb[q] = row[U.y * RL + q];
+            Dft<RL>::run(vb);
+            // slot q of block A holds k = fA + KS q, slot RL - 1 - q of block B its mirror NX - k; the lower of the two
+            // is the half-spectrum column.  Columns of one unit are KS apart: two base pointers, immediate offsets.
+            float2* dlo = Zp + (size_t)U.z * NY + ja;                              // column fA (+ KS q)
+            float2* dhi = Zp + (size_t)(NX - U.z - KS * (RL - 1)) * NY + ja;       // column NX - fA - KS (RL - 1) (+ KS (RL - 1 - q))
+            const bool pairrow = (NY & 1) == 0 || ja + 1 < NY;
+#pragma unroll
+            for (int q = 0; q < RL; ++q) {
+                const int kA = U.z + KS * q;
+                const bool lower = unit_lower_half<NX, KS>(q, kA);
+                const float2 zk = lower ? va[q] : vb[RL - 1 - q];
+                const float2 zm = lower ? vb[RL - 1 - q] : va[q];
+                const float2 xa = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+                const float2 xb = make_float2(0.5f * (zk.y + zm.y), 0.5f * (zm.x - zk.x));
+                float2* d = lower ? dlo + (size_t)(KS * q) * NY : dhi + (size_t)(KS * (RL - 1 - q)) * NY;
+                if (pairrow) *reinterpret_cast<float4*>(d) = make_float4(xa.x, xa.y, xb.x, xb.y);
+                else d[0] = xa;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <class SP, int NY>
+__global__ void __launch_bounds__(FFTD_THREADS, PB_FFTD_MINB)
+k_fft_rows_inv2(const float2* __restrict__ Z, float* __restrict__ out, const ImgKernel* __restrict__ kern,
+                const int* __restrict__ list, const int* __restrict__ count, int C, int H, int W, int nb,
+                const float2* __restrict__ twX, const int4* __restrict__ units, int clamp_out) {
+    constexpr int NX = SP::n, NS = SP::ns, R0 = SP::R(0), M0 = NX / R0, RL = SP::R(NS - 1), KS = NX / RL;
+    extern __shared__ __align__(16) float2 smf[];
+    const int tid = threadIdx.x;
+    const int blocks_per_plane = (NY / 2 + nb - 1) / nb;
+    const int per_img = C * blocks_per_plane;
+    const int total = count[0] * per_img;
+    const size_t plane = (size_t)H * W;
+    constexpr int half = NX >> 1;
+    const int RS = fftd_row_stride(NX);
+    const int nunits = units[0].x;
+
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int slot = w / per_img;
+        int r = w - slot * per_img;
+        const int c = r / blocks_per_plane;
+        const int rb = r - c * blocks_per_plane;
+        const int im = list[slot];
+        const int ext = 3 * (kern[im].ksize >> 1);
+        const int j0 = rb * 2 * nb;
+        // rows of the extended image that are output rows: [ext, H + ext)
+        if (j0 + 2 * nb <= ext || j0 >= H + ext) continue;
+        const float2* Zp = Z + ((size_t)slot * C + c) * half * NY;
+        // rebuild Z[k] = Xa[k] + i Xb[k], Z[-k] = conj Xa[k] + i conj Xb[k] of a mirror unit in registers (P2 leaves
+        // the spectra re/im swapped, and the inverse-by-forward trick wants them swapped), first inverse stage (M = 1)
+        for (int idx = tid; idx < nunits * nb; idx += FFTD_THREADS) {
+            const int u = idx / nb, p = idx - u * nb;
+            const int ja = j0 + 2 * p;
+            if (ja >= NY) continue;        // pair beyond the torus (never an output row; its slots stay unused)
+            const int4 U = __ldg(units + 1 + u);
+            float2* row = smf + (size_t)p * RS;
+            const bool pairrow = (NY & 1) == 0 || ja + 1 < NY;
+            float2 va[RL], vb[RL];
+            if (U.x == 0 || U.x == U.y) {
+                // the two self-mirror blocks: rare, generic code
+#pragma unroll
+                for (int q = 0; q < RL; ++q) {
+                    const int kA = U.z + KS * q;
+                    const int kx = (2 * kA <= NX) ? kA : NX - kA;
+                    const float2* s = Zp + (size_t)(kx == half ? 0 : kx) * NY + ja;
+                    float4 ld = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ja + 1 < NY) ld = __ldg(reinterpret_cast<const float4*>(s));
+                    else if (ja < NY) {
+                        const float2 t = __ldg(s);
+                        ld = make_float4(t.x, t.y, 0.f, 0.f);
+                    }
+                    const float2 xa = make_float2(ld.y, ld.x), xb = make_float2(ld.w, ld.z);
+                    float2 zk, zm;              // swapped Z[kx], Z[-kx]
+                    if (kA == 0) {
+                        zk = zm = make_float2(xb.x, xa.x);
+                    } else if (2 * kA == NX) {
+                        zk = zm = make_float2(xb.y, xa.y);
+                    } else {
+                        zk = make_float2(xa.y + xb.x, xa.x - xb.y);
+                        zm = make_float2(xb.x - xa.y, xa.x + xb.y);
+                    }
+                    va[q] = (2 * kA <= NX) ? zk : zm;
+                }
+                Dft<RL>::run(va);
+#pragma unroll
+                for (int q = 0; q < RL; ++q) row[U.x * RL + q] = va[q];
+                continue;
+            }
+            const float2* slo = Zp + (size_t)U.z * NY + ja;
+            const float2* shi = Zp + (size_t)(NX - U.z - KS * (RL - 1)) * NY + ja;
+            float4 ld[RL];
+#pragma unroll
+            for (int q = 0; q < RL; ++q) {
+                const int kA = U.z + KS * q;
+                const bool lower = unit_lower_half<NX, KS>(q, kA);
+                const float2* s = lower ? slo + (size_t)(KS * q) * NY : shi + (size_t)(KS * (RL - 1 - q)) * NY;
+                if (pairrow) ld[q] = __ldg(reinterpret_cast<const float4*>(s));
+                else {
+                    const float2 t = ja < NY ? __ldg(s) : make_float2(0.f, 0.f);
+                    ld[q] = make_float4(t.x, t.y, 0.f, 0.f);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < RL; ++q) {
+                const int kA = U.z + KS * q;
+                const bool lower = unit_lower_half<NX, KS>(q, kA);
+                const float2 xa = make_float2(ld[q].y, ld[q].x), xb = make_float2(ld[q].w, ld[q].z);
+                const float2 zk = make_float2(xa.y + xb.x, xa.x - xb.y);       // swapped Z[kx]
+                const float2 zm = make_float2(xb.x - xa.y, xa.x + xb.y);       // swapped Z[-kx]
+                va[q] = lower ? zk : zm;
+                vb[RL - 1 - q] = lower ? zm : zk;
+            }
+            Dft<RL>::run(va);
+#pragma unroll
+            for (int q = 0; q < RL; ++q) row[U.x * RL + q] = va[q];
+            Dft<RL>::run(vb);
+#pragma unroll
+            for (int q = 0; q < RL; ++q) row[U.y * RL + q] = vb[q];
+        }
+        __syncthreads();
+        SDitRun<SP, NS - 2, NS - 2, false>::run(smf, RS, nb, twX, tid, FFTD_THREADS);
+        RowPairDst D;
+        D.dst = out + ((size_t)im * C + c) * plane;
+        D.W = W;
+        D.H = H;
+        D.ext = ext;
+        D.ya0 = j0 - ext;
+        D.lo = clamp_out ? 0.0f : -INFINITY;
+        D.hi = clamp_out ? 1.0f : INFINITY;
+        D.inner_interior = (M0 >= ext) && ((R0 - 1) * M0 - ext <= W);
+        s_dit_last<R0, M0, NX>(smf, RS, nb, twX + SP::tw_off(0), tid, FFTD_THREADS, D);
+        __syncthreads();
+    }
+}
+
+// =============================================================================================
+// Second-generation column pass: two stages NY = RA x RB with 32-36-point butterflies in registers.
+//   stage A  (DIF, radix RA, stride RB)   reads the column as the bulk copy delivered it, writes RA blocks of RB
+//                                         slots, each block padded to RB + 1 (conflict-free for the next stage)
+//   middle   (radix RB on one block)      DFT -> x H (real, with the re/im swap of the inverse) -> DFT, in place
+//   stage A' (DIT, radix RA)              reads the padded blocks, writes the column for the bulk store
+// Three shared-memory round trips per plane instead of five, two of six twiddle passes.  The layouts on the two
+// sides of stage A differ, so every thread holds its whole butterfly across a barrier (one butterfly per thread:
+// CB x RB <= threads).  Column kx = 0 (DC + Nyquist of the row transform, which mixes k and -k) is left to the
+// first-generation kernel, launched for that one column.
+// =============================================================================================
+#ifndef FFTC2_THREADS
+#define FFTC2_THREADS 256
+#endif
+// floats per block of H: = 4 (mod 8), so that the LDS.128 of a quarter warp (consecutive blocks) fall into different banks
+#define FFTC2_HSTRIDE(RB) ((RB) + ((4 - ((RB) & 7)) & 7))
+// float2 per padded column: RA blocks of RB + 1, rounded up to = 4 (mod 16): 16-byte aligned for the bulk copies, and
+// the butterflies of a warp that straddles two columns in stage A stay on different banks
+#define FFTC2_CSTRIDE(RA, RB) ((RA) * ((RB) + 1) + ((4 - (((RA) * ((RB) + 1)) & 15)) & 15))
+
+// DIF stage A of k_fft_cols2 on natural-order data -> padded blocks: all loads, barrier, then the stores
+// (the two layouts overlap in shared memory).  Thread = butterfly bj of column bc; idle when bc >= nseq.
+template <int RA, int RB>
+__device__ __forceinline__ void cols2_stage_a(float2* data, const float2* __restrict__ stwA, int bc, int bj, int nseq) {
+    constexpr int BS = RB + 1, CS = FFTC2_CSTRIDE(RA, RB);
+    // every thread loads and transforms (idle ones a duplicate of the last live column: values that are defined on
+    // one side of the barrier only make ptxas spill the whole butterfly around it); only the stores are predicated
+    float2 v[RA];
+    const bool on = bc < nseq;
+    float2* p = data + (size_t)(on ? bc : nseq - 1) * CS + bj;
+#pragma unroll
+    for (int m = 0; m < RA; ++m) v[m] = p[m * RB];
+    __syncthreads();
+    Dft<RA>::run(v);
+    if (on) p[0] = v[0];
+#pragma unroll
+    for (int q = 1; q < RA; ++q) {
+        const float2 t = c_mul(v[q], __ldg(stwA + (q - 1) * RB + bj));
+        if (on) p[q * BS] = t;
+    }
+    __syncthreads();
+}
+
+template <int RA, int RB>
+__global__ void __launch_bounds__(FFTC2_THREADS, 2)
+k_fft_cols2(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int* __restrict__ list,
+            const int* __restrict__ count, int C, int NX, int CB, const float2* __restrict__ twX,
+            const float2* __restrict__ stwA, float a3, float a2, float a1, float b0) {
+    constexpr int NY = RA * RB, BS = RB + 1, CS = FFTC2_CSTRIDE(RA, RB);
+    constexpr int HS = FFTC2_HSTRIDE(RB), HC = RA * HS;
+    extern __shared__ __align__(16) unsigned char smraw[];
+    float2* data = reinterpret_cast<float2*>(smraw);                         // [CB][CS]
+    float* Hs = reinterpret_cast<float*>(data + (size_t)CB * CS);            // [CB][RA][HS]
+    float2* Rk = reinterpret_cast<float2*>(Hs + (size_t)CB * HC);            // [CB][13]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(Rk + CB * 13 + 1);
+    bar = reinterpret_cast<uint64_t*>(((uintptr_t)bar + 7) & ~(uintptr_t)7);
+    const int tid = threadIdx.x;
+    const int half = NX >> 1;
+    const int nblk = (half - 1 + CB - 1) / CB;          // blocks over columns 1 .. half - 1
+    const int total = count[0] * nblk;
+    const float scale = 1.0f / ((float)NX * (float)NY);
+    uint32_t phase = 0;
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    // this thread's butterfly of stage A / A': column bc, position bj (idle when bc >= ncol)
+    const int bc = tid / RB, bj = tid - bc * RB;
+
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int slot = w / nblk;
+        const int cb = w - slot * nblk;
+        const int im = list[slot];
+        const ImgKernel* K = kern + im;
+        const int kx0 = 1 + cb * CB;
+        const int ncol = min(CB, half - kx0);
+
+        // R[col][dy] = sum_dx K[dy][dx] exp(-2 pi i kx dx / NX), dy = 0..12 (R[-dy] = conj R[dy]: point-symmetric taps);
+        // two threads per (col, dy): dx <= 0 and dx > 0
+        for (int base = 0; base < CB * 13 * 2; base += FFTC2_THREADS) {
+            const int i2 = base + tid;
+            const int idx = i2 >> 1, part = i2 & 1;
+            const int col = idx / 13, dy = idx - col * 13;
+            float2 acc = make_float2(0.f, 0.f);
+            if (idx < CB * 13 && col < ncol) {
+                const int kx = kx0 + col;
+                const int dx0 = part ? 1 : -PB_PAD;
+                unsigned t = ((unsigned)kx * (unsigned)(dx0 + NX)) % (unsigned)NX;
+                const float* kr = &K->k[(dy + PB_PAD) * PB_KS + dx0 + PB_PAD];
+                float kv[PB_PAD + 1];
+                float2 e[PB_PAD + 1];
+#pragma unroll
+                for (int u = 0; u <= PB_PAD; ++u) {
+                    const bool on = part ? (u < PB_PAD) : true;          // 13 taps below, 12 above
+                    kv[u] = on ? __ldg(kr + u) : 0.f;
+                    e[u] = on ? __ldg(twX + t) : make_float2(0.f, 0.f);
+                    t += kx;
+                    if (t >= (unsigned)NX) t -= NX;
+                }
+                if (dy == 0 && !part) kv[PB_PAD] -= 1.0f;     // spectrum of D = K - I (small where K^ ~ 1)
+#pragma unroll
+                for (int u = 0; u <= PB_PAD; ++u) {
+                    acc.x = fmaf(kv[u], e[u].x, acc.x);
+                    acc.y = fmaf(kv[u], e[u].y, acc.y);
+                }
+            }
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 1);
+            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 1);
+            if (!part && idx < CB * 13) Rk[idx] = acc;
+        }
+        // K^(ky, kx) = length-NY DFT of the sparse sequence r[dy mod NY] = R[dy]; real, so two columns share one
+        // complex transform, run through the same two stages: the result arrives in the slot order of the data
+        const int nseq = (ncol + 1) >> 1;
+        for (int idx = tid; idx < nseq * CS; idx += FFTC2_THREADS) {
+            const int q = idx / CS;
+            data[(size_t)q * CS + (idx - q * CS)] = make_float2(0.f, 0.f);
+        }
+        __syncthreads();
+        for (int idx = tid; idx < nseq * PB_KS; idx += FFTC2_THREADS) {
+            const int q = idx / PB_KS, d = idx - q * PB_KS - PB_PAD;
+            const int ca = 2 * q, cb2 = 2 * q + 1;
+            const int ad = d < 0 ? -d : d;
+            float2 ra = Rk[ca * 13 + ad];
+            float2 rb = make_float2(0.f, 0.f);
+            if (cb2 < ncol) rb = Rk[cb2 * 13 + ad];
+            if (d < 0) {
+                ra.y = -ra.y;
+                rb.y = -rb.y;
+            }
+            data[(size_t)q * CS + (d < 0 ? d + NY : d)] = make_float2(ra.x - rb.y, ra.y + rb.x);
+        }
+        __syncthreads();
+        cols2_stage_a<RA, RB>(data, stwA, bc, bj, nseq);
+        // last DIF stage of the kernel spectra on each padded block, then Hs[col][block][q] = scale * P(K^)
+        for (int idx = tid; idx < nseq * RA; idx += FFTC2_THREADS) {
+            const int f = idx / RA, blk = idx - f * RA;
+            float2* p = data + (size_t)f * CS + blk * BS;
+            float2 v[RB];
+#pragma unroll
+            for (int m = 0; m < RB; ++m) v[m] = p[m];
+            Dft<RB>::run(v);
+            float* h0 = Hs + (size_t)(2 * f) * HC + blk * HS;
+            const bool two = 2 * f + 1 < ncol;
+#pragma unroll
+            for (int m = 0; m < RB; ++m) {
+                // a3..b0 hold c3, c2, c1, 1 of the D = K - I form: H = 1 + D^ (c1 + D^ (c2 + c3 D^))
+                h0[m] = fmaf(fmaf(fmaf(a3, v[m].x, a2), v[m].x, a1), v[m].x, b0) * scale;
+                if (two) h0[HC + m] = fmaf(fmaf(fmaf(a3, v[m].y, a2), v[m].y, a1), v[m].y, b0) * scale;
+            }
+        }
+        __syncthreads();
+
+        float2* Z0 = Z + ((size_t)slot * C * half + kx0) * NY;
+        if (tid == 0) {
+            fence_async_smem();
+            mbar_expect_tx(bar, (uint32_t)((size_t)ncol * NY * sizeof(float2)));
+            for (int col = 0; col < ncol; ++col)
+                bulk_g2s(data + (size_t)col * CS, Z0 + (size_t)col * NY, (uint32_t)(NY * sizeof(float2)), bar);
+        }
+        for (int c = 0; c < C; ++c) {
+            float2* Zc = Z0 + (size_t)c * half * NY;
+            mbar_wait(bar, phase);
+            phase ^= 1;
+            cols2_stage_a<RA, RB>(data, stwA, bc, bj, ncol);
+            // middle: DFT_RB -> y = H z with the re/im swap -> DFT_RB, on one padded block per thread
+            for (int idx = tid; idx < ncol * RA; idx += FFTC2_THREADS) {
+                const int f = idx / RA, blk = idx - f * RA;
+                float2* p = data + (size_t)f * CS + blk * BS;
+                float2 v[RB];
+#pragma unroll
+                for (int m = 0; m < RB; ++m) v[m] = p[m];
+                Dft<RB>::run(v);
+                const float4* h4 = reinterpret_cast<const float4*>(Hs + (size_t)f * HC + blk * HS);
+#pragma unroll
+                for (int m4 = 0; m4 < RB / 4; ++m4) {
+                    const float4 h = h4[m4];
+                    v[4 * m4 + 0] = make_float2(h.x * v[4 * m4 + 0].y, h.x * v[4 * m4 + 0].x);
+                    v[4 * m4 + 1] = make_float2(h.y * v[4 * m4 + 1].y, h.y * v[4 * m4 + 1].x);
+                    v[4 * m4 + 2] = make_float2(h.z * v[4 * m4 + 2].y, h.z * v[4 * m4 + 2].x);
+                    v[4 * m4 + 3] = make_float2(h.w * v[4 * m4 + 3].y, h.w * v[4 * m4 + 3].x);
+                }
+                Dft<RB>::run(v);
+#pragma unroll
+                for (int m = 0; m < RB; ++m) p[m] = v[m];
+            }
+            __syncthreads();
+            // DIT stage A': padded blocks -> natural order.  All loads, barrier, then the stores.
+            {
+                float2 v[RA];
+                const bool on = bc < ncol;
+                float2* p = data + (size_t)(on ? bc : ncol - 1) * CS + bj;
+                v[0] = p[0];
+#pragma unroll
+                for (int q = 1; q < RA; ++q) v[q] = c_mul(p[q * BS], __ldg(stwA + (q - 1) * RB + bj));
+                __syncthreads();
+                Dft<RA>::run(v);
+#pragma unroll
+                for (int m = 0; m < RA; ++m)
+                    if (on) p[m * RB] = v[m];
+            }
+            fence_async_smem();
+            __syncthreads();
+            if (tid == 0) {
+                for (int col = 0; col < ncol; ++col)
+                    bulk_s2g(Zc + (size_t)col * NY, data + (size_t)col * CS, (uint32_t)(NY * sizeof(float2)));
+                bulk_commit();
+                bulk_wait_all();
+                if (c + 1 < C) {
+                    const float2* Zn = Zc + (size_t)half * NY;
+                    mbar_expect_tx(bar, (uint32_t)((size_t)ncol * NY * sizeof(float2)));
+                    for (int col = 0; col < ncol; ++col)
+                        bulk_g2s(data + (size_t)col * CS, Zn + (size_t)col * NY, (uint32_t)(NY * sizeof(float2)), bar);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // ---- host side ------------------------------------------------------------------------------
 
 // Torus length for n samples: the even m in [n, 1.1 n] with the cheapest plan, cost = m x
@@ -606,6 +1142,8 @@ size_t fft_engine_workspace(int B, int C, int H, int W, int pad, FftEngineLayout
     l.off_slotX = take((size_t)l.NX * sizeof(int));
     l.off_slotY = take((size_t)l.NY * sizeof(int));
     l.off_freqY = take((size_t)l.NY * sizeof(int));
+    l.off_unitsX = take((size_t)(l.NX / 2 + 2) * sizeof(int4));
+    l.off_stwY2 = take((size_t)l.NY * sizeof(float2));
     l.off_Z = take((size_t)B * C * (l.NX / 2) * l.NY * sizeof(float2));
     l.total = o;
     if (L) *L = l;
@@ -626,6 +1164,7 @@ int fft_engine_prepare(char* base, const FftEngineLayout& L, FftEngineTables* T,
     T->slotX = reinterpret_cast<int*>(base + L.off_slotX);
     T->slotY = reinterpret_cast<int*>(base + L.off_slotY);
     T->freqY = reinterpret_cast<int*>(base + L.off_freqY);
+    T->unitsX = reinterpret_cast<int4*>(base + L.off_unitsX);
     T->Z = reinterpret_cast<float2*>(base + L.off_Z);
     jobs->add(TJ_TWIDDLES, L.NX, T->twX, nullptr, nullptr);
     jobs->add(TJ_TWIDDLES, L.NY, T->twY, nullptr, nullptr);
@@ -633,6 +1172,23 @@ int fft_engine_prepare(char* base, const FftEngineLayout& L, FftEngineTables* T,
     jobs->add(TJ_STAGE_TW, T->planY.tw_total, T->stwY, nullptr, &T->planY);
     jobs->add(TJ_PERM, L.NX, T->slotX, nullptr, &T->planX);
     jobs->add(TJ_PERM, L.NY, T->slotY, T->freqY, &T->planY);
+    jobs->add(TJ_UNITS, 256, T->unitsX, nullptr, &T->planX);
+    T->stwY2 = reinterpret_cast<float2*>(base + L.off_stwY2);
+    T->ra2 = T->rb2 = 0;
+    if (L.NY == 36 * 32) {              // two-stage column plans with a compiled kernel (k_fft_cols2<RA, RB>)
+        const bool big_first = env_int("PB_FFT_RA36", 1) != 0;      // measured: 1.92 ms against 2.02 ms per step (C2)
+        T->ra2 = big_first ? 36 : 32;
+        T->rb2 = big_first ? 32 : 36;
+    }
+    if (T->ra2) {
+        Fft2Plan p2;
+        p2.n = L.NY;
+        p2.ns = 2;
+        p2.radix[0] = T->ra2;
+        p2.radix[1] = T->rb2;
+        fft2_plan_offsets(&p2);
+        jobs->add(TJ_STAGE_TW, p2.tw_total, T->stwY2, nullptr, &p2);
+    }
     return PB_OK;
 }
 
@@ -664,27 +1220,72 @@ int launch_deconv_fft(const float* img, float* out, const ImgKernel* kern, const
                                                                                G.clamp_out);                     \
         }                                                                                                        \
     } while (0)
+    // second-generation row passes (fused first / last stages) for the compile-time plans
+#define PB_FFT_ROWS2(SP, NYC)                                                                                         \
+    do {                                                                                                         \
+        auto kf = k_fft_rows_fwd2<SP, NYC>;                                                                      \
+        auto ki = k_fft_rows_inv2<SP, NYC>;                                                                      \
+        PB_CUDA_TRY(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));      \
+        PB_CUDA_TRY(cudaFuncSetAttribute(ki, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));      \
+        if (fwd) {                                                                                               \
+            ProfScope prof(PROF_FFT_ROWS_FWD, stream);                                                           \
+            kf<<<grid_rows, FFTD_THREADS, smem_rows, stream>>>(img, T.Z, kern, list, count, C, H, W, nb, T.stwX,  \
+                                                               T.unitsX, G);                                     \
+        } else {                                                                                                 \
+            ProfScope prof(PROF_FFT_ROWS_INV, stream);                                                           \
+            ki<<<grid_rows, FFTD_THREADS, smem_rows, stream>>>(T.Z, out, kern, list, count, C, H, W, nb, T.stwX,  \
+                                                               T.unitsX, G.clamp_out);                           \
+        }                                                                                                        \
+    } while (0)
 #define PB_FFT_COLS(SP)                                                                                          \
     do {                                                                                                         \
         PB_CUDA_TRY(cudaFuncSetAttribute(k_fft_cols<SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols)); \
         ProfScope prof(PROF_FFT_COLS, stream);                                                                   \
         k_fft_cols<SP><<<grid_cols, FFTC_THREADS, smem_cols, stream>>>(T.Z, kern, list, count, C, NX, NY, CB, T.planY, \
-                                                                       T.twX, T.stwY, T.slotY, a3, a2, a1, b0);  \
+                                                                       T.twX, T.stwY, T.slotY, a3, a2, a1, b0, 0); \
     } while (0)
+    // second-generation column pass: columns 1 .. NX/2 - 1 by k_fft_cols2, column 0 by the first-generation kernel
+#define PB_FFT_COLS2(RA, RB)                                                                                     \
+    do {                                                                                                         \
+        const int CB2 = FFTC2_THREADS / (RB) < 8 ? FFTC2_THREADS / (RB) : 8;                                     \
+        const int cb2 = env_int("PB_FFT_CB2", 7) < CB2 ? env_int("PB_FFT_CB2", 7) : CB2;                         \
+        const size_t cs2 = FFTC2_CSTRIDE(RA, RB);                                                                \
+        const size_t smem2 = cb2 * cs2 * sizeof(float2) + (size_t)cb2 * (RA) * FFTC2_HSTRIDE(RB) * sizeof(float) + \
+                             (size_t)cb2 * 13 * sizeof(float2) + 64;                                             \
+        const size_t smem0 = (size_t)NY * 12 + (size_t)NY * 8 + 2 * 13 * 8 + 64;                                 \
+        const long long items2 = (long long)B * ((NX / 2 - 1 + cb2 - 1) / cb2);                                  \
+        const int grid2 = (int)(items2 < 2 * PB_NUM_SMS ? items2 : 2 * PB_NUM_SMS);                              \
+        PB_CUDA_TRY(cudaFuncSetAttribute(k_fft_cols2<RA, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); \
+        PB_CUDA_TRY(cudaFuncSetAttribute(k_fft_cols<NoStaticPlan>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0)); \
+        ProfScope prof(PROF_FFT_COLS, stream);                                                                   \
+        k_fft_cols2<RA, RB><<<grid2, FFTC2_THREADS, smem2, stream>>>(T.Z, kern, list, count, C, NX, cb2, T.twX, T.stwY2, \
+                                                                     a3, a2, a1, b0);                            \
+        k_fft_cols<NoStaticPlan><<<B < cap ? B : cap, FFTC_THREADS, smem0, stream>>>(T.Z, kern, list, count, C, NX, NY, 1, \
+                                                                     T.planY, T.twX, T.stwY, T.slotY, a3, a2, a1, b0, 1); \
+    } while (0)
+    static const bool rows_v1 = env_int("PB_FFT_ROWS_V1", 0) != 0;     // A/B against the first-generation passes
+    static const bool cols_v1 = env_int("PB_FFT_COLS_V1", 0) != 0;
     for (int pass = 0; pass < 3; ++pass) {
         const bool fwd = pass == 0;
         if (pass == 1) {
-            if (PlanY1152::matches(T.planY)) PB_FFT_COLS(PlanY1152);
+            if (T.ra2 == 36 && T.rb2 == 32 && !cols_v1) PB_FFT_COLS2(36, 32);
+            else if (T.ra2 == 32 && T.rb2 == 36 && !cols_v1) PB_FFT_COLS2(32, 36);
+            else if (PlanY1152::matches(T.planY)) PB_FFT_COLS(PlanY1152);
             else if (PlanY2304::matches(T.planY)) PB_FFT_COLS(PlanY2304);
             else PB_FFT_COLS(NoStaticPlan);
         } else {
-            if (PlanX2016::matches(T.planX)) PB_FFT_ROWS(PlanX2016);
-            else if (PlanX4000::matches(T.planX)) PB_FFT_ROWS(PlanX4000);
-            else PB_FFT_ROWS(NoStaticPlan);
+            // (the second-generation kernels also fix NY at compile time: the 1080p and 4K tori)
+            if (PlanX2016::matches(T.planX)) {
+                if (rows_v1 || NY != 1152) PB_FFT_ROWS(PlanX2016); else PB_FFT_ROWS2(PlanX2016, 1152);
+            } else if (PlanX4000::matches(T.planX)) {
+                if (rows_v1 || NY != 2304) PB_FFT_ROWS(PlanX4000); else PB_FFT_ROWS2(PlanX4000, 2304);
+            } else PB_FFT_ROWS(NoStaticPlan);
         }
     }
 #undef PB_FFT_ROWS
+#undef PB_FFT_ROWS2
 #undef PB_FFT_COLS
+#undef PB_FFT_COLS2
     PB_LAUNCH_CHECK("fft deconvolution passes");
     return PB_OK;
 }

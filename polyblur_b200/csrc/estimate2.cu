@@ -47,9 +47,54 @@ __global__ void k_fft2_stage_tw(float2* __restrict__ stw, Fft2Plan plan) {
     if (i < plan.tw_total) stw[i] = fft2_stage_twiddle(i, plan);
 }
 
+// Mirror units of a plan (used by the FFT engine's row passes, deconv_fft.cu): the last DIF stage (M = 1) leaves
+// the frequencies k = f_A + (n / R_last) q, q < R_last, in the R_last contiguous slots of block A, and their
+// mirrors n - k all lie in ONE other block B = mirror(A) (the digit-wise negation with carry of A's index), at
+// position R_last - 1 - q (block 0 mirrors onto itself at (R_last - q) mod R_last).  One thread that owns a unit
+// {A, B} therefore holds every pair {Z[k], Z[n - k]} it needs to separate (forward) or rebuild (inverse) the
+// spectra of the two real rows packed into one complex transform, in registers.
+//   out[0] = (number of units, R_last, n / R_last, 0);  out[1 + u] = (A, B, f_A, 0), A <= B, ascending A.
+__device__ void build_mirror_units(const TableJob& J) {
+    __shared__ int s_warp[8];
+    __shared__ int s_base;
+    const Fft2Plan& plan = J.plan;
+    const int n = plan.n, RL = plan.radix[plan.ns - 1], NB = n / RL;
+    int4* out = static_cast<int4*>(J.out);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int base = 0; base < NB; base += 256) {
+        const int a = base + tid;
+        int flag = 0, B = 0, fA = 0;
+        if (a < NB) {
+            fA = fft2_freq_of_slot(a * RL, plan);
+            B = fft2_slot_of_freq((n - fA) % n, plan) / RL;
+            flag = a <= B;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, flag);
+        if (lane == 0) s_warp[w] = __popc(bal);
+        __syncthreads();
+        int off = s_base + __popc(bal & ((1u << lane) - 1u));
+        for (int i = 0; i < w; ++i) off += s_warp[i];
+        if (flag) out[1 + off] = make_int4(a, B, fA, 0);
+        __syncthreads();
+        if (tid == 0) {
+            int t = 0;
+            for (int i = 0; i < 8; ++i) t += s_warp[i];
+            s_base += t;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) out[0] = make_int4(s_base, RL, NB, 0);
+}
+
 // all tables of one API call in one launch: blockIdx.y = job
 __global__ void __launch_bounds__(256) k_table_jobs(const TableJobs jobs) {
     const TableJob& J = jobs.job[blockIdx.y];
+    if (J.kind == TJ_UNITS) {
+        if (blockIdx.x == 0) build_mirror_units(J);
+        return;
+    }
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= J.n) return;
     switch (J.kind) {

@@ -215,6 +215,13 @@ template <> struct Dft<12> { static PB_HD void run(float2 (&v)[12]) { DftAB<3, 4
 template <> struct Dft<14> { static PB_HD void run(float2 (&v)[14]) { DftAB<2, 7>::run(v); } };
 template <> struct Dft<15> { static PB_HD void run(float2 (&v)[15]) { DftAB<3, 5>::run(v); } };
 template <> struct Dft<16> { static PB_HD void run(float2 (&v)[16]) { DftAB<4, 4>::run(v); } };
+// large radices of the two-stage column plans (deconv_fft.cu k_fft_cols2): 64-72 data registers per thread
+template <> struct Dft<18> { static PB_HD void run(float2 (&v)[18]) { DftAB<2, 9>::run(v); } };
+template <> struct Dft<20> { static PB_HD void run(float2 (&v)[20]) { DftAB<4, 5>::run(v); } };
+template <> struct Dft<24> { static PB_HD void run(float2 (&v)[24]) { DftAB<3, 8>::run(v); } };
+template <> struct Dft<30> { static PB_HD void run(float2 (&v)[30]) { DftAB<5, 6>::run(v); } };
+template <> struct Dft<32> { static PB_HD void run(float2 (&v)[32]) { DftAB<4, 8>::run(v); } };
+template <> struct Dft<36> { static PB_HD void run(float2 (&v)[36]) { DftAB<4, 9>::run(v); } };
 
 // Odd primes 11 and 13: direct O(R^2) sum with constant twiddles (rare sizes only).
 template <int R>

@@ -109,6 +109,47 @@ PB_HD void s_mid_stage(float2* x, int stride, int nb, int tid, int nthr, const f
     }
 }
 
+// ---- fused first / last stages (see fft2_dif_first / fft2_dit_last in fft2.cuh) ---------------------
+// The first DIF stage (sub-length N) reads every sample exactly once and the last DIT stage writes every
+// sample exactly once, at x[j + m M] with j running over consecutive threads: a functor feeds / drains
+// them straight from / to global memory (coalesced over j), so a kernel needs no staging pass through
+// shared memory and no separate output pass.
+//     Src::load<R, M>(int f, int j, float2 (&v)[R])         v[m] = sample j + m M of sequence f
+//     Dst::store<R, M>(int f, int j, const float2 (&v)[R])  v[m] = result j + m M of sequence f
+template <int R, int M, int N, class Src>
+PB_HD void s_dif_first(float2* x, int stride, int nb, const float2* __restrict__ stw, int tid, int nthr, Src& src) {
+    static_assert(R * M == N, "first stage works on the whole sequence");
+    const int total = nb * M;
+    for (int idx = tid; idx < total; idx += nthr) {
+        const int f = idx / M;
+        const int j = idx - f * M;
+        float2 v[R];
+        src.template load<R, M>(f, j, v);
+        Dft<R>::run(v);
+        float2* p = x + f * stride + j;
+        p[0] = v[0];
+#pragma unroll
+        for (int q = 1; q < R; ++q) p[q * M] = (M == 1) ? v[q] : c_mul(v[q], PB_LDG(stw + (q - 1) * M + j));
+    }
+}
+
+template <int R, int M, int N, class Dst>
+PB_HD void s_dit_last(const float2* x, int stride, int nb, const float2* __restrict__ stw, int tid, int nthr, Dst& dst) {
+    static_assert(R * M == N, "last stage works on the whole sequence");
+    const int total = nb * M;
+    for (int idx = tid; idx < total; idx += nthr) {
+        const int f = idx / M;
+        const int j = idx - f * M;
+        const float2* p = x + f * stride + j;
+        float2 v[R];
+        v[0] = p[0];
+#pragma unroll
+        for (int q = 1; q < R; ++q) v[q] = (M == 1) ? p[q] : c_mul(p[q * M], PB_LDG(stw + (q - 1) * M + j));
+        Dft<R>::run(v);
+        dst.template store<R, M>(f, j, v);
+    }
+}
+
 // ---- drivers (compile-time recursion over the stages) ---------------------------------------
 template <class P, int S, int COUNT, bool WARP>
 struct SDifRun {     // DIF stages S, S+1, ... (COUNT of them)

@@ -149,8 +149,8 @@ def test_every_method_gives_the_fft_result(pb):
     a = pb.deblurring.inverse_filtering_rank3(cu(st["deconv/in"]), cu(st["kern/k"]), alpha=6, b=1, method="direct")
     b = pb.deblurring.inverse_filtering_rank3(cu(st["deconv/in"]), cu(st["kern/k"]), alpha=6, b=1, method="fft")
     assert torch.equal(a, b) and maxabs(a.cpu().numpy(), st["deconv/a6b1"]) < 3e-6
-    mod = pb.PolyblurDeblurring(method="direct_separable")
-    assert torch.equal(mod(x, n_iter=3, alpha=6, beta=1, b=0.768), outs["fft"])
+    mod = pb.PolyblurDeblurring()
+    assert torch.equal(mod(x, n_iter=3, alpha=6, beta=1, b=0.768, method="direct_separable"), outs["fft"])
     with pytest.raises(ValueError):
         pb.polyblur_deblurring(x, method="winograd")
 
