@@ -69,6 +69,9 @@ __device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t by
                  "r"(bytes)
                  : "memory");
 }
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // Waits until the bulk stores have READ their shared-memory source (the buffer may be reused); the
 // global writes need no further ordering inside this kernel (nobody re-reads Z before the next
@@ -377,13 +380,15 @@ k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int
         }
 
         float2* Z0 = Z + ((size_t)slot * C * half + kx0) * NY;
+        // first_block_only: one CTA per plane (blockIdx.y), so that the single column of every plane runs in parallel
+        const int c_begin = first_block_only ? (int)blockIdx.y : 0, c_end = first_block_only ? (int)blockIdx.y + 1 : C;
         if (tid == 0) {
             fence_async_smem();
             mbar_expect_tx(bar, (uint32_t)((size_t)ncol * NY * sizeof(float2)));
             for (int col = 0; col < ncol; ++col)
-                bulk_g2s(data + (size_t)col * NY, Z0 + (size_t)col * NY, (uint32_t)(NY * sizeof(float2)), bar);
+                bulk_g2s(data + (size_t)col * NY, Z0 + ((size_t)c_begin * half + col) * NY, (uint32_t)(NY * sizeof(float2)), bar);
         }
-        for (int c = 0; c < C; ++c) {
+        for (int c = c_begin; c < c_end; ++c) {
             float2* Zc = Z0 + (size_t)c * half * NY;
             mbar_wait(bar, phase);
             phase ^= 1;
@@ -418,7 +423,7 @@ k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int
                 bulk_wait_all();
                 // the buffer has been read out: fetch the next plane right away, the other threads
                 // go straight to the mbarrier
-                if (c + 1 < C) {
+                if (c + 1 < c_end) {
                     const float2* Zn = Zc + (size_t)half * NY;
                     mbar_expect_tx(bar, (uint32_t)((size_t)ncol * NY * sizeof(float2)));
                     for (int col = 0; col < ncol; ++col)
@@ -883,7 +888,7 @@ k_fft_rows_inv2(const float2* __restrict__ Z, float* __restrict__ out, const Img
 // DIF stage A of k_fft_cols2 on natural-order data -> padded blocks: all loads, barrier, then the stores
 // (the two layouts overlap in shared memory).  Thread = butterfly bj of column bc; idle when bc >= nseq.
 template <int RA, int RB>
-__device__ __forceinline__ void cols2_stage_a(float2* data, const float2* __restrict__ stwA, int bc, int bj, int nseq) {
+__device__ __forceinline__ void cols2_stage_a(float2* data, const float2* stwA, int bc, int bj, int nseq) {
     constexpr int BS = RB + 1, CS = FFTC2_CSTRIDE(RA, RB);
     // every thread loads and transforms (idle ones a duplicate of the last live column: values that are defined on
     // one side of the barrier only make ptxas spill the whole butterfly around it); only the stores are predicated
@@ -897,7 +902,7 @@ __device__ __forceinline__ void cols2_stage_a(float2* data, const float2* __rest
     if (on) p[0] = v[0];
 #pragma unroll
     for (int q = 1; q < RA; ++q) {
-        const float2 t = c_mul(v[q], __ldg(stwA + (q - 1) * RB + bj));
+        const float2 t = c_mul(v[q], stwA[(q - 1) * RB + bj]);
         if (on) p[q * BS] = t;
     }
     __syncthreads();
@@ -914,7 +919,8 @@ k_fft_cols2(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const in
     float2* data = reinterpret_cast<float2*>(smraw);                         // [CB][CS]
     float* Hs = reinterpret_cast<float*>(data + (size_t)CB * CS);            // [CB][RA][HS]
     float2* Rk = reinterpret_cast<float2*>(Hs + (size_t)CB * HC);            // [CB][13]
-    uint64_t* bar = reinterpret_cast<uint64_t*>(Rk + CB * 13 + 1);
+    float2* tws = Rk + CB * 13;                                              // [(RA - 1) RB] stage-A twiddles
+    uint64_t* bar = reinterpret_cast<uint64_t*>(tws + (RA - 1) * RB + 1);
     bar = reinterpret_cast<uint64_t*>(((uintptr_t)bar + 7) & ~(uintptr_t)7);
     const int tid = threadIdx.x;
     const int half = NX >> 1;
@@ -923,6 +929,9 @@ k_fft_cols2(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const in
     const float scale = 1.0f / ((float)NX * (float)NY);
     uint32_t phase = 0;
     if (tid == 0) mbar_init(bar, 1);
+    // the stage twiddles stay in shared memory for the life of the (persistent) CTA: with ~20 KB of L1 left beside
+    // the 2 x 110 KB of shared memory, the table reads of stage A / A' kept missing it (long-scoreboard stalls)
+    for (int i = tid; i < (RA - 1) * RB; i += FFTC2_THREADS) tws[i] = __ldg(stwA + i);
     __syncthreads();
     // this thread's butterfly of stage A / A': column bc, position bj (idle when bc >= ncol)
     const int bc = tid / RB, bj = tid - bc * RB;
@@ -990,7 +999,7 @@ k_fft_cols2(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const in
             data[(size_t)q * CS + (d < 0 ? d + NY : d)] = make_float2(ra.x - rb.y, ra.y + rb.x);
         }
         __syncthreads();
-        cols2_stage_a<RA, RB>(data, stwA, bc, bj, nseq);
+        cols2_stage_a<RA, RB>(data, tws, bc, bj, nseq);
         // last DIF stage of the kernel spectra on each padded block, then Hs[col][block][q] = scale * P(K^)
         for (int idx = tid; idx < nseq * RA; idx += FFTC2_THREADS) {
             const int f = idx / RA, blk = idx - f * RA;
@@ -1021,7 +1030,22 @@ k_fft_cols2(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const in
             float2* Zc = Z0 + (size_t)c * half * NY;
             mbar_wait(bar, phase);
             phase ^= 1;
-            cols2_stage_a<RA, RB>(data, stwA, bc, bj, ncol);
+            if (tid == 32) {
+                // the next plane's columns (or the first plane of this CTA's next work item) on their way into L2
+                // while this one is transformed: the bulk load, issued once the buffer is free again, finds them there
+                const float2* Zn = nullptr;
+                int ncn = ncol;
+                if (c + 1 < C) {
+                    Zn = Zc + (size_t)half * NY;
+                } else if (w + (int)gridDim.x < total) {
+                    const int w2 = w + gridDim.x, slot2 = w2 / nblk, kx2 = 1 + (w2 - slot2 * nblk) * CB;
+                    Zn = Z + ((size_t)slot2 * C * half + kx2) * NY;
+                    ncn = min(CB, half - kx2);
+                }
+                if (Zn)
+                    for (int col = 0; col < ncn; ++col) bulk_prefetch_l2(Zn + (size_t)col * NY, (uint32_t)(NY * sizeof(float2)));
+            }
+            cols2_stage_a<RA, RB>(data, tws, bc, bj, ncol);
             // middle: DFT_RB -> y = H z with the re/im swap -> DFT_RB, on one padded block per thread
             for (int idx = tid; idx < ncol * RA; idx += FFTC2_THREADS) {
                 const int f = idx / RA, blk = idx - f * RA;
@@ -1051,7 +1075,7 @@ k_fft_cols2(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const in
                 float2* p = data + (size_t)(on ? bc : ncol - 1) * CS + bj;
                 v[0] = p[0];
 #pragma unroll
-                for (int q = 1; q < RA; ++q) v[q] = c_mul(p[q * BS], __ldg(stwA + (q - 1) * RB + bj));
+                for (int q = 1; q < RA; ++q) v[q] = c_mul(p[q * BS], tws[(q - 1) * RB + bj]);
                 __syncthreads();
                 Dft<RA>::run(v);
 #pragma unroll
@@ -1251,7 +1275,7 @@ int launch_deconv_fft(const float* img, float* out, const ImgKernel* kern, const
         const int cb2 = env_int("PB_FFT_CB2", 7) < CB2 ? env_int("PB_FFT_CB2", 7) : CB2;                         \
         const size_t cs2 = FFTC2_CSTRIDE(RA, RB);                                                                \
         const size_t smem2 = cb2 * cs2 * sizeof(float2) + (size_t)cb2 * (RA) * FFTC2_HSTRIDE(RB) * sizeof(float) + \
-                             (size_t)cb2 * 13 * sizeof(float2) + 64;                                             \
+                             (size_t)cb2 * 13 * sizeof(float2) + (size_t)((RA) - 1) * (RB) * sizeof(float2) + 64;  \
         const size_t smem0 = (size_t)NY * 12 + (size_t)NY * 8 + 2 * 13 * 8 + 64;                                 \
         const long long items2 = (long long)B * ((NX / 2 - 1 + cb2 - 1) / cb2);                                  \
         const int grid2 = (int)(items2 < 2 * PB_NUM_SMS ? items2 : 2 * PB_NUM_SMS);                              \
@@ -1260,7 +1284,7 @@ int launch_deconv_fft(const float* img, float* out, const ImgKernel* kern, const
         ProfScope prof(PROF_FFT_COLS, stream);                                                                   \
         k_fft_cols2<RA, RB><<<grid2, FFTC2_THREADS, smem2, stream>>>(T.Z, kern, list, count, C, NX, cb2, T.twX, T.stwY2, \
                                                                      a3, a2, a1, b0);                            \
-        k_fft_cols<NoStaticPlan><<<B < cap ? B : cap, FFTC_THREADS, smem0, stream>>>(T.Z, kern, list, count, C, NX, NY, 1, \
+        k_fft_cols<NoStaticPlan><<<dim3(B < cap ? B : cap, C), FFTC_THREADS, smem0, stream>>>(T.Z, kern, list, count, C, NX, NY, 1, \
                                                                      T.planY, T.twX, T.stwY, T.slotY, a3, a2, a1, b0, 1); \
     } while (0)
     static const bool rows_v1 = env_int("PB_FFT_ROWS_V1", 0) != 0;     // A/B against the first-generation passes

@@ -133,6 +133,14 @@ int launch_table_jobs(const TableJobs& jobs, cudaStream_t stream) {
     return PB_OK;
 }
 
+// s / 3 correctly rounded: q = RN(s y), r = s - 3 q (exact in an FMA), q' = RN(q + r y), y = RN(1/3)
+__device__ __forceinline__ float pb_div3(float s) {
+    const float y = 0x1.555556p-2f;
+    const float q = __fmul_rn(s, y);
+    const float r = __fmaf_rn(-3.0f, q, s);
+    return __fmaf_rn(r, y, q);
+}
+
 #ifndef R2_THREADS
 #define R2_THREADS 256
 #endif
@@ -174,6 +182,12 @@ k_rows2(const float* __restrict__ img, float* __restrict__ gray, float* __restri
     const float qlo = qn ? qrange[2 * im] : 0.f;
     const float qden = qn ? __fsub_rn(qrange[2 * im + 1], qlo) : 1.f;
 #define PB_QNORM(v) fminf(fmaxf(__fdiv_rn(__fsub_rn((v), qlo), qden), 0.0f), 1.0f)
+    // channel mean = sum / C, correctly rounded like the reference's (blur_estimation.py:36-37).  C = 3: Markstein's
+    // FMA correction of s * RN(1/3) -- bit-identical to the IEEE division for every float (checked exhaustively,
+    // tools/ubench/div3_exhaustive.c) at 3 instructions instead of ~12; C = 2, 4: exact scalings; else the division.
+    const int cmode = (C == 3) ? 3 : (C == 2 || C == 4) ? 2 : (C == 1 ? 1 : 0);
+    const float cscale = 1.0f / fC;
+#define PB_CMEAN(s) (cmode == 3 ? pb_div3(s) : cmode == 2 ? __fmul_rn((s), cscale) : cmode == 1 ? (s) : __fdiv_rn((s), fC))
 
     if ((W & 3) == 0) {
         const int w4 = W >> 2;
@@ -230,12 +244,10 @@ k_rows2(const float* __restrict__ img, float* __restrict__ gray, float* __restri
                             g[h].z = __fadd_rn(g[h].z, v.z);
                             g[h].w = __fadd_rn(g[h].w, v.w);
                         }
-                        if (C > 1) {
-                            g[h].x = __fdiv_rn(g[h].x, fC);
-                            g[h].y = __fdiv_rn(g[h].y, fC);
-                            g[h].z = __fdiv_rn(g[h].z, fC);
-                            g[h].w = __fdiv_rn(g[h].w, fC);
-                        }
+                        g[h].x = PB_CMEAN(g[h].x);
+                        g[h].y = PB_CMEAN(g[h].y);
+                        g[h].z = PB_CMEAN(g[h].z);
+                        g[h].w = PB_CMEAN(g[h].w);
                         if (qn) g[h] = make_float4(PB_QNORM(g[h].x), PB_QNORM(g[h].y), PB_QNORM(g[h].z), PB_QNORM(g[h].w));
                         *reinterpret_cast<float4*>(gray + (size_t)im * plane + (size_t)y * W + xx[u]) = g[h];
                         lmin = fminf(lmin, fminf(fminf(g[h].x, g[h].y), fminf(g[h].z, g[h].w)));
@@ -262,7 +274,7 @@ k_rows2(const float* __restrict__ img, float* __restrict__ gray, float* __restri
                     g[h] = __ldg(q);
                     if (EST) {
                         for (int c = 1; c < C; ++c) g[h] = __fadd_rn(g[h], __ldg(q + (size_t)c * plane));
-                        if (C > 1) g[h] = __fdiv_rn(g[h], fC);
+                        g[h] = PB_CMEAN(g[h]);
                         if (qn) g[h] = PB_QNORM(g[h]);
                         gray[(size_t)im * plane + (size_t)y * W + x] = g[h];
                         lmin = fminf(lmin, g[h]);
@@ -274,6 +286,7 @@ k_rows2(const float* __restrict__ img, float* __restrict__ gray, float* __restri
         }
     }
 #undef PB_QNORM
+#undef PB_CMEAN
     __syncthreads();
     // forward, multiply by i omega, inverse -- the two innermost stages fused in registers; SP = a
     // compile-time plan for the standard widths (fft2_static.cuh), else the run-time core
@@ -398,36 +411,40 @@ k_cols2(const float* __restrict__ plane_in, const float* __restrict__ gx, float*
     const float* gxp = gx + (size_t)im * plane;
     // saturation mask: un-normalised gray > 0.99 (blur_estimation.py:59, 83-88)
     const float* msk = (mask_src ? mask_src : plane_in) + (size_t)im * plane;
-    // four pixel pairs per trip: the d/dx (and mask) loads of all four are in flight before the first use
+    // Four pixel pairs per trip, the d/dx (and mask) loads of all four in flight before the first use.  Pixels
+    // that do not count (beyond the right edge, saturated) enter as gx = gy = 0: |0| never raises a maximum that
+    // starts at 0, so the inner loop has no branches.  Angle 0 has cos = 1, sin = 0: the value is gx itself.
     for (int base = tid; base < H * nb; base += 4 * THREADS) {
-        float2 zz[4], gxx[4], grr[4];
-        int cnt[4];                      // live pixels of the pair: 0, 1 or 2
+        float2 zz[4], gxx[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int idx = base + u * THREADS;
-            cnt[u] = 0;
             gxx[u] = make_float2(0.f, 0.f);
-            grr[u] = make_float2(0.f, 0.f);
             zz[u] = make_float2(0.f, 0.f);
             if (idx < H * nb) {
                 const int y = fast_div(idx, nb, inv_nb);
                 const int p = idx - y * nb;
                 const int x = x0 + 2 * p;
                 if (x < W) {
-                    cnt[u] = (x + 1 < W) ? 2 : 1;
                     const size_t o = (size_t)y * W + x;
+                    float2 gr = make_float2(0.f, 0.f);
                     if (vec2) {
                         gxx[u] = __ldcs(reinterpret_cast<const float2*>(gxp + o));    // read once: evict-first (-3.6 % measured)
-                        if (discard_saturation) grr[u] = __ldg(reinterpret_cast<const float2*>(msk + o));
+                        if (discard_saturation) gr = __ldg(reinterpret_cast<const float2*>(msk + o));
                     } else {
                         gxx[u].x = __ldg(gxp + o);
-                        if (cnt[u] == 2) gxx[u].y = __ldg(gxp + o + 1);
+                        if (x + 1 < W) gxx[u].y = __ldg(gxp + o + 1);
                         if (discard_saturation) {
-                            grr[u].x = __ldg(msk + o);
-                            if (cnt[u] == 2) grr[u].y = __ldg(msk + o + 1);
+                            gr.x = __ldg(msk + o);
+                            if (x + 1 < W) gr.y = __ldg(msk + o + 1);
                         }
                     }
                     zz[u] = sm2[(size_t)p * stride + y];
+                    if (x + 1 >= W) zz[u].x = 0.f;               // .x carries d/dy of the pair's second column
+                    if (discard_saturation) {
+                        if (gr.x > 0.99f) { gxx[u].x = 0.f; zz[u].y = 0.f; }
+                        if (gr.y > 0.99f) { gxx[u].y = 0.f; zz[u].x = 0.f; }
+                    }
                 }
             }
         }
@@ -435,13 +452,11 @@ k_cols2(const float* __restrict__ plane_in, const float* __restrict__ gx, float*
         for (int u = 0; u < 4; ++u) {
             const float gyv[2] = {zz[u].y * inv, zz[u].x * inv};
             const float gxv[2] = {gxx[u].x, gxx[u].y};
-            const float gr[2] = {grr[u].x, grr[u].y};
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                if (h >= cnt[u]) continue;
-                if (discard_saturation && gr[h] > 0.99f) continue;
+                m[0] = fmaxf(m[0], fabsf(gxv[h]));
 #pragma unroll
-                for (int j = 0; j < 7; ++j) {
+                for (int j = 1; j < 7; ++j) {
                     const float v = __fsub_rn(__fmul_rn(cs7[j], gxv[h]), __fmul_rn(sn7[j], gyv[h]));
                     m[j] = fmaxf(m[j], fabsf(v));
                 }
