@@ -76,21 +76,29 @@ class GraphedPolyblur:
         y = g(x)            # copies x into the static input, replays, returns the static output
     """
 
-    def __init__(self, shape, device=None, **kw):
+    def __init__(self, shape, device=None, params=None, uint8_io=False, **kw):
         B, Cn, H, W = shape
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        self.params = _make_params(kw.pop("n_iter", 1), kw.pop("c", 0.352), kw.pop("b", 0.768), kw.pop("alpha", 2),
-                                   kw.pop("beta", 3), kw.pop("sigma_r", 0.8), kw.pop("sigma_s", 2.0),
-                                   kw.pop("ker_size", 25), kw.pop("q", 0.0), kw.pop("remove_halo", False),
-                                   kw.pop("edgetaping", False), kw.pop("prefiltering", False),
-                                   kw.pop("discard_saturation", False), **kw)
+        if params is not None:
+            self.params = _lib.PbParams.from_buffer_copy(bytes(params))
+        else:
+            self.params = _make_params(kw.pop("n_iter", 1), kw.pop("c", 0.352), kw.pop("b", 0.768), kw.pop("alpha", 2),
+                                       kw.pop("beta", 3), kw.pop("sigma_r", 0.8), kw.pop("sigma_s", 2.0),
+                                       kw.pop("ker_size", 25), kw.pop("q", 0.0), kw.pop("remove_halo", False),
+                                       kw.pop("edgetaping", False), kw.pop("prefiltering", False),
+                                       kw.pop("discard_saturation", False), **kw)
         if self.params.n_iter < 1:
             raise ValueError("n_iter must be >= 1")
+        self.uint8_io = bool(uint8_io)
         with torch.cuda.device(dev):
             self.x = torch.zeros(B, Cn, H, W, dtype=torch.float32, device=dev)
             self.out = torch.empty_like(self.x)
             self.ws = _lib.workspace(B, Cn, H, W, self.params, dev)
             self.x.uniform_(0, 1)                 # a non-constant image for the warm-up call
+            if self.uint8_io:
+                # 8-bit HWC in / out (csrc/io.cu) inside the same graph: x_u8 -> x -> Polyblur -> out -> out_u8
+                self.x_u8 = (self.x.permute(0, 2, 3, 1) * 255).to(torch.uint8).contiguous()
+                self.out_u8 = torch.empty_like(self.x_u8)
             side = torch.cuda.Stream(dev)
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):
@@ -102,15 +110,98 @@ class GraphedPolyblur:
 
     def _enqueue(self, stream):
         B, Cn, H, W = self.x.shape
+        if self.uint8_io:
+            _lib.check(_lib.lib().pb_u8hwc_to_f32nchw(self.x_u8.data_ptr(), self.x.data_ptr(), B, H, W, Cn, stream),
+                       "pb_u8hwc_to_f32nchw")
         rc = _lib.lib().pb_polyblur_f32(self.x.data_ptr(), self.out.data_ptr(), B, Cn, H, W, C.byref(self.params),
                                         self.ws.data_ptr(), self.ws.numel(), None, stream)
         _lib.check(rc, "pb_polyblur_f32")
+        if self.uint8_io:
+            _lib.check(_lib.lib().pb_f32nchw_to_u8hwc(self.out.data_ptr(), self.out_u8.data_ptr(), B, Cn, H, W, stream),
+                       "pb_f32nchw_to_u8hwc")
 
     def __call__(self, x=None):
         if x is not None:
-            self.x.copy_(x, non_blocking=True)
+            (self.x_u8 if self.uint8_io and x.dtype == torch.uint8 else self.x).copy_(x, non_blocking=True)
         self.graph.replay()
-        return self.out
+        return self.out_u8 if self.uint8_io else self.out
+
+
+# ---- host <-> device pipeline with cached, graph-captured chunk engines --------------------------------------------
+# The chunked host paths (CPU tensor in -> CPU tensor out) run one engine call per chunk.  Enqueueing a chunk eagerly
+# costs ~60 launches with idle gaps between the small kernels (4 x 8 images: 9.4 ms against 8.0 ms for one call of 32,
+# tools/e2e_probe.py) and allocates staging buffers per call.  Instead every (device, chunk shape, parameters, 8-bit?)
+# gets two GraphedPolyblur engines (double buffering) that are kept across calls: the copies go straight into / out of
+# their static buffers and a chunk is one graph launch.  A small LRU bounds the device memory this holds.
+_ENGINE_CACHE: "dict[tuple, list]" = {}
+_ENGINE_CACHE_MAX_BYTES = 24 << 30          # device memory the cached engines may hold (per process)
+
+
+def clear_cache() -> None:
+    """Drops the cached chunk engines (graphs, staging buffers, workspaces) of the host pipelines."""
+    _ENGINE_CACHE.clear()
+
+
+def _chunk_engines(dev: torch.device, shape, p: "_lib.PbParams", uint8_io: bool):
+    key = (dev.index, tuple(shape), bytes(p), bool(uint8_io))
+    hit = _ENGINE_CACHE.pop(key, None)
+    if hit is None:
+        hit = [GraphedPolyblur(shape, device=dev, params=p, uint8_io=uint8_io) for _ in range(2)]
+    _ENGINE_CACHE[key] = hit                       # most recently used last
+
+    def held(engs):
+        return sum(t.numel() * t.element_size() for g in engs for t in (g.x, g.out, g.ws))
+
+    while len(_ENGINE_CACHE) > 1 and sum(held(v) for v in _ENGINE_CACHE.values()) > _ENGINE_CACHE_MAX_BYTES:
+        _ENGINE_CACHE.pop(next(iter(_ENGINE_CACHE)))
+    return hit
+
+
+def _run_host_pipeline(x: torch.Tensor, host: torch.Tensor, sizes, p: "_lib.PbParams", dev: torch.device,
+                       uint8_io: bool):
+    """x, host: pinned CPU tensors, (B,C,H,W) float32 or (B,H,W,C) uint8; chunks of ``sizes`` images flow through
+    three streams: H2D of chunk k+1 | graph of chunk k | D2H of chunk k-1.  One host synchronisation at the end."""
+    bounds = [0]
+    for n_k in sizes:
+        bounds.append(bounds[-1] + n_k)
+    with torch.cuda.device(dev):
+        s_in, s_run, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        start = torch.cuda.current_stream(dev).record_event()
+        for st in (s_in, s_run, s_out):
+            st.wait_stream(torch.cuda.current_stream(dev))
+        del start
+        # every chunk size's engines exist (captured on first use) before the first copy is in flight
+        engines = {}
+        for n in sorted(set(sizes)):
+            shape = (n, x.shape[3], x.shape[1], x.shape[2]) if uint8_io else (n,) + tuple(x.shape[1:])
+            engines[n] = _chunk_engines(dev, shape, p, uint8_io)
+        used = {}                                   # (size, slot) -> [event: input consumed, event: output copied]
+        for k, (a, b) in enumerate(zip(bounds, bounds[1:])):
+            n = b - a
+            slot = sum(1 for kk in range(k) if bounds[kk + 1] - bounds[kk] == n) & 1
+            g = engines[n][slot]
+            ev = used.setdefault((n, slot), [None, None])
+            gin = g.x_u8 if uint8_io else g.x
+            gout = g.out_u8 if uint8_io else g.out
+            with torch.cuda.stream(s_in):
+                if ev[0] is not None:
+                    s_in.wait_event(ev[0])
+                gin.copy_(x[a:b], non_blocking=True)
+                loaded = s_in.record_event()
+            with torch.cuda.stream(s_run):
+                s_run.wait_event(loaded)
+                if ev[1] is not None:
+                    s_run.wait_event(ev[1])
+                g.graph.replay()
+                done = s_run.record_event()
+                ev[0] = done
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(done)
+                host[a:b].copy_(gout, non_blocking=True)
+                ev[1] = s_out.record_event()
+        s_out.synchronize()
+        s_run.synchronize()
+    return host
 
 
 def polyblur_deblurring(img, n_iter=1, c=0.352, b=0.768, alpha=2, beta=3, sigma_r=0.8, sigma_s=2.0,
@@ -186,62 +277,22 @@ def polyblur_deblurring(img, n_iter=1, c=0.352, b=0.768, alpha=2, beta=3, sigma_
 
 
 def _polyblur_host_pipelined(x: torch.Tensor, p: "_lib.PbParams", dev: torch.device, max_chunks: int = 16,
-                             ramp=()):
+                             ramp=(1,)):
     """CPU tensor in -> CPU tensor out with the PCIe transfers hidden behind the kernels.
 
     Images are independent, so the batch is cut into chunks that flow through three streams:
-    host->device copy of chunk k+1, the Polyblur kernels of chunk k and the device->host copy of
-    chunk k-1 run concurrently (the link is full duplex).  Results are identical to the one-shot
-    path; the only host synchronisation is the final one."""
+    host->device copy of chunk k+1, the Polyblur kernels of chunk k (one CUDA-graph launch of a cached
+    engine) and the device->host copy of chunk k-1 run concurrently (the link is full duplex).  Results are
+    identical to the one-shot path; the only host synchronisation is the final one."""
     B = x.shape[0]
     x = x.contiguous()
     if not x.is_pinned():
         x = x.pin_memory()
-    # float32 over PCIe is the bottleneck (1.6 GB per 32 x 1080p step against 8 ms of kernels): many small
-    # chunks (measured with tools/e2e_probe.py: 16 uniform chunks 19.1 ms against 15.9 ms for the bare
-    # concurrent copies; smaller first / last chunks did not help)
+    # float32 over PCIe is the bottleneck (1.6 GB per 32 x 1080p step against 7 ms of kernels): many small chunks,
+    # with one-image chunks first and last so that only 1/B of the transfer is not overlapped
     sizes = sharding.pipeline_chunks(B, -(-B // max(1, min(max_chunks, B))), ramp)
-    bounds = [0]
-    for n_k in sizes:
-        bounds.append(bounds[-1] + n_k)
     host = torch.empty(x.shape, dtype=torch.float32, pin_memory=True)
-    with torch.cuda.device(dev):
-        s_in, s_run, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-        start = torch.cuda.current_stream(dev).record_event()
-        for st in (s_in, s_run, s_out):
-            st.wait_event(start)
-        biggest = max(b - a for a, b in zip(bounds, bounds[1:]))
-        Cn, H, W = x.shape[1:]
-        # two device input / output buffers (double buffering); one workspace, reused in stream order
-        xin = [torch.empty(biggest, Cn, H, W, dtype=torch.float32, device=dev) for _ in range(2)]
-        yout = [torch.empty(biggest, Cn, H, W, dtype=torch.float32, device=dev) for _ in range(2)]
-        ws = _lib.workspace(biggest, Cn, H, W, p, dev)
-        free_in = [None, None]      # event: the kernels that read xin[i] are done
-        free_out = [None, None]     # event: the copy that read yout[i] is done
-        for k, (a, b) in enumerate(zip(bounds, bounds[1:])):
-            i = k & 1
-            n = b - a
-            with torch.cuda.stream(s_in):
-                if free_in[i] is not None:
-                    s_in.wait_event(free_in[i])
-                xin[i][:n].copy_(x[a:b], non_blocking=True)
-                loaded = s_in.record_event()
-            with torch.cuda.stream(s_run):
-                s_run.wait_event(loaded)
-                if free_out[i] is not None:
-                    s_run.wait_event(free_out[i])
-                rc = _lib.lib().pb_polyblur_f32(xin[i].data_ptr(), yout[i].data_ptr(), n, Cn, H, W, C.byref(p),
-                                                ws.data_ptr(), ws.numel(), None, s_run.cuda_stream)
-                _lib.check(rc, "pb_polyblur_f32")
-                done = s_run.record_event()
-                free_in[i] = done
-            with torch.cuda.stream(s_out):
-                s_out.wait_event(done)
-                host[a:b].copy_(yout[i][:n], non_blocking=True)
-                free_out[i] = s_out.record_event()
-        s_out.synchronize()
-        s_run.synchronize()
-    return host
+    return _run_host_pipeline(x, host, sizes, p, dev, uint8_io=False)
 
 
 def inverse_filtering_rank3(img, kernel, alpha=2, b=4, correlate=False, remove_halo=False,

@@ -85,51 +85,14 @@ def deblur_uint8(images, n_iter=1, c=0.352, b=0.768, alpha=2, beta=3, sigma_r=0.
 
 
 def _host_pipeline_u8(x: torch.Tensor, p, dev: torch.device, max_chunks: int, ramp=(2,)) -> torch.Tensor:
-    B, H, W, Cn = x.shape
+    """(B,H,W,C) uint8 CPU tensor in -> same out.  One byte per sample over PCIe: the kernels are the bottleneck, so
+    few large chunks for their efficiency (each is one CUDA-graph launch of a cached engine: conversion, Polyblur,
+    conversion -- deblurring._run_host_pipeline), with small chunks first and last so that the kernels start early and
+    the copy left over at the end is short."""
+    from .deblurring import _run_host_pipeline
+    B = x.shape[0]
     if not x.is_pinned():
         x = x.pin_memory()
     host = torch.empty(x.shape, dtype=torch.uint8, pin_memory=True)
-    # one byte per sample over PCIe: the kernels are the bottleneck, so few large chunks for their
-    # efficiency, with a 2-image chunk first and last so that they start early and the tail copy is short
-    # (tools/e2e_probe.py: 13.3 ms against 13.7 ms for 4 uniform chunks at 32 x 1080p)
     sizes = sharding.pipeline_chunks(B, -(-B // max(1, min(max_chunks, B))), ramp)
-    bounds = [0]
-    for n_k in sizes:
-        bounds.append(bounds[-1] + n_k)
-    biggest = max(b - a for a, b in zip(bounds, bounds[1:]))
-    s_in, s_run, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    start = torch.cuda.current_stream(dev).record_event()
-    for st in (s_in, s_run, s_out):
-        st.wait_event(start)
-    xin = [torch.empty(biggest, H, W, Cn, dtype=torch.uint8, device=dev) for _ in range(2)]
-    yout = [torch.empty(biggest, H, W, Cn, dtype=torch.uint8, device=dev) for _ in range(2)]
-    xf = torch.empty(biggest, Cn, H, W, dtype=torch.float32, device=dev)
-    yf = torch.empty_like(xf)
-    ws = _lib.workspace(biggest, Cn, H, W, p, dev)
-    free_in = [None, None]
-    free_out = [None, None]
-    for k, (a, b) in enumerate(zip(bounds, bounds[1:])):
-        i, n = k & 1, b - a
-        with torch.cuda.stream(s_in):
-            if free_in[i] is not None:
-                s_in.wait_event(free_in[i])
-            xin[i][:n].copy_(x[a:b], non_blocking=True)
-            loaded = s_in.record_event()
-        with torch.cuda.stream(s_run):
-            s_run.wait_event(loaded)
-            if free_out[i] is not None:
-                s_run.wait_event(free_out[i])
-            _convert_in(xin[i][:n], xf[:n], s_run.cuda_stream)
-            free_in[i] = s_run.record_event()
-            rc = _lib.lib().pb_polyblur_f32(xf.data_ptr(), yf.data_ptr(), n, Cn, H, W, C.byref(p), ws.data_ptr(),
-                                            ws.numel(), None, s_run.cuda_stream)
-            _lib.check(rc, "pb_polyblur_f32")
-            _convert_out(yf[:n], yout[i][:n], s_run.cuda_stream)
-            done = s_run.record_event()
-        with torch.cuda.stream(s_out):
-            s_out.wait_event(done)
-            host[a:b].copy_(yout[i][:n], non_blocking=True)
-            free_out[i] = s_out.record_event()
-    s_out.synchronize()
-    s_run.synchronize()
-    return host
+    return _run_host_pipeline(x, host, sizes, p, dev, uint8_io=True)
