@@ -204,6 +204,20 @@ PB_API int pb_recursive_filter_f32(const float* img, const float* joint, float* 
 PB_API int pb_u8hwc_to_f32nchw(const uint8_t* in, float* out, int B, int H, int W, int C, void* stream);
 PB_API int pb_f32nchw_to_u8hwc(const float* in, uint8_t* out, int B, int C, int H, int W, void* stream);
 
+/* Patch decomposition of PolyblurDeblurring.forward (deblurring.py:269-340) on the device.
+ * Geometry (all in pixels): the (h, w) image -- already cropped to even sides, :273-279; plane_stride / row_stride
+ * in floats address it inside a larger allocation -- is centre-padded (replicate, :282-287, :368-377) by pad_top /
+ * pad_left to the patch grid of ny x nx patches of ph x pw stepping by step_h / step_w.
+ *   pb_patch_extract_f32: patches[(p * B + b)][c][y][x], p = iy * nx + ix  (the order of the reference's torch.cat)
+ *   pb_patch_blend_f32:   out (B,C,h,w) = clamp(sum_p patches_p w / (sum_p w + 1e-8), 0, 1), w[y][x] = win_y[y] win_x[x]
+ *                         (:312-339 overlap-add with build_window :349-366, summed in patch order, then cropped). */
+PB_API int pb_patch_extract_f32(const float* img, size_t plane_stride, size_t row_stride, float* patches, int B, int C,
+                         int h, int w, int ph, int pw, int step_h, int step_w, int ny, int nx, int pad_top,
+                         int pad_left, void* stream);
+PB_API int pb_patch_blend_f32(const float* patches, const float* win_y, const float* win_x, float* out, int B, int C,
+                       int h, int w, int ph, int pw, int step_h, int step_w, int ny, int nx, int pad_top,
+                       int pad_left, void* stream);
+
 /* Domain-transform normalized convolution: the reference's native prototype
  * normalized_convolution(I, sigma_s, sigma_r, num_iterations) (polyblur/domain_transform/NC.cpp:143-204,
  * exported at :210), here for any batch size and channel count.

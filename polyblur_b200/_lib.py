@@ -80,6 +80,8 @@ _SIGS = {
                                           C.c_float, C.c_int, _P, C.c_size_t, _P]),
     "pb_u8hwc_to_f32nchw": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "pb_f32nchw_to_u8hwc": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "pb_patch_extract_f32": (C.c_int, [_P, C.c_size_t, C.c_size_t, _P] + [C.c_int] * 12 + [_P]),
+    "pb_patch_blend_f32": (C.c_int, [_P, _P, _P, _P] + [C.c_int] * 12 + [_P]),
     "pb_normalized_convolution_f32": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                                 C.c_float, C.c_int, _P, C.c_size_t, _P]),
 }

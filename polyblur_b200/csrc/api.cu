@@ -1001,6 +1001,46 @@ int pb_normalized_convolution_f32(const float* img, float* out, int B, int C, in
                                          workspace, (cudaStream_t)stream_);
 }
 
+static int check_patch_geometry(int B, int C, int h, int w, int ph, int pw, int step_h, int step_w, int ny, int nx,
+                                int pad_top, int pad_left) {
+    if (B < 1 || C < 1 || h < 1 || w < 1 || ph < 1 || pw < 1 || step_h < 1 || step_w < 1 || ny < 1 || nx < 1 ||
+        pad_top < 0 || pad_left < 0 || step_h > ph || step_w > pw) {
+        set_error("bad patch geometry");
+        return PB_ERR_ARG;
+    }
+    // the patch grid must cover the padded image
+    if ((ny - 1) * step_h + ph < h + pad_top || (nx - 1) * step_w + pw < w + pad_left) {
+        set_error("patch grid %d x %d does not cover the padded %d x %d image", ny, nx, h, w);
+        return PB_ERR_ARG;
+    }
+    return PB_OK;
+}
+
+int pb_patch_extract_f32(const float* img, size_t plane_stride, size_t row_stride, float* patches, int B, int C, int h,
+                         int w, int ph, int pw, int step_h, int step_w, int ny, int nx, int pad_top, int pad_left,
+                         void* stream_) {
+    int rc;
+    if ((rc = check_patch_geometry(B, C, h, w, ph, pw, step_h, step_w, ny, nx, pad_top, pad_left))) return rc;
+    if (!img || !patches) {
+        set_error("null pointer");
+        return PB_ERR_ARG;
+    }
+    return launch_patch_extract(img, plane_stride, row_stride, patches, B, C, h, w, ph, pw, step_h, step_w, ny, nx, pad_top,
+                                pad_left, (cudaStream_t)stream_);
+}
+
+int pb_patch_blend_f32(const float* patches, const float* win_y, const float* win_x, float* out, int B, int C, int h, int w,
+                       int ph, int pw, int step_h, int step_w, int ny, int nx, int pad_top, int pad_left, void* stream_) {
+    int rc;
+    if ((rc = check_patch_geometry(B, C, h, w, ph, pw, step_h, step_w, ny, nx, pad_top, pad_left))) return rc;
+    if (!patches || !win_y || !win_x || !out) {
+        set_error("null pointer");
+        return PB_ERR_ARG;
+    }
+    return launch_patch_blend(patches, win_y, win_x, out, B, C, h, w, ph, pw, step_h, step_w, ny, nx, pad_top, pad_left,
+                              (cudaStream_t)stream_);
+}
+
 int pb_u8hwc_to_f32nchw(const uint8_t* in, float* out, int B, int H, int W, int C, void* stream_) {
     int rc;
     if ((rc = check_shape(B, C, H, W))) return rc;

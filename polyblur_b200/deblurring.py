@@ -165,11 +165,12 @@ def _run_host_pipeline(x: torch.Tensor, host: torch.Tensor, sizes, p: "_lib.PbPa
     for n_k in sizes:
         bounds.append(bounds[-1] + n_k)
     with torch.cuda.device(dev):
-        s_in, s_run, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-        start = torch.cuda.current_stream(dev).record_event()
-        for st in (s_in, s_run, s_out):
+        # two compute streams, chunks alternate between them: the kernels of a chunk are persistent grids that end in
+        # a partial wave (a chunk of 8 images is 3.9 waves of the column pass), and the other chunk's kernels fill it
+        s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        s_runs = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+        for st in [s_in, s_out] + s_runs:
             st.wait_stream(torch.cuda.current_stream(dev))
-        del start
         # every chunk size's engines exist (captured on first use) before the first copy is in flight
         engines = {}
         for n in sorted(set(sizes)):
@@ -188,8 +189,11 @@ def _run_host_pipeline(x: torch.Tensor, host: torch.Tensor, sizes, p: "_lib.PbPa
                     s_in.wait_event(ev[0])
                 gin.copy_(x[a:b], non_blocking=True)
                 loaded = s_in.record_event()
+            s_run = s_runs[k & 1]
             with torch.cuda.stream(s_run):
                 s_run.wait_event(loaded)
+                if ev[0] is not None:
+                    s_run.wait_event(ev[0])         # the engine's previous replay (it may have run on the other stream)
                 if ev[1] is not None:
                     s_run.wait_event(ev[1])
                 g.graph.replay()
@@ -200,7 +204,8 @@ def _run_host_pipeline(x: torch.Tensor, host: torch.Tensor, sizes, p: "_lib.PbPa
                 host[a:b].copy_(gout, non_blocking=True)
                 ev[1] = s_out.record_event()
         s_out.synchronize()
-        s_run.synchronize()
+        for st in s_runs:
+            st.synchronize()
     return host
 
 
@@ -392,37 +397,63 @@ class PolyblurDeblurring(nn.Module):
             raise TypeError(f"float32 only (got {images.dtype}), like the reference")
         src_device = images.device
         dev = _lib.require_cuda(images)
-        x = images.detach().to(dev)
+        x = images.detach().to(dev).contiguous()
+        nimg, Cn, H0, W0 = x.shape
         ph, pw = self.patch_size
-        # even dimensions (:273-279), replicate pad to a whole number of steps (:282-287)
-        h, w = x.shape[-2:]
-        if h % 2 == 1:
-            x = x[..., :-1, :]
-            h -= 1
-        if w % 2 == 1:
-            x = x[..., :, :-1]
-            w -= 1
+        # even dimensions (:273-279: the last row / column is dropped), centre replicate pad to a whole number of
+        # steps (:282-287) -- both as index arithmetic inside the extraction kernel, nothing is copied
+        h, w = H0 - (H0 % 2), W0 - (W0 % 2)
         step_h = int(ph * (1 - self.patch_overlap))
         step_w = int(pw * (1 - self.patch_overlap))
+        if step_h < 1 or step_w < 1:
+            raise ValueError("patch_overlap leaves no step between patches")
         new_h = int(np.ceil((h - ph) / step_h) * step_h) + ph
         new_w = int(np.ceil((w - pw) / step_w) * step_w) + pw
-        padded = self.pad_with_new_size(x, (new_h, new_w), mode='replicate')
-        H2, W2 = padded.shape[-2:]
-        coords = [(i0, j0) for i0 in range(0, H2 - ph + 1, step_h) for j0 in range(0, W2 - pw + 1, step_w)]
-        window = self.build_window((ph, pw), 'kaiser').to(dev)[None, None]
-        restored = torch.zeros_like(padded)
-        window_sum = torch.zeros(1, 1, H2, W2, device=dev)
-        nimg = x.shape[0]
-        for m in range(0, len(coords), max(1, self.batch_size)):
-            chunk = coords[m:m + max(1, self.batch_size)]
-            patches = torch.cat([padded[..., i0:i0 + ph, j0:j0 + pw] for (i0, j0) in chunk], dim=0).contiguous()
-            out = polyblur_deblurring(patches, **kw)
-            for n, (i0, j0) in enumerate(chunk):
-                restored[..., i0:i0 + ph, j0:j0 + pw] += out[n * nimg:(n + 1) * nimg] * window
-                window_sum[..., i0:i0 + ph, j0:j0 + pw] += window
-        restored = (restored / (window_sum + 1e-8)).clamp(0.0, 1.0)
-        restored = self.crop_with_old_size(restored, (h, w))
-        return restored.contiguous().to(src_device)
+        if new_h < h or new_w < w:
+            raise ValueError(f"patch_size {self.patch_size} is larger than the ({h}, {w}) image")
+        pad_top, pad_left = int(np.floor((new_h - h) / 2)), int(np.floor((new_w - w) / 2))
+        ny, nx = (new_h - ph) // step_h + 1, (new_w - pw) // step_w + 1
+        npatch = ny * nx
+        p = _make_params(n_iter, c, b, alpha, beta, sigma_r, sigma_s, ker_size, q, remove_halo, edgetaping,
+                         prefiltering, discard_saturation)
+        if method not in _METHODS:
+            raise ValueError(f"unknown method {method!r}; expected one of {_METHODS}")
+        if n_angles != 6 or n_interpolated_angles != 30:
+            raise ValueError("only n_angles=6 and n_interpolated_angles=30 work in the reference "
+                             "(SURVEY.md Appendix B.10); other values are rejected here")
+        with torch.cuda.device(dev):
+            st = _lib.stream_ptr(dev)
+            wy, wx = self._window_1d(ph, dev), self._window_1d(pw, dev)
+            patches = torch.empty(npatch * nimg, Cn, ph, pw, dtype=torch.float32, device=dev)
+            geom = (nimg, Cn, h, w, ph, pw, step_h, step_w, ny, nx, pad_top, pad_left)
+            rc = _lib.lib().pb_patch_extract_f32(x.data_ptr(), H0 * W0, W0, patches.data_ptr(), *geom, st)
+            _lib.check(rc, "pb_patch_extract_f32")
+            # every patch of every image is an independent "image" of the engine (its own blur estimate); the batch
+            # goes through in as few calls as ~1 GB of patches per call allows (results do not depend on the split)
+            done = torch.empty_like(patches)
+            per_call = max(1, min(patches.shape[0], (1 << 30) // (Cn * ph * pw * 4)))
+            if p.flags & _lib.FLAG_EDGETAPER_BATCHMAX:
+                # the reference's edgetaper normalises by the max over the patches of one call (edgetaper.py:15,21):
+                # keep its grouping, batch_size patch positions x the image batch
+                per_call = max(1, self.batch_size) * nimg
+            for a in range(0, patches.shape[0], per_call):
+                if p.n_iter == 0:
+                    done[a:a + per_call].copy_(patches[a:a + per_call])
+                else:
+                    polyblur_device(patches[a:a + per_call], p, out=done[a:a + per_call])
+            restored = torch.empty(nimg, Cn, h, w, dtype=torch.float32, device=dev)
+            rc = _lib.lib().pb_patch_blend_f32(done.data_ptr(), wy.data_ptr(), wx.data_ptr(), restored.data_ptr(), *geom, st)
+            _lib.check(rc, "pb_patch_blend_f32")
+        return restored.to(src_device)
+
+    _WINDOWS: dict = {}
+
+    def _window_1d(self, n, dev):
+        """torch.kaiser_window(n, beta=5, periodic=True) (deblurring.py:349-366), cached per length and device."""
+        key = (int(n), str(dev))
+        if key not in self._WINDOWS:
+            self._WINDOWS[key] = torch.kaiser_window(int(n), beta=5, periodic=True).to(dev).contiguous()
+        return self._WINDOWS[key]
 
     def build_window(self, image_size, window_type='kaiser'):
         """Separable 2-D window (deblurring.py:349-366)."""

@@ -84,7 +84,7 @@ def deblur_uint8(images, n_iter=1, c=0.352, b=0.768, alpha=2, beta=3, sigma_r=0.
     return out.numpy() if is_np else out
 
 
-def _host_pipeline_u8(x: torch.Tensor, p, dev: torch.device, max_chunks: int, ramp=(2,)) -> torch.Tensor:
+def _host_pipeline_u8(x: torch.Tensor, p, dev: torch.device, max_chunks: int, ramp=(2, 4)) -> torch.Tensor:
     """(B,H,W,C) uint8 CPU tensor in -> same out.  One byte per sample over PCIe: the kernels are the bottleneck, so
     few large chunks for their efficiency (each is one CUDA-graph launch of a cached engine: conversion, Polyblur,
     conversion -- deblurring._run_host_pipeline), with small chunks first and last so that the kernels start early and

@@ -53,6 +53,12 @@ def main():
         prefiltering=True, prefilter="rf")
     for kind in ("white", "mosaic"):
         run(f"C4 single 12000x9000 {kind}", synthetic.make(kind, 1, 3, 9000, 12000, device=dev), 5)
+    # patch decomposition on the device: one 4K image, 400-px patches, 25 % overlap = 7 x 13 patches
+    x4k = synthetic.make("mosaic", 1, 3, 2160, 3840, device=dev)
+    mod = pb.PolyblurDeblurring(patch_decomposition=True, patch_size=400, patch_overlap=0.25, batch_size=8)
+    ms = timed(lambda: mod(x4k, n_iter=3, alpha=6, beta=1, b=0.768))
+    print(json.dumps({"config": "f3 patch decomposition, 1 x 4K, 400-px patches (91 patches)", "n_iter": 3, "ms": round(ms, 3),
+                      "Mpix_s": round(2160 * 3840 / 1e6 / (ms / 1e3), 1)}), flush=True)
     # forward + backward on 8 x 1080p, with and without the estimator's gradient
     xb = synthetic.make("mosaic", 8, 3, 1080, 1920, device=dev)
     for flag in (True, False):
