@@ -94,7 +94,7 @@ int launch_bilateral(const float* img, float* out, int planes, int H, int W, flo
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_rf_weights(const float* __restrict__ joint, float* __restrict__ Vh, float* __restrict__ Vv, int C, int H, int W,
-             float a, float ratio) {
+             float log2a, float ratio) {
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
     const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (x >= W || y >= H) return;
@@ -107,22 +107,32 @@ k_rf_weights(const float* __restrict__ joint, float* __restrict__ Vh, float* __r
         if (y > 0) dy = __fadd_rn(dy, fabsf(__fsub_rn(v, __ldg(J + c * plane + (size_t)(y - 1) * W + x))));
     }
     const size_t o = (size_t)blockIdx.z * plane + (size_t)y * W + x;
-    Vh[o] = powf(a, __fadd_rn(1.0f, __fmul_rn(ratio, dx)));
-    Vv[o] = powf(a, __fadd_rn(1.0f, __fmul_rn(ratio, dy)));
+    // a ^ e = 2 ^ (e log2 a), log2 a rounded from the double on the host: exp2f is 2 ulp, the product adds
+    // |e log2 a| 2^-24 <~ 4e-7 relative for the exponents that occur -- against ~35 instructions of powf
+    Vh[o] = exp2f(__fmul_rn(__fadd_rn(1.0f, __fmul_rn(ratio, dx)), log2a));
+    Vv[o] = exp2f(__fmul_rn(__fadd_rn(1.0f, __fmul_rn(ratio, dy)), log2a));
 }
 
 // One warp = 32 consecutive rows of one plane, lane = row.  The rows are walked in tiles of 32
 // columns: the tile of F and of V is transposed through shared memory (coalesced 128-byte global
 // accesses, conflict-free 33-float pitch), every lane runs the reference's update on its row's 32
 // samples with the carry in a register, and the tile is written back.  Left -> right sweep, then
-// right -> left.
+// right -> left.  The recurrence is sequential along a row, so B*C*H lanes are all the parallelism there is
+// (a few warps per SM): the tiles are double buffered with cp.async, the next tile's 64 loads per lane are in
+// flight while the current one is filtered (was: four exposed load round trips per tile, 1.1 ms -> see profiles/).
 #define RF_ROW_WARPS 4
+
+__device__ __forceinline__ void rf_cp4(float* dst_smem, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src)
+                 : "memory");
+}
+__device__ __forceinline__ void rf_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void rf_cp_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 __global__ void __launch_bounds__(RF_ROW_WARPS * 32)
 k_rf_rows(const float* in, float* out, const float* __restrict__ Vh, int C, int H, int W,
           int groups_per_plane, int groups_total) {   // in may alias out (iterations >= 2)
-    __shared__ float tf[RF_ROW_WARPS][32][33];
-    __shared__ float tv[RF_ROW_WARPS][32][33];
+    extern __shared__ float rf_sm[];                  // [warps][2 buffers][F, V][32][33]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = blockIdx.x * RF_ROW_WARPS + warp;
     if (grp >= groups_total) return;
@@ -132,80 +142,82 @@ k_rf_rows(const float* in, float* out, const float* __restrict__ Vh, int C, int 
     const float* f_in = in + (size_t)pl * plane;
     float* f_out = out + (size_t)pl * plane;
     const float* v = Vh + (size_t)(pl / C) * plane;
-    float (*F)[33] = tf[warp];
-    float (*V)[33] = tv[warp];
+    float* base = rf_sm + (size_t)warp * 4 * 32 * 33;
     const int nrows = min(32, H - y0);
     const int ntiles = (W + 31) / 32;
-    // tile load: 8 rows of F and V in flight per lane before the first shared-memory store
-#define RF_LOAD_TILE(SRC)                                                           \
-    for (int r0 = 0; r0 < nrows; r0 += 8) {                                         \
-        float a_[8], b_[8];                                                         \
-        const int x = x0 + lane;                                                    \
-        _Pragma("unroll") for (int u = 0; u < 8; ++u) {                             \
-            const int r = min(r0 + u, nrows - 1);                                   \
-            const size_t o = (size_t)(y0 + r) * W + min(x, W - 1);                  \
-            a_[u] = (SRC)[o];                                                       \
-            b_[u] = __ldg(v + o);                                                   \
-        }                                                                           \
-        _Pragma("unroll") for (int u = 0; u < 8; ++u) {                             \
-            if (r0 + u < nrows) {                                                   \
-                F[r0 + u][lane] = a_[u];                                            \
-                V[r0 + u][lane] = b_[u];                                            \
-            }                                                                       \
-        }                                                                           \
-    }
+    // asynchronous transposing load of tile t of `src` and of V into buffer `buf` (clamped at the edges)
+    auto prefetch = [&](const float* src, int t, int buf) {
+        float* F = base + (size_t)buf * 2 * 32 * 33;
+        float* V = F + 32 * 33;
+        const int x = min(t * 32 + lane, W - 1);
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+            const size_t o = (size_t)(y0 + min(r, nrows - 1)) * W + x;
+            rf_cp4(F + r * 33 + lane, src + o);
+            rf_cp4(V + r * 33 + lane, v + o);
+        }
+        rf_cp_commit();
+    };
     // ---- left -> right:  F[x] += V[x] (F[x-1] - F[x]),  x >= 1
     float carry = 0.f;
+    prefetch(f_in, 0, 0);
     for (int t = 0; t < ntiles; ++t) {
         const int x0 = t * 32;
-        RF_LOAD_TILE(f_in);
+        float* F = base + (size_t)(t & 1) * 2 * 32 * 33;
+        float* V = F + 32 * 33;
+        rf_cp_wait_all();
         __syncwarp();
+        if (t + 1 < ntiles) prefetch(f_in, t + 1, (t + 1) & 1);
         if (lane < nrows) {
             const int n = min(32, W - x0);
 #pragma unroll 8
             for (int i = 0; i < n; ++i) {
-                float cur = F[lane][i];
-                if (x0 + i > 0) cur = __fadd_rn(cur, __fmul_rn(V[lane][i], __fsub_rn(carry, cur)));
-                F[lane][i] = cur;
+                float cur = F[lane * 33 + i];
+                if (x0 + i > 0) cur = __fadd_rn(cur, __fmul_rn(V[lane * 33 + i], __fsub_rn(carry, cur)));
+                F[lane * 33 + i] = cur;
                 carry = cur;
             }
         }
         __syncwarp();
         for (int r = 0; r < nrows; ++r) {
             const int x = x0 + lane;
-            if (x < W) f_out[(size_t)(y0 + r) * W + x] = F[r][lane];
+            if (x < W) f_out[(size_t)(y0 + r) * W + x] = F[r * 33 + lane];
         }
         __syncwarp();
     }
     // ---- right -> left:  F[x] += V[x+1] (F[x+1] - F[x]),  x <= W-2   (reads the sweep above back)
     float vnext = 0.f;                                    // V[x+1] of the sample just processed
+    __threadfence_block();
+    prefetch(f_out, ntiles - 1, (ntiles - 1) & 1);
     for (int t = ntiles - 1; t >= 0; --t) {
         const int x0 = t * 32;
-        RF_LOAD_TILE(f_out);
+        float* F = base + (size_t)(t & 1) * 2 * 32 * 33;
+        float* V = F + 32 * 33;
+        rf_cp_wait_all();
         __syncwarp();
+        if (t > 0) prefetch(f_out, t - 1, (t - 1) & 1);
         if (lane < nrows) {
             const int n = min(32, W - x0);
 #pragma unroll 8
             for (int i = n - 1; i >= 0; --i) {
-                float cur = F[lane][i];
+                float cur = F[lane * 33 + i];
                 if (x0 + i < W - 1) cur = __fadd_rn(cur, __fmul_rn(vnext, __fsub_rn(carry, cur)));
-                F[lane][i] = cur;
+                F[lane * 33 + i] = cur;
                 carry = cur;
-                vnext = V[lane][i];
+                vnext = V[lane * 33 + i];
             }
         }
         __syncwarp();
         for (int r = 0; r < nrows; ++r) {
             const int x = x0 + lane;
-            if (x < W) f_out[(size_t)(y0 + r) * W + x] = F[r][lane];
+            if (x < W) f_out[(size_t)(y0 + r) * W + x] = F[r * 33 + lane];
         }
         __syncwarp();
     }
 }
 
-#undef RF_LOAD_TILE
-
-// the same recurrence down the columns, one thread per column (coalesced); loads run 8 rows ahead
+// the same recurrence down the columns, one thread per column (coalesced); the loads of the next block of rows are
+// in flight (registers) while the current block is filtered
 __global__ void __launch_bounds__(128)
 k_rf_cols(float* __restrict__ img, const float* __restrict__ Vv, int C, int H, int W) {
     const int x = blockIdx.x * 128 + threadIdx.x;
@@ -216,13 +228,27 @@ k_rf_cols(float* __restrict__ img, const float* __restrict__ Vv, int C, int H, i
     const float* v = Vv + (size_t)(pl / C) * plane + x;
     constexpr int U = 8;
     float prev = f[0];
+    float nf[U], nv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int y = min(1 + u, H - 1);
+        nf[u] = f[(size_t)y * W];
+        nv[u] = __ldg(v + (size_t)y * W);
+    }
     for (int y0 = 1; y0 < H; y0 += U) {
         float cf[U], cv[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int y = min(y0 + u, H - 1);
-            cf[u] = f[(size_t)y * W];
-            cv[u] = __ldg(v + (size_t)y * W);
+            cf[u] = nf[u];
+            cv[u] = nv[u];
+        }
+        if (y0 + U < H) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int y = min(y0 + U + u, H - 1);
+                nf[u] = f[(size_t)y * W];
+                nv[u] = __ldg(v + (size_t)y * W);
+            }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -234,13 +260,26 @@ k_rf_cols(float* __restrict__ img, const float* __restrict__ Vv, int C, int H, i
         }
     }
     // bottom -> top: F[y] += V[y+1] (F[y+1] - F[y])
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int y = max(H - 2 - u, 0);
+        nf[u] = f[(size_t)y * W];
+        nv[u] = __ldg(v + (size_t)(y + 1) * W);
+    }
     for (int y0 = H - 2; y0 >= 0; y0 -= U) {
         float cf[U], cv[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int y = max(y0 - u, 0);
-            cf[u] = f[(size_t)y * W];
-            cv[u] = __ldg(v + (size_t)(y + 1) * W);
+            cf[u] = nf[u];
+            cv[u] = nv[u];
+        }
+        if (y0 - U >= 0) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int y = max(y0 - U - u, 0);
+                nf[u] = f[(size_t)y * W];
+                nv[u] = __ldg(v + (size_t)(y + 1) * W);
+            }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -271,12 +310,15 @@ int launch_recursive_filter(const float* in, const float* joint, float* out, int
         // sigma_H_i and the feedback coefficient in Python doubles (domain_transform.py:50-53)
         const double sigma_i = sigma_s * sqrt(3.0) * pow(2.0, (double)(num_iterations - (i + 1))) /
                                sqrt(pow(4.0, (double)num_iterations) - 1.0);
-        const float a = (float)exp(-sqrt(2.0) / sigma_i);
+        // log2 of the feedback coefficient exp(-sqrt(2) / sigma_i) as torch.pow sees it (a float32 base)
+        const float a = (float)log2((double)(float)exp(-sqrt(2.0) / sigma_i));
         dim3 gw((W + 31) / 32, (H + 7) / 8, B);
         k_rf_weights<<<gw, 256, 0, stream>>>(joint ? joint : in, Vh, Vv, C, H, W, a, (float)(sigma_s / sigma_r));
         const int groups_per_plane = (H + 31) / 32;
         const int groups_total = B * C * groups_per_plane;
-        k_rf_rows<<<(groups_total + RF_ROW_WARPS - 1) / RF_ROW_WARPS, RF_ROW_WARPS * 32, 0, stream>>>(
+        const size_t rows_smem = (size_t)RF_ROW_WARPS * 4 * 32 * 33 * sizeof(float);
+        PB_CUDA_TRY(cudaFuncSetAttribute(k_rf_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rows_smem));
+        k_rf_rows<<<(groups_total + RF_ROW_WARPS - 1) / RF_ROW_WARPS, RF_ROW_WARPS * 32, rows_smem, stream>>>(
             cur, out, Vh, C, H, W, groups_per_plane, groups_total);
         dim3 gc((W + 127) / 128, B * C);
         k_rf_cols<<<gc, 128, 0, stream>>>(out, Vv, C, H, W);
