@@ -702,6 +702,25 @@ k_fft_rows_fwd2(const float* __restrict__ img, float2* __restrict__ Z, const Img
         S.Win = G.Win;
         S.pad = pad;
         S.inner_interior = (M0 >= ext) && ((R0 - 1) * M0 - ext <= W);
+#ifdef PB_ROWS_PREFETCH        // measured slower (+4 % on both row passes): off
+        {
+            // the image rows of this CTA's next work item on their way into L2 (128-byte lines)
+            const int wn = w + gridDim.x * PB_ROWS_CHUNK;
+            if (wn < total) {
+                const int slotn = wn / per_img;
+                const int rn = wn - slotn * per_img;
+                const int cn = rn / blocks_per_plane;
+                const int jn = (rn - cn * blocks_per_plane) * 2 * nb;
+                const float* srcn = img + ((size_t)list[slotn] * C + cn) * (size_t)G.Hin * G.Win;
+                const int lines = (G.Win + 31) / 32;
+                for (int i = tid; i < 2 * nb * lines; i += FFTD_THREADS) {
+                    const int rr = i / lines, ln = i - rr * lines;
+                    const int sr = (jn + rr < NY) ? ext_src(jn + rr, H, ext, G.Hin, G.off, pad) : -1;
+                    if (sr >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(srcn + (size_t)sr * G.Win + ln * 32));
+                }
+            }
+        }
+#endif
         s_dif_first<R0, M0, NX>(smf, RS, nb, twX + SP::tw_off(0), tid, FFTD_THREADS, S);
         __syncthreads();
         SDifRun<SP, 1, NS - 2, false>::run(smf, RS, nb, twX, tid, FFTD_THREADS);
@@ -794,6 +813,21 @@ k_fft_rows_inv2(const float2* __restrict__ Z, float* __restrict__ out, const Img
         // rows of the extended image that are output rows: [ext, H + ext)
         if (j0 + 2 * nb <= ext || j0 >= H + ext) continue;
         const float2* Zp = Z + ((size_t)slot * C + c) * half * NY;
+#ifdef PB_ROWS_PREFETCH        // measured slower (+4 % on both row passes): off
+        {
+            // this CTA's next work item reads the same columns a few rows further: start its 64-byte pieces (one
+            // per half-spectrum column) on their way into L2 now, the loads below then cost an L2 hit, not DRAM
+            const int wn = w + gridDim.x * PB_ROWS_CHUNK;
+            if (wn < total) {
+                const int slotn = wn / per_img;
+                const int rn = wn - slotn * per_img;
+                const int cn = rn / blocks_per_plane;
+                const float2* Zn = Z + ((size_t)slotn * C + cn) * half * NY + (size_t)(rn - cn * blocks_per_plane) * 2 * nb;
+                for (int kx = tid; kx < half; kx += FFTD_THREADS)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(Zn + (size_t)kx * NY));
+            }
+        }
+#endif
         // rebuild Z[k] = Xa[k] + i Xb[k], Z[-k] = conj Xa[k] + i conj Xb[k] of a mirror unit in registers (P2 leaves
         // the spectra re/im swapped, and the inverse-by-forward trick wants them swapped), first inverse stage (M = 1)
         for (int idx = tid; idx < nunits * nb; idx += FFTD_THREADS) {
