@@ -73,7 +73,10 @@ typedef struct pb_params {
     uint32_t flags;       /* PB_FLAG_*                                                  */
     int32_t  engine;      /* PB_ENGINE_*                                                */
     float    tap_rel_threshold; /* spatial engine: drop taps < thr * max tap (0 = default 1e-8) */
-    int32_t  chunk_images;      /* images per launch group (0 = auto); tuning knob only  */
+    int32_t  chunk_images;      /* pb_polyblur_f32: images per engine pass (0 = the whole batch).  The batch runs
+                                 * in groups of this many images, each through the whole loop, and the workspace
+                                 * (pb_workspace_bytes) is sized for one group: bounds device memory for huge batches.
+                                 * Results do not depend on it; not combinable with PB_FLAG_EDGETAPER_BATCHMAX. */
 } pb_params;
 
 /* ---- library / host-only entry points (usable without a GPU) ------------------------- */

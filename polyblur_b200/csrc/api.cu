@@ -423,8 +423,14 @@ int pb_fft_plan(int n, int* radices) {
     return p.ns;
 }
 
+// images one engine pass of pb_polyblur_f32 works on: pb_params.chunk_images bounds it (and with it the workspace)
+static int group_size(int B, const pb_params* p) {
+    return (p && p->chunk_images > 0 && p->chunk_images < B) ? p->chunk_images : B;
+}
+
 size_t pb_workspace_bytes(int B, int C, int H, int W, const pb_params* p) {
     if (B < 1 || C < 1 || H < 1 || W < 1) return 0;
+    B = group_size(B, p);
     return layout(B, C, H, W, p ? p->n_iter : 1, p ? p->ker_size : PB_KS, p ? p->engine : PB_ENGINE_AUTO,
                   p ? p->flags : 0, p ? p->q : 0.0).total;
 }
@@ -453,12 +459,37 @@ static int validate_params(const pb_params* p) {
     return PB_OK;
 }
 
+static int polyblur_group(const float* in, float* out, int B, int C, int H, int W, const pb_params* p, void* workspace,
+                          size_t workspace_bytes, float* est_out, int est_batch, void* stream_);
+
 int pb_polyblur_f32(const float* in, float* out, int B, int C, int H, int W, const pb_params* p,
                     void* workspace, size_t workspace_bytes, float* est_out, void* stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
     int rc;
     if ((rc = check_shape(B, C, H, W))) return rc;
     if ((rc = validate_params(p))) return rc;
+    const int G = group_size(B, p);
+    if (G == B) return polyblur_group(in, out, B, C, H, W, p, workspace, workspace_bytes, est_out, B, stream_);
+    // chunk_images: the batch goes through in groups of G images, each running the whole loop in a workspace sized
+    // for G (images are independent; the one batch-coupled option is the reference's edgetaper normalisation)
+    if (p->flags & PB_FLAG_EDGETAPER_BATCHMAX) {
+        set_error("chunk_images cannot be combined with PB_FLAG_EDGETAPER_BATCHMAX (a batch-global maximum)");
+        return PB_ERR_ARG;
+    }
+    const size_t per = (size_t)C * H * W;
+    for (int b0 = 0; b0 < B; b0 += G) {
+        const int n = (B - b0 < G) ? B - b0 : G;
+        float* est = est_out ? est_out + (size_t)b0 * PB_EST_STRIDE : nullptr;
+        if ((rc = polyblur_group(in + b0 * per, out + b0 * per, n, C, H, W, p, workspace, workspace_bytes, est, B, stream_)))
+            return rc;
+    }
+    return PB_OK;
+}
+
+// est_batch: batch size of the est_out array (rows of one iteration are est_batch records apart)
+static int polyblur_group(const float* in, float* out, int B, int C, int H, int W, const pb_params* p, void* workspace,
+                          size_t workspace_bytes, float* est_out, int est_batch, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc;
     if (!in || !out || in == out) {
         set_error("in/out must be distinct non-null device pointers");
         return PB_ERR_ARG;
@@ -503,7 +534,7 @@ int pb_polyblur_f32(const float* in, float* out, int B, int C, int H, int W, con
     const float* cur = in;
     for (int it = 0; it < p->n_iter; ++it) {
         float* dst = ((p->n_iter - 1 - it) & 1) ? tmp : out;
-        float* est = est_out ? est_out + (size_t)it * B * PB_EST_STRIDE : nullptr;
+        float* est = est_out ? est_out + (size_t)it * est_batch * PB_EST_STRIDE : nullptr;
         if ((rc = estimate_into(cur, B, C, H, W, p->c, p->b, p->q, p->flags, est, ws, L, T, p->ker_size, thr, p->engine,
                                 L.has_fft ? PB_FFT_RADIUS_MIN : (1 << 30), stream)))
             return rc;

@@ -93,6 +93,9 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // float2 per row pair in shared memory: the sequence + 4, so that the same slot of the nb row pairs
 // of a CTA falls into different banks (the spectrum passes of P1 / P3 touch one slot of every pair)
 __host__ __device__ inline int fftd_row_stride(int NX) { return NX + 4; }
+// second-generation row kernels (64-bit shared-memory accesses only): the mirror-unit stage reads slot A R_last + q of
+// every pair of the CTA for consecutive blocks A; with an even last radix the pairs must sit an odd number of float2 apart
+__host__ __device__ constexpr int fftd_row_stride2(int NX, int RL) { return NX + ((RL & 1) ? 4 : 5); }
 // threads of the column kernel (288 = 9 warps would divide the butterfly counts of a 4-column block of
 // 1152 evenly, but its 72-register budget spills: measured equal to 256)
 #ifndef FFTC_THREADS
@@ -1222,6 +1225,8 @@ size_t fft_engine_workspace(int B, int C, int H, int W, int pad, FftEngineLayout
     l.off_freqY = take((size_t)l.NY * sizeof(int));
     l.off_unitsX = take((size_t)(l.NX / 2 + 2) * sizeof(int4));
     l.off_stwY2 = take((size_t)l.NY * sizeof(float2));
+    l.off_stwX2 = take((size_t)l.NX * sizeof(float2));
+    l.off_unitsX2 = take((size_t)(l.NX / 2 + 2) * sizeof(int4));
     l.off_Z = take((size_t)B * C * (l.NX / 2) * l.NY * sizeof(float2));
     l.total = o;
     if (L) *L = l;
@@ -1257,6 +1262,21 @@ int fft_engine_prepare(char* base, const FftEngineLayout& L, FftEngineTables* T,
         const bool big_first = env_int("PB_FFT_RA36", 1) != 0;      // measured: 1.92 ms against 2.02 ms per step (C2)
         T->ra2 = big_first ? 36 : 32;
         T->rb2 = big_first ? 32 : 36;
+    }
+    T->stwX2 = reinterpret_cast<float2*>(base + L.off_stwX2);
+    T->unitsX2 = reinterpret_cast<int4*>(base + L.off_unitsX2);
+    T->rowplan2 = 0;
+    if (L.NX == 4000 && L.NY == 2304 && env_int("PB_FFT_ROWS_4STAGE", 0) == 0) {
+        Fft2Plan px;
+        px.n = 4000;
+        px.ns = 3;
+        px.radix[0] = 20;
+        px.radix[1] = 20;
+        px.radix[2] = 10;
+        fft2_plan_offsets(&px);
+        T->rowplan2 = 1;
+        jobs->add(TJ_STAGE_TW, px.tw_total, T->stwX2, nullptr, &px);
+        jobs->add(TJ_UNITS, 256, T->unitsX2, nullptr, &px);
     }
     if (T->ra2) {
         Fft2Plan p2;
@@ -1299,20 +1319,20 @@ int launch_deconv_fft(const float* img, float* out, const ImgKernel* kern, const
         }                                                                                                        \
     } while (0)
     // second-generation row passes (fused first / last stages) for the compile-time plans
-#define PB_FFT_ROWS2(SP, NYC)                                                                                         \
+#define PB_FFT_ROWS2(SP, NYC, TW, UN)                                                                                         \
     do {                                                                                                         \
         auto kf = k_fft_rows_fwd2<SP, NYC>;                                                                      \
         auto ki = k_fft_rows_inv2<SP, NYC>;                                                                      \
+        const size_t smem_rows = (size_t)nb * fftd_row_stride2(SP::n, SP::R(SP::ns - 1)) * sizeof(float2);      \
         PB_CUDA_TRY(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));      \
         PB_CUDA_TRY(cudaFuncSetAttribute(ki, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));      \
         if (fwd) {                                                                                               \
             ProfScope prof(PROF_FFT_ROWS_FWD, stream);                                                           \
-            kf<<<grid_rows, FFTD_THREADS, smem_rows, stream>>>(img, T.Z, kern, list, count, C, H, W, nb, T.stwX,  \
-                                                               T.unitsX, G);                                     \
+            kf<<<grid_rows, FFTD_THREADS, smem_rows, stream>>>(img, T.Z, kern, list, count, C, H, W, nb, TW, UN, G); \
         } else {                                                                                                 \
             ProfScope prof(PROF_FFT_ROWS_INV, stream);                                                           \
-            ki<<<grid_rows, FFTD_THREADS, smem_rows, stream>>>(T.Z, out, kern, list, count, C, H, W, nb, T.stwX,  \
-                                                               T.unitsX, G.clamp_out);                           \
+            ki<<<grid_rows, FFTD_THREADS, smem_rows, stream>>>(T.Z, out, kern, list, count, C, H, W, nb, TW, UN,  \
+                                                               G.clamp_out);                                     \
         }                                                                                                        \
     } while (0)
 #define PB_FFT_COLS(SP)                                                                                          \
@@ -1354,9 +1374,11 @@ int launch_deconv_fft(const float* img, float* out, const ImgKernel* kern, const
         } else {
             // (the second-generation kernels also fix NY at compile time: the 1080p and 4K tori)
             if (PlanX2016::matches(T.planX)) {
-                if (rows_v1 || NY != 1152) PB_FFT_ROWS(PlanX2016); else PB_FFT_ROWS2(PlanX2016, 1152);
+                if (rows_v1 || NY != 1152) PB_FFT_ROWS(PlanX2016); else PB_FFT_ROWS2(PlanX2016, 1152, T.stwX, T.unitsX);
             } else if (PlanX4000::matches(T.planX)) {
-                if (rows_v1 || NY != 2304) PB_FFT_ROWS(PlanX4000); else PB_FFT_ROWS2(PlanX4000, 2304);
+                if (rows_v1 || NY != 2304) PB_FFT_ROWS(PlanX4000);
+                else if (T.rowplan2 == 1) PB_FFT_ROWS2(PlanX4000b, 2304, T.stwX2, T.unitsX2);
+                else PB_FFT_ROWS2(PlanX4000, 2304, T.stwX, T.unitsX);
             } else PB_FFT_ROWS(NoStaticPlan);
         }
     }

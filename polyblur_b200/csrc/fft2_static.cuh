@@ -206,7 +206,8 @@ using PlanX2016 = StaticPlan<2016, 16, 14, 9>;
 using PlanY1152 = StaticPlan<1152, 8, 16, 9>;
 using PlanW3840 = StaticPlan<3840, 16, 16, 15>;
 using PlanH2160 = StaticPlan<2160, 15, 16, 9>;
-using PlanX4000 = StaticPlan<4000, 10, 10, 8, 5>;
+using PlanX4000 = StaticPlan<4000, 10, 10, 8, 5>;       // what the run-time planner (radices <= 16) gives: four stages
+using PlanX4000b = StaticPlan<4000, 20, 20, 10>;        // three stages with 20-point butterflies (second-generation row passes)
 using PlanY2304 = StaticPlan<2304, 16, 16, 9>;
 
 }  // namespace pb

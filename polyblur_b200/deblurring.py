@@ -23,7 +23,7 @@ _METHODS = ("fft", "direct", "direct_separable")
 
 def _make_params(n_iter, c, b, alpha, beta, sigma_r, sigma_s, ker_size, q, remove_halo, edgetaping,
                  prefiltering, discard_saturation, engine=_lib.ENGINE_AUTO, prefilter="bilateral",
-                 tap_rel_threshold=0.0):
+                 tap_rel_threshold=0.0, chunk_images=0):
     p = _lib.default_params()
     p.n_iter = int(n_iter)
     p.c, p.b, p.alpha, p.beta = float(c), float(b), float(alpha), float(beta)
@@ -41,6 +41,9 @@ def _make_params(n_iter, c, b, alpha, beta, sigma_r, sigma_s, ker_size, q, remov
     p.flags = flags
     p.engine = int(engine)
     p.tap_rel_threshold = float(tap_rel_threshold)
+    p.chunk_images = int(chunk_images)
+    if p.chunk_images > 0 and edgetaping:
+        p.flags &= ~_lib.FLAG_EDGETAPER_BATCHMAX        # groups cannot share the reference's batch-global maximum
     return p
 
 
@@ -219,7 +222,7 @@ def polyblur_deblurring(img, n_iter=1, c=0.352, b=0.768, alpha=2, beta=3, sigma_
     ``img``: (H,W) / (H,W,C) ndarray -> float32 ndarray squeezed like ``utils.to_array``;
     or a (B,C,H,W) float32 tensor -> tensor on the same device.  Every ``method`` gives the
     reference's ``'fft'`` result (its other methods are broken for batches).
-    Extra keyword arguments (``engine``, ``prefilter``, ``tap_rel_threshold``,
+    Extra keyword arguments (``engine``, ``prefilter``, ``tap_rel_threshold``, ``chunk_images``,
     ``return_estimates``) are engine knobs that the reference does not have.
     """
     if method not in _METHODS:

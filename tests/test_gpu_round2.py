@@ -192,3 +192,18 @@ def test_two_rank_gathered_output_is_bitwise_the_single_gpu_output():
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "SHARDED_BITWISE_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_chunk_images_bounds_the_workspace_and_keeps_the_result(pb):
+    """pb_params.chunk_images: the batch runs in groups through the whole loop, in a workspace sized for one group."""
+    import ctypes as C
+    from polyblur_b200 import _lib, deblurring, synthetic
+    x = synthetic.make("mosaic", 5, 3, 135, 240).cuda()
+    whole, e0 = pb.polyblur_deblurring(x, n_iter=3, alpha=6, beta=1, return_estimates=True)
+    grouped, e1 = pb.polyblur_deblurring(x, n_iter=3, alpha=6, beta=1, return_estimates=True, chunk_images=2)
+    assert torch.equal(whole, grouped) and torch.equal(e0, e1)
+    p_all = deblurring._make_params(3, 0.352, 0.768, 6, 1, 0.8, 2.0, 25, 0.0, False, False, False, False)
+    p_grp = deblurring._make_params(3, 0.352, 0.768, 6, 1, 0.8, 2.0, 25, 0.0, False, False, False, False, chunk_images=2)
+    n_all = _lib.lib().pb_workspace_bytes(5, 3, 135, 240, C.byref(p_all))
+    n_grp = _lib.lib().pb_workspace_bytes(5, 3, 135, 240, C.byref(p_grp))
+    assert n_grp < 0.6 * n_all
