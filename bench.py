@@ -274,7 +274,8 @@ def binding_unit(members_ms, key_suffix):
     pipes = load_json("roofline_pipes.json")
     acc, tot, src = {}, 0.0, set()
     for name, ms in members_ms.items():
-        rec = pipes.get(f"{name}:{key_suffix}")
+        # the profiler's class names are generation-neutral; the captured kernels of the current build may carry a "2"
+        rec = pipes.get(f"{name}2:{key_suffix}") or pipes.get(f"{name}:{key_suffix}")
         if not rec or ms <= 0:
             continue
         tot += ms

@@ -38,7 +38,10 @@ def to_bytes(v, unit):
 
 def main():
     rep, out = sys.argv[1], sys.argv[2]
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):         # a raw page exported on the GPU box: ncu -i X.ncu-rep --page raw --csv > X.raw.csv
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, body = rows[0], rows[1], rows[2:]
     idx = {h: i for i, h in enumerate(hdr)}

@@ -9,11 +9,11 @@ for f in config_sweep parity_report fuzz_parity; do [ -s $O/$f.jsonl ] && cp $O/
 [ -s $O/rf_timing.txt ] && cp $O/rf_timing.txt $P/${R}_rf_timing.txt
 grep -v "^==" $O/launches_mosaic_b32.csv > $P/${R}_launches_mosaic_b32.csv
 python tools/launch_summary.py $O/launches_mosaic_b32.csv $P/${R}_launches_mosaic_b32.md "ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ -c 400: python bench.py --steps 2 --warmup 1 --no-graph (C2 mosaic)"
-python tools/ncu_summary.py $O/prof_mosaic32.ncu-rep $P/${R}_ncu_mosaic_b32.md --traffic mosaic:32x1080x1920 $P/roofline_traffic.json --pipes mosaic:32x1080x1920 $P/roofline_pipes.json --csv $P/${R}_ncu_mosaic_b32.csv
-python tools/ncu_summary.py $O/prof_white32.ncu-rep $P/${R}_ncu_white_b32.md --traffic white:32x1080x1920 $P/roofline_traffic.json --pipes white:32x1080x1920 $P/roofline_pipes.json --csv $P/${R}_ncu_white_b32.csv
-[ -s $O/prof_mosaic_c3.ncu-rep ] && python tools/ncu_summary.py $O/prof_mosaic_c3.ncu-rep $P/${R}_ncu_mosaic_4k_b8.md --pipes mosaic:8x2160x3840 $P/roofline_pipes.json --csv $P/${R}_ncu_mosaic_4k_b8.csv
-for rep in prof_mosaic32 prof_white32; do
-  ncu -i $O/$rep.ncu-rep --page source --csv --print-source sass 2>/dev/null | python tools/ncu_source_mix.py > $P/${R}_sass_mix_${rep#prof_}.md
+python tools/ncu_summary.py $O/prof_mosaic32.raw.csv $P/${R}_ncu_mosaic_b32.md --traffic mosaic:32x1080x1920 $P/roofline_traffic.json --pipes mosaic:32x1080x1920 $P/roofline_pipes.json --csv $P/${R}_ncu_mosaic_b32.csv
+python tools/ncu_summary.py $O/prof_white32.raw.csv $P/${R}_ncu_white_b32.md --traffic white:32x1080x1920 $P/roofline_traffic.json --pipes white:32x1080x1920 $P/roofline_pipes.json --csv $P/${R}_ncu_white_b32.csv
+[ -s $O/prof_mosaic_c3.raw.csv ] && python tools/ncu_summary.py $O/prof_mosaic_c3.raw.csv $P/${R}_ncu_mosaic_4k_b8.md --pipes mosaic:8x2160x3840 $P/roofline_pipes.json --csv $P/${R}_ncu_mosaic_4k_b8.csv
+for rep in prof_mosaic32 prof_white32 prof_mosaic_c3; do
+  [ -s $O/$rep.sass_mix.md ] && cp $O/$rep.sass_mix.md $P/${R}_sass_mix_${rep#prof_}.md
 done
 # SASS evidence: mnemonic counts of the shipped library (whole library and the hot kernels)
 python tools/sass_listing.py polyblur_b200/libpolyblur_sm100.so $P/${R}_sass_summary.md
