@@ -276,6 +276,9 @@ def binding_unit(members_ms, key_suffix):
     for name, ms in members_ms.items():
         # the profiler's class names are generation-neutral; the captured kernels of the current build may carry a "2"
         rec = pipes.get(f"{name}2:{key_suffix}") or pipes.get(f"{name}:{key_suffix}")
+        if not rec:                  # the estimate kernels do the same work for both synthetic distributions
+            alt = key_suffix.replace("white:", "mosaic:") if key_suffix.startswith("white:") else key_suffix.replace("mosaic:", "white:")
+            rec = pipes.get(f"{name}2:{alt}") or pipes.get(f"{name}:{alt}")
         if not rec or ms <= 0:
             continue
         tot += ms
