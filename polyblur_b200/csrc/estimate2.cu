@@ -523,6 +523,10 @@ bool fft2_supported(int H, int W) {
 int launch_rows2(bool est, const float* img, float* gray, float* gx, unsigned* stats, int nimg, int C,
                  int H, int W, const Fft2Plan& planW, const float2* twW, const float* omegaW,
                  const float* qrange, cudaStream_t stream) {
+    if (est && !qrange) {
+        const int r3 = launch_rows3(img, gray, gx, stats, nimg, C, H, W, planW, twW, omegaW, stream);
+        if (r3 != 1) return r3;
+    }
     int nb = pairs_for(W, 8, PB_R2_SMEM);
     const int pairs_total = (H + 1) / 2;
     if (nb > pairs_total) nb = pairs_total;
@@ -552,6 +556,10 @@ int launch_rows2(bool est, const float* img, float* gray, float* gx, unsigned* s
 int launch_cols2(bool est, const float* plane_in, const float* gx, float* gy, unsigned* stats, int nimg,
                  int H, int W, const Fft2Plan& planH, const float2* twH, const float* omegaH,
                  int discard_saturation, const float* mask_src, cudaStream_t stream) {
+    if (est) {
+        const int r3 = launch_cols3(plane_in, gx, stats, nimg, H, W, planH, twH, omegaH, discard_saturation, mask_src, stream);
+        if (r3 != 1) return r3;
+    }
     // 8 pairs = 16 columns = 64-byte row segments; fall back to fewer when H is very long
     int nb = pairs_for(H, PB_C2_NB, 200 * 1024);
     // three resident CTAs of 4+ pairs (32-byte row segments) beat one big CTA of 8 (measured at H = 2160:
