@@ -278,19 +278,24 @@ __global__ void __launch_bounds__(FFTC_THREADS, PB_FFTC_MINB)
 k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int* __restrict__ list,
            const int* __restrict__ count, int C, int NX, int NY, int CB, Fft2Plan planY,
            const float2* __restrict__ twX, const float2* __restrict__ stwY, const int* __restrict__ slotY,
-           float a3, float a2, float a1, float b0, int first_block_only) {
+           float a3, float a2, float a1, float b0, int mode) {
+    // mode 0: every block of columns; 1: only the block that holds kx = 0 (the other columns are left to another
+    // launch), one CTA per plane; 2: every block but that one -- Hn / Hb are then not needed and not allocated
+    // (for a long column they are the difference between one and two resident CTAs)
+    const int first_block_only = mode == 1;
     extern __shared__ __align__(16) unsigned char smraw[];
     float2* data = reinterpret_cast<float2*>(smraw);
     float* Hs = reinterpret_cast<float*>(data + (size_t)CB * NY);
     float* Hn = Hs + (size_t)CB * NY;
     float* Hb = Hn + NY;
-    float2* Rk = reinterpret_cast<float2*>(Hb + NY);                  // [(CB + 1)][13]
+    float2* Rk = reinterpret_cast<float2*>(mode == 2 ? Hn : Hb + NY);  // [(CB + 1)][13]
     uint64_t* bar = reinterpret_cast<uint64_t*>(Rk + (CB + 1) * 13 + 1);
     bar = reinterpret_cast<uint64_t*>(((uintptr_t)bar + 7) & ~(uintptr_t)7);
     const int tid = threadIdx.x;
     const int half = NX >> 1;
     // first_block_only: just the block that holds kx = 0 (the second-generation kernel does the other columns)
-    const int nblk = first_block_only ? 1 : (half + CB - 1) / CB;
+    const int blk0 = mode == 2 ? 1 : 0;
+    const int nblk = first_block_only ? 1 : (half + CB - 1) / CB - blk0;
     const int total = count[0] * nblk;
     const float scale = 1.0f / ((float)NX * (float)NY);
     const float inv_ny = 1.0f / (float)NY;
@@ -300,7 +305,7 @@ k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int
 
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
         const int slot = w / nblk;
-        const int cb = w - slot * nblk;
+        const int cb = w - slot * nblk + blk0;
         const int im = list[slot];
         const ImgKernel* K = kern + im;
         const int kx0 = cb * CB;
@@ -1361,6 +1366,19 @@ int launch_deconv_fft(const float* img, float* out, const ImgKernel* kern, const
         k_fft_cols<NoStaticPlan><<<dim3(B < cap ? B : cap, C), FFTC_THREADS, smem0, stream>>>(T.Z, kern, list, count, C, NX, NY, 1, \
                                                                      T.planY, T.twX, T.stwY, T.slotY, a3, a2, a1, b0, 1); \
     } while (0)
+    // long columns (one column per CTA): the block of column 0 in its own launch, so that the other CTAs do without its
+    // two extra NY-float arrays and two of them fit an SM
+#define PB_FFT_COLS_LONG(SP)                                                                                     \
+    do {                                                                                                         \
+        const size_t smem1 = (size_t)CB * NY * 12 + (size_t)(CB + 1) * 13 * 8 + 64;                              \
+        const long long items1 = (long long)B * ((NX / 2 + CB - 1) / CB - 1);                                    \
+        PB_CUDA_TRY(cudaFuncSetAttribute(k_fft_cols<SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols)); \
+        ProfScope prof(PROF_FFT_COLS, stream);                                                                   \
+        k_fft_cols<SP><<<(int)(items1 < cap ? items1 : cap), FFTC_THREADS, smem1, stream>>>(                     \
+            T.Z, kern, list, count, C, NX, NY, CB, T.planY, T.twX, T.stwY, T.slotY, a3, a2, a1, b0, 2);          \
+        k_fft_cols<SP><<<dim3(B < cap ? B : cap, C), FFTC_THREADS, smem_cols, stream>>>(                         \
+            T.Z, kern, list, count, C, NX, NY, CB, T.planY, T.twX, T.stwY, T.slotY, a3, a2, a1, b0, 1);          \
+    } while (0)
     static const bool rows_v1 = env_int("PB_FFT_ROWS_V1", 0) != 0;     // A/B against the first-generation passes
     static const bool cols_v1 = env_int("PB_FFT_COLS_V1", 0) != 0;
     for (int pass = 0; pass < 3; ++pass) {
@@ -1370,6 +1388,7 @@ int launch_deconv_fft(const float* img, float* out, const ImgKernel* kern, const
             else if (T.ra2 == 32 && T.rb2 == 36 && !cols_v1) PB_FFT_COLS2(32, 36);
             else if (PlanY1152::matches(T.planY)) PB_FFT_COLS(PlanY1152);
             else if (PlanY2304::matches(T.planY)) PB_FFT_COLS(PlanY2304);
+            else if (PlanY9216::matches(T.planY) && CB == 1 && !cols_v1) PB_FFT_COLS_LONG(PlanY9216);
             else PB_FFT_COLS(NoStaticPlan);
         } else {
             // (the second-generation kernels also fix NY at compile time: the 1080p and 4K tori)
@@ -1379,6 +1398,8 @@ int launch_deconv_fft(const float* img, float* out, const ImgKernel* kern, const
                 if (rows_v1 || NY != 2304) PB_FFT_ROWS(PlanX4000);
                 else if (T.rowplan2 == 1) PB_FFT_ROWS2(PlanX4000b, 2304, T.stwX2, T.unitsX2);
                 else PB_FFT_ROWS2(PlanX4000, 2304, T.stwX, T.unitsX);
+            } else if (PlanX12096::matches(T.planX) && NY == 9216 && !rows_v1) {
+                PB_FFT_ROWS2(PlanX12096, 9216, T.stwX, T.unitsX);
             } else PB_FFT_ROWS(NoStaticPlan);
         }
     }
@@ -1386,6 +1407,7 @@ int launch_deconv_fft(const float* img, float* out, const ImgKernel* kern, const
 #undef PB_FFT_ROWS2
 #undef PB_FFT_COLS
 #undef PB_FFT_COLS2
+#undef PB_FFT_COLS_LONG
     PB_LAUNCH_CHECK("fft deconvolution passes");
     return PB_OK;
 }

@@ -34,18 +34,14 @@ static __device__ __forceinline__ float gray3(float a, float b, float c) {
     return div3_rn(__fadd_rn(__fadd_rn(a, b), c));        // (r + g + b) / 3 in the reference's order
 }
 
-#define E3_THREADS 256
-#ifndef PB_E3_MINB
-#define PB_E3_MINB 3
-#endif
 
 // ---------------------------------------------------------------------------------------------
 // rows: CTA = nb row pairs (rows y0 .. y0 + 2 nb - 1) of one image, C = 3.
 // A thread owns WIDE adjacent columns j .. j + WIDE - 1 of a pair: WIDE butterflies side by side, so
 // global accesses are 8 bytes and shared-memory accesses 16 bytes wide when WIDE = 2.
 // ---------------------------------------------------------------------------------------------
-template <class SP, int WIDE>
-__global__ void __launch_bounds__(E3_THREADS, PB_E3_MINB)
+template <class SP, int WIDE, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
 k_rows3(const float* __restrict__ img, float* __restrict__ gray, float* __restrict__ gx,
         unsigned* __restrict__ stats, int H, int nb, const float2* __restrict__ tw,
         const float* __restrict__ omega) {
@@ -63,7 +59,7 @@ k_rows3(const float* __restrict__ img, float* __restrict__ gray, float* __restri
     float lmin = INFINITY, lmax = -INFINITY;
 
     // ---- stage 0 (DIF), fed from global memory -------------------------------------------------
-    for (int idx = tid; idx < nb * JM; idx += E3_THREADS) {
+    for (int idx = tid; idx < nb * JM; idx += THREADS) {
         const int f = idx / JM;
         const int j = (idx - f * JM) * WIDE;
         const int y = y0 + 2 * f;
@@ -133,15 +129,15 @@ k_rows3(const float* __restrict__ img, float* __restrict__ gray, float* __restri
     __syncthreads();
 
     // ---- inner stages: DIF 1 .. NS-2, [DIF NS-1, i omega, DIT NS-1] in registers, DIT NS-2 .. 1 ---
-    SDifRun<SP, 1, NS - 2, false>::run(sm2, W, nb, tw, tid, E3_THREADS);
-    s_mid_stage<SP::R(NS - 1), W, 1>(sm2, W, nb, tid, E3_THREADS, omega);
+    SDifRun<SP, 1, NS - 2, false>::run(sm2, W, nb, tw, tid, THREADS);
+    s_mid_stage<SP::R(NS - 1), W, 1>(sm2, W, nb, tid, THREADS, omega);
     __syncthreads();
-    SDitRun<SP, NS - 2, NS - 2, false>::run(sm2, W, nb, tw, tid, E3_THREADS);
+    SDitRun<SP, NS - 2, NS - 2, false>::run(sm2, W, nb, tw, tid, THREADS);
 
     // ---- stage 0 (DIT), drained to global memory: r = DFT(swap(.)): row a = r.y / n, row b = r.x / n
     const float inv = 1.0f / (float)W;
     float* gxd = gx + (size_t)im * plane;
-    for (int idx = tid; idx < nb * JM; idx += E3_THREADS) {
+    for (int idx = tid; idx < nb * JM; idx += THREADS) {
         const int f = idx / JM;
         const int j = (idx - f * JM) * WIDE;
         const int y = y0 + 2 * f;
@@ -191,8 +187,8 @@ k_rows3(const float* __restrict__ img, float* __restrict__ gray, float* __restri
 // columns: CTA = NB column pairs (2 NB adjacent columns) of one gray plane; consecutive threads take
 // consecutive pairs of one row (8 NB contiguous bytes), then the next row.
 // ---------------------------------------------------------------------------------------------
-template <class SP, int NB>
-__global__ void __launch_bounds__(E3_THREADS, PB_E3_MINB)
+template <class SP, int NB, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
 k_cols3(const float* __restrict__ g, const float* __restrict__ gx, unsigned* __restrict__ stats, int W, int stride,
         const float2* __restrict__ tw, const float* __restrict__ omega, int discard_saturation,
         const float* __restrict__ mask_src) {
@@ -200,7 +196,7 @@ k_cols3(const float* __restrict__ g, const float* __restrict__ gx, unsigned* __r
     static_assert(NS >= 3, "needs an inner stage besides the fused middle one");
     static_assert((NB & (NB - 1)) == 0, "pairs per CTA: a power of two");
     extern __shared__ __align__(16) float2 sm2[];
-    __shared__ float red[E3_THREADS / 32][8];
+    __shared__ float red[THREADS / 32][8];
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * 2 * NB;
     const int im = blockIdx.y;
@@ -209,7 +205,7 @@ k_cols3(const float* __restrict__ g, const float* __restrict__ gx, unsigned* __r
     const float2* stw0 = tw + SP::tw_off(0);
 
     // ---- stage 0 (DIF), fed from global memory -------------------------------------------------
-    for (int idx = tid; idx < NB * M0; idx += E3_THREADS) {
+    for (int idx = tid; idx < NB * M0; idx += THREADS) {
         const int j = idx / NB, f = idx & (NB - 1);
         const int x = x0 + 2 * f;
         float2 v[R0];
@@ -229,10 +225,10 @@ k_cols3(const float* __restrict__ g, const float* __restrict__ gx, unsigned* __r
     }
     __syncthreads();
 
-    SDifRun<SP, 1, NS - 2, false>::run(sm2, stride, NB, tw, tid, E3_THREADS);
-    s_mid_stage<SP::R(NS - 1), H, 1>(sm2, stride, NB, tid, E3_THREADS, omega);
+    SDifRun<SP, 1, NS - 2, false>::run(sm2, stride, NB, tw, tid, THREADS);
+    s_mid_stage<SP::R(NS - 1), H, 1>(sm2, stride, NB, tid, THREADS, omega);
     __syncthreads();
-    SDitRun<SP, NS - 2, NS - 2, false>::run(sm2, stride, NB, tw, tid, E3_THREADS);
+    SDitRun<SP, NS - 2, NS - 2, false>::run(sm2, stride, NB, tw, tid, THREADS);
 
     // ---- stage 0 (DIT) in registers + the 7 directional maxima (blur_estimation.py:122-134) ------
     // cos / sin of torch.linspace(0, pi, 7) as torch (float32) evaluates them (same bit patterns as estimate2.cu)
@@ -246,7 +242,7 @@ k_cols3(const float* __restrict__ g, const float* __restrict__ gx, unsigned* __r
     const float inv = 1.0f / (float)H;
     const float* gxp = gx + (size_t)im * plane;
     const float* msk = (mask_src ? mask_src : g) + (size_t)im * plane;   // un-normalised gray > 0.99 is saturated
-    for (int idx = tid; idx < NB * M0; idx += E3_THREADS) {
+    for (int idx = tid; idx < NB * M0; idx += THREADS) {
         const int j = idx / NB, f = idx & (NB - 1);
         const int x = x0 + 2 * f;
         if (x >= W) continue;
@@ -296,19 +292,24 @@ k_cols3(const float* __restrict__ g, const float* __restrict__ gx, unsigned* __r
     __syncthreads();
     if (tid < 7) {
         float r = 0.0f;
-        for (int w = 0; w < E3_THREADS / 32; ++w) r = fmaxf(r, red[w][tid]);
+        for (int w = 0; w < THREADS / 32; ++w) r = fmaxf(r, red[w][tid]);
         atomicMax(&stats[im * PB_STATS_STRIDE + 2 + tid], __float_as_uint(r));
     }
 }
 
 // ---- host side ------------------------------------------------------------------------------
+static int env3(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
 static bool est_gen3() {
-    static const int on = [] {
-        const char* v = getenv("PB_EST_GEN");
-        return v ? atoi(v) : 3;
-    }();
+    static const int on = env3("PB_EST_GEN", 3);
     return on >= 3;
 }
+
+// the single-image 12000 x 9000 configuration (BASELINE C4): the run-time planner's radix orders
+using PlanW12000 = StaticPlan<12000, 10, 5, 16, 15>;
+using PlanH9000 = StaticPlan<9000, 15, 15, 8, 5>;
 
 template <typename KernelT>
 static int set_smem3(KernelT kern, size_t bytes) {
@@ -322,21 +323,23 @@ int launch_rows3(const float* img, float* gray, float* gx, unsigned* stats, int 
     if (!est_gen3() || C != 3) return 1;
     const int pairs_total = (H + 1) / 2;
     int rc;
-#define PB_ROWS3(SP, WIDE, NBMAX)                                                                              \
+    // nb row pairs per CTA: what fits BUDGET bytes of shared memory (at least one)
+#define PB_ROWS3(SP, WIDE, THREADS, MINB, BUDGET)                                                              \
     do {                                                                                                       \
-        int nb = (64 * 1024) / (int)(sizeof(float2) * SP::n);                                                  \
-        if (nb > (NBMAX)) nb = (NBMAX);                                                                        \
+        int nb = (BUDGET) / (int)(sizeof(float2) * SP::n);                                                     \
+        if (nb < 1) nb = 1;                                                                                    \
         if (nb > pairs_total) nb = pairs_total;                                                                \
         const size_t smem = (size_t)nb * SP::n * sizeof(float2);                                               \
-        if ((rc = set_smem3(k_rows3<SP, WIDE>, smem))) return rc;                                              \
+        if ((rc = set_smem3(k_rows3<SP, WIDE, THREADS, MINB>, smem))) return rc;                               \
         ProfScope prof(PROF_ROWS, stream);                                                                     \
-        k_rows3<SP, WIDE><<<dim3((pairs_total + nb - 1) / nb, nimg), E3_THREADS, smem, stream>>>(              \
+        k_rows3<SP, WIDE, THREADS, MINB><<<dim3((pairs_total + nb - 1) / nb, nimg), THREADS, smem, stream>>>(  \
             img, gray, gx, stats, H, nb, twW, omegaW);                                                         \
         PB_LAUNCH_CHECK("k_rows3");                                                                            \
         return PB_OK;                                                                                          \
     } while (0)
-    if (PlanW1920::matches(planW)) PB_ROWS3(PlanW1920, 2, 8);
-    if (PlanW3840::matches(planW)) PB_ROWS3(PlanW3840, 1, 8);
+    if (PlanW1920::matches(planW)) PB_ROWS3(PlanW1920, 2, 256, 3, 64 * 1024);
+    if (PlanW3840::matches(planW)) PB_ROWS3(PlanW3840, 1, 256, 3, 64 * 1024);
+    if (PlanW12000::matches(planW)) PB_ROWS3(PlanW12000, 2, 256, 2, 100 * 1024);     // one pair (94 KB), two CTAs per SM
 #undef PB_ROWS3
     return 1;
 }
@@ -347,19 +350,28 @@ int launch_cols3(const float* g, const float* gx, unsigned* stats, int nimg, int
     if (!est_gen3() || (W & 1)) return 1;
     const int pairs_total = W / 2;
     int rc;
-#define PB_COLS3(SP, NB)                                                                                       \
+#define PB_COLS3(SP, NB, THREADS, MINB)                                                                        \
     do {                                                                                                       \
         const int stride = SP::n + ((2 - SP::n) & 3);      /* = 2 (mod 4) float2: see launch_cols2 */           \
         const size_t smem = (size_t)(NB) * stride * sizeof(float2);                                            \
-        if ((rc = set_smem3(k_cols3<SP, NB>, smem))) return rc;                                                \
+        if ((rc = set_smem3(k_cols3<SP, NB, THREADS, MINB>, smem))) return rc;                                 \
         ProfScope prof(PROF_COLS, stream);                                                                     \
-        k_cols3<SP, NB><<<dim3((pairs_total + (NB) - 1) / (NB), nimg), E3_THREADS, smem, stream>>>(            \
+        k_cols3<SP, NB, THREADS, MINB><<<dim3((pairs_total + (NB) - 1) / (NB), nimg), THREADS, smem, stream>>>(\
             g, gx, stats, W, stride, twH, omegaH, discard_saturation, mask_src);                               \
         PB_LAUNCH_CHECK("k_cols3");                                                                            \
         return PB_OK;                                                                                          \
     } while (0)
-    if (PlanH1080::matches(planH)) PB_COLS3(PlanH1080, 8);
-    if (PlanH2160::matches(planH)) PB_COLS3(PlanH2160, 4);
+    // (192 threads, which divide the butterfly counts of the 1080 / 2160 stages evenly where 256 leave a quarter of a
+    // trip idle, measured the same as 256: the trips are not what binds)
+    if (PlanH1080::matches(planH)) PB_COLS3(PlanH1080, 8, 256, 3);
+    if (PlanH2160::matches(planH)) PB_COLS3(PlanH2160, 4, 256, 3);
+    if (PlanH9000::matches(planH)) {
+        // one pair is 70 KB: two pairs in one CTA of 512 threads (16-byte row segments), or -- PB_E3_NB9000=1 -- one
+        // pair in each of two resident CTAs of 256 threads (8-byte segments, but independent CTAs overlap their phases)
+        static const int nb9000 = env3("PB_E3_NB9000", 2);
+        if (nb9000 == 1) PB_COLS3(PlanH9000, 1, 256, 2);
+        PB_COLS3(PlanH9000, 2, 512, 1);
+    }
 #undef PB_COLS3
     return 1;
 }

@@ -209,5 +209,8 @@ using PlanH2160 = StaticPlan<2160, 15, 16, 9>;
 using PlanX4000 = StaticPlan<4000, 10, 10, 8, 5>;       // what the run-time planner (radices <= 16) gives: four stages
 using PlanX4000b = StaticPlan<4000, 20, 20, 10>;        // three stages with 20-point butterflies (second-generation row passes)
 using PlanY2304 = StaticPlan<2304, 16, 16, 9>;
+// the torus of the single 12000 x 9000 image (BASELINE C4): the run-time planner's orders
+using PlanX12096 = StaticPlan<12096, 16, 9, 12, 7>;
+using PlanY9216 = StaticPlan<9216, 16, 4, 16, 9>;
 
 }  // namespace pb

@@ -207,3 +207,30 @@ def test_chunk_images_bounds_the_workspace_and_keeps_the_result(pb):
     n_all = _lib.lib().pb_workspace_bytes(5, 3, 135, 240, C.byref(p_all))
     n_grp = _lib.lib().pb_workspace_bytes(5, 3, 135, 240, C.byref(p_grp))
     assert n_grp < 0.6 * n_all
+
+
+# ---- third-generation estimator kernels (csrc/estimate3.cu): edge shapes of the compile-time plans -------------
+@pytest.mark.parametrize("shape,discard", [((2, 3, 1081, 1920), False),     # odd height: the last row pair has one row
+                                           ((1, 3, 6, 1920), False),        # fewer row pairs than a CTA holds
+                                           ((1, 3, 1080, 1090), False),     # width not a multiple of the 16-column tile
+                                           ((1, 3, 1080, 34), True),        # narrow, with the saturation mask
+                                           ((1, 3, 2160, 70), False),       # 4K column plan
+                                           ((1, 3, 20, 3840), False)])      # 4K row plan
+def test_estimator_gen3_edge_shapes(pb, shape, discard):
+    """blur_estimation.py:18-65, 96-134 on shapes whose sides take the fused-stage kernels (1920 / 3840 wide rows,
+    1080 / 2160 tall columns) with ragged other sides: directional maxima, direction index and sigma / rho
+    against the CPU oracle."""
+    rng = np.random.default_rng(7)
+    B, C, H, W = shape
+    x = rng.random(shape, dtype=np.float32)
+    # a smooth component so that the estimate is not the clamped white-noise one, and some saturated pixels
+    yy = np.linspace(0, 3, H, dtype=np.float32)[:, None]
+    xx = np.linspace(0, 5, W, dtype=np.float32)[None, :]
+    x = np.clip(0.25 * x + 0.5 + 0.45 * np.sin(yy * 2.1 + 0.3) * np.cos(xx * 1.7), 0, 1).astype(np.float32)
+    tr = []
+    po.gaussian_blur_estimation(x, c=0.352, b=0.768, q=0.0, discard_saturation=discard, trace=tr)
+    e = pb.blur_estimation.estimate_parameters(cu(x), c=0.352, b=0.768, q=0.0, discard_saturation=discard)
+    np.testing.assert_allclose(e["mags"].cpu().numpy(), tr[0]["mags"], rtol=3e-5, atol=3e-6)
+    assert np.array_equal(e["theta_deg"].cpu().numpy().astype(np.int64), tr[0]["theta_deg"])
+    np.testing.assert_allclose(e["sigma"].cpu().numpy(), tr[0]["sigma"], rtol=1e-4)
+    np.testing.assert_allclose(e["rho"].cpu().numpy(), tr[0]["rho"], rtol=1e-4)
