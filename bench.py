@@ -275,10 +275,15 @@ def binding_unit(members_ms, key_suffix):
     acc, tot, src = {}, 0.0, set()
     for name, ms in members_ms.items():
         # the profiler's class names are generation-neutral; the captured kernels of the current build may carry a "2"
-        rec = pipes.get(f"{name}2:{key_suffix}") or pipes.get(f"{name}:{key_suffix}")
+        def lookup(sfx):
+            for gen in ("3", "2", ""):
+                if f"{name}{gen}:{sfx}" in pipes:
+                    return pipes[f"{name}{gen}:{sfx}"]
+            return None
+        rec = lookup(key_suffix)
         if not rec:                  # the estimate kernels do the same work for both synthetic distributions
             alt = key_suffix.replace("white:", "mosaic:") if key_suffix.startswith("white:") else key_suffix.replace("mosaic:", "white:")
-            rec = pipes.get(f"{name}2:{alt}") or pipes.get(f"{name}:{alt}")
+            rec = lookup(alt)
         if not rec or ms <= 0:
             continue
         tot += ms
@@ -408,10 +413,10 @@ def run_cuda(a):
 
     # ---- roofline of the dominant kernel group (CUDA events recorded by the library around each launch)
     # One "launch" of a group = the kernels one Polyblur iteration runs for it over the whole batch:
-    #   estimate      = k_rows2 + k_cols2 + k_params                        12 B/px/iter algorithmic
+    #   estimate      = k_rows + k_cols + k_params (k_rows3 / k_cols3 of csrc/estimate3.cu for the named shapes)   12 B/px/iter algorithmic
     #   deconvolution = the engines (narrow / tiled / FFT passes; every image goes through exactly one,
     #                   chosen on the device, so their times add up to one pass over the batch)  24 B/px/iter
-    EST = ("k_cols2", "k_rows2", "k_params")      # (k_cols / k_rows of estimate.cu for lengths with a prime factor > 13)
+    EST = ("k_cols", "k_rows", "k_params")        # the profiler's class names are generation-neutral
     DEC = ("k_deconv_narrow", "k_deconv_spatial", "k_fft_rows_fwd", "k_fft_cols", "k_fft_rows_inv")
     groups = {"estimate": sum(prof.get(k, (0.0, 0))[0] for k in EST),
               "deconvolution": sum(prof.get(k, (0.0, 0))[0] for k in DEC)}

@@ -31,7 +31,7 @@ static std::mutex g_prof_mu;
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
 static std::vector<cudaEvent_t> g_event_pool;
-static const char* kProfNames[PROF_NCLASSES] = {"setup", "k_cols2", "k_rows2", "k_params", "k_deconv_spatial",
+static const char* kProfNames[PROF_NCLASSES] = {"setup", "k_cols", "k_rows", "k_params", "k_deconv_spatial",
                                                 "k_fft_rows_fwd", "k_fft_cols", "k_fft_rows_inv", "other",
                                                 "k_deconv_narrow"};
 

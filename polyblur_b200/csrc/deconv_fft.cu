@@ -273,8 +273,8 @@ k_fft_rows_fwd(const float* __restrict__ img, float2* __restrict__ Z, const ImgK
 //                  | R[CB+1][13] float2 | mbarrier
 //   Leaves r = DFT(swap(Y)) in Z: the inverse transform is swap(r), P3 swaps while loading.
 // ---------------------------------------------------------------------------------------------
-template <class SP>
-__global__ void __launch_bounds__(FFTC_THREADS, PB_FFTC_MINB)
+template <class SP, int THREADS = FFTC_THREADS>
+__global__ void __launch_bounds__(THREADS, (THREADS > 256 ? 2 : PB_FFTC_MINB))
 k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int* __restrict__ list,
            const int* __restrict__ count, int C, int NX, int NY, int CB, Fft2Plan planY,
            const float2* __restrict__ twX, const float2* __restrict__ stwY, const int* __restrict__ slotY,
@@ -314,7 +314,7 @@ k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int
         // R[col][dy] = sum_dx K[dy][dx] exp(-2 pi i kx dx / NX), dy = 0..12 (R[-dy] = conj R[dy]);
         // entry CB is the Nyquist column kx = NX / 2 (needed by the block that holds kx = 0)
         // two threads per (col, dy): dx <= 0 and dx > 0, all loads of a thread issued together
-        for (int base = 0; base < (CB + 1) * 13 * 2; base += FFTC_THREADS) {
+        for (int base = 0; base < (CB + 1) * 13 * 2; base += THREADS) {
             const int i2 = base + tid;
             const int idx = i2 >> 1, part = i2 & 1;
             const int col = idx / 13, dy = idx - col * 13;
@@ -351,9 +351,9 @@ k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int
         // (r_A + i r_B -> K^_A + i K^_B), run by the same DIF core: the result arrives in slot order.
         const int ncolh = ncol + (cb == 0 ? 1 : 0);            // + the Nyquist column
         const int nseq = (ncolh + 1) >> 1;
-        for (int idx = tid; idx < nseq * NY; idx += FFTC_THREADS) data[idx] = make_float2(0.f, 0.f);
+        for (int idx = tid; idx < nseq * NY; idx += THREADS) data[idx] = make_float2(0.f, 0.f);
         __syncthreads();
-        for (int idx = tid; idx < nseq * PB_KS; idx += FFTC_THREADS) {
+        for (int idx = tid; idx < nseq * PB_KS; idx += THREADS) {
             const int q = idx / PB_KS, d = idx - q * PB_KS - PB_PAD;
             const int ca = 2 * q, cb2 = 2 * q + 1;
             const int ad = d < 0 ? -d : d;
@@ -368,11 +368,11 @@ k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int
         }
         __syncthreads();
         if constexpr (std::is_same<SP, NoStaticPlan>::value)
-            fft2_forward_dif(data, NY, nseq, planY, stwY, tid, FFTC_THREADS);
+            fft2_forward_dif(data, NY, nseq, planY, stwY, tid, THREADS);
         else
-            s_forward_dif<SP>(data, NY, nseq, stwY, tid, FFTC_THREADS);
+            s_forward_dif<SP>(data, NY, nseq, stwY, tid, THREADS);
         // Hs[col][slot] = scale * P(K^)
-        for (int idx = tid; idx < ncolh * NY; idx += FFTC_THREADS) {
+        for (int idx = tid; idx < ncolh * NY; idx += THREADS) {
             const int col = fast_div(idx, NY, inv_ny);
             const int s = idx - col * NY;
             const float2 z = data[(size_t)(col >> 1) * NY + s];
@@ -386,7 +386,7 @@ k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int
             // column 0 carries DC (real part) and Nyquist (imaginary part) of two real spectra:
             // Y[k] = A Z[k] + B conj Z[-k], A = (H0 + Hn) / 2, B = (H0 - Hn) / 2; it is filtered by a
             // separate pass below, so its fused multiplier becomes 1
-            for (int s = tid; s < NY; s += FFTC_THREADS) {
+            for (int s = tid; s < NY; s += THREADS) {
                 const float h0 = Hs[s], hn = Hn[s];
                 Hn[s] = 0.5f * (h0 + hn);
                 Hb[s] = 0.5f * (h0 - hn);
@@ -409,9 +409,9 @@ k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int
             mbar_wait(bar, phase);
             phase ^= 1;
             if (cb == 0) {
-                fft2_forward_dif(data, NY, ncol, planY, stwY, tid, FFTC_THREADS);
+                fft2_forward_dif(data, NY, ncol, planY, stwY, tid, THREADS);
                 // the pair {k, -k} of column 0 goes to one thread (in place, no hazard)
-                for (int ky = tid; ky <= NY / 2; ky += FFTC_THREADS) {
+                for (int ky = tid; ky <= NY / 2; ky += THREADS) {
                     const int s1 = __ldg(slotY + ky);
                     const int s2 = __ldg(slotY + (NY - ky) % NY);
                     const float2 z1 = data[s1], z2 = data[s2];
@@ -422,13 +422,13 @@ k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int
                 __syncthreads();
                 // inverse-direction transform with the multiplication by H (and the re/im swap) folded
                 // into its first stage
-                fft2_forward_dit(data, NY, ncol, planY, stwY, tid, FFTC_THREADS, Hs, 2);
+                fft2_forward_dit(data, NY, ncol, planY, stwY, tid, THREADS, Hs, 2);
             } else {
                 // forward, multiply by H (with the re/im swap), inverse: innermost stages fused in registers
                 if constexpr (std::is_same<SP, NoStaticPlan>::value)
-                    fft2_forward_mul_inverse(data, NY, ncol, planY, stwY, tid, FFTC_THREADS, Hs, 2);
+                    fft2_forward_mul_inverse(data, NY, ncol, planY, stwY, tid, THREADS, Hs, 2);
                 else
-                    s_forward_mul_inverse<SP, 2>(data, NY, ncol, stwY, tid, FFTC_THREADS, Hs);
+                    s_forward_mul_inverse<SP, 2>(data, NY, ncol, stwY, tid, THREADS, Hs);
             }
             fence_async_smem();
             __syncthreads();
@@ -670,8 +670,8 @@ __device__ __forceinline__ bool unit_maybe_nyquist(int q) { return 2 * KS * q <=
 #define PB_ROWS_CHUNK 1      // measured: 4 consecutive blocks per CTA is 8 % slower (1.48 / 1.63 ms against 1.38 / 1.50 ms per step)
 #endif
 
-template <class SP, int NY>
-__global__ void __launch_bounds__(FFTD_THREADS, PB_FFTD_MINB)
+template <class SP, int NY, int THREADS>
+__global__ void __launch_bounds__(THREADS, (THREADS > 256 ? 2 : PB_FFTD_MINB))
 k_fft_rows_fwd2(const float* __restrict__ img, float2* __restrict__ Z, const ImgKernel* __restrict__ kern,
                 const int* __restrict__ list, const int* __restrict__ count, int C, int H, int W, int nb,
                 const float2* __restrict__ twX, const int4* __restrict__ units, SrcGeom G) {
@@ -721,7 +721,7 @@ k_fft_rows_fwd2(const float* __restrict__ img, float2* __restrict__ Z, const Img
                 const int jn = (rn - cn * blocks_per_plane) * 2 * nb;
                 const float* srcn = img + ((size_t)list[slotn] * C + cn) * (size_t)G.Hin * G.Win;
                 const int lines = (G.Win + 31) / 32;
-                for (int i = tid; i < 2 * nb * lines; i += FFTD_THREADS) {
+                for (int i = tid; i < 2 * nb * lines; i += THREADS) {
                     const int rr = i / lines, ln = i - rr * lines;
                     const int sr = (jn + rr < NY) ? ext_src(jn + rr, H, ext, G.Hin, G.off, pad) : -1;
                     if (sr >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(srcn + (size_t)sr * G.Win + ln * 32));
@@ -729,13 +729,13 @@ k_fft_rows_fwd2(const float* __restrict__ img, float2* __restrict__ Z, const Img
             }
         }
 #endif
-        s_dif_first<R0, M0, NX>(smf, RS, nb, twX + SP::tw_off(0), tid, FFTD_THREADS, S);
+        s_dif_first<R0, M0, NX>(smf, RS, nb, twX + SP::tw_off(0), tid, THREADS, S);
         __syncthreads();
-        SDifRun<SP, 1, NS - 2, false>::run(smf, RS, nb, twX, tid, FFTD_THREADS);
+        SDifRun<SP, 1, NS - 2, false>::run(smf, RS, nb, twX, tid, THREADS);
         // last stage (M = 1) on the two blocks of a mirror unit, then
         //   Xa[k] = (Z[k] + conj Z[-k]) / 2,  Xb[k] = (Z[k] - conj Z[-k]) / (2i)   ->  Z[plane][kx][row pair]
         float2* Zp = Z + ((size_t)slot * C + c) * half * NY;
-        for (int idx = tid; idx < nunits * nb; idx += FFTD_THREADS) {
+        for (int idx = tid; idx < nunits * nb; idx += THREADS) {
             const int u = idx / nb, p = idx - u * nb;
             const int ja = j0 + 2 * p;
             if (ja >= NY) continue;
@@ -792,8 +792,8 @@ k_fft_rows_fwd2(const float* __restrict__ img, float2* __restrict__ Z, const Img
     }
 }
 
-template <class SP, int NY>
-__global__ void __launch_bounds__(FFTD_THREADS, PB_FFTD_MINB)
+template <class SP, int NY, int THREADS>
+__global__ void __launch_bounds__(THREADS, (THREADS > 256 ? 2 : PB_FFTD_MINB))
 k_fft_rows_inv2(const float2* __restrict__ Z, float* __restrict__ out, const ImgKernel* __restrict__ kern,
                 const int* __restrict__ list, const int* __restrict__ count, int C, int H, int W, int nb,
                 const float2* __restrict__ twX, const int4* __restrict__ units, int clamp_out) {
@@ -831,14 +831,14 @@ k_fft_rows_inv2(const float2* __restrict__ Z, float* __restrict__ out, const Img
                 const int rn = wn - slotn * per_img;
                 const int cn = rn / blocks_per_plane;
                 const float2* Zn = Z + ((size_t)slotn * C + cn) * half * NY + (size_t)(rn - cn * blocks_per_plane) * 2 * nb;
-                for (int kx = tid; kx < half; kx += FFTD_THREADS)
+                for (int kx = tid; kx < half; kx += THREADS)
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(Zn + (size_t)kx * NY));
             }
         }
 #endif
         // rebuild Z[k] = Xa[k] + i Xb[k], Z[-k] = conj Xa[k] + i conj Xb[k] of a mirror unit in registers (P2 leaves
         // the spectra re/im swapped, and the inverse-by-forward trick wants them swapped), first inverse stage (M = 1)
-        for (int idx = tid; idx < nunits * nb; idx += FFTD_THREADS) {
+        for (int idx = tid; idx < nunits * nb; idx += THREADS) {
             const int u = idx / nb, p = idx - u * nb;
             const int ja = j0 + 2 * p;
             if (ja >= NY) continue;        // pair beyond the torus (never an output row; its slots stay unused)
@@ -912,7 +912,7 @@ k_fft_rows_inv2(const float2* __restrict__ Z, float* __restrict__ out, const Img
             for (int q = 0; q < RL; ++q) row[U.y * RL + q] = vb[q];
         }
         __syncthreads();
-        SDitRun<SP, NS - 2, NS - 2, false>::run(smf, RS, nb, twX, tid, FFTD_THREADS);
+        SDitRun<SP, NS - 2, NS - 2, false>::run(smf, RS, nb, twX, tid, THREADS);
         RowPairDst D;
         D.dst = out + ((size_t)im * C + c) * plane;
         D.W = W;
@@ -922,7 +922,7 @@ k_fft_rows_inv2(const float2* __restrict__ Z, float* __restrict__ out, const Img
         D.lo = clamp_out ? 0.0f : -INFINITY;
         D.hi = clamp_out ? 1.0f : INFINITY;
         D.inner_interior = (M0 >= ext) && ((R0 - 1) * M0 - ext <= W);
-        s_dit_last<R0, M0, NX>(smf, RS, nb, twX + SP::tw_off(0), tid, FFTD_THREADS, D);
+        s_dit_last<R0, M0, NX>(smf, RS, nb, twX + SP::tw_off(0), tid, THREADS, D);
         __syncthreads();
     }
 }
@@ -1304,7 +1304,8 @@ int launch_deconv_fft(const float* img, float* out, const ImgKernel* kern, const
     const size_t smem_cols = (size_t)CB * NY * 12 + (size_t)NY * 8 + (size_t)(CB + 1) * 13 * 8 + 64;
     const long long row_items = (long long)B * C * ((NY / 2 + nb - 1) / nb);
     const long long col_items = (long long)B * ((NX / 2 + CB - 1) / CB);
-    const int cap = PB_NUM_SMS * 6;
+    static const int cap_per_sm = env_int("PB_FFT_CTAS_PER_SM", 6);      // persistent CTAs launched per SM (3 are resident)
+    const int cap = PB_NUM_SMS * cap_per_sm;
     const int grid_rows = (int)(row_items < cap ? row_items : cap);
     const int grid_cols = (int)(col_items < cap ? col_items : cap);
     // compile-time plans for the standard tori (1080p: 2016 x 1152, 4K: 4000 x 2304), else the run-time core
@@ -1324,19 +1325,19 @@ int launch_deconv_fft(const float* img, float* out, const ImgKernel* kern, const
         }                                                                                                        \
     } while (0)
     // second-generation row passes (fused first / last stages) for the compile-time plans
-#define PB_FFT_ROWS2(SP, NYC, TW, UN)                                                                                         \
+#define PB_FFT_ROWS2(SP, NYC, TW, UN, TH)                                                                                        \
     do {                                                                                                         \
-        auto kf = k_fft_rows_fwd2<SP, NYC>;                                                                      \
-        auto ki = k_fft_rows_inv2<SP, NYC>;                                                                      \
+        auto kf = k_fft_rows_fwd2<SP, NYC, TH>;                                                                      \
+        auto ki = k_fft_rows_inv2<SP, NYC, TH>;                                                                      \
         const size_t smem_rows = (size_t)nb * fftd_row_stride2(SP::n, SP::R(SP::ns - 1)) * sizeof(float2);      \
         PB_CUDA_TRY(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));      \
         PB_CUDA_TRY(cudaFuncSetAttribute(ki, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));      \
         if (fwd) {                                                                                               \
             ProfScope prof(PROF_FFT_ROWS_FWD, stream);                                                           \
-            kf<<<grid_rows, FFTD_THREADS, smem_rows, stream>>>(img, T.Z, kern, list, count, C, H, W, nb, TW, UN, G); \
+            kf<<<grid_rows, TH, smem_rows, stream>>>(img, T.Z, kern, list, count, C, H, W, nb, TW, UN, G); \
         } else {                                                                                                 \
             ProfScope prof(PROF_FFT_ROWS_INV, stream);                                                           \
-            ki<<<grid_rows, FFTD_THREADS, smem_rows, stream>>>(T.Z, out, kern, list, count, C, H, W, nb, TW, UN,  \
+            ki<<<grid_rows, TH, smem_rows, stream>>>(T.Z, out, kern, list, count, C, H, W, nb, TW, UN,  \
                                                                G.clamp_out);                                     \
         }                                                                                                        \
     } while (0)
@@ -1368,13 +1369,14 @@ int launch_deconv_fft(const float* img, float* out, const ImgKernel* kern, const
     } while (0)
     // long columns (one column per CTA): the block of column 0 in its own launch, so that the other CTAs do without its
     // two extra NY-float arrays and two of them fit an SM
-#define PB_FFT_COLS_LONG(SP)                                                                                     \
+#define PB_FFT_COLS_LONG(SP, TH)                                                                                 \
     do {                                                                                                         \
         const size_t smem1 = (size_t)CB * NY * 12 + (size_t)(CB + 1) * 13 * 8 + 64;                              \
         const long long items1 = (long long)B * ((NX / 2 + CB - 1) / CB - 1);                                    \
+        PB_CUDA_TRY(cudaFuncSetAttribute(k_fft_cols<SP, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1)); \
         PB_CUDA_TRY(cudaFuncSetAttribute(k_fft_cols<SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols)); \
         ProfScope prof(PROF_FFT_COLS, stream);                                                                   \
-        k_fft_cols<SP><<<(int)(items1 < cap ? items1 : cap), FFTC_THREADS, smem1, stream>>>(                     \
+        k_fft_cols<SP, TH><<<(int)(items1 < cap ? items1 : cap), TH, smem1, stream>>>(                           \
             T.Z, kern, list, count, C, NX, NY, CB, T.planY, T.twX, T.stwY, T.slotY, a3, a2, a1, b0, 2);          \
         k_fft_cols<SP><<<dim3(B < cap ? B : cap, C), FFTC_THREADS, smem_cols, stream>>>(                         \
             T.Z, kern, list, count, C, NX, NY, CB, T.planY, T.twX, T.stwY, T.slotY, a3, a2, a1, b0, 1);          \
@@ -1388,18 +1390,23 @@ int launch_deconv_fft(const float* img, float* out, const ImgKernel* kern, const
             else if (T.ra2 == 32 && T.rb2 == 36 && !cols_v1) PB_FFT_COLS2(32, 36);
             else if (PlanY1152::matches(T.planY)) PB_FFT_COLS(PlanY1152);
             else if (PlanY2304::matches(T.planY)) PB_FFT_COLS(PlanY2304);
-            else if (PlanY9216::matches(T.planY) && CB == 1 && !cols_v1) PB_FFT_COLS_LONG(PlanY9216);
+            else if (PlanY9216::matches(T.planY) && CB == 1 && !cols_v1) {
+                static const int th_long = env_int("PB_FFT_COLS_LONG_T", 384);
+                if (th_long == 384) PB_FFT_COLS_LONG(PlanY9216, 384); else PB_FFT_COLS_LONG(PlanY9216, 256);
+            }
             else PB_FFT_COLS(NoStaticPlan);
         } else {
             // (the second-generation kernels also fix NY at compile time: the 1080p and 4K tori)
             if (PlanX2016::matches(T.planX)) {
-                if (rows_v1 || NY != 1152) PB_FFT_ROWS(PlanX2016); else PB_FFT_ROWS2(PlanX2016, 1152, T.stwX, T.unitsX);
+                if (rows_v1 || NY != 1152) PB_FFT_ROWS(PlanX2016); else PB_FFT_ROWS2(PlanX2016, 1152, T.stwX, T.unitsX, FFTD_THREADS);
             } else if (PlanX4000::matches(T.planX)) {
                 if (rows_v1 || NY != 2304) PB_FFT_ROWS(PlanX4000);
-                else if (T.rowplan2 == 1) PB_FFT_ROWS2(PlanX4000b, 2304, T.stwX2, T.unitsX2);
-                else PB_FFT_ROWS2(PlanX4000, 2304, T.stwX, T.unitsX);
+                else if (T.rowplan2 == 1) PB_FFT_ROWS2(PlanX4000b, 2304, T.stwX2, T.unitsX2, FFTD_THREADS);
+                else PB_FFT_ROWS2(PlanX4000, 2304, T.stwX, T.unitsX, FFTD_THREADS);
             } else if (PlanX12096::matches(T.planX) && NY == 9216 && !rows_v1) {
-                PB_FFT_ROWS2(PlanX12096, 9216, T.stwX, T.unitsX);
+                // one row pair (95 KB) per CTA, two CTAs per SM (384 threads per CTA, which fill the register file at
+                // 2 x 384 x 80, measured slower: P1 7.1 against 6.5 ms per C4 step, P3 equal)
+                PB_FFT_ROWS2(PlanX12096, 9216, T.stwX, T.unitsX, 256);
             } else PB_FFT_ROWS(NoStaticPlan);
         }
     }

@@ -339,7 +339,8 @@ int launch_rows3(const float* img, float* gray, float* gx, unsigned* stats, int 
     } while (0)
     if (PlanW1920::matches(planW)) PB_ROWS3(PlanW1920, 2, 256, 3, 64 * 1024);
     if (PlanW3840::matches(planW)) PB_ROWS3(PlanW3840, 1, 256, 3, 64 * 1024);
-    if (PlanW12000::matches(planW)) PB_ROWS3(PlanW12000, 2, 256, 2, 100 * 1024);     // one pair (94 KB), two CTAs per SM
+    // one pair (94 KB), two CTAs per SM (384 threads per CTA measured the same as 256)
+    if (PlanW12000::matches(planW)) PB_ROWS3(PlanW12000, 2, 256, 2, 100 * 1024);
 #undef PB_ROWS3
     return 1;
 }
@@ -365,13 +366,12 @@ int launch_cols3(const float* g, const float* gx, unsigned* stats, int nimg, int
     // trip idle, measured the same as 256: the trips are not what binds)
     if (PlanH1080::matches(planH)) PB_COLS3(PlanH1080, 8, 256, 3);
     if (PlanH2160::matches(planH)) PB_COLS3(PlanH2160, 4, 256, 3);
-    if (PlanH9000::matches(planH)) {
-        // one pair is 70 KB: two pairs in one CTA of 512 threads (16-byte row segments), or -- PB_E3_NB9000=1 -- one
-        // pair in each of two resident CTAs of 256 threads (8-byte segments, but independent CTAs overlap their phases)
-        static const int nb9000 = env3("PB_E3_NB9000", 2);
-        if (nb9000 == 1) PB_COLS3(PlanH9000, 1, 256, 2);
-        PB_COLS3(PlanH9000, 2, 512, 1);
-    }
+    // one pair of 9000 rows is 70 KB: two pairs in one CTA of 512 threads (16-byte row segments).  Measured and left out:
+    // one pair in each of two resident CTAs of 256 threads (8-byte segments; C4 step 5.31 against 5.09 ms), and a
+    // persistent variant of this kernel that runs the last stage of an item and the first stage of the CTA's next
+    // item in one loop (same thread, same shared-memory slots, so no barrier and the next item's loads are in flight
+    // during the reduce): C2 0.88 against 0.82 ms per step, C4 4.95 against 5.07 ms -- the loads are not what binds.
+    if (PlanH9000::matches(planH)) PB_COLS3(PlanH9000, 2, 512, 1);
 #undef PB_COLS3
     return 1;
 }

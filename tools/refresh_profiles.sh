@@ -19,11 +19,11 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k
     python bench.py --steps 2 --warmup 1 --no-graph --no-e2e --no-cpu-baseline --no-secondary > $O/launches.log 2>&1
 fi
 if [ "$PART" = "2" ]; then
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_rows2|k_cols2|k_params|k_fft_rows|k_fft_cols" -s 0 -c 7 -f -o $O/prof_mosaic32 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_rows3|k_cols3|k_params|k_fft_rows|k_fft_cols" -s 0 -c 7 -f -o $O/prof_mosaic32 \
     python bench.py --steps 1 --warmup 1 --no-graph --no-e2e --no-cpu-baseline --no-secondary > $O/ncu_mosaic.log 2>&1
 timeout 900 ncu --set full --clock-control none -k regex:"k_deconv_narrow" -s 0 -c 2 -f -o $O/prof_white32 \
     python bench.py --dist white --steps 1 --warmup 1 --no-graph --no-e2e --no-cpu-baseline --no-secondary > $O/ncu_white.log 2>&1
-timeout 900 ncu --set full --clock-control none -k regex:"k_rows2|k_cols2|k_fft_rows|k_fft_cols" -s 0 -c 7 -f -o $O/prof_mosaic_c3 \
+timeout 900 ncu --set full --clock-control none -k regex:"k_rows3|k_cols3|k_fft_rows|k_fft_cols" -s 0 -c 7 -f -o $O/prof_mosaic_c3 \
     python bench.py --config C3 --batch 8 --steps 1 --warmup 1 --no-graph --no-e2e --no-cpu-baseline --no-secondary > $O/ncu_c3.log 2>&1
 # the reports themselves are too large to travel together: export the raw pages and the per-instruction mix here
 for rep in prof_mosaic32 prof_white32 prof_mosaic_c3; do

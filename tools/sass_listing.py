@@ -12,7 +12,7 @@ import sys
 
 WATCH = ["FFMA", "FADD", "FMUL", "LDS", "STS", "LDG", "STG", "LDL", "STL", "SHFL", "BAR", "UBLKCP", "SYNCS", "LDGSTS",
          "UTMALDG", "UTMASTG", "UTCHMMA", "UTCQMMA", "LDTM", "STTM", "HMMA", "CCTL"]
-HOT = ("k_fft_rows_fwd2", "k_fft_rows_inv2", "k_fft_cols2", "k_fft_cols", "k_rows2", "k_cols2", "k_deconv_narrow", "k_rf_rows",
+HOT = ("k_fft_rows_fwd2", "k_fft_rows_inv2", "k_fft_cols2", "k_fft_cols", "k_rows3", "k_cols3", "k_rows2", "k_cols2", "k_deconv_narrow", "k_rf_rows",
        "k_patch", "k_table_jobs")
 
 
