@@ -1304,8 +1304,11 @@ int launch_deconv_fft(const float* img, float* out, const ImgKernel* kern, const
     const size_t smem_cols = (size_t)CB * NY * 12 + (size_t)NY * 8 + (size_t)(CB + 1) * 13 * 8 + 64;
     const long long row_items = (long long)B * C * ((NY / 2 + nb - 1) / nb);
     const long long col_items = (long long)B * ((NX / 2 + CB - 1) / CB);
-    static const int cap_per_sm = env_int("PB_FFT_CTAS_PER_SM", 6);      // persistent CTAs launched per SM (3 are resident)
-    const int cap = PB_NUM_SMS * cap_per_sm;
+    // CTAs launched per SM for the grid-stride kernels (0 = one work item per CTA).  Measured at C2: 6 per SM (two
+    // waves of persistent CTAs, 15 items each) 1.375 / 1.498 ms per step for P1 / P3, 24 per SM 1.383 / 1.412, one item
+    // per CTA 1.33 / 1.36: the hardware's CTA scheduler balances the tail better than long-lived CTAs do.
+    static const int cap_per_sm = env_int("PB_FFT_CTAS_PER_SM", 0);
+    const int cap = cap_per_sm > 0 ? PB_NUM_SMS * cap_per_sm : (1 << 30);
     const int grid_rows = (int)(row_items < cap ? row_items : cap);
     const int grid_cols = (int)(col_items < cap ? col_items : cap);
     // compile-time plans for the standard tori (1080p: 2016 x 1152, 4K: 4000 x 2304), else the run-time core
@@ -1358,7 +1361,9 @@ int launch_deconv_fft(const float* img, float* out, const ImgKernel* kern, const
                              (size_t)cb2 * 13 * sizeof(float2) + (size_t)((RA) - 1) * (RB) * sizeof(float2) + 64;  \
         const size_t smem0 = (size_t)NY * 12 + (size_t)NY * 8 + 2 * 13 * 8 + 64;                                 \
         const long long items2 = (long long)B * ((NX / 2 - 1 + cb2 - 1) / cb2);                                  \
-        const int grid2 = (int)(items2 < 2 * PB_NUM_SMS ? items2 : 2 * PB_NUM_SMS);                              \
+        static const int c2_per_sm = env_int("PB_FFT_COLS2_CTAS_PER_SM", 4);                                     \
+        const long long cap2 = c2_per_sm > 0 ? (long long)c2_per_sm * PB_NUM_SMS : (1LL << 30);                  \
+        const int grid2 = (int)(items2 < cap2 ? items2 : cap2);                                                  \
         PB_CUDA_TRY(cudaFuncSetAttribute(k_fft_cols2<RA, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); \
         PB_CUDA_TRY(cudaFuncSetAttribute(k_fft_cols<NoStaticPlan>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0)); \
         ProfScope prof(PROF_FFT_COLS, stream);                                                                   \

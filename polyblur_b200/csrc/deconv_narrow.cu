@@ -21,6 +21,8 @@
 // Work items (image of this class, channel, tile) are taken grid-stride from the per-class image
 // list that k_params fills on the device, so no host synchronisation is needed to choose the
 // engine per image.
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace pb {
@@ -229,7 +231,9 @@ static int launch_one(const float* img, float* out, const ImgKernel* kern, const
     const int tilesX = (W + Cfg::VW - 1) / Cfg::VW, tilesY = (H + TH - 1) / TH;
     const long long items = (long long)B * C * tilesX * tilesY;
     const long long want = (items + 3) / 4;
-    int grid = (int)(want < (long long)PB_NUM_SMS * 8 ? want : (long long)PB_NUM_SMS * 8);
+    static const int per_sm = [] { const char* v = getenv("PB_NARROW_CTAS_PER_SM"); return v ? atoi(v) : 16; }();   // measured at C2 white: 8 per SM 1.58 ms per step, 16: 1.50, unlimited: 1.51
+    const long long capn = per_sm > 0 ? (long long)PB_NUM_SMS * per_sm : (1LL << 30);
+    int grid = (int)(want < capn ? want : capn);
     if (grid < 1) grid = 1;
     k_deconv_narrow<RX, RY><<<grid, NARROW_THREADS, 0, stream>>>(img, out, kern, list, count, C, H, W, TH, a3, a2,
                                                                  a1, b0, G);
