@@ -575,6 +575,18 @@ k_fft_rows_inv(const float2* __restrict__ Z, float* __restrict__ out, const ImgK
 // instructions of P1 / 47 % of P3 in the load / separation passes -- profiles/r02_sass_segments.md.)
 // =============================================================================================
 
+// shared-memory layout of the second-generation row kernels: padded stage-1 blocks for the three-stage plans
+// (fft2_static.cuh: LayoutPad1), and the distance RS between the row pairs of a CTA -- the mirror-unit stage reads
+// one block of R_last slots per (unit, pair): with an odd R_last consecutive units already fall into different
+// bank pairs and the pairs sit 4 (mod 16) apart, with an even R_last the pairs must sit an odd distance apart
+template <class SP, bool PADL>
+struct Rows2Layout {
+    using LY = typename std::conditional<(PADL && SP::ns == 3), PadFor<SP>, LayoutFlat>::type;
+    static constexpr int LEN = SP::n + SP::R(0) * LY::PAD;
+    static constexpr int WANT = (SP::R(SP::ns - 1) & 1) ? 4 : 5;
+    static constexpr int RS = LEN + ((WANT - LEN) % 16 + 16) % 16;
+};
+
 // feeds stage 0 of P1: sample e = j + m M of row pair f = (extended rows 2f, 2f + 1) of one plane
 struct RowPairSrc {
     const float* src;      // plane
@@ -670,7 +682,7 @@ __device__ __forceinline__ bool unit_maybe_nyquist(int q) { return 2 * KS * q <=
 #define PB_ROWS_CHUNK 1      // measured: 4 consecutive blocks per CTA is 8 % slower (1.48 / 1.63 ms against 1.38 / 1.50 ms per step)
 #endif
 
-template <class SP, int NY, int THREADS>
+template <class SP, int NY, int THREADS, bool PADL>
 __global__ void __launch_bounds__(THREADS, (THREADS > 256 ? 2 : PB_FFTD_MINB))
 k_fft_rows_fwd2(const float* __restrict__ img, float2* __restrict__ Z, const ImgKernel* __restrict__ kern,
                 const int* __restrict__ list, const int* __restrict__ count, int C, int H, int W, int nb,
@@ -683,7 +695,8 @@ k_fft_rows_fwd2(const float* __restrict__ img, float2* __restrict__ Z, const Img
     const int per_img = C * blocks_per_plane;
     const int total = count[0] * per_img;
     constexpr int half = NX >> 1;
-    const int RS = fftd_row_stride(NX);
+    using LY = typename Rows2Layout<SP, PADL>::LY;
+    constexpr int RS = Rows2Layout<SP, PADL>::RS;
     const int nunits = units[0].x;
 
     // a CTA takes PB_ROWS_CHUNK consecutive row blocks of a plane (they share 256-byte pieces of the spectrum columns)
@@ -729,9 +742,9 @@ k_fft_rows_fwd2(const float* __restrict__ img, float2* __restrict__ Z, const Img
             }
         }
 #endif
-        s_dif_first<R0, M0, NX>(smf, RS, nb, twX + SP::tw_off(0), tid, THREADS, S);
+        s_dif_first<R0, M0, NX, RowPairSrc, LY>(smf, RS, nb, twX + SP::tw_off(0), tid, THREADS, S);
         __syncthreads();
-        SDifRun<SP, 1, NS - 2, false>::run(smf, RS, nb, twX, tid, THREADS);
+        SDifRun<SP, 1, NS - 2, false, LY>::run(smf, RS, nb, twX, tid, THREADS);
         // last stage (M = 1) on the two blocks of a mirror unit, then
         //   Xa[k] = (Z[k] + conj Z[-k]) / 2,  Xb[k] = (Z[k] - conj Z[-k]) / (2i)   ->  Z[plane][kx][row pair]
         float2* Zp = Z + ((size_t)slot * C + c) * half * NY;
@@ -743,7 +756,7 @@ k_fft_rows_fwd2(const float* __restrict__ img, float2* __restrict__ Z, const Img
             const float2* row = smf + (size_t)p * RS;
             float2 va[RL], vb[RL];
 #pragma unroll
-            for (int q = 0; q < RL; ++q) va[q] = row[U.x * RL + q];
+            for (int q = 0; q < RL; ++q) va[q] = row[LY::off(U.x * RL) + q];
             Dft<RL>::run(va);
             if (U.x == 0 || U.x == U.y) {
                 // the two self-mirror blocks (block 0; the block that holds NX / 2): rare, generic code
@@ -768,7 +781,7 @@ k_fft_rows_fwd2(const float* __restrict__ img, float2* __restrict__ Z, const Img
                 continue;
             }
 #pragma unroll
-            for (int q = 0; q < RL; ++q) vb[q] = row[U.y * RL + q];
+            for (int q = 0; q < RL; ++q) vb[q] = row[LY::off(U.y * RL) + q];
             Dft<RL>::run(vb);
             // slot q of block A holds k = fA + KS q, slot RL - 1 - q of block B its mirror NX - k; the lower of the two
             // is the half-spectrum column.  Columns of one unit are KS apart: two base pointers, immediate offsets.
@@ -792,7 +805,7 @@ k_fft_rows_fwd2(const float* __restrict__ img, float2* __restrict__ Z, const Img
     }
 }
 
-template <class SP, int NY, int THREADS>
+template <class SP, int NY, int THREADS, bool PADL>
 __global__ void __launch_bounds__(THREADS, (THREADS > 256 ? 2 : PB_FFTD_MINB))
 k_fft_rows_inv2(const float2* __restrict__ Z, float* __restrict__ out, const ImgKernel* __restrict__ kern,
                 const int* __restrict__ list, const int* __restrict__ count, int C, int H, int W, int nb,
@@ -805,7 +818,8 @@ k_fft_rows_inv2(const float2* __restrict__ Z, float* __restrict__ out, const Img
     const int total = count[0] * per_img;
     const size_t plane = (size_t)H * W;
     constexpr int half = NX >> 1;
-    const int RS = fftd_row_stride(NX);
+    using LY = typename Rows2Layout<SP, PADL>::LY;
+    constexpr int RS = Rows2Layout<SP, PADL>::RS;
     const int nunits = units[0].x;
 
     // a CTA takes PB_ROWS_CHUNK consecutive row blocks of a plane (they share 256-byte pieces of the spectrum columns)
@@ -873,7 +887,7 @@ k_fft_rows_inv2(const float2* __restrict__ Z, float* __restrict__ out, const Img
                 }
                 Dft<RL>::run(va);
 #pragma unroll
-                for (int q = 0; q < RL; ++q) row[U.x * RL + q] = va[q];
+                for (int q = 0; q < RL; ++q) row[LY::off(U.x * RL) + q] = va[q];
                 continue;
             }
             const float2* slo = Zp + (size_t)U.z * NY + ja;
@@ -906,13 +920,13 @@ k_fft_rows_inv2(const float2* __restrict__ Z, float* __restrict__ out, const Img
             }
             Dft<RL>::run(va);
 #pragma unroll
-            for (int q = 0; q < RL; ++q) row[U.x * RL + q] = va[q];
+            for (int q = 0; q < RL; ++q) row[LY::off(U.x * RL) + q] = va[q];
             Dft<RL>::run(vb);
 #pragma unroll
-            for (int q = 0; q < RL; ++q) row[U.y * RL + q] = vb[q];
+            for (int q = 0; q < RL; ++q) row[LY::off(U.y * RL) + q] = vb[q];
         }
         __syncthreads();
-        SDitRun<SP, NS - 2, NS - 2, false>::run(smf, RS, nb, twX, tid, THREADS);
+        SDitRun<SP, NS - 2, NS - 2, false, LY>::run(smf, RS, nb, twX, tid, THREADS);
         RowPairDst D;
         D.dst = out + ((size_t)im * C + c) * plane;
         D.W = W;
@@ -922,7 +936,7 @@ k_fft_rows_inv2(const float2* __restrict__ Z, float* __restrict__ out, const Img
         D.lo = clamp_out ? 0.0f : -INFINITY;
         D.hi = clamp_out ? 1.0f : INFINITY;
         D.inner_interior = (M0 >= ext) && ((R0 - 1) * M0 - ext <= W);
-        s_dit_last<R0, M0, NX>(smf, RS, nb, twX + SP::tw_off(0), tid, THREADS, D);
+        s_dit_last<R0, M0, NX, RowPairDst, LY>(smf, RS, nb, twX + SP::tw_off(0), tid, THREADS, D);
         __syncthreads();
     }
 }
@@ -1328,11 +1342,11 @@ int launch_deconv_fft(const float* img, float* out, const ImgKernel* kern, const
         }                                                                                                        \
     } while (0)
     // second-generation row passes (fused first / last stages) for the compile-time plans
-#define PB_FFT_ROWS2(SP, NYC, TW, UN, TH)                                                                                        \
+#define PB_FFT_ROWS2(SP, NYC, TW, UN, TH, PADL)                                                                                        \
     do {                                                                                                         \
-        auto kf = k_fft_rows_fwd2<SP, NYC, TH>;                                                                      \
-        auto ki = k_fft_rows_inv2<SP, NYC, TH>;                                                                      \
-        const size_t smem_rows = (size_t)nb * fftd_row_stride2(SP::n, SP::R(SP::ns - 1)) * sizeof(float2);      \
+        auto kf = k_fft_rows_fwd2<SP, NYC, TH, PADL>;                                                                      \
+        auto ki = k_fft_rows_inv2<SP, NYC, TH, PADL>;                                                                      \
+        const size_t smem_rows = (size_t)nb * Rows2Layout<SP, PADL>::RS * sizeof(float2);      \
         PB_CUDA_TRY(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));      \
         PB_CUDA_TRY(cudaFuncSetAttribute(ki, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows));      \
         if (fwd) {                                                                                               \
@@ -1387,6 +1401,10 @@ int launch_deconv_fft(const float* img, float* out, const ImgKernel* kern, const
             T.Z, kern, list, count, C, NX, NY, CB, T.planY, T.twX, T.stwY, T.slotY, a3, a2, a1, b0, 1);          \
     } while (0)
     static const bool rows_v1 = env_int("PB_FFT_ROWS_V1", 0) != 0;     // A/B against the first-generation passes
+    // padded stage-1 blocks (Rows2Layout): 1 = the 4K plan only, 2 = the 1080p plan too.  Measured: 4K P1 1.58 -> 1.53,
+    // P3 1.60 -> 1.57 ms per step (8 images); 1080p P1 1.33 -> 1.52, P3 1.36 -> 1.66 -- there the three CTAs grow from
+    // 194 to 211 KB of shared memory and the 16 KB of L1 that remain no longer hold the twiddle tables.
+    static const int rows_pad = env_int("PB_FFT_ROWS_PAD", 1);
     static const bool cols_v1 = env_int("PB_FFT_COLS_V1", 0) != 0;
     for (int pass = 0; pass < 3; ++pass) {
         const bool fwd = pass == 0;
@@ -1403,15 +1421,18 @@ int launch_deconv_fft(const float* img, float* out, const ImgKernel* kern, const
         } else {
             // (the second-generation kernels also fix NY at compile time: the 1080p and 4K tori)
             if (PlanX2016::matches(T.planX)) {
-                if (rows_v1 || NY != 1152) PB_FFT_ROWS(PlanX2016); else PB_FFT_ROWS2(PlanX2016, 1152, T.stwX, T.unitsX, FFTD_THREADS);
+                if (rows_v1 || NY != 1152) PB_FFT_ROWS(PlanX2016);
+                else if (rows_pad >= 2) PB_FFT_ROWS2(PlanX2016, 1152, T.stwX, T.unitsX, FFTD_THREADS, true);
+                else PB_FFT_ROWS2(PlanX2016, 1152, T.stwX, T.unitsX, FFTD_THREADS, false);
             } else if (PlanX4000::matches(T.planX)) {
                 if (rows_v1 || NY != 2304) PB_FFT_ROWS(PlanX4000);
-                else if (T.rowplan2 == 1) PB_FFT_ROWS2(PlanX4000b, 2304, T.stwX2, T.unitsX2, FFTD_THREADS);
-                else PB_FFT_ROWS2(PlanX4000, 2304, T.stwX, T.unitsX, FFTD_THREADS);
+                else if (T.rowplan2 == 1 && rows_pad) PB_FFT_ROWS2(PlanX4000b, 2304, T.stwX2, T.unitsX2, FFTD_THREADS, true);
+                else if (T.rowplan2 == 1) PB_FFT_ROWS2(PlanX4000b, 2304, T.stwX2, T.unitsX2, FFTD_THREADS, false);
+                else PB_FFT_ROWS2(PlanX4000, 2304, T.stwX, T.unitsX, FFTD_THREADS, false);
             } else if (PlanX12096::matches(T.planX) && NY == 9216 && !rows_v1) {
                 // one row pair (95 KB) per CTA, two CTAs per SM (384 threads per CTA, which fill the register file at
                 // 2 x 384 x 80, measured slower: P1 7.1 against 6.5 ms per C4 step, P3 equal)
-                PB_FFT_ROWS2(PlanX12096, 9216, T.stwX, T.unitsX, 256);
+                PB_FFT_ROWS2(PlanX12096, 9216, T.stwX, T.unitsX, 256, false);
             } else PB_FFT_ROWS(NoStaticPlan);
         }
     }

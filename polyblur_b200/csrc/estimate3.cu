@@ -17,6 +17,7 @@
 // Reference being replaced: blur_estimation.gaussian_blur_estimation up to the directional maxima
 // (polyblur/blur_estimation.py:18-65, 96-134), filters.fourier_gradients (polyblur/filters.py:159-186).
 #include <cstdlib>
+#include <type_traits>
 
 #include "fft2_static.cuh"
 #include "kernels.cuh"
@@ -40,12 +41,16 @@ static __device__ __forceinline__ float gray3(float a, float b, float c) {
 // A thread owns WIDE adjacent columns j .. j + WIDE - 1 of a pair: WIDE butterflies side by side, so
 // global accesses are 8 bytes and shared-memory accesses 16 bytes wide when WIDE = 2.
 // ---------------------------------------------------------------------------------------------
-template <class SP, int WIDE, int THREADS, int MINB>
+template <class SP, int WIDE, int THREADS, int MINB, bool PADL>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_rows3(const float* __restrict__ img, float* __restrict__ gray, float* __restrict__ gx,
         unsigned* __restrict__ stats, int H, int nb, const float2* __restrict__ tw,
         const float* __restrict__ omega) {
     constexpr int W = SP::n, NS = SP::ns, R0 = SP::R(0), M0 = W / R0, JM = M0 / WIDE;
+    // padded stage-1 blocks (fft2_static.cuh: LayoutPad1) for the three-stage plans; RS = float2 per row pair
+    using LY = typename std::conditional<(PADL && NS == 3), PadFor<SP>, LayoutFlat>::type;
+    constexpr int M0P = M0 + LY::PAD, RS = W + R0 * LY::PAD;
+    constexpr bool V4 = WIDE == 2 && (M0P % 2 == 0);        // 16-byte shared-memory accesses need even block starts
     static_assert(M0 % WIDE == 0 && (WIDE == 1 || WIDE == 2), "column groups must tile the first stage");
     static_assert(NS >= 3, "needs an inner stage besides the fused middle one");
     extern __shared__ __align__(16) float2 sm2[];
@@ -110,7 +115,7 @@ k_rows3(const float* __restrict__ img, float* __restrict__ gray, float* __restri
         }
 #pragma unroll
         for (int w = 0; w < WIDE; ++w) Dft<R0>::run(v[w]);
-        float2* p = sm2 + (size_t)f * W + j;
+        float2* p = sm2 + (size_t)f * RS + j;
         if constexpr (WIDE == 2) {
             *reinterpret_cast<float4*>(p) = make_float4(v[0][0].x, v[0][0].y, v[1][0].x, v[1][0].y);
 #pragma unroll
@@ -118,21 +123,26 @@ k_rows3(const float* __restrict__ img, float* __restrict__ gray, float* __restri
                 const float4 t = __ldg(reinterpret_cast<const float4*>(stw0 + (q - 1) * M0 + j));
                 const float2 r0 = c_mul(v[0][q], make_float2(t.x, t.y));
                 const float2 r1 = c_mul(v[1][q], make_float2(t.z, t.w));
-                *reinterpret_cast<float4*>(p + q * M0) = make_float4(r0.x, r0.y, r1.x, r1.y);
+                if constexpr (V4) {
+                    *reinterpret_cast<float4*>(p + q * M0P) = make_float4(r0.x, r0.y, r1.x, r1.y);
+                } else {
+                    p[q * M0P] = r0;
+                    p[q * M0P + 1] = r1;
+                }
             }
         } else {
             p[0] = v[0][0];
 #pragma unroll
-            for (int q = 1; q < R0; ++q) p[q * M0] = c_mul(v[0][q], __ldg(stw0 + (q - 1) * M0 + j));
+            for (int q = 1; q < R0; ++q) p[q * M0P] = c_mul(v[0][q], __ldg(stw0 + (q - 1) * M0 + j));
         }
     }
     __syncthreads();
 
     // ---- inner stages: DIF 1 .. NS-2, [DIF NS-1, i omega, DIT NS-1] in registers, DIT NS-2 .. 1 ---
-    SDifRun<SP, 1, NS - 2, false>::run(sm2, W, nb, tw, tid, THREADS);
-    s_mid_stage<SP::R(NS - 1), W, 1>(sm2, W, nb, tid, THREADS, omega);
+    SDifRun<SP, 1, NS - 2, false, LY>::run(sm2, RS, nb, tw, tid, THREADS);
+    s_mid_stage<SP::R(NS - 1), W, 1, LY>(sm2, RS, nb, tid, THREADS, omega);
     __syncthreads();
-    SDitRun<SP, NS - 2, NS - 2, false>::run(sm2, W, nb, tw, tid, THREADS);
+    SDitRun<SP, NS - 2, NS - 2, false, LY>::run(sm2, RS, nb, tw, tid, THREADS);
 
     // ---- stage 0 (DIT), drained to global memory: r = DFT(swap(.)): row a = r.y / n, row b = r.x / n
     const float inv = 1.0f / (float)W;
@@ -143,7 +153,7 @@ k_rows3(const float* __restrict__ img, float* __restrict__ gray, float* __restri
         const int y = y0 + 2 * f;
         if (y >= H) continue;
         const bool okb = y + 1 < H;
-        const float2* p = sm2 + (size_t)f * W + j;
+        const float2* p = sm2 + (size_t)f * RS + j;
         float2 v[WIDE][R0];
         if constexpr (WIDE == 2) {
             const float4 z0 = *reinterpret_cast<const float4*>(p);
@@ -151,7 +161,13 @@ k_rows3(const float* __restrict__ img, float* __restrict__ gray, float* __restri
             v[1][0] = make_float2(z0.z, z0.w);
 #pragma unroll
             for (int q = 1; q < R0; ++q) {
-                const float4 z = *reinterpret_cast<const float4*>(p + q * M0);
+                float4 z;
+                if constexpr (V4) {
+                    z = *reinterpret_cast<const float4*>(p + q * M0P);
+                } else {
+                    const float2 za = p[q * M0P], zb = p[q * M0P + 1];
+                    z = make_float4(za.x, za.y, zb.x, zb.y);
+                }
                 const float4 t = __ldg(reinterpret_cast<const float4*>(stw0 + (q - 1) * M0 + j));
                 v[0][q] = c_mul(make_float2(z.x, z.y), make_float2(t.x, t.y));
                 v[1][q] = c_mul(make_float2(z.z, z.w), make_float2(t.z, t.w));
@@ -159,7 +175,7 @@ k_rows3(const float* __restrict__ img, float* __restrict__ gray, float* __restri
         } else {
             v[0][0] = p[0];
 #pragma unroll
-            for (int q = 1; q < R0; ++q) v[0][q] = c_mul(p[q * M0], __ldg(stw0 + (q - 1) * M0 + j));
+            for (int q = 1; q < R0; ++q) v[0][q] = c_mul(p[q * M0P], __ldg(stw0 + (q - 1) * M0 + j));
         }
 #pragma unroll
         for (int w = 0; w < WIDE; ++w) Dft<R0>::run(v[w]);
@@ -187,12 +203,14 @@ k_rows3(const float* __restrict__ img, float* __restrict__ gray, float* __restri
 // columns: CTA = NB column pairs (2 NB adjacent columns) of one gray plane; consecutive threads take
 // consecutive pairs of one row (8 NB contiguous bytes), then the next row.
 // ---------------------------------------------------------------------------------------------
-template <class SP, int NB, int THREADS, int MINB>
+template <class SP, int NB, int THREADS, int MINB, bool PADL>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_cols3(const float* __restrict__ g, const float* __restrict__ gx, unsigned* __restrict__ stats, int W, int stride,
         const float2* __restrict__ tw, const float* __restrict__ omega, int discard_saturation,
         const float* __restrict__ mask_src) {
     constexpr int H = SP::n, NS = SP::ns, R0 = SP::R(0), M0 = H / R0;
+    using LY = typename std::conditional<(PADL && NS == 3), PadFor<SP>, LayoutFlat>::type;
+    constexpr int M0P = M0 + LY::PAD;
     static_assert(NS >= 3, "needs an inner stage besides the fused middle one");
     static_assert((NB & (NB - 1)) == 0, "pairs per CTA: a power of two");
     extern __shared__ __align__(16) float2 sm2[];
@@ -221,14 +239,14 @@ k_cols3(const float* __restrict__ g, const float* __restrict__ gx, unsigned* __r
         float2* p = sm2 + (size_t)f * stride + j;
         p[0] = v[0];
 #pragma unroll
-        for (int q = 1; q < R0; ++q) p[q * M0] = c_mul(v[q], __ldg(stw0 + (q - 1) * M0 + j));
+        for (int q = 1; q < R0; ++q) p[q * M0P] = c_mul(v[q], __ldg(stw0 + (q - 1) * M0 + j));
     }
     __syncthreads();
 
-    SDifRun<SP, 1, NS - 2, false>::run(sm2, stride, NB, tw, tid, THREADS);
-    s_mid_stage<SP::R(NS - 1), H, 1>(sm2, stride, NB, tid, THREADS, omega);
+    SDifRun<SP, 1, NS - 2, false, LY>::run(sm2, stride, NB, tw, tid, THREADS);
+    s_mid_stage<SP::R(NS - 1), H, 1, LY>(sm2, stride, NB, tid, THREADS, omega);
     __syncthreads();
-    SDitRun<SP, NS - 2, NS - 2, false>::run(sm2, stride, NB, tw, tid, THREADS);
+    SDitRun<SP, NS - 2, NS - 2, false, LY>::run(sm2, stride, NB, tw, tid, THREADS);
 
     // ---- stage 0 (DIT) in registers + the 7 directional maxima (blur_estimation.py:122-134) ------
     // cos / sin of torch.linspace(0, pi, 7) as torch (float32) evaluates them (same bit patterns as estimate2.cu)
@@ -258,7 +276,7 @@ k_cols3(const float* __restrict__ g, const float* __restrict__ gx, unsigned* __r
         float2 v[R0];
         v[0] = p[0];
 #pragma unroll
-        for (int q = 1; q < R0; ++q) v[q] = c_mul(p[q * M0], __ldg(stw0 + (q - 1) * M0 + j));
+        for (int q = 1; q < R0; ++q) v[q] = c_mul(p[q * M0P], __ldg(stw0 + (q - 1) * M0 + j));
         Dft<R0>::run(v);
 #pragma unroll
         for (int m = 0; m < R0; ++m) {
@@ -324,23 +342,33 @@ int launch_rows3(const float* img, float* gray, float* gx, unsigned* stats, int 
     const int pairs_total = (H + 1) / 2;
     int rc;
     // nb row pairs per CTA: what fits BUDGET bytes of shared memory (at least one)
-#define PB_ROWS3(SP, WIDE, THREADS, MINB, BUDGET)                                                              \
+#define PB_ROWS3(SP, WIDE, THREADS, MINB, BUDGET, PADL)                                                        \
     do {                                                                                                       \
         int nb = (BUDGET) / (int)(sizeof(float2) * SP::n);                                                     \
         if (nb < 1) nb = 1;                                                                                    \
         if (nb > pairs_total) nb = pairs_total;                                                                \
-        const size_t smem = (size_t)nb * SP::n * sizeof(float2);                                               \
-        if ((rc = set_smem3(k_rows3<SP, WIDE, THREADS, MINB>, smem))) return rc;                               \
+        const size_t len = SP::n + ((PADL) && SP::ns == 3 ? SP::R(0) * PadFor<SP>::PAD : 0);                   \
+        const size_t smem = (size_t)nb * len * sizeof(float2);                                                 \
+        if ((rc = set_smem3(k_rows3<SP, WIDE, THREADS, MINB, PADL>, smem))) return rc;                         \
         ProfScope prof(PROF_ROWS, stream);                                                                     \
-        k_rows3<SP, WIDE, THREADS, MINB><<<dim3((pairs_total + nb - 1) / nb, nimg), THREADS, smem, stream>>>(  \
+        k_rows3<SP, WIDE, THREADS, MINB, PADL><<<dim3((pairs_total + nb - 1) / nb, nimg), THREADS, smem, stream>>>( \
             img, gray, gx, stats, H, nb, twW, omegaW);                                                         \
         PB_LAUNCH_CHECK("k_rows3");                                                                            \
         return PB_OK;                                                                                          \
     } while (0)
-    if (PlanW1920::matches(planW)) PB_ROWS3(PlanW1920, 2, 256, 3, 64 * 1024);
-    if (PlanW3840::matches(planW)) PB_ROWS3(PlanW3840, 1, 256, 3, 64 * 1024);
+    // padded stage-1 blocks (conflict-free middle stage): 1 = the 4K lengths, 2 = the 1080p lengths too (measured
+    // neutral there: 0.81 / 0.80 ms per step either way; 4K rows 0.86 -> 0.83, columns 1.35 -> 1.32)
+    static const int pad3 = env3("PB_E3_PAD", 1);
+    if (PlanW1920::matches(planW)) {
+        if (pad3 >= 2) PB_ROWS3(PlanW1920, 2, 256, 3, 64 * 1024, true);
+        PB_ROWS3(PlanW1920, 2, 256, 3, 64 * 1024, false);
+    }
+    if (PlanW3840::matches(planW)) {
+        if (pad3) PB_ROWS3(PlanW3840, 1, 256, 3, 64 * 1024, true);
+        PB_ROWS3(PlanW3840, 1, 256, 3, 64 * 1024, false);
+    }
     // one pair (94 KB), two CTAs per SM (384 threads per CTA measured the same as 256)
-    if (PlanW12000::matches(planW)) PB_ROWS3(PlanW12000, 2, 256, 2, 100 * 1024);
+    if (PlanW12000::matches(planW)) PB_ROWS3(PlanW12000, 2, 256, 2, 100 * 1024, false);
 #undef PB_ROWS3
     return 1;
 }
@@ -351,27 +379,35 @@ int launch_cols3(const float* g, const float* gx, unsigned* stats, int nimg, int
     if (!est_gen3() || (W & 1)) return 1;
     const int pairs_total = W / 2;
     int rc;
-#define PB_COLS3(SP, NB, THREADS, MINB)                                                                        \
+#define PB_COLS3(SP, NB, THREADS, MINB, PADL)                                                                  \
     do {                                                                                                       \
-        const int stride = SP::n + ((2 - SP::n) & 3);      /* = 2 (mod 4) float2: see launch_cols2 */           \
+        const int len = SP::n + ((PADL) && SP::ns == 3 ? SP::R(0) * PadFor<SP>::PAD : 0);                      \
+        const int stride = len + ((2 - len) & 3);          /* = 2 (mod 4) float2: see launch_cols2 */           \
         const size_t smem = (size_t)(NB) * stride * sizeof(float2);                                            \
-        if ((rc = set_smem3(k_cols3<SP, NB, THREADS, MINB>, smem))) return rc;                                 \
+        if ((rc = set_smem3(k_cols3<SP, NB, THREADS, MINB, PADL>, smem))) return rc;                           \
         ProfScope prof(PROF_COLS, stream);                                                                     \
-        k_cols3<SP, NB, THREADS, MINB><<<dim3((pairs_total + (NB) - 1) / (NB), nimg), THREADS, smem, stream>>>(\
+        k_cols3<SP, NB, THREADS, MINB, PADL><<<dim3((pairs_total + (NB) - 1) / (NB), nimg), THREADS, smem, stream>>>(\
             g, gx, stats, W, stride, twH, omegaH, discard_saturation, mask_src);                               \
         PB_LAUNCH_CHECK("k_cols3");                                                                            \
         return PB_OK;                                                                                          \
     } while (0)
     // (192 threads, which divide the butterfly counts of the 1080 / 2160 stages evenly where 256 leave a quarter of a
     // trip idle, measured the same as 256: the trips are not what binds)
-    if (PlanH1080::matches(planH)) PB_COLS3(PlanH1080, 8, 256, 3);
-    if (PlanH2160::matches(planH)) PB_COLS3(PlanH2160, 4, 256, 3);
+    static const int pad3 = env3("PB_E3_PAD", 1);
+    if (PlanH1080::matches(planH)) {
+        if (pad3 >= 2) PB_COLS3(PlanH1080, 8, 256, 3, true);
+        PB_COLS3(PlanH1080, 8, 256, 3, false);
+    }
+    if (PlanH2160::matches(planH)) {
+        if (pad3) PB_COLS3(PlanH2160, 4, 256, 3, true);
+        PB_COLS3(PlanH2160, 4, 256, 3, false);
+    }
     // one pair of 9000 rows is 70 KB: two pairs in one CTA of 512 threads (16-byte row segments).  Measured and left out:
     // one pair in each of two resident CTAs of 256 threads (8-byte segments; C4 step 5.31 against 5.09 ms), and a
     // persistent variant of this kernel that runs the last stage of an item and the first stage of the CTA's next
     // item in one loop (same thread, same shared-memory slots, so no barrier and the next item's loads are in flight
     // during the reduce): C2 0.88 against 0.82 ms per step, C4 4.95 against 5.07 ms -- the loads are not what binds.
-    if (PlanH9000::matches(planH)) PB_COLS3(PlanH9000, 2, 512, 1);
+    if (PlanH9000::matches(planH)) PB_COLS3(PlanH9000, 2, 512, 1, false);
 #undef PB_COLS3
     return 1;
 }

@@ -44,8 +44,31 @@ struct StaticPlan {
 
 struct NoStaticPlan {};     // kernels instantiated with this use the run-time core
 
-template <int R, int M, int N>
+// ---- shared-memory layout of one sequence ------------------------------------------------------------------
+// A stage with M < 16 makes the 16 lanes of a half warp straddle blocks: butterfly t = (blk, j) touches
+// blk L + j + m M, and unless L = M (mod 16) two lanes of the half warp meet in one bank pair -- every such access
+// then costs two wavefronts (ncu: 30 % of the shared-memory wavefronts of the row / column kernels were excess).
+// In a three-stage plan that stage is stage 1 (M = the last radix).  LayoutPad1 pads the R0 blocks of length
+// L1 = n / R0 that stage 0 produces by PAD float2 so that L1 + PAD = M1 (mod 16): slot t of stage 1 then falls into
+// bank pair t mod 16 for every butterfly input, conflict-free; natural slot i lives at i + (i / L1) PAD.
+struct LayoutFlat {
+    static constexpr int L1 = 1 << 30, PAD = 0;
+    static PB_HDC int off(int i) { return i; }
+};
+template <int L1_, int PAD_>
+struct LayoutPad1 {
+    static constexpr int L1 = L1_, PAD = PAD_;
+    static PB_HDC int off(int i) { return i + (i / L1_) * PAD_; }
+};
+// the padded layout of a plan with >= 3 stages, and the float2 one sequence occupies in it
+template <class P>
+using PadFor = LayoutPad1<P::L(1), ((P::L(2) - P::L(1)) % 16 + 16) % 16>;
+template <class P, class LY>
+constexpr int padded_len() { return P::n + P::R(0) * LY::PAD; }
+
+template <int R, int M, int N, class LY = LayoutFlat>
 PB_HD void s_dif_stage(float2* x, int stride, int nb, const float2* __restrict__ stw, int tid, int nthr) {
+    static_assert(R * M <= LY::L1, "a padded layout serves the stages inside the padded blocks only");
     constexpr int L = R * M, bps = N / R;
     const int total = nb * bps;
     for (int idx = tid; idx < total; idx += nthr) {
@@ -53,7 +76,7 @@ PB_HD void s_dif_stage(float2* x, int stride, int nb, const float2* __restrict__
         const int rem = idx - f * bps;
         const int blk = rem / M;
         const int j = rem - blk * M;
-        float2* p = x + f * stride + blk * L + j;
+        float2* p = x + f * stride + LY::off(blk * L + j);
         float2 v[R];
 #pragma unroll
         for (int m = 0; m < R; ++m) v[m] = p[m * M];
@@ -64,8 +87,9 @@ PB_HD void s_dif_stage(float2* x, int stride, int nb, const float2* __restrict__
     }
 }
 
-template <int R, int M, int N>
+template <int R, int M, int N, class LY = LayoutFlat>
 PB_HD void s_dit_stage(float2* x, int stride, int nb, const float2* __restrict__ stw, int tid, int nthr) {
+    static_assert(R * M <= LY::L1, "a padded layout serves the stages inside the padded blocks only");
     constexpr int L = R * M, bps = N / R;
     const int total = nb * bps;
     for (int idx = tid; idx < total; idx += nthr) {
@@ -73,7 +97,7 @@ PB_HD void s_dit_stage(float2* x, int stride, int nb, const float2* __restrict__
         const int rem = idx - f * bps;
         const int blk = rem / M;
         const int j = rem - blk * M;
-        float2* p = x + f * stride + blk * L + j;
+        float2* p = x + f * stride + LY::off(blk * L + j);
         float2 v[R];
         v[0] = p[0];
 #pragma unroll
@@ -85,14 +109,14 @@ PB_HD void s_dit_stage(float2* x, int stride, int nb, const float2* __restrict__
 }
 
 // last DIF stage + pointwise multiplier + first DIT stage (see fft2_mid_stage)
-template <int R, int N, int PREMODE>
+template <int R, int N, int PREMODE, class LY = LayoutFlat>
 PB_HD void s_mid_stage(float2* x, int stride, int nb, int tid, int nthr, const float* premul) {
     constexpr int bps = N / R;
     const int total = nb * bps;
     for (int idx = tid; idx < total; idx += nthr) {
         const int f = idx / bps;
         const int blk = idx - f * bps;
-        float2* p = x + f * stride + blk * R;
+        float2* p = x + f * stride + LY::off(blk * R);
         float2 v[R];
 #pragma unroll
         for (int m = 0; m < R; ++m) v[m] = p[m];
@@ -116,7 +140,7 @@ PB_HD void s_mid_stage(float2* x, int stride, int nb, int tid, int nthr, const f
 // shared memory and no separate output pass.
 //     Src::load<R, M>(int f, int j, float2 (&v)[R])         v[m] = sample j + m M of sequence f
 //     Dst::store<R, M>(int f, int j, const float2 (&v)[R])  v[m] = result j + m M of sequence f
-template <int R, int M, int N, class Src>
+template <int R, int M, int N, class Src, class LY = LayoutFlat>
 PB_HD void s_dif_first(float2* x, int stride, int nb, const float2* __restrict__ stw, int tid, int nthr, Src& src) {
     static_assert(R * M == N, "first stage works on the whole sequence");
     const int total = nb * M;
@@ -129,11 +153,11 @@ PB_HD void s_dif_first(float2* x, int stride, int nb, const float2* __restrict__
         float2* p = x + f * stride + j;
         p[0] = v[0];
 #pragma unroll
-        for (int q = 1; q < R; ++q) p[q * M] = (M == 1) ? v[q] : c_mul(v[q], PB_LDG(stw + (q - 1) * M + j));
+        for (int q = 1; q < R; ++q) p[q * (M + LY::PAD)] = (M == 1) ? v[q] : c_mul(v[q], PB_LDG(stw + (q - 1) * M + j));
     }
 }
 
-template <int R, int M, int N, class Dst>
+template <int R, int M, int N, class Dst, class LY = LayoutFlat>
 PB_HD void s_dit_last(const float2* x, int stride, int nb, const float2* __restrict__ stw, int tid, int nthr, Dst& dst) {
     static_assert(R * M == N, "last stage works on the whole sequence");
     const int total = nb * M;
@@ -144,38 +168,38 @@ PB_HD void s_dit_last(const float2* x, int stride, int nb, const float2* __restr
         float2 v[R];
         v[0] = p[0];
 #pragma unroll
-        for (int q = 1; q < R; ++q) v[q] = (M == 1) ? p[q] : c_mul(p[q * M], PB_LDG(stw + (q - 1) * M + j));
+        for (int q = 1; q < R; ++q) v[q] = (M == 1) ? p[q] : c_mul(p[q * (M + LY::PAD)], PB_LDG(stw + (q - 1) * M + j));
         Dft<R>::run(v);
         dst.template store<R, M>(f, j, v);
     }
 }
 
 // ---- drivers (compile-time recursion over the stages) ---------------------------------------
-template <class P, int S, int COUNT, bool WARP>
+template <class P, int S, int COUNT, bool WARP, class LY = LayoutFlat>
 struct SDifRun {     // DIF stages S, S+1, ... (COUNT of them)
     static PB_HD void run(float2* x, int stride, int nb, const float2* __restrict__ tw, int tid, int nthr) {
         constexpr int R = P::R(S), L = P::L(S);
-        s_dif_stage<R, L / R, P::n>(x, stride, nb, tw + P::tw_off(S), tid, nthr);
+        s_dif_stage<R, L / R, P::n, LY>(x, stride, nb, tw + P::tw_off(S), tid, nthr);
         fft2_sync<WARP>();
-        SDifRun<P, S + 1, COUNT - 1, WARP>::run(x, stride, nb, tw, tid, nthr);
+        SDifRun<P, S + 1, COUNT - 1, WARP, LY>::run(x, stride, nb, tw, tid, nthr);
     }
 };
-template <class P, int S, bool WARP>
-struct SDifRun<P, S, 0, WARP> {
+template <class P, int S, bool WARP, class LY>
+struct SDifRun<P, S, 0, WARP, LY> {
     static PB_HD void run(float2*, int, int, const float2* __restrict__, int, int) {}
 };
 
-template <class P, int S, int COUNT, bool WARP>
+template <class P, int S, int COUNT, bool WARP, class LY = LayoutFlat>
 struct SDitRun {     // DIT stages S, S-1, ... (COUNT of them)
     static PB_HD void run(float2* x, int stride, int nb, const float2* __restrict__ tw, int tid, int nthr) {
         constexpr int R = P::R(S), L = P::L(S);
-        s_dit_stage<R, L / R, P::n>(x, stride, nb, tw + P::tw_off(S), tid, nthr);
+        s_dit_stage<R, L / R, P::n, LY>(x, stride, nb, tw + P::tw_off(S), tid, nthr);
         fft2_sync<WARP>();
-        SDitRun<P, S - 1, COUNT - 1, WARP>::run(x, stride, nb, tw, tid, nthr);
+        SDitRun<P, S - 1, COUNT - 1, WARP, LY>::run(x, stride, nb, tw, tid, nthr);
     }
 };
-template <class P, int S, bool WARP>
-struct SDitRun<P, S, 0, WARP> {
+template <class P, int S, bool WARP, class LY>
+struct SDitRun<P, S, 0, WARP, LY> {
     static PB_HD void run(float2*, int, int, const float2* __restrict__, int, int) {}
 };
 
