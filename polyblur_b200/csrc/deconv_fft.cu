@@ -1412,7 +1412,12 @@ int launch_deconv_fft(const float* img, float* out, const ImgKernel* kern, const
             if (T.ra2 == 36 && T.rb2 == 32 && !cols_v1) PB_FFT_COLS2(36, 32);
             else if (T.ra2 == 32 && T.rb2 == 36 && !cols_v1) PB_FFT_COLS2(32, 36);
             else if (PlanY1152::matches(T.planY)) PB_FFT_COLS(PlanY1152);
-            else if (PlanY2304::matches(T.planY)) PB_FFT_COLS(PlanY2304);
+            else if (PlanY2304::matches(T.planY)) {
+                // (the block of column 0 in its own launch, so that three CTAs take 166 instead of 222 KB of shared memory and
+                // the L1 that remains holds the 18 KB of stage twiddles, measured slower here: 2.23 against 2.16 ms per step)
+                static const int split = env_int("PB_FFT_COLS_SPLIT", 0);
+                if (split && !cols_v1) PB_FFT_COLS_LONG(PlanY2304, 256); else PB_FFT_COLS(PlanY2304);
+            }
             else if (PlanY9216::matches(T.planY) && CB == 1 && !cols_v1) {
                 static const int th_long = env_int("PB_FFT_COLS_LONG_T", 384);
                 if (th_long == 384) PB_FFT_COLS_LONG(PlanY9216, 384); else PB_FFT_COLS_LONG(PlanY9216, 256);
