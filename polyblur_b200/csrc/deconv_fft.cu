@@ -26,6 +26,8 @@
 // HBM bytes per pixel-channel: P1 4 read + ~4.4 written, P2 ~4.4 + ~4.4, P3 ~4.4 read + 4
 // written = ~26 B against 8 B algorithmic; independent of the blur.
 #include <cstdlib>
+#include <mutex>
+#include <unordered_map>
 
 #include <type_traits>
 
@@ -1183,6 +1185,15 @@ k_fft_cols2(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const in
 // fft2_plan_cost -- three conflict-free stages beat four, and pure powers of two (whose last
 // stage is 8- or 16-way bank conflicted) lose to their neighbours.
 int fft_engine_length(int n) {
+    // memoised: the search plans ~n / 20 candidate lengths, and every entry point lays out its workspace twice per call
+    // (pb_workspace_bytes, then the call itself) -- 0.7 ms of host time per 1080p call, 1.7 ms per 4K call without this
+    static std::mutex mu;
+    static std::unordered_map<int, int> cache;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        auto it = cache.find(n);
+        if (it != cache.end()) return it->second;
+    }
     Fft2Plan p;
     int best = 0;
     double best_cost = 1e300;
@@ -1195,6 +1206,8 @@ int fft_engine_length(int n) {
             best = m;
         }
     }
+    std::lock_guard<std::mutex> lock(mu);
+    cache[n] = best;
     return best;
 }
 

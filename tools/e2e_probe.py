@@ -30,7 +30,7 @@ def main():
     xh.copy_(x)
     xu = (x.permute(0, 2, 3, 1) * 255).round().to(torch.uint8).contiguous().cpu().pin_memory()
     variants = {}
-    for mc, ramp in ((16, ()), (16, (1,)), (8, (1, 2)), (32, (1,))):
+    for mc, ramp in ((16, ()), (16, (1,)), (32, ()), (32, (1,))):
         def f(mc=mc, ramp=ramp):
             orig = deblurring._polyblur_host_pipelined
             deblurring._polyblur_host_pipelined = functools.partial(orig, max_chunks=mc, ramp=ramp)
@@ -39,7 +39,7 @@ def main():
             finally:
                 deblurring._polyblur_host_pipelined = orig
         variants[f"f32 chunks{mc} ramp{ramp}"] = f
-    for mc, ramp in ((4, ()), (4, (4,)), (4, (2,)), (4, (2, 4)), (6, (4,)), (8, (2,)), (8, (4,))):
+    for mc, ramp in ((4, ()), (4, (2,)), (4, (2, 4)), (4, (1, 2, 4)), (3, (2, 4)), (5, (2, 4)), (6, (2, 4)), (8, (2,))):
         def g(mc=mc, ramp=ramp):
             orig = pbio._host_pipeline_u8
             pbio._host_pipeline_u8 = functools.partial(orig, ramp=ramp)
