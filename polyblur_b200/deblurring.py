@@ -11,6 +11,7 @@ copied to the GPU and back.  There is no CPU fallback.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -137,6 +138,7 @@ class GraphedPolyblur:
 # gets two GraphedPolyblur engines (double buffering) that are kept across calls: the copies go straight into / out of
 # their static buffers and a chunk is one graph launch.  A small LRU bounds the device memory this holds.
 _ENGINE_CACHE: "dict[tuple, list]" = {}
+_PIPE_COMPUTE_STREAMS = int(os.environ.get("PB_PIPE_STREAMS", "2"))   # compute streams the chunks alternate between
 _ENGINE_CACHE_MAX_BYTES = 24 << 30          # device memory the cached engines may hold (per process)
 
 
@@ -171,7 +173,7 @@ def _run_host_pipeline(x: torch.Tensor, host: torch.Tensor, sizes, p: "_lib.PbPa
         # two compute streams, chunks alternate between them: the kernels of a chunk are persistent grids that end in
         # a partial wave (a chunk of 8 images is 3.9 waves of the column pass), and the other chunk's kernels fill it
         s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-        s_runs = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+        s_runs = [torch.cuda.Stream(dev) for _ in range(_PIPE_COMPUTE_STREAMS)]
         for st in [s_in, s_out] + s_runs:
             st.wait_stream(torch.cuda.current_stream(dev))
         # every chunk size's engines exist (captured on first use) before the first copy is in flight
@@ -192,7 +194,7 @@ def _run_host_pipeline(x: torch.Tensor, host: torch.Tensor, sizes, p: "_lib.PbPa
                     s_in.wait_event(ev[0])
                 gin.copy_(x[a:b], non_blocking=True)
                 loaded = s_in.record_event()
-            s_run = s_runs[k & 1]
+            s_run = s_runs[k % len(s_runs)]
             with torch.cuda.stream(s_run):
                 s_run.wait_event(loaded)
                 if ev[0] is not None:
