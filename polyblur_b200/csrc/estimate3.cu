@@ -266,7 +266,7 @@ k_cols3(const float* __restrict__ g, const float* __restrict__ gx, unsigned* __r
         if (x >= W) continue;
         const size_t o = (size_t)j * W + x;
         // d g / d x of the same pixels: all loads in flight before the butterfly when the registers allow it
-        constexpr bool PRE = R0 <= 10;
+        constexpr bool PRE = R0 <= 10 || (THREADS * MINB <= 576);   // the registers of a second butterfly must be there
         float2 gxv[PRE ? R0 : 1];
         if constexpr (PRE) {
 #pragma unroll
@@ -399,6 +399,12 @@ int launch_cols3(const float* g, const float* gx, unsigned* stats, int nimg, int
         PB_COLS3(PlanH1080, 8, 256, 3, false);
     }
     if (PlanH2160::matches(planH)) {
+        // 15-point first / last stage: the d g / d x loads of a butterfly are all in flight before it only when a thread may
+        // use ~110 registers.  Measured (8 x 4K, ms per step): 256 threads x 3 CTAs at 80 registers (loads issued late,
+        // 108 bytes of spills) 1.32, 192 x 3 at 96 registers 1.19, 256 x 2 at 128 registers 0.91.
+        static const int t2160 = env3("PB_E3_T2160", 512);
+        if (t2160 == 192) PB_COLS3(PlanH2160, 4, 192, 3, true);
+        if (t2160 == 512) PB_COLS3(PlanH2160, 4, 256, 2, true);
         if (pad3) PB_COLS3(PlanH2160, 4, 256, 3, true);
         PB_COLS3(PlanH2160, 4, 256, 3, false);
     }
