@@ -1322,9 +1322,32 @@ int fft_engine_prepare(char* base, const FftEngineLayout& L, FftEngineTables* T,
     return PB_OK;
 }
 
+// A side stream (per host thread and device) for the one-column DC / Nyquist launch of the column pass: it touches
+// column 0 of every plane, the main launch columns 1 .., so the two run side by side -- forked and joined with
+// events, which is also how a stream capture records them as parallel branches of the graph.
+struct SideStream {
+    int dev = -1;
+    cudaStream_t s = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+static int side_stream(SideStream** out) {
+    static thread_local SideStream ss;
+    int dev = 0;
+    PB_CUDA_TRY(cudaGetDevice(&dev));
+    if (ss.dev != dev) {                       // (a thread that moves to another device keeps one set per visit)
+        PB_CUDA_TRY(cudaStreamCreateWithFlags(&ss.s, cudaStreamNonBlocking));
+        PB_CUDA_TRY(cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming));
+        PB_CUDA_TRY(cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming));
+        ss.dev = dev;
+    }
+    *out = &ss;
+    return PB_OK;
+}
+
 int launch_deconv_fft(const float* img, float* out, const ImgKernel* kern, const int* list, const int* count,
                       int B, int C, int H, int W, const FftEngineTables& T, float a3, float a2, float a1,
                       float b0, const SrcGeom& G, cudaStream_t stream) {
+    int rc = PB_OK;
     const int NX = T.NX, NY = T.NY;
     const int nb = rows_nb(NX), CB = cols_cb(NY);
     const size_t smem_rows = (size_t)nb * fftd_row_stride(NX) * sizeof(float2);
@@ -1394,10 +1417,21 @@ int launch_deconv_fft(const float* img, float* out, const ImgKernel* kern, const
         PB_CUDA_TRY(cudaFuncSetAttribute(k_fft_cols2<RA, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); \
         PB_CUDA_TRY(cudaFuncSetAttribute(k_fft_cols<NoStaticPlan>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0)); \
         ProfScope prof(PROF_FFT_COLS, stream);                                                                   \
+        static const bool side_on = env_int("PB_FFT_SIDE", 1) != 0;                                              \
+        SideStream* ss = nullptr;                                                                                \
+        if (side_on && (rc = side_stream(&ss))) return rc;                                                       \
+        cudaStream_t s0 = stream;                                                                                \
+        if (ss) {                                                                                                \
+            PB_CUDA_TRY(cudaEventRecord(ss->fork, stream));                                                      \
+            PB_CUDA_TRY(cudaStreamWaitEvent(ss->s, ss->fork, 0));                                                \
+            s0 = ss->s;                                                                                          \
+        }                                                                                                        \
+        k_fft_cols<NoStaticPlan><<<dim3(B < cap ? B : cap, C), FFTC_THREADS, smem0, s0>>>(T.Z, kern, list, count, C, NX, NY, 1, \
+                                                                     T.planY, T.twX, T.stwY, T.slotY, a3, a2, a1, b0, 1); \
+        if (ss) PB_CUDA_TRY(cudaEventRecord(ss->join, ss->s));                                                   \
         k_fft_cols2<RA, RB><<<grid2, FFTC2_THREADS, smem2, stream>>>(T.Z, kern, list, count, C, NX, cb2, T.twX, T.stwY2, \
                                                                      a3, a2, a1, b0);                            \
-        k_fft_cols<NoStaticPlan><<<dim3(B < cap ? B : cap, C), FFTC_THREADS, smem0, stream>>>(T.Z, kern, list, count, C, NX, NY, 1, \
-                                                                     T.planY, T.twX, T.stwY, T.slotY, a3, a2, a1, b0, 1); \
+        if (ss) PB_CUDA_TRY(cudaStreamWaitEvent(stream, ss->join, 0));                                           \
     } while (0)
     // long columns (one column per CTA): the block of column 0 in its own launch, so that the other CTAs do without its
     // two extra NY-float arrays and two of them fit an SM
@@ -1408,10 +1442,21 @@ int launch_deconv_fft(const float* img, float* out, const ImgKernel* kern, const
         PB_CUDA_TRY(cudaFuncSetAttribute(k_fft_cols<SP, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1)); \
         PB_CUDA_TRY(cudaFuncSetAttribute(k_fft_cols<SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols)); \
         ProfScope prof(PROF_FFT_COLS, stream);                                                                   \
+        static const bool side_on = env_int("PB_FFT_SIDE", 1) != 0;                                              \
+        SideStream* ss = nullptr;                                                                                \
+        if (side_on && (rc = side_stream(&ss))) return rc;                                                       \
+        cudaStream_t s0 = stream;                                                                                \
+        if (ss) {                                                                                                \
+            PB_CUDA_TRY(cudaEventRecord(ss->fork, stream));                                                      \
+            PB_CUDA_TRY(cudaStreamWaitEvent(ss->s, ss->fork, 0));                                                \
+            s0 = ss->s;                                                                                          \
+        }                                                                                                        \
+        k_fft_cols<SP><<<dim3(B < cap ? B : cap, C), FFTC_THREADS, smem_cols, s0>>>(                             \
+            T.Z, kern, list, count, C, NX, NY, CB, T.planY, T.twX, T.stwY, T.slotY, a3, a2, a1, b0, 1);          \
+        if (ss) PB_CUDA_TRY(cudaEventRecord(ss->join, ss->s));                                                   \
         k_fft_cols<SP, TH><<<(int)(items1 < cap ? items1 : cap), TH, smem1, stream>>>(                           \
             T.Z, kern, list, count, C, NX, NY, CB, T.planY, T.twX, T.stwY, T.slotY, a3, a2, a1, b0, 2);          \
-        k_fft_cols<SP><<<dim3(B < cap ? B : cap, C), FFTC_THREADS, smem_cols, stream>>>(                         \
-            T.Z, kern, list, count, C, NX, NY, CB, T.planY, T.twX, T.stwY, T.slotY, a3, a2, a1, b0, 1);          \
+        if (ss) PB_CUDA_TRY(cudaStreamWaitEvent(stream, ss->join, 0));                                           \
     } while (0)
     static const bool rows_v1 = env_int("PB_FFT_ROWS_V1", 0) != 0;     // A/B against the first-generation passes
     // padded stage-1 blocks (Rows2Layout): 1 = the 4K plan only, 2 = the 1080p plan too.  Measured: 4K P1 1.58 -> 1.53,
