@@ -359,7 +359,11 @@ int launch_rows3(const float* img, float* gray, float* gx, unsigned* stats, int 
     // padded stage-1 blocks (conflict-free middle stage): 1 = the 4K lengths, 2 = the 1080p lengths too (measured
     // neutral there: 0.81 / 0.80 ms per step either way; 4K rows 0.86 -> 0.83, columns 1.35 -> 1.32)
     static const int pad3 = env3("PB_E3_PAD", 1);
+    // 1920: two CTAs per SM at 128 registers (the 48 64-bit loads of a butterfly pair in flight together) measured
+    // 0.77 against 0.80 ms per step at three CTAs of 80; 3840 (16-point first stage, one column per thread): equal
+    static const int rminb = env3("PB_E3_RMINB", 2);
     if (PlanW1920::matches(planW)) {
+        if (rminb == 2) PB_ROWS3(PlanW1920, 2, 256, 2, 64 * 1024, false);
         if (pad3 >= 2) PB_ROWS3(PlanW1920, 2, 256, 3, 64 * 1024, true);
         PB_ROWS3(PlanW1920, 2, 256, 3, 64 * 1024, false);
     }
