@@ -990,7 +990,7 @@ template <int RA, int RB>
 __global__ void __launch_bounds__(FFTC2_THREADS, 2)
 k_fft_cols2(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int* __restrict__ list,
             const int* __restrict__ count, int C, int NX, int CB, const float2* __restrict__ twX,
-            const float2* __restrict__ stwA, float a3, float a2, float a1, float b0) {
+            const float2* __restrict__ stwA, float a3, float a2, float a1, float b0, int rev) {
     constexpr int NY = RA * RB, BS = RB + 1, CS = FFTC2_CSTRIDE(RA, RB);
     constexpr int HS = FFTC2_HSTRIDE(RB), HC = RA * HS;
     extern __shared__ __align__(16) unsigned char smraw[];
@@ -1014,7 +1014,10 @@ k_fft_cols2(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const in
     // this thread's butterfly of stage A / A': column bc, position bj (idle when bc >= ncol)
     const int bc = tid / RB, bj = tid - bc * RB;
 
-    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+    // rev: the work items are taken last first -- P1 wrote the spectrum forwards, so its last ~100 MB are still in the L2
+    // when this pass starts with them, and this pass ends at the first image, where P3 (forwards) begins
+    for (int w0 = blockIdx.x; w0 < total; w0 += gridDim.x) {
+        const int w = rev ? total - 1 - w0 : w0;
         const int slot = w / nblk;
         const int cb = w - slot * nblk;
         const int im = list[slot];
@@ -1115,8 +1118,9 @@ k_fft_cols2(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const in
                 int ncn = ncol;
                 if (c + 1 < C) {
                     Zn = Zc + (size_t)half * NY;
-                } else if (w + (int)gridDim.x < total) {
-                    const int w2 = w + gridDim.x, slot2 = w2 / nblk, kx2 = 1 + (w2 - slot2 * nblk) * CB;
+                } else if (w0 + (int)gridDim.x < total) {
+                    const int w2 = rev ? total - 1 - (w0 + (int)gridDim.x) : w0 + (int)gridDim.x;
+                    const int slot2 = w2 / nblk, kx2 = 1 + (w2 - slot2 * nblk) * CB;
                     Zn = Z + ((size_t)slot2 * C * half + kx2) * NY;
                     ncn = min(CB, half - kx2);
                 }
@@ -1429,8 +1433,9 @@ int launch_deconv_fft(const float* img, float* out, const ImgKernel* kern, const
         k_fft_cols<NoStaticPlan><<<dim3(B < cap ? B : cap, C), FFTC_THREADS, smem0, s0>>>(T.Z, kern, list, count, C, NX, NY, 1, \
                                                                      T.planY, T.twX, T.stwY, T.slotY, a3, a2, a1, b0, 1); \
         if (ss) PB_CUDA_TRY(cudaEventRecord(ss->join, ss->s));                                                   \
+        static const int rev2 = env_int("PB_REVERSE", 1);                                                        \
         k_fft_cols2<RA, RB><<<grid2, FFTC2_THREADS, smem2, stream>>>(T.Z, kern, list, count, C, NX, cb2, T.twX, T.stwY2, \
-                                                                     a3, a2, a1, b0);                            \
+                                                                     a3, a2, a1, b0, rev2);                      \
         if (ss) PB_CUDA_TRY(cudaStreamWaitEvent(stream, ss->join, 0));                                           \
     } while (0)
     // long columns (one column per CTA): the block of column 0 in its own launch, so that the other CTAs do without its

@@ -45,7 +45,7 @@ template <class SP, int WIDE, int THREADS, int MINB, bool PADL>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_rows3(const float* __restrict__ img, float* __restrict__ gray, float* __restrict__ gx,
         unsigned* __restrict__ stats, int H, int nb, const float2* __restrict__ tw,
-        const float* __restrict__ omega) {
+        const float* __restrict__ omega, int rev) {
     constexpr int W = SP::n, NS = SP::ns, R0 = SP::R(0), M0 = W / R0, JM = M0 / WIDE;
     // padded stage-1 blocks (fft2_static.cuh: LayoutPad1) for the three-stage plans; RS = float2 per row pair
     using LY = typename std::conditional<(PADL && NS == 3), PadFor<SP>, LayoutFlat>::type;
@@ -55,8 +55,11 @@ k_rows3(const float* __restrict__ img, float* __restrict__ gray, float* __restri
     static_assert(NS >= 3, "needs an inner stage besides the fused middle one");
     extern __shared__ __align__(16) float2 sm2[];
     const int tid = threadIdx.x;
-    const int y0 = blockIdx.x * 2 * nb;
-    const int im = blockIdx.y;
+    // rev: the grid walks the batch backwards (last image, last rows first).  The kernel that produced the iterate
+    // (P3 / the narrow engine) walked it forwards, so the ~100 MB it wrote last are still in the 126 MB L2 when
+    // this kernel starts with them; it ends at image 0, where the column pass (forwards) picks g and d g / d x up.
+    const int y0 = (rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * 2 * nb;
+    const int im = rev ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
     const size_t plane = (size_t)H * W;
     const float* src = img + (size_t)im * 3 * plane;
     float* gdst = gray + (size_t)im * plane;
@@ -339,6 +342,7 @@ static int set_smem3(KernelT kern, size_t bytes) {
 int launch_rows3(const float* img, float* gray, float* gx, unsigned* stats, int nimg, int C, int H, int W,
                  const Fft2Plan& planW, const float2* twW, const float* omegaW, cudaStream_t stream) {
     if (!est_gen3() || C != 3) return 1;
+    static const int rev3 = env3("PB_REVERSE", 1);
     const int pairs_total = (H + 1) / 2;
     int rc;
     // nb row pairs per CTA: what fits BUDGET bytes of shared memory (at least one)
@@ -352,7 +356,7 @@ int launch_rows3(const float* img, float* gray, float* gx, unsigned* stats, int 
         if ((rc = set_smem3(k_rows3<SP, WIDE, THREADS, MINB, PADL>, smem))) return rc;                         \
         ProfScope prof(PROF_ROWS, stream);                                                                     \
         k_rows3<SP, WIDE, THREADS, MINB, PADL><<<dim3((pairs_total + nb - 1) / nb, nimg), THREADS, smem, stream>>>( \
-            img, gray, gx, stats, H, nb, twW, omegaW);                                                         \
+            img, gray, gx, stats, H, nb, twW, omegaW, rev3);                                                   \
         PB_LAUNCH_CHECK("k_rows3");                                                                            \
         return PB_OK;                                                                                          \
     } while (0)
