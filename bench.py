@@ -279,6 +279,17 @@ def binding_unit(members_ms, key_suffix):
             for gen in ("3", "2", ""):
                 if f"{name}{gen}:{sfx}" in pipes:
                     return pipes[f"{name}{gen}:{sfx}"]
+            # the same image size at another batch size: the per-kernel utilisation does not depend on the batch once
+            # the grid fills the GPU (the 4K capture is taken at 8 images, the C3 line runs 32)
+            dist_, _, shape_ = sfx.partition(":")
+            hw = shape_.split("x", 1)[1] if "x" in shape_ else None
+            for gen in ("3", "2", ""):
+                for k, v in pipes.items():
+                    kn, kd, ks = (k.split(":") + ["", ""])[:3]
+                    if kn == f"{name}{gen}" and kd == dist_ and hw and ks.split("x", 1)[-1] == hw:
+                        v = dict(v)
+                        v["source"] = v.get("source", "?") + f" (captured at {ks})"
+                        return v
             return None
         rec = lookup(key_suffix)
         if not rec:                  # the estimate kernels do the same work for both synthetic distributions

@@ -25,12 +25,14 @@ timeout 900 ncu --set full --clock-control none -k regex:"k_deconv_narrow" -s 0 
     python bench.py --dist white --steps 1 --warmup 1 --no-graph --no-e2e --no-cpu-baseline --no-secondary > $O/ncu_white.log 2>&1
 timeout 900 ncu --set full --clock-control none -k regex:"k_rows3|k_cols3|k_fft_rows|k_fft_cols" -s 0 -c 7 -f -o $O/prof_mosaic_c3 \
     python bench.py --config C3 --batch 8 --steps 1 --warmup 1 --no-graph --no-e2e --no-cpu-baseline --no-secondary > $O/ncu_c3.log 2>&1
+timeout 900 ncu --set full --clock-control none -k regex:"k_rows3|k_cols3|k_fft_rows|k_fft_cols" -s 0 -c 7 -f -o $O/prof_mosaic_c4 \
+    python bench.py --config C4 --steps 1 --warmup 1 --no-graph --no-e2e --no-cpu-baseline --no-secondary > $O/ncu_c4.log 2>&1
 # the reports themselves are too large to travel together: export the raw pages and the per-instruction mix here
-for rep in prof_mosaic32 prof_white32 prof_mosaic_c3; do
+for rep in prof_mosaic32 prof_white32 prof_mosaic_c3 prof_mosaic_c4; do
   ncu -i $O/$rep.ncu-rep --page raw --csv > $O/$rep.raw.csv 2>/dev/null
   ncu -i $O/$rep.ncu-rep --page source --csv --print-source sass 2>/dev/null | python tools/ncu_source_mix.py > $O/$rep.sass_mix.md
 done
-rm -f $O/prof_white32.ncu-rep $O/prof_mosaic_c3.ncu-rep      # prof_mosaic32.ncu-rep (~40 MB) comes back whole
+rm -f $O/prof_white32.ncu-rep $O/prof_mosaic_c3.ncu-rep $O/prof_mosaic_c4.ncu-rep      # prof_mosaic32.ncu-rep (~40 MB) comes back whole
 fi
 if [ "$PART" = "1" ] && [ -z "${REFRESH_QUICK:-}" ]; then
 timeout 600 python tools/config_sweep.py > $O/config_sweep.jsonl 2> $O/config_sweep.err

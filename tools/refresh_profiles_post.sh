@@ -12,7 +12,8 @@ python tools/launch_summary.py $O/launches_mosaic_b32.csv $P/${R}_launches_mosai
 python tools/ncu_summary.py $O/prof_mosaic32.raw.csv $P/${R}_ncu_mosaic_b32.md --traffic mosaic:32x1080x1920 $P/roofline_traffic.json --pipes mosaic:32x1080x1920 $P/roofline_pipes.json --csv $P/${R}_ncu_mosaic_b32.csv
 python tools/ncu_summary.py $O/prof_white32.raw.csv $P/${R}_ncu_white_b32.md --traffic white:32x1080x1920 $P/roofline_traffic.json --pipes white:32x1080x1920 $P/roofline_pipes.json --csv $P/${R}_ncu_white_b32.csv
 [ -s $O/prof_mosaic_c3.raw.csv ] && python tools/ncu_summary.py $O/prof_mosaic_c3.raw.csv $P/${R}_ncu_mosaic_4k_b8.md --pipes mosaic:8x2160x3840 $P/roofline_pipes.json --csv $P/${R}_ncu_mosaic_4k_b8.csv
-for rep in prof_mosaic32 prof_white32 prof_mosaic_c3; do
+[ -s $O/prof_mosaic_c4.raw.csv ] && python tools/ncu_summary.py $O/prof_mosaic_c4.raw.csv $P/${R}_ncu_mosaic_c4.md --pipes mosaic:1x9000x12000 $P/roofline_pipes.json --csv $P/${R}_ncu_mosaic_c4.csv
+for rep in prof_mosaic32 prof_white32 prof_mosaic_c3 prof_mosaic_c4; do
   [ -s $O/$rep.sass_mix.md ] && cp $O/$rep.sass_mix.md $P/${R}_sass_mix_${rep#prof_}.md
 done
 # SASS evidence: mnemonic counts of the shipped library (whole library and the hot kernels)
