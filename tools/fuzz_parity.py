@@ -13,7 +13,9 @@ import polyblur_b200 as pb  # noqa: E402
 from oracle import polyblur_oracle as po  # noqa: E402
 
 
-def main(n_cases=40, seed=0):
+def main(n_cases=40, seed=0, plan_sides=False):
+    """plan_sides: one side is a length with a compile-time plan (1080 / 1920 / 2160 / 3840: the fused-stage kernels of
+    csrc/estimate3.cu and the second-generation FFT passes), the other side random."""
     rng = np.random.default_rng(seed)
     worst = 0.0            # worst error against the float32 oracle among the cases inside 1e-5 of it
     worst_arb = 0.0        # worst error against the float64 restatement among the arbitrated cases
@@ -24,9 +26,17 @@ def main(n_cases=40, seed=0):
         C = int(rng.choice([1, 2, 3, 3, 3, 4]))
         H = int(rng.choice([1, 2, 3, 5, 8, 13, 24, 37, 64, 97, 100, 131, 180, 256]))
         W = int(rng.choice([1, 2, 4, 7, 8, 16, 25, 53, 64, 101, 120, 128, 200, 243]))
+        if plan_sides:
+            B = int(rng.integers(1, 3))
+            C = int(rng.choice([1, 3, 3, 3]))
+            other = int(rng.choice([2, 3, 9, 16, 31, 64, 100, 150, 257]))
+            if rng.random() < 0.5:
+                H, W = int(rng.choice([1080, 2160])), other
+            else:
+                H, W = other, int(rng.choice([1920, 3840]))
         if H * W < 4:
             H = 4
-        n_iter = int(rng.integers(1, 5))
+        n_iter = int(rng.integers(1, 3 if plan_sides else 5))
         kind = rng.choice(["noise", "blocks", "smooth"])
         x = rng.random((B, C, H, W), dtype=np.float32)
         if kind == "blocks":
@@ -84,4 +94,7 @@ def main(n_cases=40, seed=0):
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "plan-sides":
+        main(n_cases=int(sys.argv[2]) if len(sys.argv) > 2 else 16, seed=1, plan_sides=True)
+    else:
+        main()
