@@ -372,6 +372,17 @@ int launch_recursive_filter(const float* in, const float* joint, float* out, int
 // Elementwise epilogues.
 // ---------------------------------------------------------------------------------------------
 // impred = clip(deconv(smooth) + (impred - smooth), 0, 1)          (deblurring.py:80-88)
+__global__ void k_residual_add4(float4* __restrict__ dec, const float4* __restrict__ cur, const float4* __restrict__ smooth,
+                                size_t n4) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n4) {
+        const float4 c = __ldg(cur + i), s = __ldg(smooth + i), d = dec[i];
+        dec[i] = make_float4(fminf(fmaxf(__fadd_rn(d.x, __fsub_rn(c.x, s.x)), 0.0f), 1.0f),
+                             fminf(fmaxf(__fadd_rn(d.y, __fsub_rn(c.y, s.y)), 0.0f), 1.0f),
+                             fminf(fmaxf(__fadd_rn(d.z, __fsub_rn(c.z, s.z)), 0.0f), 1.0f),
+                             fminf(fmaxf(__fadd_rn(d.w, __fsub_rn(c.w, s.w)), 0.0f), 1.0f));
+    }
+}
 __global__ void k_residual_add(float* __restrict__ dec, const float* __restrict__ cur, const float* __restrict__ smooth,
                                size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -383,7 +394,12 @@ __global__ void k_residual_add(float* __restrict__ dec, const float* __restrict_
 
 int launch_residual_add(float* dec, const float* cur, const float* smooth, size_t n, cudaStream_t stream) {
     ProfScope prof(PROF_OTHER, stream);
-    k_residual_add<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(dec, cur, smooth, n);
+    if ((n & 3) == 0 && ((((uintptr_t)dec | (uintptr_t)cur | (uintptr_t)smooth) & 15) == 0)) {
+        k_residual_add4<<<(unsigned)((n / 4 + 255) / 256), 256, 0, stream>>>(
+            reinterpret_cast<float4*>(dec), reinterpret_cast<const float4*>(cur), reinterpret_cast<const float4*>(smooth), n / 4);
+    } else {
+        k_residual_add<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(dec, cur, smooth, n);
+    }
     PB_LAUNCH_CHECK("k_residual_add");
     return PB_OK;
 }
