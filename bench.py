@@ -326,6 +326,9 @@ def run_cuda(a):
         raise SystemExit("bench.py --impl cuda needs a GPU (there is no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # one process per GPU: keep it (and the pinned staging buffers it allocates) on the GPU's NUMA node, so that the
+    # host <-> device copies of the N ranks of a box do not cross the socket link (BENCH_NUMA=0 turns it off)
+    numa = sharding.bind_to_gpu_numa_node(local) if (world > 1 and os.environ.get("BENCH_NUMA", "1") != "0") else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 

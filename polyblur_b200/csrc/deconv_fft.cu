@@ -36,6 +36,13 @@
 
 namespace pb {
 
+// Timing experiment only (results are wrong): -DPB_ZMOD=n folds the half spectra of all images onto n slots, i.e. what the
+// passes would cost if `Z` never left the L2 (profiles/r02_l2_probe.md).
+#ifdef PB_ZMOD
+#define PB_ZSLOT(s) ((s) % PB_ZMOD)
+#else
+#define PB_ZSLOT(s) (s)
+#endif
 static int env_int(const char* name, int dflt);
 
 // ---- PTX wrappers: mbarrier + 1-D bulk (TMA) copies ---------------------------------------
@@ -223,7 +230,7 @@ k_fft_rows_fwd(const float* __restrict__ img, float2* __restrict__ Z, const ImgK
         else
             s_forward_dif<SP>(smf, RS, nb, twX, tid, FFTD_THREADS);
         // separate the two real rows: Xa[k] = (Z[k] + conj Z[-k]) / 2, Xb[k] = (Z[k] - conj Z[-k]) / (2i)
-        float2* Zp = Z + ((size_t)slot * C + c) * half * NY;
+        float2* Zp = Z + ((size_t)PB_ZSLOT(slot) * C + c) * half * NY;
         // four (kx, pair) items per trip: slot lookups first, then the scattered shared-memory reads
         for (int base = tid; base < nb * half; base += 4 * FFTD_THREADS) {
             int s1[4], s2[4], pp[4], kk[4];
@@ -397,7 +404,7 @@ k_fft_cols(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int
             __syncthreads();
         }
 
-        float2* Z0 = Z + ((size_t)slot * C * half + kx0) * NY;
+        float2* Z0 = Z + ((size_t)PB_ZSLOT(slot) * C * half + kx0) * NY;
         // first_block_only: one CTA per plane (blockIdx.y), so that the single column of every plane runs in parallel
         const int c_begin = first_block_only ? (int)blockIdx.y : 0, c_end = first_block_only ? (int)blockIdx.y + 1 : C;
         if (tid == 0) {
@@ -483,7 +490,7 @@ k_fft_rows_inv(const float2* __restrict__ Z, float* __restrict__ out, const ImgK
         const int j0 = rb * 2 * nb;
         // rows of the extended image that are output rows: [ext, H + ext)
         if (j0 + 2 * nb <= ext || j0 >= H + ext) continue;
-        const float2* Zp = Z + ((size_t)slot * C + c) * half * NY;
+        const float2* Zp = Z + ((size_t)PB_ZSLOT(slot) * C + c) * half * NY;
         // four (kx, pair) items per trip: their 128-bit spectrum loads and slot lookups are all in flight
         // before the first is used
         for (int base = tid; base < nb * half; base += 4 * FFTD_THREADS) {
@@ -749,7 +756,7 @@ k_fft_rows_fwd2(const float* __restrict__ img, float2* __restrict__ Z, const Img
         SDifRun<SP, 1, NS - 2, false, LY>::run(smf, RS, nb, twX, tid, THREADS);
         // last stage (M = 1) on the two blocks of a mirror unit, then
         //   Xa[k] = (Z[k] + conj Z[-k]) / 2,  Xb[k] = (Z[k] - conj Z[-k]) / (2i)   ->  Z[plane][kx][row pair]
-        float2* Zp = Z + ((size_t)slot * C + c) * half * NY;
+        float2* Zp = Z + ((size_t)PB_ZSLOT(slot) * C + c) * half * NY;
         for (int idx = tid; idx < nunits * nb; idx += THREADS) {
             const int u = idx / nb, p = idx - u * nb;
             const int ja = j0 + 2 * p;
@@ -836,7 +843,7 @@ k_fft_rows_inv2(const float2* __restrict__ Z, float* __restrict__ out, const Img
         const int j0 = rb * 2 * nb;
         // rows of the extended image that are output rows: [ext, H + ext)
         if (j0 + 2 * nb <= ext || j0 >= H + ext) continue;
-        const float2* Zp = Z + ((size_t)slot * C + c) * half * NY;
+        const float2* Zp = Z + ((size_t)PB_ZSLOT(slot) * C + c) * half * NY;
 #ifdef PB_ROWS_PREFETCH        // measured slower (+4 % on both row passes): off
         {
             // this CTA's next work item reads the same columns a few rows further: start its 64-byte pieces (one
@@ -846,7 +853,7 @@ k_fft_rows_inv2(const float2* __restrict__ Z, float* __restrict__ out, const Img
                 const int slotn = wn / per_img;
                 const int rn = wn - slotn * per_img;
                 const int cn = rn / blocks_per_plane;
-                const float2* Zn = Z + ((size_t)slotn * C + cn) * half * NY + (size_t)(rn - cn * blocks_per_plane) * 2 * nb;
+                const float2* Zn = Z + ((size_t)PB_ZSLOT(slotn) * C + cn) * half * NY + (size_t)(rn - cn * blocks_per_plane) * 2 * nb;
                 for (int kx = tid; kx < half; kx += THREADS)
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(Zn + (size_t)kx * NY));
             }
@@ -1100,7 +1107,7 @@ k_fft_cols2(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const in
         }
         __syncthreads();
 
-        float2* Z0 = Z + ((size_t)slot * C * half + kx0) * NY;
+        float2* Z0 = Z + ((size_t)PB_ZSLOT(slot) * C * half + kx0) * NY;
         if (tid == 0) {
             fence_async_smem();
             mbar_expect_tx(bar, (uint32_t)((size_t)ncol * NY * sizeof(float2)));
@@ -1121,7 +1128,7 @@ k_fft_cols2(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const in
                 } else if (w0 + (int)gridDim.x < total) {
                     const int w2 = rev ? total - 1 - (w0 + (int)gridDim.x) : w0 + (int)gridDim.x;
                     const int slot2 = w2 / nblk, kx2 = 1 + (w2 - slot2 * nblk) * CB;
-                    Zn = Z + ((size_t)slot2 * C * half + kx2) * NY;
+                    Zn = Z + ((size_t)PB_ZSLOT(slot2) * C * half + kx2) * NY;
                     ncn = min(CB, half - kx2);
                 }
                 if (Zn)

@@ -16,6 +16,33 @@ def shard_range(n_items: int, rank: int, world: int):
     return start, start + base + (1 if rank < extra else 0)
 
 
+def bind_to_gpu_numa_node(device_index: int):
+    """Pins the calling process to the CPUs of the NUMA node the GPU hangs off (one process per GPU: its pinned staging
+    buffers are then allocated on that node and the host <-> device copies of N ranks do not cross the socket link).
+    Returns {"node": n, "cpus": k} or None when the topology is flat, unknown or the affinity cannot be changed."""
+    import os
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {"node": node, "cpus": len(cpus)}
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        return None
+
+
 def gather_outputs(local: torch.Tensor, n_items: int, group=None) -> torch.Tensor:
     """All-gather the per-rank output slices back into the full batch (NCCL on GPUs, gloo on
     CPU tensors).  Off the timed path; ragged shards are padded to the largest one."""
