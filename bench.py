@@ -516,14 +516,16 @@ def run_cuda(a):
                 ev[3].record()
             torch.cuda.synchronize()
             rates.append((probe_n / ev[0].elapsed_time(ev[1]) / 1e6, probe_n / ev[2].elapsed_time(ev[3]) / 1e6))
-        best = [max(r[0] for r in rates), max(r[1] for r in rates)]
+        best = [max(r[0] for r in rates), max(r[1] for r in rates), float(numa["node"]) if numa else -1.0]
         per_rank = gather_floats(best)
         h2d = [round(r[0], 2) for r in per_rank]
         d2h = [round(r[1], 2) for r in per_rank]
+        numa_nodes = [int(r[2]) for r in per_rank]
         ceil_ms = max(nbytes / (min(h2d) * 1e6), nbytes / (min(d2h) * 1e6))
         e2e["link_probe"] = {"h2d_gbs_per_rank": h2d, "d2h_gbs_per_rank": d2h, "bytes": probe_n,
                              "how": "pinned host <-> device copies of this size in both directions at once on every "
                                     "rank simultaneously, best of 3, CUDA events",
+                             "numa_node_per_rank": numa_nodes if world > 1 else None,   # -1: process not bound
                              "link_bound_ms_per_step": ceil_ms,
                              "link_bound_value": pix_all / 1e6 / (ceil_ms / 1e3),
                              "e2e_over_link_bound": (pix_all / 1e6 / (ms_e2e / 1e3)) / (pix_all / 1e6 / (ceil_ms / 1e3))}

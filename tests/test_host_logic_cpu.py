@@ -120,3 +120,47 @@ def test_maxima_gradient_chain_matches_reference_autograd():
     # image 1 has rho on the lower clamp (0.3) and still gets the sigma term
     assert np.allclose(sr[2], 4.0) and float(got[2].abs().max()) == 0.0
     assert np.isclose(sr[1, 1], 0.3) and float(got[1].abs().max()) > 0.0
+
+
+def test_import_name_drop_in():
+    """polyblur_b200.compat.install(): `import polyblur` and the reference's module names resolve to this package
+    (polyblur/__init__.py:1), and a foreign `polyblur` already imported is not silently replaced."""
+    import importlib
+    import sys
+    import types
+
+    import polyblur_b200
+    from polyblur_b200 import compat
+
+    saved = {k: v for k, v in sys.modules.items() if k == "polyblur" or k.startswith("polyblur.")}
+    for k in saved:
+        del sys.modules[k]
+    try:
+        compat.install()
+        import polyblur
+        from polyblur import PolyblurDeblurring, polyblur_deblurring
+        from polyblur.deblurring import inverse_filtering_rank3
+        from polyblur.blur_estimation import gaussian_blur_estimation
+        from polyblur.filters import fourier_gradients
+        from polyblur.edgetaper import edgetaper
+        from polyblur.domain_transform import recursive_filter
+        from polyblur.utils import to_tensor, to_array
+        assert polyblur is polyblur_b200
+        assert polyblur_deblurring is polyblur_b200.polyblur_deblurring
+        assert PolyblurDeblurring is polyblur_b200.PolyblurDeblurring
+        assert inverse_filtering_rank3 is polyblur_b200.deblurring.inverse_filtering_rank3
+        assert importlib.import_module("polyblur.filters") is polyblur_b200.filters
+        for f in (gaussian_blur_estimation, fourier_gradients, edgetaper, recursive_filter, to_tensor, to_array):
+            assert callable(f)
+        compat.uninstall()
+        assert "polyblur" not in sys.modules and "polyblur.deblurring" not in sys.modules
+        sys.modules["polyblur"] = types.ModuleType("polyblur")          # somebody else's package of that name
+        with pytest.raises(ImportError):
+            compat.install()
+        compat.install(force=True)
+        assert sys.modules["polyblur"] is polyblur_b200
+        compat.uninstall()
+    finally:
+        for k in [k for k in sys.modules if k == "polyblur" or k.startswith("polyblur.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
