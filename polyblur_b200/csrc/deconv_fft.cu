@@ -972,7 +972,9 @@ k_fft_rows_inv2(const float2* __restrict__ Z, float* __restrict__ out, const Img
 
 // DIF stage A of k_fft_cols2 on natural-order data -> padded blocks: all loads, barrier, then the stores
 // (the two layouts overlap in shared memory).  Thread = butterfly bj of column bc; idle when bc >= nseq.
-template <int RA, int RB>
+// WARPCOL (RB == 32: a warp is a column): only this warp reads and writes the column, so the barrier between the loads and
+// the stores is a warp barrier (an idle warp reads a duplicate column that its owner may be rewriting: never stored).
+template <int RA, int RB, bool WARPCOL = false>
 __device__ __forceinline__ void cols2_stage_a(float2* data, const float2* stwA, int bc, int bj, int nseq) {
     constexpr int BS = RB + 1, CS = FFTC2_CSTRIDE(RA, RB);
     // every thread loads and transforms (idle ones a duplicate of the last live column: values that are defined on
@@ -982,7 +984,7 @@ __device__ __forceinline__ void cols2_stage_a(float2* data, const float2* stwA, 
     float2* p = data + (size_t)(on ? bc : nseq - 1) * CS + bj;
 #pragma unroll
     for (int m = 0; m < RA; ++m) v[m] = p[m * RB];
-    __syncthreads();
+    if (WARPCOL) __syncwarp(); else __syncthreads();
     Dft<RA>::run(v);
     if (on) p[0] = v[0];
 #pragma unroll
@@ -993,7 +995,9 @@ __device__ __forceinline__ void cols2_stage_a(float2* data, const float2* stwA, 
     __syncthreads();
 }
 
-template <int RA, int RB>
+// PC (per-column hand-off, RB == 32): every column has its own mbarrier and its warp stores it, waits for the read-out and
+// fetches the same column of the next plane on its own -- no CTA barrier between stage A' of one plane and stage A of the next.
+template <int RA, int RB, bool PC = false>
 __global__ void __launch_bounds__(FFTC2_THREADS, 2)
 k_fft_cols2(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const int* __restrict__ list,
             const int* __restrict__ count, int C, int NX, int CB, const float2* __restrict__ twX,
@@ -1012,8 +1016,13 @@ k_fft_cols2(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const in
     const int nblk = (half - 1 + CB - 1) / CB;          // blocks over columns 1 .. half - 1
     const int total = count[0] * nblk;
     const float scale = 1.0f / ((float)NX * (float)NY);
-    uint32_t phase = 0;
-    if (tid == 0) mbar_init(bar, 1);
+    static_assert(!PC || RB == 32, "per-column hand-off needs one warp per column");
+    uint32_t phase = 0;                                  // PC: of this warp's own barrier bar[bc]
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        if (PC)
+            for (int i = 1; i < FFTC2_THREADS / RB; ++i) mbar_init(bar + i, 1);
+    }
     // the stage twiddles stay in shared memory for the life of the (persistent) CTA: with ~20 KB of L1 left beside
     // the 2 x 110 KB of shared memory, the table reads of stage A / A' kept missing it (long-scoreboard stalls)
     for (int i = tid; i < (RA - 1) * RB; i += FFTC2_THREADS) tws[i] = __ldg(stwA + i);
@@ -1110,14 +1119,21 @@ k_fft_cols2(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const in
         float2* Z0 = Z + ((size_t)PB_ZSLOT(slot) * C * half + kx0) * NY;
         if (tid == 0) {
             fence_async_smem();
-            mbar_expect_tx(bar, (uint32_t)((size_t)ncol * NY * sizeof(float2)));
-            for (int col = 0; col < ncol; ++col)
-                bulk_g2s(data + (size_t)col * CS, Z0 + (size_t)col * NY, (uint32_t)(NY * sizeof(float2)), bar);
+            if (!PC) mbar_expect_tx(bar, (uint32_t)((size_t)ncol * NY * sizeof(float2)));
+            for (int col = 0; col < ncol; ++col) {
+                if (PC) mbar_expect_tx(bar + col, (uint32_t)(NY * sizeof(float2)));
+                bulk_g2s(data + (size_t)col * CS, Z0 + (size_t)col * NY, (uint32_t)(NY * sizeof(float2)), PC ? bar + col : bar);
+            }
         }
         for (int c = 0; c < C; ++c) {
             float2* Zc = Z0 + (size_t)c * half * NY;
-            mbar_wait(bar, phase);
-            phase ^= 1;
+            if (!PC) {
+                mbar_wait(bar, phase);
+                phase ^= 1;
+            } else if (bc < ncol) {
+                mbar_wait(bar + bc, phase);
+                phase ^= 1;
+            }
             if (tid == 32) {
                 // the next plane's columns (or the first plane of this CTA's next work item) on their way into L2
                 // while this one is transformed: the bulk load, issued once the buffer is free again, finds them there
@@ -1134,7 +1150,7 @@ k_fft_cols2(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const in
                 if (Zn)
                     for (int col = 0; col < ncn; ++col) bulk_prefetch_l2(Zn + (size_t)col * NY, (uint32_t)(NY * sizeof(float2)));
             }
-            cols2_stage_a<RA, RB>(data, tws, bc, bj, ncol);
+            cols2_stage_a<RA, RB, PC>(data, tws, bc, bj, ncol);
             // middle: DFT_RB -> y = H z with the re/im swap -> DFT_RB, on one padded block per thread
             for (int idx = tid; idx < ncol * RA; idx += FFTC2_THREADS) {
                 const int f = idx / RA, blk = idx - f * RA;
@@ -1165,13 +1181,27 @@ k_fft_cols2(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const in
                 v[0] = p[0];
 #pragma unroll
                 for (int q = 1; q < RA; ++q) v[q] = c_mul(p[q * BS], tws[(q - 1) * RB + bj]);
-                __syncthreads();
+                if (PC) __syncwarp(); else __syncthreads();
                 Dft<RA>::run(v);
 #pragma unroll
                 for (int m = 0; m < RA; ++m)
                     if (on) p[m * RB] = v[m];
             }
             fence_async_smem();
+            if (PC) {
+                // this warp's column out, and the same column of the next plane in as soon as it has been read out
+                __syncwarp();
+                if (bj == 0 && bc < ncol) {
+                    bulk_s2g(Zc + (size_t)bc * NY, data + (size_t)bc * CS, (uint32_t)(NY * sizeof(float2)));
+                    bulk_commit();
+                    bulk_wait_all();
+                    if (c + 1 < C) {
+                        mbar_expect_tx(bar + bc, (uint32_t)(NY * sizeof(float2)));
+                        bulk_g2s(data + (size_t)bc * CS, Zc + ((size_t)half + bc) * NY, (uint32_t)(NY * sizeof(float2)), bar + bc);
+                    }
+                }
+                continue;
+            }
             __syncthreads();
             if (tid == 0) {
                 for (int col = 0; col < ncol; ++col)
@@ -1419,13 +1449,15 @@ int launch_deconv_fft(const float* img, float* out, const ImgKernel* kern, const
         const int cb2 = env_int("PB_FFT_CB2", 7) < CB2 ? env_int("PB_FFT_CB2", 7) : CB2;                         \
         const size_t cs2 = FFTC2_CSTRIDE(RA, RB);                                                                \
         const size_t smem2 = cb2 * cs2 * sizeof(float2) + (size_t)cb2 * (RA) * FFTC2_HSTRIDE(RB) * sizeof(float) + \
-                             (size_t)cb2 * 13 * sizeof(float2) + (size_t)((RA) - 1) * (RB) * sizeof(float2) + 64;  \
+                             (size_t)cb2 * 13 * sizeof(float2) + (size_t)((RA) - 1) * (RB) * sizeof(float2) + 128;  \
         const size_t smem0 = (size_t)NY * 12 + (size_t)NY * 8 + 2 * 13 * 8 + 64;                                 \
         const long long items2 = (long long)B * ((NX / 2 - 1 + cb2 - 1) / cb2);                                  \
         static const int c2_per_sm = env_int("PB_FFT_COLS2_CTAS_PER_SM", 4);                                     \
         const long long cap2 = c2_per_sm > 0 ? (long long)c2_per_sm * PB_NUM_SMS : (1LL << 30);                  \
         const int grid2 = (int)(items2 < cap2 ? items2 : cap2);                                                  \
-        PB_CUDA_TRY(cudaFuncSetAttribute(k_fft_cols2<RA, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)); \
+        static const bool percol = env_int("PB_FFT_COLS2_PERCOL", 1) != 0;     /* per-column hand-off between planes */ \
+        auto kc2 = percol ? k_fft_cols2<RA, RB, (RB) == 32> : k_fft_cols2<RA, RB, false>;                        \
+        PB_CUDA_TRY(cudaFuncSetAttribute(kc2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));         \
         PB_CUDA_TRY(cudaFuncSetAttribute(k_fft_cols<NoStaticPlan>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0)); \
         ProfScope prof(PROF_FFT_COLS, stream);                                                                   \
         static const bool side_on = env_int("PB_FFT_SIDE", 1) != 0;                                              \
@@ -1441,8 +1473,8 @@ int launch_deconv_fft(const float* img, float* out, const ImgKernel* kern, const
                                                                      T.planY, T.twX, T.stwY, T.slotY, a3, a2, a1, b0, 1); \
         if (ss) PB_CUDA_TRY(cudaEventRecord(ss->join, ss->s));                                                   \
         static const int rev2 = env_int("PB_REVERSE", 1);                                                        \
-        k_fft_cols2<RA, RB><<<grid2, FFTC2_THREADS, smem2, stream>>>(T.Z, kern, list, count, C, NX, cb2, T.twX, T.stwY2, \
-                                                                     a3, a2, a1, b0, rev2);                      \
+        kc2<<<grid2, FFTC2_THREADS, smem2, stream>>>(T.Z, kern, list, count, C, NX, cb2, T.twX, T.stwY2,         \
+                                                     a3, a2, a1, b0, rev2);                                      \
         if (ss) PB_CUDA_TRY(cudaStreamWaitEvent(stream, ss->join, 0));                                           \
     } while (0)
     // long columns (one column per CTA): the block of column 0 in its own launch, so that the other CTAs do without its
