@@ -981,10 +981,25 @@ __device__ __forceinline__ void cols2_stage_a(float2* data, const float2* stwA, 
     // one side of the barrier only make ptxas spill the whole butterfly around it); only the stores are predicated
     float2 v[RA];
     const bool on = bc < nseq;
+    if constexpr (WARPCOL) {
+        // `on` is uniform over the warp: an idle warp skips the stage (and touches no column that its owner is rewriting)
+        if (on) {
+            float2* p = data + (size_t)bc * CS + bj;
+#pragma unroll
+            for (int m = 0; m < RA; ++m) v[m] = p[m * RB];
+            __syncwarp();
+            Dft<RA>::run(v);
+            p[0] = v[0];
+#pragma unroll
+            for (int q = 1; q < RA; ++q) p[q * BS] = c_mul(v[q], stwA[(q - 1) * RB + bj]);
+        }
+        __syncthreads();
+        return;
+    }
     float2* p = data + (size_t)(on ? bc : nseq - 1) * CS + bj;
 #pragma unroll
     for (int m = 0; m < RA; ++m) v[m] = p[m * RB];
-    if (WARPCOL) __syncwarp(); else __syncthreads();
+    __syncthreads();
     Dft<RA>::run(v);
     if (on) p[0] = v[0];
 #pragma unroll
@@ -1096,7 +1111,7 @@ k_fft_cols2(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const in
             data[(size_t)q * CS + (d < 0 ? d + NY : d)] = make_float2(ra.x - rb.y, ra.y + rb.x);
         }
         __syncthreads();
-        cols2_stage_a<RA, RB>(data, tws, bc, bj, nseq);
+        cols2_stage_a<RA, RB, PC>(data, tws, bc, bj, nseq);
         // last DIF stage of the kernel spectra on each padded block, then Hs[col][block][q] = scale * P(K^)
         for (int idx = tid; idx < nseq * RA; idx += FFTC2_THREADS) {
             const int f = idx / RA, blk = idx - f * RA;
@@ -1174,6 +1189,33 @@ k_fft_cols2(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const in
             }
             __syncthreads();
             // DIT stage A': padded blocks -> natural order.  All loads, barrier, then the stores.
+            if constexpr (PC) {
+                // a warp is a column: idle warps skip the stage; this warp's column goes out, and the same column of the
+                // next plane comes in as soon as it has been read out
+                if (bc < ncol) {
+                    float2 v[RA];
+                    float2* p = data + (size_t)bc * CS + bj;
+                    v[0] = p[0];
+#pragma unroll
+                    for (int q = 1; q < RA; ++q) v[q] = c_mul(p[q * BS], tws[(q - 1) * RB + bj]);
+                    __syncwarp();
+                    Dft<RA>::run(v);
+#pragma unroll
+                    for (int m = 0; m < RA; ++m) p[m * RB] = v[m];
+                    fence_async_smem();
+                    __syncwarp();
+                    if (bj == 0) {
+                        bulk_s2g(Zc + (size_t)bc * NY, data + (size_t)bc * CS, (uint32_t)(NY * sizeof(float2)));
+                        bulk_commit();
+                        bulk_wait_all();
+                        if (c + 1 < C) {
+                            mbar_expect_tx(bar + bc, (uint32_t)(NY * sizeof(float2)));
+                            bulk_g2s(data + (size_t)bc * CS, Zc + ((size_t)half + bc) * NY, (uint32_t)(NY * sizeof(float2)), bar + bc);
+                        }
+                    }
+                }
+                continue;
+            }
             {
                 float2 v[RA];
                 const bool on = bc < ncol;
@@ -1181,27 +1223,13 @@ k_fft_cols2(float2* __restrict__ Z, const ImgKernel* __restrict__ kern, const in
                 v[0] = p[0];
 #pragma unroll
                 for (int q = 1; q < RA; ++q) v[q] = c_mul(p[q * BS], tws[(q - 1) * RB + bj]);
-                if (PC) __syncwarp(); else __syncthreads();
+                __syncthreads();
                 Dft<RA>::run(v);
 #pragma unroll
                 for (int m = 0; m < RA; ++m)
                     if (on) p[m * RB] = v[m];
             }
             fence_async_smem();
-            if (PC) {
-                // this warp's column out, and the same column of the next plane in as soon as it has been read out
-                __syncwarp();
-                if (bj == 0 && bc < ncol) {
-                    bulk_s2g(Zc + (size_t)bc * NY, data + (size_t)bc * CS, (uint32_t)(NY * sizeof(float2)));
-                    bulk_commit();
-                    bulk_wait_all();
-                    if (c + 1 < C) {
-                        mbar_expect_tx(bar + bc, (uint32_t)(NY * sizeof(float2)));
-                        bulk_g2s(data + (size_t)bc * CS, Zc + ((size_t)half + bc) * NY, (uint32_t)(NY * sizeof(float2)), bar + bc);
-                    }
-                }
-                continue;
-            }
             __syncthreads();
             if (tid == 0) {
                 for (int col = 0; col < ncol; ++col)
