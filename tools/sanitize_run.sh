@@ -1,0 +1,7 @@
+mkdir -p gpurun_out/san
+: > gpurun_out/san/sanitizer.txt
+for T in memcheck racecheck synccheck; do
+  echo "== compute-sanitizer --tool $T python tools/sanitize_static_plans.py" >> gpurun_out/san/sanitizer.txt
+  timeout 600 compute-sanitizer --tool $T python tools/sanitize_static_plans.py 2>&1 | grep -v "^=========     " | tail -14 >> gpurun_out/san/sanitizer.txt
+done
+cat gpurun_out/san/sanitizer.txt | grep -i "summary\|error\|hazard" | head -20
