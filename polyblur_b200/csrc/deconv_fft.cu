@@ -692,7 +692,7 @@ __device__ __forceinline__ bool unit_maybe_nyquist(int q) { return 2 * KS * q <=
 #endif
 
 template <class SP, int NY, int THREADS, bool PADL>
-__global__ void __launch_bounds__(THREADS, (THREADS > 256 ? 2 : PB_FFTD_MINB))
+__global__ void __launch_bounds__(THREADS, (THREADS > 256 || SP::R(0) > 20 ? 2 : PB_FFTD_MINB))
 k_fft_rows_fwd2(const float* __restrict__ img, float2* __restrict__ Z, const ImgKernel* __restrict__ kern,
                 const int* __restrict__ list, const int* __restrict__ count, int C, int H, int W, int nb,
                 const float2* __restrict__ twX, const int4* __restrict__ units, SrcGeom G) {
@@ -815,7 +815,7 @@ k_fft_rows_fwd2(const float* __restrict__ img, float2* __restrict__ Z, const Img
 }
 
 template <class SP, int NY, int THREADS, bool PADL>
-__global__ void __launch_bounds__(THREADS, (THREADS > 256 ? 2 : PB_FFTD_MINB))
+__global__ void __launch_bounds__(THREADS, (THREADS > 256 || SP::R(0) > 20 ? 2 : PB_FFTD_MINB))
 k_fft_rows_inv2(const float2* __restrict__ Z, float* __restrict__ out, const ImgKernel* __restrict__ kern,
                 const int* __restrict__ list, const int* __restrict__ count, int C, int H, int W, int nb,
                 const float2* __restrict__ twX, const int4* __restrict__ units, int clamp_out) {
@@ -1379,6 +1379,18 @@ int fft_engine_prepare(char* base, const FftEngineLayout& L, FftEngineTables* T,
         jobs->add(TJ_STAGE_TW, px.tw_total, T->stwX2, nullptr, &px);
         jobs->add(TJ_UNITS, 256, T->unitsX2, nullptr, &px);
     }
+    if (L.NX == 12096 && L.NY == 9216 && env_int("PB_FFT_ROWS_C4_3STAGE", 1) != 0) {
+        Fft2Plan px;
+        px.n = 12096;
+        px.ns = 3;
+        px.radix[0] = 36;
+        px.radix[1] = 24;
+        px.radix[2] = 14;
+        fft2_plan_offsets(&px);
+        T->rowplan2 = 2;
+        jobs->add(TJ_STAGE_TW, px.tw_total, T->stwX2, nullptr, &px);
+        jobs->add(TJ_UNITS, 256, T->unitsX2, nullptr, &px);
+    }
     if (T->ra2) {
         Fft2Plan p2;
         p2.n = L.NY;
@@ -1567,7 +1579,8 @@ int launch_deconv_fft(const float* img, float* out, const ImgKernel* kern, const
             } else if (PlanX12096::matches(T.planX) && NY == 9216 && !rows_v1) {
                 // one row pair (95 KB) per CTA, two CTAs per SM (384 threads per CTA, which fill the register file at
                 // 2 x 384 x 80, measured slower: P1 7.1 against 6.5 ms per C4 step, P3 equal)
-                PB_FFT_ROWS2(PlanX12096, 9216, T.stwX, T.unitsX, 256, false);
+                if (T.rowplan2 == 2) PB_FFT_ROWS2(PlanX12096b, 9216, T.stwX2, T.unitsX2, 256, false);
+                else PB_FFT_ROWS2(PlanX12096, 9216, T.stwX, T.unitsX, 256, false);
             } else PB_FFT_ROWS(NoStaticPlan);
         }
     }

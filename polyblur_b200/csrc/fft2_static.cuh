@@ -236,5 +236,8 @@ using PlanY2304 = StaticPlan<2304, 16, 16, 9>;
 // the torus of the single 12000 x 9000 image (BASELINE C4): the run-time planner's orders
 using PlanX12096 = StaticPlan<12096, 16, 9, 12, 7>;
 using PlanY9216 = StaticPlan<9216, 16, 4, 16, 9>;
+// three stages for the second-generation row passes of that torus: a 36-point first stage (128 registers per thread, two
+// CTAs per SM are all the 95 KB sequences allow anyway), 14-point mirror units last
+using PlanX12096b = StaticPlan<12096, 36, 24, 14>;
 
 }  // namespace pb
