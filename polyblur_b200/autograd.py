@@ -17,9 +17,15 @@ The reference is differentiable because it is written in torch ops (README.md:70
   estimator under ``torch.no_grad()``), which removes the spiky rows / columns through the arg-max
   pixels from the gradient.
 
-Only the default options are differentiable (no halo masking, edgetaper, prefilter, quantile
-normalisation, saturation mask); the kernels, the estimator traces and the unclamped iterates are kept
-for the backward pass (n_iter extra images of memory).
+Halo masking (``remove_halo=True``, polyblur/deblurring.py:171-208) is differentiable as a composite:
+``EstimateKernelFunction`` (the estimator as a node: image -> kernel taps) -> ``DeconvolutionFunction`` without
+its clamp -> ``halo_masking`` written with the differentiable ``filters.fourier_gradients`` of this package and
+elementwise torch operations -> clamp.  It matches torch.autograd over the reference (tests/golden/vjp_halo.npz),
+including the path through the gradients of the original image that the mask is built from.
+
+The other options are not differentiable here (edgetaper, prefilter, quantile normalisation, saturation mask:
+they raise); the kernels, the estimator traces and the unclamped iterates are kept for the backward pass (n_iter
+extra images of memory).
 """
 from __future__ import annotations
 
@@ -178,31 +184,98 @@ class DeconvolutionFunction(torch.autograd.Function):
     the kernel taps."""
 
     @staticmethod
-    def forward(ctx, img, kernel, alpha, beta, engine):
+    def forward(ctx, img, kernel, alpha, beta, engine, clamp=True):
         dev = _lib.require_cuda(img)
         x = img.detach().to(dev).contiguous()
         k = kernel.detach().to(dev, torch.float32)
         k = k.expand(x.shape[0], 1, k.shape[-2], k.shape[-1]).contiguous()
         v = _deconv_noclamp(x, k, alpha, beta, engine)
         ctx.save_for_backward(x, k, v)
-        ctx.meta = (alpha, beta, engine, img.device, tuple(kernel.shape), kernel.device, kernel.dtype)
-        return v.clamp(0.0, 1.0).to(img.device)
+        ctx.meta = (alpha, beta, engine, img.device, tuple(kernel.shape), kernel.device, kernel.dtype, bool(clamp))
+        return (v.clamp(0.0, 1.0) if clamp else v).to(img.device)
 
     @staticmethod
     def backward(ctx, grad_out):
         x, k, v = ctx.saved_tensors
-        alpha, beta, engine, src, kshape, kdev, kdtype = ctx.meta
+        alpha, beta, engine, src, kshape, kdev, kdtype, clamp = ctx.meta
         go = grad_out.detach().to(x.device).contiguous()
+        pre = v if clamp else None          # clamp=False: the unclamped result was handed out (halo masking follows)
         g = gk = None
         if ctx.needs_input_grad[0]:
-            g = inverse_filtering_rank3_vjp(go, k, alpha, beta, preclamp=v, engine=engine).to(src)
+            g = inverse_filtering_rank3_vjp(go, k, alpha, beta, preclamp=pre, engine=engine).to(src)
         if ctx.needs_input_grad[1]:
             # d <grad_out, y> / d taps (pb_kernel_grad_f32); a kernel shared by the batch collects every image's term
-            gk = kernel_grad(x, go, v, k, alpha, beta, engine)
+            gk = kernel_grad(x, go, pre, k, alpha, beta, engine)
             if kshape[0] == 1 and gk.shape[0] != 1:
                 gk = gk.sum(dim=0, keepdim=True)
             gk = gk.to(kdev, kdtype)
-        return g, gk, None, None, None
+        return g, gk, None, None, None, None
+
+
+class EstimateKernelFunction(torch.autograd.Function):
+    """``gaussian_blur_estimation(img)`` (default options, polyblur/blur_estimation.py:18-79) as a node of the
+    autograd graph: image -> (B,1,ks,ks) kernel taps; backward = taps -> 7 directional maxima (``_maxima_grad``) ->
+    arg-max pixels, transposed spectral derivative, range normalisation (``pb_estimator_vjp_f32``)."""
+
+    @staticmethod
+    def forward(ctx, img, c, b, ker_size):
+        dev = _lib.require_cuda(img)
+        x = img.detach().to(dev).contiguous()
+        k = blur_estimation.gaussian_blur_estimation(x, q=0.0, c=c, b=b, ker_size=ker_size).contiguous()
+        tf, tp = estimate_trace(x)
+        ctx.save_for_backward(x, tf, tp)
+        ctx.meta = (float(c), float(b), int(ker_size), img.device)
+        return k.to(img.device)
+
+    @staticmethod
+    def backward(ctx, kbar):
+        x, tf, tp = ctx.saved_tensors
+        c, b, ks, src = ctx.meta
+        kb = kbar.detach().to(x.device, torch.float32).contiguous()
+        mbar = _maxima_grad(tf[:, :7], kb, c, b, ks)
+        gin = torch.zeros_like(x)
+        estimator_vjp(x, mbar, tf, tp, gin)
+        return gin.to(src), None, None, None
+
+
+def halo_masking(img: torch.Tensor, imout: torch.Tensor, grad_img=None) -> torch.Tensor:
+    """Differentiable ``halo_masking`` (polyblur/deblurring.py:171-208), bug-compatible like the fused kernels
+    (csrc/stages.cu): M = -gx gout_x - gy gy (:174), z = max(M / (nM + M), 0), out = imout + z (img - imout).
+    The spectral derivatives are this package's CUDA kernels (``filters.fourier_gradients``, differentiable)."""
+    from . import filters
+    gx, gy = filters.fourier_gradients(img) if grad_img is None else grad_img
+    gout_x, _ = filters.fourier_gradients(imout)
+    M = (-gx * gout_x) + (-gy * gy)
+    nM = torch.sum(gx * gx + gy * gy, dim=(-2, -1), keepdim=True)
+    z = torch.clamp(M / (nM + M), min=0)
+    return imout + z * (img - imout)
+
+
+def inverse_filtering_rank3_halo(img, kernel, alpha, beta, grad_img, engine) -> torch.Tensor:
+    """Differentiable ``inverse_filtering_rank3(..., remove_halo=True)`` (no edgetaper): deblurring.py:225-239."""
+    v = DeconvolutionFunction.apply(img, kernel, alpha, beta, engine, False)
+    return torch.clamp(halo_masking(img, v, grad_img), 0.0, 1.0)
+
+
+def polyblur_deblurring_halo_grad(img: torch.Tensor, n_iter=1, c=0.352, b=0.768, alpha=2, beta=3, ker_size=25,
+                                  engine=_lib.ENGINE_AUTO, estimate_grad=True) -> torch.Tensor:
+    """Differentiable ``polyblur_deblurring(..., remove_halo=True)`` (deblurring.py:60-88): the mask of every iteration
+    is built from the gradients of the ORIGINAL image, which therefore also receives gradient through them."""
+    if img.dtype != torch.float32 or img.ndim != 4:
+        raise TypeError("img must be a float32 (B,C,H,W) tensor")
+    from . import filters
+    dev = _lib.require_cuda(img)
+    x = img.to(dev)
+    grad_img = filters.fourier_gradients(x)
+    cur = x
+    for _ in range(int(n_iter)):
+        if estimate_grad:
+            k = EstimateKernelFunction.apply(cur, c, b, ker_size)
+        else:
+            with torch.no_grad():
+                k = blur_estimation.gaussian_blur_estimation(cur.detach(), q=0.0, c=c, b=b, ker_size=ker_size)
+        cur = inverse_filtering_rank3_halo(cur, k, alpha, beta, grad_img, engine).clamp(0.0, 1.0)
+    return cur.to(img.device)
 
 
 class PolyblurFunction(torch.autograd.Function):

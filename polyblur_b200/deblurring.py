@@ -252,11 +252,15 @@ def polyblur_deblurring(img, n_iter=1, c=0.352, b=0.768, alpha=2, beta=3, sigma_
         return utils.to_array(x) if flag_numpy else img
     if not flag_numpy and x.requires_grad and torch.is_grad_enabled():
         # differentiable path (autograd.py): gradient with respect to the image, blur estimates held constant
-        if remove_halo or edgetaping or prefiltering or return_estimates or q > 0 or discard_saturation:
-            raise NotImplementedError("gradients are implemented for the default options only (no remove_halo / "
+        if edgetaping or prefiltering or return_estimates or q > 0 or discard_saturation:
+            raise NotImplementedError("gradients are implemented for the default options and remove_halo only (no "
                                       "edgetaping / prefiltering / q / discard_saturation); call under "
                                       "torch.no_grad() or detach the input")
         from . import autograd as _autograd
+        if remove_halo:
+            return _autograd.polyblur_deblurring_halo_grad(x, n_iter=n_iter, c=c, b=b, alpha=alpha, beta=beta,
+                                                           ker_size=ker_size, engine=p.engine,
+                                                           estimate_grad=estimate_grad)
         return _autograd.polyblur_deblurring_grad(x, n_iter=n_iter, c=c, b=b, alpha=alpha, beta=beta,
                                                   ker_size=ker_size, engine=p.engine, estimate_grad=estimate_grad)
 
@@ -317,13 +321,15 @@ def inverse_filtering_rank3(img, kernel, alpha=2, b=4, correlate=False, remove_h
     if img.dtype != torch.float32 or img.ndim != 4:
         raise TypeError("img must be a float32 (B,C,H,W) tensor")
     if (img.requires_grad or (isinstance(kernel, torch.Tensor) and kernel.requires_grad)) and torch.is_grad_enabled():
-        if remove_halo or do_edgetaper:
-            raise NotImplementedError("gradients are implemented for the default flags only")
+        if do_edgetaper:
+            raise NotImplementedError("gradients are not implemented through the edgetaper")
         if kernel.shape[1] != 1 or kernel.shape[-1] != kernel.shape[-2]:
             raise NotImplementedError("one square kernel per image (B,1,k,k) or (1,1,k,k)")
         from . import autograd as _autograd
         kk = torch.rot90(kernel, k=2, dims=(-2, -1)) if correlate else kernel
-        return _autograd.DeconvolutionFunction.apply(img, kk, alpha, b, engine)
+        if remove_halo:
+            return _autograd.inverse_filtering_rank3_halo(img, kk, alpha, b, grad_img, engine)
+        return _autograd.DeconvolutionFunction.apply(img, kk, alpha, b, engine, True)
     dev = _lib.require_cuda(img)
     src = img.device
     x = img.detach().to(dev).contiguous()

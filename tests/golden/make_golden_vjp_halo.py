@@ -1,0 +1,84 @@
+"""Golden vectors for the backward pass THROUGH HALO MASKING, from torch.autograd over the LIVE reference.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden_vjp_halo.py
+
+Writes vjp_halo.npz next to this file:
+  * stage_*: ``inverse_filtering_rank3(x, k, remove_halo=True, method='fft')`` (deblurring.py:211-239 with the
+    bug-compatible mask of :171-208) and the gradients of sum(y * ybar) with respect to the image and to the kernel
+    taps, with ``grad_img=None`` (gradients of the image itself) and with the gradients of another image ``x0``
+    (then also the gradient with respect to ``x0``);
+  * loop_*: ``polyblur_deblurring(x, n_iter=2, alpha=6, beta=1, remove_halo=True)`` and the gradient with respect to
+    the input, estimator in the graph.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import make_golden_vjp as base  # noqa: E402  (imports the reference, defines the synthetic images)
+from polyblur import deblurring, filters  # noqa: E402
+
+
+def main():
+    out = {}
+    g = torch.Generator().manual_seed(17)
+    B, C, H, W = 2, 3, 40, 52
+    x = base.mosaic(B, C, H, W, seed=4)
+    x0 = base.textured(B, C, H, W, seed=6)
+    kw = torch.from_numpy(filters.gaussian_filter((2.5, 1.2), 30 * np.pi / 180, k_size=np.array([25, 25])))
+    kn = torch.from_numpy(filters.gaussian_filter((1.1, 0.8), 100 * np.pi / 180, k_size=np.array([25, 25])))
+    kernels = torch.stack([kw, kn])[:, None].float().contiguous()
+    ybar = torch.randn(B, C, H, W, generator=g)
+    # grad_img = None
+    xr = x.clone().requires_grad_(True)
+    kr = kernels.clone().requires_grad_(True)
+    y = deblurring.inverse_filtering_rank3(xr, kr, alpha=6, b=1, remove_halo=True, method="fft")
+    gx, gk = torch.autograd.grad((y * ybar).sum(), (xr, kr))
+    out["stage_x"] = x.numpy()
+    out["stage_x0"] = x0.numpy()
+    out["stage_kernels"] = kernels.numpy()
+    out["stage_ybar"] = ybar.numpy()
+    out["stage_self_y"] = y.detach().numpy()
+    out["stage_self_grad"] = gx.numpy()
+    out["stage_self_kernel_grad"] = gk.numpy()
+    # grad_img of another image
+    xr = x.clone().requires_grad_(True)
+    x0r = x0.clone().requires_grad_(True)
+    y = deblurring.inverse_filtering_rank3(xr, kernels, alpha=6, b=1, remove_halo=True,
+                                           grad_img=filters.fourier_gradients(x0r), method="fft")
+    gx, g0 = torch.autograd.grad((y * ybar).sum(), (xr, x0r))
+    out["stage_other_y"] = y.detach().numpy()
+    out["stage_other_grad"] = gx.numpy()
+    out["stage_other_grad_x0"] = g0.numpy()
+    frac = float(((y.detach() - deblurring.inverse_filtering_rank3(x, kernels, alpha=6, b=1, method="fft")).abs() > 1e-6)
+                 .float().mean())
+    print("stage: fraction of pixels the mask changes =", frac)
+
+    # two iterations of the loop
+    B, C, H, W = 2, 3, 64, 80
+    x = base.textured(B, C, H, W, seed=5)
+    ybar = torch.randn(B, C, H, W, generator=g)
+    assert base.unique_maxima_margin(x) > 1e-4
+    xr = x.clone().requires_grad_(True)
+    y = deblurring.polyblur_deblurring(xr, n_iter=2, alpha=6, beta=1, remove_halo=True)
+    (gx,) = torch.autograd.grad((y * ybar).sum(), xr)
+    with torch.no_grad():
+        x1 = deblurring.polyblur_deblurring(x, n_iter=1, alpha=6, beta=1, remove_halo=True)
+    print("loop: smallest top-2 gap, iteration 2 =", base.unique_maxima_margin(x1))
+    assert base.unique_maxima_margin(x1) > 1e-4
+    out["loop_x"] = x.numpy()
+    out["loop_ybar"] = ybar.numpy()
+    out["loop_y"] = y.detach().numpy()
+    out["loop_grad"] = gx.numpy()
+    np.savez_compressed(os.path.join(HERE, "vjp_halo.npz"), **out)
+    for k, v in out.items():
+        print(k, v.shape, float(np.abs(v).max()))
+
+
+if __name__ == "__main__":
+    main()

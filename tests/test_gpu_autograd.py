@@ -166,11 +166,53 @@ def test_polyblur_gradient(pb, gold):
 
 def test_gradient_unsupported_options_raise(pb, gold):
     x = cu(gold["chain_x"]).requires_grad_(True)
-    for kw in (dict(remove_halo=True), dict(edgetaping=True), dict(prefiltering=True), dict(q=0.01),
-               dict(discard_saturation=True)):
+    for kw in (dict(edgetaping=True), dict(prefiltering=True), dict(q=0.01), dict(discard_saturation=True),
+               dict(remove_halo=True, edgetaping=True)):
         with pytest.raises(NotImplementedError):
             pb.polyblur_deblurring(x, n_iter=1, **kw)
     with pytest.raises(NotImplementedError):
         pb.PolyblurDeblurring(patch_decomposition=True, patch_size=32)(x, n_iter=1)
     with torch.no_grad():
         pb.polyblur_deblurring(x, n_iter=1, remove_halo=True)
+
+
+def test_halo_masking_gradients_golden(pb):
+    """remove_halo=True under autograd (polyblur/deblurring.py:171-239): the stage with its own and with another
+    image's gradients (image, kernel taps and that other image receive gradient), and two iterations of the loop
+    with the estimator in the graph, against torch.autograd over the reference (tests/golden/vjp_halo.npz)."""
+    gold = np.load(os.path.join(G, "vjp_halo.npz"))
+    x, x0 = cu(gold["stage_x"]), cu(gold["stage_x0"])
+    k, ybar = cu(gold["stage_kernels"]), cu(gold["stage_ybar"])
+    # forward of the differentiable composite = the fused no-grad path = the reference
+    with torch.no_grad():
+        y_fused = pb.deblurring.inverse_filtering_rank3(x, k, alpha=6, b=1, remove_halo=True)
+    xr, kr = x.clone().requires_grad_(True), k.clone().requires_grad_(True)
+    y = pb.deblurring.inverse_filtering_rank3(xr, kr, alpha=6, b=1, remove_halo=True)
+    assert float((y.detach() - y_fused).abs().max()) < 2e-6
+    assert np.abs(y.detach().cpu().numpy() - gold["stage_self_y"]).max() < 1e-5
+    (y * ybar).sum().backward()
+    assert rel(xr.grad.cpu().numpy(), gold["stage_self_grad"]) < 5e-5
+    assert rel(kr.grad.cpu().numpy(), gold["stage_self_kernel_grad"]) < 2e-4
+    # the mask from another image's gradients: that image gets gradient too
+    xr, x0r = x.clone().requires_grad_(True), x0.clone().requires_grad_(True)
+    y = pb.deblurring.inverse_filtering_rank3(xr, k, alpha=6, b=1, remove_halo=True,
+                                              grad_img=pb.filters.fourier_gradients(x0r))
+    assert np.abs(y.detach().cpu().numpy() - gold["stage_other_y"]).max() < 1e-5
+    (y * ybar).sum().backward()
+    assert rel(xr.grad.cpu().numpy(), gold["stage_other_grad"]) < 5e-5
+    assert rel(x0r.grad.cpu().numpy(), gold["stage_other_grad_x0"]) < 2e-4
+    # the loop
+    x, ybar = cu(gold["loop_x"]), cu(gold["loop_ybar"])
+    with torch.no_grad():
+        y_fused = pb.polyblur_deblurring(x, n_iter=2, alpha=6, beta=1, remove_halo=True)
+    xr = x.clone().requires_grad_(True)
+    y = pb.polyblur_deblurring(xr, n_iter=2, alpha=6, beta=1, remove_halo=True)
+    assert float((y.detach() - y_fused).abs().max()) < 5e-6
+    assert np.abs(y.detach().cpu().numpy() - gold["loop_y"]).max() < 1e-5
+    (y * ybar).sum().backward()
+    assert rel(xr.grad.cpu().numpy(), gold["loop_grad"]) < 5e-4
+    # the module surface routes the same way
+    xm = x.clone().requires_grad_(True)
+    ym = pb.PolyblurDeblurring()(xm, n_iter=2, c=0.352, b=0.768, alpha=6, beta=1, remove_halo=True)
+    (ym * ybar).sum().backward()
+    assert rel(xm.grad.cpu().numpy(), gold["loop_grad"]) < 5e-4
