@@ -181,6 +181,10 @@ PB_API int pb_deconv_vjp_f32(const float* grad_out, const float* preclamp, float
 PB_API size_t pb_backward_workspace_bytes(int B, int C, int H, int W, int ksize, int engine);
 PB_API int pb_estimate_trace_f32(const float* img, int B, int C, int H, int W, float* trace_f, int* trace_pos,
                           void* workspace, size_t workspace_bytes, void* stream);
+/* The same with flags = 0 or PB_FLAG_DISCARD_SATURATION: the arg-max search then leaves out the pixels whose gray value
+ * is > 0.99 (get_saturation_mask + compute_gradients, blur_estimation.py:83-88, 112-119). */
+PB_API int pb_estimate_trace_ex_f32(const float* img, int B, int C, int H, int W, uint32_t flags, float* trace_f,
+                             int* trace_pos, void* workspace, size_t workspace_bytes, void* stream);
 PB_API int pb_kernel_grad_f32(const float* img, const float* grad_out, const float* preclamp, int B, int C,
                        int H, int W, const float* kernel, int ksize, double alpha, double beta, int engine,
                        float* kernel_grad, void* workspace, size_t workspace_bytes, void* stream);

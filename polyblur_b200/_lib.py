@@ -70,6 +70,8 @@ _SIGS = {
                                     C.c_double, C.c_int, _P, C.c_size_t, _P]),
     "pb_backward_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "pb_estimate_trace_f32": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_size_t, _P]),
+    "pb_estimate_trace_ex_f32": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, _P, _P, _P, C.c_size_t,
+                                           _P]),
     "pb_kernel_grad_f32": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.c_double,
                                      C.c_double, C.c_int, _P, _P, C.c_size_t, _P]),
     "pb_estimator_vjp_f32": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_size_t, _P]),

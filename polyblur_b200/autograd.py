@@ -23,8 +23,9 @@ its clamp -> ``halo_masking`` written with the differentiable ``filters.fourier_
 elementwise torch operations -> clamp.  It matches torch.autograd over the reference (tests/golden/vjp_halo.npz),
 including the path through the gradients of the original image that the mask is built from.
 
-The other options are not differentiable here (edgetaper, prefilter, quantile normalisation, saturation mask:
-they raise); the kernels, the estimator traces and the unclamped iterates are kept for the backward pass (n_iter
+``discard_saturation=True`` is differentiable as well (the trace's arg-max search leaves the saturated pixels out, as
+the forward estimator does).  The other options are not differentiable here (edgetaper, prefilter, quantile
+normalisation: they raise); the kernels, the estimator traces and the unclamped iterates are kept for the backward pass (n_iter
 extra images of memory).
 """
 from __future__ import annotations
@@ -91,17 +92,19 @@ def _bw_workspace(B, Cn, H, W, ks, engine, dev):
     return torch.empty(n, dtype=torch.uint8, device=dev)
 
 
-def estimate_trace(x: torch.Tensor):
-    """Forward trace of the estimator (pb_estimate_trace_f32): (B,24) floats and (B,8) pixel indices."""
+def estimate_trace(x: torch.Tensor, discard_saturation: bool = False):
+    """Forward trace of the estimator (pb_estimate_trace_ex_f32): (B,24) floats and (B,8) pixel indices;
+    ``discard_saturation`` leaves the pixels with gray > 0.99 out of the arg-max search (blur_estimation.py:83-88)."""
     B, Cn, H, W = x.shape
     dev = x.device
     with torch.cuda.device(dev):
         ws = _bw_workspace(B, Cn, H, W, 25, _lib.ENGINE_AUTO, dev)
         tf = torch.empty(B, 24, dtype=torch.float32, device=dev)
         tp = torch.empty(B, 8, dtype=torch.int32, device=dev)
-        rc = _lib.lib().pb_estimate_trace_f32(x.data_ptr(), B, Cn, H, W, tf.data_ptr(), tp.data_ptr(), ws.data_ptr(),
-                                              ws.numel(), _lib.stream_ptr(dev))
-        _lib.check(rc, "pb_estimate_trace_f32")
+        flags = _lib.FLAG_DISCARD_SATURATION if discard_saturation else 0
+        rc = _lib.lib().pb_estimate_trace_ex_f32(x.data_ptr(), B, Cn, H, W, flags, tf.data_ptr(), tp.data_ptr(),
+                                                 ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev))
+        _lib.check(rc, "pb_estimate_trace_ex_f32")
     return tf, tp
 
 
@@ -218,11 +221,12 @@ class EstimateKernelFunction(torch.autograd.Function):
     arg-max pixels, transposed spectral derivative, range normalisation (``pb_estimator_vjp_f32``)."""
 
     @staticmethod
-    def forward(ctx, img, c, b, ker_size):
+    def forward(ctx, img, c, b, ker_size, discard_saturation=False):
         dev = _lib.require_cuda(img)
         x = img.detach().to(dev).contiguous()
-        k = blur_estimation.gaussian_blur_estimation(x, q=0.0, c=c, b=b, ker_size=ker_size).contiguous()
-        tf, tp = estimate_trace(x)
+        k = blur_estimation.gaussian_blur_estimation(x, q=0.0, c=c, b=b, ker_size=ker_size,
+                                                     discard_saturation=bool(discard_saturation)).contiguous()
+        tf, tp = estimate_trace(x, bool(discard_saturation))
         ctx.save_for_backward(x, tf, tp)
         ctx.meta = (float(c), float(b), int(ker_size), img.device)
         return k.to(img.device)
@@ -235,7 +239,7 @@ class EstimateKernelFunction(torch.autograd.Function):
         mbar = _maxima_grad(tf[:, :7], kb, c, b, ks)
         gin = torch.zeros_like(x)
         estimator_vjp(x, mbar, tf, tp, gin)
-        return gin.to(src), None, None, None
+        return gin.to(src), None, None, None, None
 
 
 def halo_masking(img: torch.Tensor, imout: torch.Tensor, grad_img=None) -> torch.Tensor:
@@ -258,7 +262,7 @@ def inverse_filtering_rank3_halo(img, kernel, alpha, beta, grad_img, engine) -> 
 
 
 def polyblur_deblurring_halo_grad(img: torch.Tensor, n_iter=1, c=0.352, b=0.768, alpha=2, beta=3, ker_size=25,
-                                  engine=_lib.ENGINE_AUTO, estimate_grad=True) -> torch.Tensor:
+                                  engine=_lib.ENGINE_AUTO, estimate_grad=True, discard_saturation=False) -> torch.Tensor:
     """Differentiable ``polyblur_deblurring(..., remove_halo=True)`` (deblurring.py:60-88): the mask of every iteration
     is built from the gradients of the ORIGINAL image, which therefore also receives gradient through them."""
     if img.dtype != torch.float32 or img.ndim != 4:
@@ -270,10 +274,11 @@ def polyblur_deblurring_halo_grad(img: torch.Tensor, n_iter=1, c=0.352, b=0.768,
     cur = x
     for _ in range(int(n_iter)):
         if estimate_grad:
-            k = EstimateKernelFunction.apply(cur, c, b, ker_size)
+            k = EstimateKernelFunction.apply(cur, c, b, ker_size, bool(discard_saturation))
         else:
             with torch.no_grad():
-                k = blur_estimation.gaussian_blur_estimation(cur.detach(), q=0.0, c=c, b=b, ker_size=ker_size)
+                k = blur_estimation.gaussian_blur_estimation(cur.detach(), q=0.0, c=c, b=b, ker_size=ker_size,
+                                                             discard_saturation=bool(discard_saturation))
         cur = inverse_filtering_rank3_halo(cur, k, alpha, beta, grad_img, engine).clamp(0.0, 1.0)
     return cur.to(img.device)
 
@@ -282,17 +287,18 @@ class PolyblurFunction(torch.autograd.Function):
     """The Polyblur loop (polyblur/deblurring.py:68-88, default options), differentiable in the image."""
 
     @staticmethod
-    def forward(ctx, img, n_iter, c, b, alpha, beta, ker_size, engine, estimate_grad):
+    def forward(ctx, img, n_iter, c, b, alpha, beta, ker_size, engine, estimate_grad, discard_saturation=False):
         dev = _lib.require_cuda(img)
         x0 = img.detach().to(dev).contiguous()
         cur = x0
         saved = [x0]
         for _ in range(int(n_iter)):
-            k = blur_estimation.gaussian_blur_estimation(cur, q=0.0, c=c, b=b, ker_size=ker_size).contiguous()
+            k = blur_estimation.gaussian_blur_estimation(cur, q=0.0, c=c, b=b, ker_size=ker_size,
+                                                         discard_saturation=bool(discard_saturation)).contiguous()
             v = _deconv_noclamp(cur, k, alpha, beta, engine)
             saved += [k, v]
             if estimate_grad:
-                saved += list(estimate_trace(cur))
+                saved += list(estimate_trace(cur, bool(discard_saturation)))
             cur = v.clamp(0.0, 1.0)
         ctx.save_for_backward(*saved)
         ctx.meta = (int(n_iter), c, b, alpha, beta, int(ker_size), engine, bool(estimate_grad), img.device)
@@ -316,12 +322,14 @@ class PolyblurFunction(torch.autograd.Function):
                 mbar = _maxima_grad(tf[:, :7], kb, float(c), float(b), ks)
                 estimator_vjp(xt, mbar, tf, tp, gin)
             g = gin
-        return (g.to(src),) + (None,) * 8
+        return (g.to(src),) + (None,) * 9
 
 
 def polyblur_deblurring_grad(img: torch.Tensor, n_iter=1, c=0.352, b=0.768, alpha=2, beta=3, ker_size=25,
-                             engine=_lib.ENGINE_AUTO, estimate_grad=True) -> torch.Tensor:
-    """Differentiable ``polyblur_deblurring`` for (B,C,H,W) float32 tensors (default options only)."""
+                             engine=_lib.ENGINE_AUTO, estimate_grad=True, discard_saturation=False) -> torch.Tensor:
+    """Differentiable ``polyblur_deblurring`` for (B,C,H,W) float32 tensors (default options, optionally with the
+    estimator's saturation mask)."""
     if img.dtype != torch.float32 or img.ndim != 4:
         raise TypeError("img must be a float32 (B,C,H,W) tensor")
-    return PolyblurFunction.apply(img, n_iter, c, b, alpha, beta, ker_size, engine, estimate_grad)
+    return PolyblurFunction.apply(img, n_iter, c, b, alpha, beta, ker_size, engine, estimate_grad,
+                                  bool(discard_saturation))

@@ -823,7 +823,16 @@ size_t pb_backward_workspace_bytes(int B, int C, int H, int W, int ksize, int en
 
 int pb_estimate_trace_f32(const float* img, int B, int C, int H, int W, float* trace_f, int* trace_pos,
                           void* workspace, size_t workspace_bytes, void* stream_) {
+    return pb_estimate_trace_ex_f32(img, B, C, H, W, 0, trace_f, trace_pos, workspace, workspace_bytes, stream_);
+}
+
+int pb_estimate_trace_ex_f32(const float* img, int B, int C, int H, int W, uint32_t flags, float* trace_f,
+                             int* trace_pos, void* workspace, size_t workspace_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
+    if (flags & ~(uint32_t)PB_FLAG_DISCARD_SATURATION) {
+        set_error("pb_estimate_trace_ex_f32 understands PB_FLAG_DISCARD_SATURATION only");
+        return PB_ERR_UNSUPPORTED;
+    }
     int rc;
     if ((rc = check_shape(B, C, H, W))) return rc;
     if (!img || !trace_f || !trace_pos) {
@@ -846,7 +855,8 @@ int pb_estimate_trace_f32(const float* img, int B, int C, int H, int W, float* t
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(ws + V.off_keys);
     if ((rc = launch_bw_trace(img, g, gn, stats, keys, B, C, H, W, stream))) return rc;
     if ((rc = gradients_into(gn, gx, gy, B, H, W, T, stream))) return rc;
-    return launch_bw_dirmax(gx, gy, g, keys, stats, trace_f, trace_pos, B, H, W, stream);
+    return launch_bw_dirmax(gx, gy, g, keys, stats, trace_f, trace_pos, B, H, W,
+                            (flags & PB_FLAG_DISCARD_SATURATION) ? 1 : 0, stream);
 }
 
 int pb_kernel_grad_f32(const float* img, const float* grad_out, const float* preclamp, int B, int C, int H, int W,

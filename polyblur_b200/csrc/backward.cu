@@ -77,8 +77,11 @@ __global__ void k_bw_normalize(const float* __restrict__ g, float* __restrict__ 
 }
 
 // per angle: the largest |cos gx - sin gy| and where (first pixel on ties) as one 64-bit key
+// discard: pixels whose un-normalised gray value is > 0.99 have their gradients zeroed (get_saturation_mask +
+// compute_gradients, blur_estimation.py:83-88, 112-119)
 __global__ void k_bw_dirmax(const float* __restrict__ gx, const float* __restrict__ gy, const float* __restrict__ g,
-                            unsigned long long* __restrict__ keys, unsigned* __restrict__ stats, size_t plane) {
+                            unsigned long long* __restrict__ keys, unsigned* __restrict__ stats, size_t plane,
+                            int discard) {
     const int b = blockIdx.y;
     const float mn = ord2f(stats[4 * b]), mx = ord2f(stats[4 * b + 1]);
     unsigned nmin = 0, nmax = 0;
@@ -86,10 +89,11 @@ __global__ void k_bw_dirmax(const float* __restrict__ gx, const float* __restric
 #pragma unroll
     for (int j = 0; j < 7; ++j) best[j] = 0ull;
     for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < plane; o += (size_t)gridDim.x * blockDim.x) {
-        const float x = gx[(size_t)b * plane + o], y = gy[(size_t)b * plane + o];
+        float x = gx[(size_t)b * plane + o], y = gy[(size_t)b * plane + o];
         const float gv = g[(size_t)b * plane + o];
         nmin += (gv == mn);
         nmax += (gv == mx);
+        if (discard && gv > 0.99f) x = y = 0.0f;
 #pragma unroll
         for (int j = 0; j < 7; ++j) {
             const float v = fabsf(__fsub_rn(__fmul_rn(c_bw_cos7[j], x), __fmul_rn(c_bw_sin7[j], y)));
@@ -117,16 +121,17 @@ __global__ void k_bw_dirmax(const float* __restrict__ gx, const float* __restric
 
 // one warp per image: decode the arg-max pixels and the sign there
 //   trace_f[b][0..6] maxima, [7..13] sign, [14] min, [15] max, [16] #min, [17] #max;  trace_pos[b][0..6] pixel
-__global__ void k_bw_finish(const float* __restrict__ gx, const float* __restrict__ gy,
+__global__ void k_bw_finish(const float* __restrict__ gx, const float* __restrict__ gy, const float* __restrict__ g,
                             const unsigned long long* __restrict__ keys, const unsigned* __restrict__ stats,
-                            float* __restrict__ trace_f, int* __restrict__ trace_pos, size_t plane) {
+                            float* __restrict__ trace_f, int* __restrict__ trace_pos, size_t plane, int discard) {
     const int b = blockIdx.x;
     float* tf = trace_f + (size_t)b * PB_BW_TRACE_STRIDE;
     if (threadIdx.x < 7) {
         const int j = threadIdx.x;
         const unsigned long long k = keys[b * 7 + j];
         const unsigned o = 0xffffffffu - (unsigned)(k & 0xffffffffull);
-        const float x = gx[(size_t)b * plane + o], y = gy[(size_t)b * plane + o];
+        float x = gx[(size_t)b * plane + o], y = gy[(size_t)b * plane + o];
+        if (discard && g[(size_t)b * plane + o] > 0.99f) x = y = 0.0f;     // (every unmasked pixel has a zero gradient)
         const float v = __fsub_rn(__fmul_rn(c_bw_cos7[j], x), __fmul_rn(c_bw_sin7[j], y));
         tf[j] = fabsf(v);
         tf[7 + j] = (v > 0.0f) ? 1.0f : (v < 0.0f ? -1.0f : 0.0f);      // d|v|/dv, 0 at v = 0 like torch.abs
@@ -316,11 +321,11 @@ int launch_bw_trace(const float* img, float* g, float* gn, unsigned* stats, unsi
 }
 
 int launch_bw_dirmax(const float* gx, const float* gy, const float* g, unsigned long long* keys, unsigned* stats,
-                     float* trace_f, int* trace_pos, int B, int H, int W, cudaStream_t stream) {
+                     float* trace_f, int* trace_pos, int B, int H, int W, int discard_saturation, cudaStream_t stream) {
     const size_t plane = (size_t)H * W;
     ProfScope prof(PROF_OTHER, stream);
-    k_bw_dirmax<<<bw_grid(plane, B), 256, 0, stream>>>(gx, gy, g, keys, stats, plane);
-    k_bw_finish<<<B, 32, 0, stream>>>(gx, gy, keys, stats, trace_f, trace_pos, plane);
+    k_bw_dirmax<<<bw_grid(plane, B), 256, 0, stream>>>(gx, gy, g, keys, stats, plane, discard_saturation);
+    k_bw_finish<<<B, 32, 0, stream>>>(gx, gy, g, keys, stats, trace_f, trace_pos, plane, discard_saturation);
     PB_LAUNCH_CHECK("k_bw_dirmax / k_bw_finish");
     return PB_OK;
 }

@@ -75,6 +75,29 @@ def main():
     out["loop_ybar"] = ybar.numpy()
     out["loop_y"] = y.detach().numpy()
     out["loop_grad"] = gx.numpy()
+
+    # the estimator's saturation mask (discard_saturation=True): an image in [0.65, 1.9], so that the
+    # strongest gradients of the first iteration sit on masked pixels
+    xs = (x * 1.5 + 0.5).contiguous()           # not clamped: the estimator normalises by min / max (:92-109)
+    sat = float((xs.mean(1) > 0.99).float().mean())
+    print("saturation case: fraction of masked pixels =", sat)
+    assert sat > 0.01
+    with torch.no_grad():
+        k_on = base.blur_estimation.gaussian_blur_estimation(xs, q=0.0, c=0.352, b=0.768, discard_saturation=True)
+        k_off = base.blur_estimation.gaussian_blur_estimation(xs, q=0.0, c=0.352, b=0.768, discard_saturation=False)
+    print("saturation case: max |kernel(mask) - kernel(no mask)| =", float((k_on - k_off).abs().max()))
+    assert float((k_on - k_off).abs().max()) > 1e-5
+    xr = xs.clone().requires_grad_(True)
+    y = deblurring.polyblur_deblurring(xr, n_iter=2, alpha=6, beta=1, discard_saturation=True)
+    (gx,) = torch.autograd.grad((y * ybar).sum(), xr)
+    out["sat_x"] = xs.numpy()
+    out["sat_y"] = y.detach().numpy()
+    out["sat_grad"] = gx.numpy()
+    xr = xs.clone().requires_grad_(True)
+    y = deblurring.polyblur_deblurring(xr, n_iter=1, alpha=6, beta=1, discard_saturation=True, remove_halo=True)
+    (gx,) = torch.autograd.grad((y * ybar).sum(), xr)
+    out["sat_halo_y"] = y.detach().numpy()
+    out["sat_halo_grad"] = gx.numpy()
     np.savez_compressed(os.path.join(HERE, "vjp_halo.npz"), **out)
     for k, v in out.items():
         print(k, v.shape, float(np.abs(v).max()))

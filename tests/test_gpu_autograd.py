@@ -166,8 +166,7 @@ def test_polyblur_gradient(pb, gold):
 
 def test_gradient_unsupported_options_raise(pb, gold):
     x = cu(gold["chain_x"]).requires_grad_(True)
-    for kw in (dict(edgetaping=True), dict(prefiltering=True), dict(q=0.01), dict(discard_saturation=True),
-               dict(remove_halo=True, edgetaping=True)):
+    for kw in (dict(edgetaping=True), dict(prefiltering=True), dict(q=0.01), dict(remove_halo=True, edgetaping=True)):
         with pytest.raises(NotImplementedError):
             pb.polyblur_deblurring(x, n_iter=1, **kw)
     with pytest.raises(NotImplementedError):
@@ -216,3 +215,28 @@ def test_halo_masking_gradients_golden(pb):
     ym = pb.PolyblurDeblurring()(xm, n_iter=2, c=0.352, b=0.768, alpha=6, beta=1, remove_halo=True)
     (ym * ybar).sum().backward()
     assert rel(xm.grad.cpu().numpy(), gold["loop_grad"]) < 5e-4
+
+
+def test_saturation_mask_gradients_golden(pb):
+    """discard_saturation=True under autograd (blur_estimation.py:83-88, 112-119): the estimator's arg-max search leaves
+    the saturated pixels out in the trace as in the forward pass; two iterations of the loop, and one with halo
+    masking on top, against torch.autograd over the reference (tests/golden/vjp_halo.npz)."""
+    gold = np.load(os.path.join(G, "vjp_halo.npz"))
+    x, ybar = cu(gold["sat_x"]), cu(gold["loop_ybar"])
+    with torch.no_grad():
+        y_fused = pb.polyblur_deblurring(x, n_iter=2, alpha=6, beta=1, discard_saturation=True)
+    xr = x.clone().requires_grad_(True)
+    y = pb.polyblur_deblurring(xr, n_iter=2, alpha=6, beta=1, discard_saturation=True)
+    assert float((y.detach() - y_fused).abs().max()) < 2e-6
+    assert np.abs(y.detach().cpu().numpy() - gold["sat_y"]).max() < 1e-5
+    (y * ybar).sum().backward()
+    assert rel(xr.grad.cpu().numpy(), gold["sat_grad"]) < 5e-4
+    # (the mask matters in this case: without it an arg-max pixel sits elsewhere and the gradient is another one)
+    xn = x.clone().requires_grad_(True)
+    (pb.polyblur_deblurring(xn, n_iter=2, alpha=6, beta=1) * ybar).sum().backward()
+    assert rel(xn.grad.cpu().numpy(), gold["sat_grad"]) > 1e-2
+    xr = x.clone().requires_grad_(True)
+    y = pb.polyblur_deblurring(xr, n_iter=1, alpha=6, beta=1, discard_saturation=True, remove_halo=True)
+    assert np.abs(y.detach().cpu().numpy() - gold["sat_halo_y"]).max() < 1e-5
+    (y * ybar).sum().backward()
+    assert rel(xr.grad.cpu().numpy(), gold["sat_halo_grad"]) < 5e-4
