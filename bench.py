@@ -627,6 +627,11 @@ def run_cuda(a):
             "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks, "roofline": roofline,
             "cpu_baseline": cpu, "secondary": secondary,
         }
+        if world > 1 and a.config == "C3":
+            # the N = 1 headline is C2 (BASELINE's metric config); the same-workload one-GPU number a weak-scaling
+            # efficiency divides by is that line's secondary.c3_shape_one_gpu.value
+            line["config"]["weak_scaling_reference"] = ("the N=1 line's secondary.c3_shape_one_gpu.value (32 x 4K on one "
+                                                        "GPU); its headline value is C2, another workload")
         if sweep is not None:
             line["sweep"] = sweep
     else:
