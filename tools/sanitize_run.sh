@@ -1,3 +1,5 @@
+#!/bin/bash
+# compute-sanitizer memcheck / racecheck / synccheck over the compile-time-plan kernels -> gpurun_out/san/sanitizer.txt
 mkdir -p gpurun_out/san
 : > gpurun_out/san/sanitizer.txt
 for T in memcheck racecheck synccheck; do
