@@ -200,6 +200,10 @@ PB_API int pb_edgetaper_f32(const float* img, float* out, int B, int C, int H, i
 /* filters.bilateral_filter (filters.py:107-148), 5x5, sigma_spatial=5, sigma_color=0.1. */
 PB_API int pb_bilateral_f32(const float* img, float* out, int B, int C, int H, int W,
                      float sigma_spatial, float sigma_color, void* stream);
+/* Vector-Jacobian product of pb_bilateral_f32 (what torch.autograd computes over filters.py:107-148): grad_img =
+ * (d out / d img)^T grad_out, every window tap's range weight differentiated; grad_img is overwritten. */
+PB_API int pb_bilateral_vjp_f32(const float* img, const float* grad_out, float* grad_img, int B, int C, int H, int W,
+                         float sigma_spatial, float sigma_color, void* stream);
 
 /* domain_transform.recursive_filter (domain_transform.py:6-85); joint may be NULL. */
 PB_API int pb_recursive_filter_f32(const float* img, const float* joint, float* out, int B, int C, int H,

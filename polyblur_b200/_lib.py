@@ -78,6 +78,7 @@ _SIGS = {
     "pb_edgetaper_f32": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.c_int,
                                    C.c_uint32, _P, C.c_size_t, _P]),
     "pb_bilateral_f32": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _P]),
+    "pb_bilateral_vjp_f32": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _P]),
     "pb_recursive_filter_f32": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                           C.c_float, C.c_int, _P, C.c_size_t, _P]),
     "pb_u8hwc_to_f32nchw": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),

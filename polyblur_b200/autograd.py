@@ -24,8 +24,9 @@ elementwise torch operations -> clamp.  It matches torch.autograd over the refer
 including the path through the gradients of the original image that the mask is built from.
 
 ``discard_saturation=True`` is differentiable as well (the trace's arg-max search leaves the saturated pixels out, as
-the forward estimator does).  The other options are not differentiable here (edgetaper, prefilter, quantile
-normalisation: they raise); the kernels, the estimator traces and the unclamped iterates are kept for the backward pass (n_iter
+the forward estimator does), and so is ``prefiltering=True`` (the reference's 5x5 bilateral filter with its own
+backward kernel, ``pb_bilateral_vjp_f32``).  Edgetaper and the quantile normalisation are not differentiable here
+(they raise); the kernels, the estimator traces and the unclamped iterates are kept for the backward pass (n_iter
 extra images of memory).
 """
 from __future__ import annotations
@@ -262,15 +263,18 @@ def inverse_filtering_rank3_halo(img, kernel, alpha, beta, grad_img, engine) -> 
 
 
 def polyblur_deblurring_halo_grad(img: torch.Tensor, n_iter=1, c=0.352, b=0.768, alpha=2, beta=3, ker_size=25,
-                                  engine=_lib.ENGINE_AUTO, estimate_grad=True, discard_saturation=False) -> torch.Tensor:
-    """Differentiable ``polyblur_deblurring(..., remove_halo=True)`` (deblurring.py:60-88): the mask of every iteration
-    is built from the gradients of the ORIGINAL image, which therefore also receives gradient through them."""
+                                  engine=_lib.ENGINE_AUTO, estimate_grad=True, discard_saturation=False,
+                                  remove_halo=True, prefiltering=False) -> torch.Tensor:
+    """Differentiable ``polyblur_deblurring`` with ``remove_halo`` and / or ``prefiltering`` (deblurring.py:60-88) as a
+    composite of autograd nodes.  The halo mask of every iteration is built from the gradients of the ORIGINAL image,
+    which therefore also receives gradient through them; with the prefilter the smooth component (5x5 bilateral filter,
+    differentiable: ``filters.bilateral_filter``) is deconvolved and the residual added back (:80-84)."""
     if img.dtype != torch.float32 or img.ndim != 4:
         raise TypeError("img must be a float32 (B,C,H,W) tensor")
     from . import filters
     dev = _lib.require_cuda(img)
     x = img.to(dev)
-    grad_img = filters.fourier_gradients(x)
+    grad_img = filters.fourier_gradients(x) if remove_halo else None
     cur = x
     for _ in range(int(n_iter)):
         if estimate_grad:
@@ -279,7 +283,15 @@ def polyblur_deblurring_halo_grad(img: torch.Tensor, n_iter=1, c=0.352, b=0.768,
             with torch.no_grad():
                 k = blur_estimation.gaussian_blur_estimation(cur.detach(), q=0.0, c=c, b=b, ker_size=ker_size,
                                                              discard_saturation=bool(discard_saturation))
-        cur = inverse_filtering_rank3_halo(cur, k, alpha, beta, grad_img, engine).clamp(0.0, 1.0)
+        src, noise = cur, None
+        if prefiltering:
+            src = filters.bilateral_filter(cur)              # edge_aware_filtering (:99-110)
+            noise = cur - src
+        if remove_halo:
+            y = inverse_filtering_rank3_halo(src, k, alpha, beta, grad_img, engine)
+        else:
+            y = DeconvolutionFunction.apply(src, k, alpha, beta, engine, True)
+        cur = (y if noise is None else y + noise).clamp(0.0, 1.0)
     return cur.to(img.device)
 
 

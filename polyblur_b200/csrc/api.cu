@@ -1014,6 +1014,17 @@ int pb_bilateral_f32(const float* img, float* out, int B, int C, int H, int W, f
     return launch_bilateral(img, out, B * C, H, W, sigma_spatial, sigma_color, (cudaStream_t)stream_);
 }
 
+int pb_bilateral_vjp_f32(const float* img, const float* grad_out, float* grad_img, int B, int C, int H, int W,
+                         float sigma_spatial, float sigma_color, void* stream_) {
+    int rc;
+    if ((rc = check_shape(B, C, H, W))) return rc;
+    if (!img || !grad_out || !grad_img || grad_img == img || grad_img == grad_out) {
+        set_error("img / grad_out / grad_img must be non-null device pointers, grad_img distinct from the inputs");
+        return PB_ERR_ARG;
+    }
+    return launch_bilateral_vjp(img, grad_out, grad_img, B * C, H, W, sigma_spatial, sigma_color, (cudaStream_t)stream_);
+}
+
 int pb_recursive_filter_f32(const float* img, const float* joint, float* out, int B, int C, int H, int W,
                             float sigma_s, float sigma_r, int num_iterations, void* workspace,
                             size_t workspace_bytes, void* stream_) {

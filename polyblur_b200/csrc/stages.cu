@@ -70,6 +70,82 @@ k_bilateral(const float* __restrict__ img, float* __restrict__ out, int H, int W
     }
 }
 
+// Vector-Jacobian product of the filter above: out_p = J_p / (W_p + eps), J_p = sum_q F_pq x_q, W_p = sum_q F_pq,
+// F_pq = gw(q - p) exp(-(x_q - x_p)^2 / var2), q over the 5 x 5 window with replicate clamping.  With a = g_p / (W_p + eps)
+// and Fbar_pq = a (x_q - out_p):   xbar_q += a F_pq - t_pq,   xbar_p += t_pq,   t_pq = Fbar_pq F_pq 2 (x_q - x_p) / var2.
+// One thread per pixel-channel p recomputes its window, scatters into the (clamped) window pixels with atomics and
+// adds its own term once; grad_in must be zeroed by the caller (launch_bilateral_vjp does).
+__global__ void __launch_bounds__(256)
+k_bilateral_vjp(const float* __restrict__ img, const float* __restrict__ gout, float* __restrict__ gin, int H, int W,
+                float var2_spatial, float var2_color) {
+    __shared__ float gw[25];
+    if (threadIdx.x < 25) {
+        const int dy = threadIdx.x / 5 - 2, dx = threadIdx.x % 5 - 2;
+        gw[threadIdx.x] = expf(-(float)(dx * dx + dy * dy) / var2_spatial);
+    }
+    __syncthreads();
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= W || y >= H) return;
+    const size_t pl = (size_t)blockIdx.z * H * W;
+    const float* p = img + pl;
+    const float nic = -1.0f / var2_color;
+    const float I = __ldg(p + (size_t)y * W + x);
+    float S[25], F[25];
+    float J = 0.f, Wt = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 5; ++dy) {
+        const float* row = p + (size_t)min(max(y + dy - 2, 0), H - 1) * W;
+        float jr = 0.f, wr = 0.f;
+#pragma unroll
+        for (int dx = 0; dx < 5; ++dx) {
+            const float s = __ldg(row + min(max(x + dx - 2, 0), W - 1));
+            const float d = __fsub_rn(s, I);
+            const float f = __fmul_rn(__expf(__fmul_rn(__fmul_rn(d, d), nic)), gw[dy * 5 + dx]);
+            S[dy * 5 + dx] = s;
+            F[dy * 5 + dx] = f;
+            jr = __fadd_rn(jr, __fmul_rn(f, s));
+            wr = __fadd_rn(wr, f);
+        }
+        J = __fadd_rn(J, jr);
+        Wt = __fadd_rn(Wt, wr);
+    }
+    const float den = __fadd_rn(Wt, 1e-5f);
+    const float o = __fdiv_rn(J, den);
+    const float a = gout[pl + (size_t)y * W + x] / den;
+    const float k2 = 2.0f / var2_color;
+    float own = 0.f;
+    float* g = gin + pl;
+#pragma unroll
+    for (int dy = 0; dy < 5; ++dy) {
+        const size_t ro = (size_t)min(max(y + dy - 2, 0), H - 1) * W;
+#pragma unroll
+        for (int dx = 0; dx < 5; ++dx) {
+            const int i = dy * 5 + dx;
+            const float d = S[i] - I;
+            const float t = a * (S[i] - o) * F[i] * k2 * d;
+            own += t;
+            atomicAdd(g + ro + min(max(x + dx - 2, 0), W - 1), a * F[i] - t);
+        }
+    }
+    atomicAdd(g + (size_t)y * W + x, own);
+}
+
+int launch_bilateral_vjp(const float* img, const float* gout, float* gin, int planes, int H, int W, float sigma_spatial,
+                         float sigma_color, cudaStream_t stream) {
+    if (planes > 65535) {
+        set_error("B*C = %d exceeds the grid z limit", planes);
+        return PB_ERR_ARG;
+    }
+    dim3 grid((W + 31) / 32, (H + 7) / 8, planes);
+    ProfScope prof(PROF_OTHER, stream);
+    PB_CUDA_TRY(cudaMemsetAsync(gin, 0, (size_t)planes * H * W * sizeof(float), stream));
+    k_bilateral_vjp<<<grid, 256, 0, stream>>>(img, gout, gin, H, W, 2.0f * sigma_spatial * sigma_spatial,
+                                             2.0f * sigma_color * sigma_color);
+    PB_LAUNCH_CHECK("k_bilateral_vjp");
+    return PB_OK;
+}
+
 int launch_bilateral(const float* img, float* out, int planes, int H, int W, float sigma_spatial,
                      float sigma_color, cudaStream_t stream) {
     if (planes > 65535) {

@@ -252,16 +252,17 @@ def polyblur_deblurring(img, n_iter=1, c=0.352, b=0.768, alpha=2, beta=3, sigma_
         return utils.to_array(x) if flag_numpy else img
     if not flag_numpy and x.requires_grad and torch.is_grad_enabled():
         # differentiable path (autograd.py): gradient with respect to the image, blur estimates held constant
-        if edgetaping or prefiltering or return_estimates or q > 0:
-            raise NotImplementedError("gradients are implemented for the default options, remove_halo and "
-                                      "discard_saturation (no edgetaping / prefiltering / q); call under "
-                                      "torch.no_grad() or detach the input")
+        if edgetaping or return_estimates or q > 0 or (p.flags & _lib.FLAG_PREFILTER_RF):
+            raise NotImplementedError("gradients are implemented for the default options, remove_halo, prefiltering "
+                                      "(bilateral) and discard_saturation (no edgetaping / q / RF prefilter); call "
+                                      "under torch.no_grad() or detach the input")
         from . import autograd as _autograd
-        if remove_halo:
+        if remove_halo or prefiltering:
             return _autograd.polyblur_deblurring_halo_grad(x, n_iter=n_iter, c=c, b=b, alpha=alpha, beta=beta,
                                                            ker_size=ker_size, engine=p.engine,
                                                            estimate_grad=estimate_grad,
-                                                           discard_saturation=discard_saturation)
+                                                           discard_saturation=discard_saturation,
+                                                           remove_halo=remove_halo, prefiltering=prefiltering)
         return _autograd.polyblur_deblurring_grad(x, n_iter=n_iter, c=c, b=b, alpha=alpha, beta=beta,
                                                   ker_size=ker_size, engine=p.engine, estimate_grad=estimate_grad,
                                                   discard_saturation=discard_saturation)

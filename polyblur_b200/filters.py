@@ -64,7 +64,9 @@ def bilateral_filter(I, ksize=5, sigma_spatial=5.0, sigma_color=0.1):
     """5x5 bilateral filter with per-channel range weights (polyblur/filters.py:107-148)."""
     if ksize != 5:
         raise NotImplementedError("only the reference's 5x5 window is built")
-    x, dev, src = _prep(I, "bilateral_filter")
+    if isinstance(I, torch.Tensor) and I.requires_grad and torch.is_grad_enabled():
+        return _BilateralFilter.apply(I, float(sigma_spatial), float(sigma_color))
+    x, dev, src = _prep(I, "bilateral_filter", differentiable=True)
     B, C, H, W = x.shape
     with torch.cuda.device(dev):
         out = torch.empty_like(x)
@@ -72,6 +74,31 @@ def bilateral_filter(I, ksize=5, sigma_spatial=5.0, sigma_color=0.1):
                                          float(sigma_color), _lib.stream_ptr(dev))
         _lib.check(rc, "pb_bilateral_f32")
     return out.to(src)
+
+
+class _BilateralFilter(torch.autograd.Function):
+    """Backward of the 5x5 bilateral filter (pb_bilateral_vjp_f32): both the averaged samples and every range weight
+    are differentiated, as torch.autograd does over filters.py:107-148."""
+
+    @staticmethod
+    def forward(ctx, I, sigma_spatial, sigma_color):
+        x = I.detach()
+        ctx.save_for_backward(x)
+        ctx.sig = (sigma_spatial, sigma_color)
+        return bilateral_filter(x, 5, sigma_spatial, sigma_color)
+
+    @staticmethod
+    def backward(ctx, gbar):
+        (x0,) = ctx.saved_tensors
+        x, dev, src = _prep(x0, "bilateral_filter", differentiable=True)
+        g = gbar.detach().to(dev, torch.float32).contiguous()
+        B, C, H, W = x.shape
+        with torch.cuda.device(dev):
+            gin = torch.empty_like(x)
+            rc = _lib.lib().pb_bilateral_vjp_f32(x.data_ptr(), g.data_ptr(), gin.data_ptr(), B, C, H, W,
+                                                 float(ctx.sig[0]), float(ctx.sig[1]), _lib.stream_ptr(dev))
+            _lib.check(rc, "pb_bilateral_vjp_f32")
+        return gin.to(src), None, None
 
 
 def gaussian_filter(sigma, theta, shift=np.array([0.0, 0.0]), k_size=np.array([15, 15])):

@@ -10,7 +10,11 @@ Writes vjp_halo.npz next to this file:
     taps, with ``grad_img=None`` (gradients of the image itself) and with the gradients of another image ``x0``
     (then also the gradient with respect to ``x0``);
   * loop_*: ``polyblur_deblurring(x, n_iter=2, alpha=6, beta=1, remove_halo=True)`` and the gradient with respect to
-    the input, estimator in the graph.
+    the input, estimator in the graph;
+  * sat_*: the same loop with ``discard_saturation=True`` on an over-range image (and with halo masking on top);
+  * bil_* / pre_*: the 5x5 bilateral filter alone, the loop with ``prefiltering=True`` (two iterations) and with halo
+    masking on top (one iteration) -- from an out-of-place restatement of the filter, because the reference's own
+    scales an autograd-saved tensor in place and raises under autograd (see main()).
 """
 import os
 import sys
@@ -98,6 +102,56 @@ def main():
     (gx,) = torch.autograd.grad((y * ybar).sum(), xr)
     out["sat_halo_y"] = y.detach().numpy()
     out["sat_halo_grad"] = gx.numpy()
+
+    # the bilateral prefilter (filters.py:107-148, deblurring.py:80-84, 99-110): the stage alone, two iterations of the
+    # loop with prefiltering=True, and one with halo masking on top
+    # The reference's own filter cannot be differentiated: bilateral_filter_loop_ scales the output of torch.exp in
+    # place (filters.py:133, `F *= gw[y]...`), so autograd raises "modified by an inplace operation".  The goldens come
+    # from the same arithmetic with that one statement out of place (checked bit-identical in the forward direction).
+    from polyblur import utils as rutils
+
+    def bilateral_oop(I, ksize=5, sigma_spatial=5.0, sigma_color=0.1):
+        t = torch.arange(-ksize // 2 + 1, ksize // 2 + 1, device=I.device)
+        xx, yy = torch.meshgrid(t, t, indexing="xy")
+        gw = torch.exp(-(xx * xx + yy * yy) / (2 * sigma_spatial * sigma_spatial))
+        I_padded = rutils.pad_with_kernel(I, ksize=ksize)
+        var2 = 2 * sigma_color * sigma_color
+        b_, c_, h, w = I.shape
+        J = torch.zeros_like(I)
+        Wt = torch.zeros_like(I)
+        for yk in range(gw.shape[0]):
+            I_shifted = rutils.extract_tiles(I_padded[..., yk:yk + h, :], kernel_size=(h, w), stride=1)
+            F = I_shifted - I.unsqueeze(1)
+            F = torch.exp(-F * F / var2)
+            F = F * gw[yk].view(-1, 1, 1, 1)
+            J = J + torch.sum(F * I_shifted, dim=1)
+            Wt = Wt + torch.sum(F, dim=1)
+        return J / (Wt + 1e-5)
+
+    xb = (x + 0.02 * torch.randn(x.shape, generator=g)).clamp(0, 1).contiguous()
+    with torch.no_grad():
+        assert torch.equal(filters.bilateral_filter(xb), bilateral_oop(xb)), "restatement differs from the reference"
+    filters.bilateral_filter = bilateral_oop          # deblurring.edge_aware_filtering looks it up at call time
+    xr = xb.clone().requires_grad_(True)
+    yb = filters.bilateral_filter(xr)
+    (gx,) = torch.autograd.grad((yb * ybar).sum(), xr)
+    out["bil_x"] = xb.numpy()
+    out["bil_y"] = yb.detach().numpy()
+    out["bil_grad"] = gx.numpy()
+    assert base.unique_maxima_margin(xb) > 1e-4
+    xr = xb.clone().requires_grad_(True)
+    y = deblurring.polyblur_deblurring(xr, n_iter=2, alpha=6, beta=1, prefiltering=True)
+    (gx,) = torch.autograd.grad((y * ybar).sum(), xr)
+    with torch.no_grad():
+        x1 = deblurring.polyblur_deblurring(xb, n_iter=1, alpha=6, beta=1, prefiltering=True)
+    print("prefilter: smallest top-2 gap, iteration 2 =", base.unique_maxima_margin(x1))
+    out["pre_y"] = y.detach().numpy()
+    out["pre_grad"] = gx.numpy()
+    xr = xb.clone().requires_grad_(True)
+    y = deblurring.polyblur_deblurring(xr, n_iter=1, alpha=6, beta=1, prefiltering=True, remove_halo=True)
+    (gx,) = torch.autograd.grad((y * ybar).sum(), xr)
+    out["pre_halo_y"] = y.detach().numpy()
+    out["pre_halo_grad"] = gx.numpy()
     np.savez_compressed(os.path.join(HERE, "vjp_halo.npz"), **out)
     for k, v in out.items():
         print(k, v.shape, float(np.abs(v).max()))

@@ -166,7 +166,7 @@ def test_polyblur_gradient(pb, gold):
 
 def test_gradient_unsupported_options_raise(pb, gold):
     x = cu(gold["chain_x"]).requires_grad_(True)
-    for kw in (dict(edgetaping=True), dict(prefiltering=True), dict(q=0.01), dict(remove_halo=True, edgetaping=True)):
+    for kw in (dict(edgetaping=True), dict(q=0.01), dict(remove_halo=True, edgetaping=True)):
         with pytest.raises(NotImplementedError):
             pb.polyblur_deblurring(x, n_iter=1, **kw)
     with pytest.raises(NotImplementedError):
@@ -240,3 +240,46 @@ def test_saturation_mask_gradients_golden(pb):
     assert np.abs(y.detach().cpu().numpy() - gold["sat_halo_y"]).max() < 1e-5
     (y * ybar).sum().backward()
     assert rel(xr.grad.cpu().numpy(), gold["sat_halo_grad"]) < 5e-4
+
+
+def test_bilateral_prefilter_gradients_golden(pb):
+    """prefiltering=True under autograd (filters.py:107-148, deblurring.py:80-84, 99-110): the 5x5 bilateral filter's own
+    backward kernel (pb_bilateral_vjp_f32: samples and range weights differentiated), two iterations of the loop, and one
+    with halo masking on top.  The reference's filter scales an autograd-saved tensor in place and raises under
+    autograd; the goldens are torch.autograd over the same arithmetic with that statement out of place
+    (tests/golden/make_golden_vjp_halo.py checks the restatement bit-identical in the forward direction)."""
+    gold = np.load(os.path.join(G, "vjp_halo.npz"))
+    x, ybar = cu(gold["bil_x"]), cu(gold["loop_ybar"])
+    xr = x.clone().requires_grad_(True)
+    y = pb.filters.bilateral_filter(xr)
+    assert np.abs(y.detach().cpu().numpy() - gold["bil_y"]).max() < 2e-6
+    (y * ybar).sum().backward()
+    assert rel(xr.grad.cpu().numpy(), gold["bil_grad"]) < 5e-5
+    # adjoint identity on another shape (ragged sides, one channel): <J u, v> = <u, J^T v> to first order
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = torch.rand(1, 1, 37, 53, device="cuda", generator=g)
+    u = torch.randn(a.shape, device="cuda", generator=g)
+    v = torch.randn(a.shape, device="cuda", generator=g)
+    ar = a.clone().requires_grad_(True)
+    (pb.filters.bilateral_filter(ar) * v).sum().backward()
+    eps = 1e-3
+    with torch.no_grad():
+        jv = (pb.filters.bilateral_filter(a + eps * u) - pb.filters.bilateral_filter(a - eps * u)) / (2 * eps)
+    lhs, rhs = float((jv * v).sum()), float((ar.grad * u).sum())
+    assert abs(lhs - rhs) < 2e-3 * max(1.0, abs(lhs)), (lhs, rhs)
+    # the loop
+    with torch.no_grad():
+        y_fused = pb.polyblur_deblurring(x, n_iter=2, alpha=6, beta=1, prefiltering=True)
+    xr = x.clone().requires_grad_(True)
+    y = pb.polyblur_deblurring(xr, n_iter=2, alpha=6, beta=1, prefiltering=True)
+    assert float((y.detach() - y_fused).abs().max()) < 5e-6
+    assert np.abs(y.detach().cpu().numpy() - gold["pre_y"]).max() < 1e-5
+    (y * ybar).sum().backward()
+    assert rel(xr.grad.cpu().numpy(), gold["pre_grad"]) < 5e-4
+    xr = x.clone().requires_grad_(True)
+    y = pb.polyblur_deblurring(xr, n_iter=1, alpha=6, beta=1, prefiltering=True, remove_halo=True)
+    assert np.abs(y.detach().cpu().numpy() - gold["pre_halo_y"]).max() < 1e-5
+    (y * ybar).sum().backward()
+    assert rel(xr.grad.cpu().numpy(), gold["pre_halo_grad"]) < 5e-4
+    with pytest.raises(NotImplementedError):
+        pb.polyblur_deblurring(x.clone().requires_grad_(True), n_iter=1, prefiltering=True, prefilter="rf")

@@ -88,7 +88,7 @@ def test_asymmetric_kernel_gradients_golden(pb, r2, engine):
 def test_stage_functions_refuse_to_drop_autograd_history(pb):
     x = torch.rand(1, 3, 24, 32, device="cuda", requires_grad=True)
     k = torch.from_numpy(po.gaussian_filter_np((1.5, 0.8), 0.3))[None, None].cuda()
-    for call in (lambda: pb.filters.bilateral_filter(x), lambda: pb.edgetaper.edgetaper(x, k),
+    for call in (lambda: pb.edgetaper.edgetaper(x, k),
                  lambda: pb.domain_transform.recursive_filter(x), lambda: pb.blur_estimation.gaussian_blur_estimation(x)):
         with pytest.raises(NotImplementedError):
             call()
