@@ -74,3 +74,15 @@ def test_gather_outputs_gloo(world, n_items):
     for p in procs:
         p.join(timeout=60)
     assert sorted(results) == [(r, True) for r in range(world)]
+
+
+def test_numa_binding_is_a_no_op_without_topology():
+    """bind_to_gpu_numa_node never raises: without a CUDA device (or on a single-node VM, numa_node = -1) it returns
+    None and leaves the process affinity alone."""
+    import os
+
+    from polyblur_b200 import sharding
+    before = os.sched_getaffinity(0)
+    assert sharding.bind_to_gpu_numa_node(0) is None or isinstance(sharding.bind_to_gpu_numa_node(0), dict)
+    if not torch.cuda.is_available():
+        assert os.sched_getaffinity(0) == before
