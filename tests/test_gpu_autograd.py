@@ -283,3 +283,9 @@ def test_bilateral_prefilter_gradients_golden(pb):
     assert rel(xr.grad.cpu().numpy(), gold["pre_halo_grad"]) < 5e-4
     with pytest.raises(NotImplementedError):
         pb.polyblur_deblurring(x.clone().requires_grad_(True), n_iter=1, prefiltering=True, prefilter="rf")
+    # CPU tensors go through the same composite: the gradient comes back on the input's device
+    xc = torch.from_numpy(gold["bil_x"]).requires_grad_(True)
+    yc = pb.polyblur_deblurring(xc, n_iter=1, alpha=6, beta=1, prefiltering=True, remove_halo=True)
+    assert yc.device.type == "cpu" and np.abs(yc.detach().numpy() - gold["pre_halo_y"]).max() < 1e-5
+    (yc * torch.from_numpy(gold["loop_ybar"])).sum().backward()
+    assert xc.grad.device.type == "cpu" and rel(xc.grad.numpy(), gold["pre_halo_grad"]) < 5e-4
