@@ -1492,7 +1492,8 @@ int launch_deconv_fft(const float* img, float* out, const ImgKernel* kern, const
                              (size_t)cb2 * 13 * sizeof(float2) + (size_t)((RA) - 1) * (RB) * sizeof(float2) + 128;  \
         const size_t smem0 = (size_t)NY * 12 + (size_t)NY * 8 + 2 * 13 * 8 + 64;                                 \
         const long long items2 = (long long)B * ((NX / 2 - 1 + cb2 - 1) / cb2);                                  \
-        static const int c2_per_sm = env_int("PB_FFT_COLS2_CTAS_PER_SM", 4);                                     \
+        /* 0 = one work item per CTA: with the per-column hand-off 1.566 ms per C2 step against 1.578 at 4 or 8 per SM */ \
+        static const int c2_per_sm = env_int("PB_FFT_COLS2_CTAS_PER_SM", 0);                                     \
         const long long cap2 = c2_per_sm > 0 ? (long long)c2_per_sm * PB_NUM_SMS : (1LL << 30);                  \
         const int grid2 = (int)(items2 < cap2 ? items2 : cap2);                                                  \
         static const bool percol = env_int("PB_FFT_COLS2_PERCOL", 1) != 0;     /* per-column hand-off between planes */ \
